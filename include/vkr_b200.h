@@ -1,0 +1,250 @@
+/* vkr_b200.h -- C-ABI of the B200-native shading pass (libvkr_b200.so).
+ *
+ * Drop-in boundary for ONE path of MomentsInGraphics/vulkan_renderer: the per-pixel shading
+ * pass (src/shaders/shading_pass.frag.glsl + polygon_sampling.glsl + the ray-query shadow test).
+ * Conventions mirror the reference's C host code: caller-owned structs, int return
+ * (0 = success), a printf diagnostic on failure, the callee destroys what it built and leaves the
+ * struct zeroed, destroy_* tolerates partially-built or zeroed objects, single caller thread.
+ * No torch / C++ types appear here; device pointers are plain void*.
+ *
+ * Every entry point names the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef VKR_B200_H
+#define VKR_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKR_B200_ABI_VERSION 1
+
+/* ---- enums: numeric values equal the reference's (src/main.h:45-92, src/polygonal_light.h:28-67,
+        src/noise_table.h:20-54) so that render_settings_t fields can be passed through unchanged */
+typedef enum vkr_sampling_strategies_e {
+	vkr_sampling_strategies_diffuse_only = 0,
+	vkr_sampling_strategies_diffuse_ggx_mis = 1,
+	vkr_sampling_strategies_diffuse_specular_separately = 2,
+	vkr_sampling_strategies_diffuse_specular_mis = 3,
+	vkr_sampling_strategies_diffuse_specular_random = 4
+} vkr_sampling_strategies_t;
+
+typedef enum vkr_mis_heuristic_e {
+	vkr_mis_heuristic_balance = 0, vkr_mis_heuristic_power = 1, vkr_mis_heuristic_weighted = 2,
+	vkr_mis_heuristic_optimal_clamped = 3, vkr_mis_heuristic_optimal = 4
+} vkr_mis_heuristic_t;
+
+/* sample_polygon_technique_t values that this library implements (src/polygonal_light.h:28-67) */
+typedef enum vkr_sample_polygon_technique_e {
+	vkr_sample_polygon_projected_solid_angle = 11,
+	vkr_sample_polygon_projected_solid_angle_biased = 12
+} vkr_sample_polygon_technique_t;
+
+typedef enum vkr_noise_type_e { vkr_noise_type_white = 0, vkr_noise_type_blue = 1, vkr_noise_type_ahmed = 2 } vkr_noise_type_t;
+
+/* ---- device (replaces create_vulkan_device, src/vulkan_basics.c:24; device_t, vulkan_basics.h:40-77) */
+typedef struct vkr_device_s {
+	int cuda_device;               /* ordinal handed to cudaSetDevice */
+	int sm_count;                  /* 148 on B200 */
+	int ray_tracing_supported;     /* always 1: the software BVH needs no RT cores (scene.c:485 gate) */
+	void* stream;                  /* cudaStream_t all asynchronous work is enqueued on */
+	int owns_stream;
+	char name[64];
+} vkr_device_t;
+
+/* stream may be NULL (the library creates one) or a caller's cudaStream_t (e.g. torch's current stream) */
+int vkr_create_device(vkr_device_t* device, int cuda_device, void* stream);
+void vkr_destroy_device(vkr_device_t* device);
+/* blocks until everything enqueued on device->stream has finished (vkQueueWaitIdle, scene.c:395) */
+int vkr_device_wait_idle(const vkr_device_t* device);
+
+/* ---- scene (replaces load_scene / destroy_scene, src/scene.h:181-184, src/scene.c:409-581) */
+typedef struct vkr_scene_s {
+	uint64_t triangle_count, material_count;
+	float dequantization_factor[3], dequantization_summand[3];
+	char** material_names;                 /* material_count malloc'ed strings */
+	float* material_params;                /* host: 8 floats per material {base.rgb, linear roughness, metalicity, normal.xy, 0} */
+	/* device buffers, byte-identical to the reference's three mesh buffers (scene.h:56-83) */
+	void* d_quantized_positions;           /* uint32[2] * 3 * triangle_count */
+	void* d_normals_and_tex_coords;        /* uint16[4] * 3 * triangle_count */
+	void* d_material_indices;              /* uint8 * triangle_count */
+	void* d_material_params;
+	/* software acceleration structures (replace VkAccelerationStructureKHR, scene.c:142-406) */
+	void* d_shadow_nodes; void* d_shadow_tris;                 /* over the scene.c:175-187 float soup (a*b+c) */
+	void* d_primary_nodes; void* d_primary_tris; void* d_primary_tri_ids; /* over shader-decoded (fma) vertices */
+	uint64_t shadow_node_count, primary_node_count;
+	uint32_t shadow_max_depth, primary_max_depth;
+	double build_seconds;
+} vkr_scene_t;
+
+/* device may be NULL for vkr_load_scene / vkr_load_ltc_table / vkr_load_noise_table: the files are parsed and the host
+   members filled, no device buffers or acceleration structures are created (loader tests without a GPU).
+   file_path: a *.vks file; texture_path: directory with <material>_{BaseColor,Specular,Normal}.vkt.
+   request_acceleration_structure mirrors load_scene's flag; without it shadow rays cannot be traced. */
+int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, const char* file_path, const char* texture_path, int request_acceleration_structure);
+void vkr_destroy_scene(vkr_scene_t* scene, const vkr_device_t* device);
+
+/* ---- LTC table (replaces load_ltc_table / destroy_ltc_table, src/ltc_table.h:69-72, ltc_table.c:23-200) */
+typedef struct vkr_ltc_constants_s { /* = ltc_constants_t, src/ltc_table.h:23-35 */
+	float fresnel_index_factor, fresnel_index_summand;
+	float roughness_factor, roughness_summand;
+	float inclination_factor, inclination_summand;
+	float padding[2];
+} vkr_ltc_constants_t;
+
+typedef struct vkr_ltc_table_s {
+	uint32_t roughness_count, inclination_count, fresnel_count;
+	void* d_table0;    /* RGBA16_UNORM [fresnel][inclination][roughness] = (inv00, -inv02, inv11, inv20) */
+	void* d_table1;    /* RG16_UNORM   (inv22, albedo) */
+	uint16_t* h_table0; uint16_t* h_table1; /* host copies (for inspection / tests) */
+	vkr_ltc_constants_t constants;
+} vkr_ltc_table_t;
+
+int vkr_load_ltc_table(vkr_ltc_table_t* table, const vkr_device_t* device, const char* directory, uint32_t fresnel_count);
+void vkr_destroy_ltc_table(vkr_ltc_table_t* table, const vkr_device_t* device);
+
+/* ---- noise table (replaces load_noise_table / set_noise_constants, src/noise_table.h:81-89, noise_table.c:46-168) */
+typedef struct vkr_noise_table_s {
+	uint32_t width, height, layers;
+	void* d_noise;        /* RGBA16_UNORM [layer][y][x] */
+	uint16_t* h_noise;
+	uint32_t random_seed;
+} vkr_noise_table_t;
+
+int vkr_load_noise_table(vkr_noise_table_t* noise, const vkr_device_t* device, uint32_t width, uint32_t height, uint32_t layers, vkr_noise_type_t noise_type);
+void vkr_destroy_noise_table(vkr_noise_table_t* noise, const vkr_device_t* device);
+void vkr_set_noise_constants(uint32_t resolution_mask[2], uint32_t* texture_index_mask, uint32_t random_numbers[4], vkr_noise_table_t* noise, int animate_noise);
+
+/* ---- camera and lights (host-only; same binary layout as src/camera.h:24-44, src/polygonal_light.h:100-129) */
+typedef struct vkr_first_person_camera_s {
+	float position_world_space[3];
+	float rotation_z, rotation_x, vertical_fov;
+	float near_plane, far_plane;
+	float speed;
+	int rotate_camera;
+	float rotation_x_0, rotation_z_0;
+} vkr_first_person_camera_t;
+
+typedef struct vkr_polygonal_light_s {
+	float rotation_angles[3]; float scaling_x;
+	float translation[3]; float scaling_y;
+	float radiant_flux[3]; float inv_scaling_x;
+	float surface_radiance[3]; float inv_scaling_y;
+	float plane[4];
+	uint32_t vertex_count; uint32_t texturing_technique; uint32_t texture_index; uint32_t padding_0;
+	float rotation[3][4];
+	float area, rcp_area; float padding_1[2];
+	char* texture_file_path;
+	float* vertices_plane_space;
+	float* vertices_world_space;
+	float* fan_areas;
+} vkr_polygonal_light_t;
+
+typedef struct vkr_scene_specification_s { /* camera + lights of scene_specification_t, src/main.h:29-42 */
+	vkr_first_person_camera_t camera;
+	uint32_t polygonal_light_count;
+	vkr_polygonal_light_t* polygonal_lights;
+} vkr_scene_specification_t;
+
+void vkr_update_polygonal_light(vkr_polygonal_light_t* light);                       /* update_polygonal_light, polygonal_light.c:46-104 */
+void vkr_set_polygonal_light_vertex_count(vkr_polygonal_light_t* light, uint32_t n); /* polygonal_light.c:24-43 */
+void vkr_destroy_polygonal_light(vkr_polygonal_light_t* light);
+void vkr_get_world_to_projection_space(float world_to_projection_space[4][4], const vkr_first_person_camera_t* camera, float aspect_ratio); /* camera.c:74-83 */
+/* quick_load / quick_save, src/main.c:49-130 (same *.save files) */
+int vkr_quick_load(vkr_scene_specification_t* spec, const char* quick_save_path);
+int vkr_quick_save(const vkr_scene_specification_t* spec, const char* quick_save_path);
+void vkr_destroy_scene_specification(vkr_scene_specification_t* spec);
+
+/* ---- render settings (the subset of render_settings_t, src/main.h:128-159, the shading pass consumes) */
+typedef struct vkr_render_settings_s {
+	float exposure_factor, roughness_factor;
+	uint32_t sample_count;
+	vkr_sampling_strategies_t sampling_strategies;
+	vkr_mis_heuristic_t mis_heuristic;
+	float mis_visibility_estimate;
+	vkr_sample_polygon_technique_t polygon_sampling_technique;
+	float error_min_exponent;
+	int animate_noise;
+	int trace_shadow_rays;
+	int show_polygonal_lights;
+} vkr_render_settings_t;
+
+void vkr_specify_default_render_settings(vkr_render_settings_t* settings); /* main.c:232-249 */
+
+/* Size of the constant block for the given lights: 256 + light_count * (160 + 16*V + 16*V + 16*(V-2)),
+   V = max vertex count over the lights (main.c:334). */
+size_t vkr_get_constants_size(const vkr_scene_specification_t* spec);
+/* Writes the per-frame constants exactly as write_constants() does (src/main.c:2114-2188). Returns bytes written. */
+size_t vkr_write_constants(void* data, const vkr_scene_specification_t* spec, const vkr_render_settings_t* settings,
+	const vkr_scene_t* scene, const vkr_ltc_table_t* ltc, vkr_noise_table_t* noise, uint32_t width, uint32_t height);
+
+/* ---- G-buffer producer (stands in for subpass 0 + get_shading_data(), src/main.c:1422-1427,
+        src/shaders/shading_pass.frag.glsl:721-822). Layout: 4 planes of width*height float4:
+        {position.xyz, roughness} {normal.xyz, 1 if surface else 0} {diffuse_albedo.rgb, 0} {fresnel_0.rgb, 0} */
+size_t vkr_gbuffer_size(uint32_t width, uint32_t height);
+/* d_visibility (uint32 per pixel, 0xFFFFFFFF = background) is written by a primary-ray cast; constants = first 256 bytes of the block (host) */
+int vkr_run_visibility_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, void* d_visibility);
+int vkr_run_gbuffer_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, const void* d_visibility, void* d_gbuffer);
+
+/* ---- the shading pass (replaces create_shading_pass src/main.c:598-940, the subpass-1 draw
+        src/main.c:1429-1434 and the per-frame part of render_frame src/main.c:2197-2270) */
+typedef struct vkr_shading_pass_desc_s {
+	uint32_t width, height;
+	/* what the reference bakes into the shader as -D defines (src/main.c:752-792) */
+	uint32_t polygonal_light_count;
+	uint32_t min_polygonal_light_vertex_count, max_polygonal_light_vertex_count;
+	uint32_t sample_count;
+	vkr_sampling_strategies_t sampling_strategies;
+	vkr_mis_heuristic_t mis_heuristic;
+	vkr_sample_polygon_technique_t polygon_sampling_technique;
+	int trace_shadow_rays;
+	int show_polygonal_lights;
+	/* screen-tile rows this pass instance shades: [row_begin, row_end); row_end = 0 means height (multi-GPU stripes) */
+	uint32_t row_begin, row_end;
+	/* resources */
+	const vkr_scene_t* scene;
+	const vkr_ltc_table_t* ltc_table;
+	const vkr_noise_table_t* noise_table;
+} vkr_shading_pass_desc_t;
+
+typedef struct vkr_shading_pass_s {
+	vkr_shading_pass_desc_t desc;
+	size_t constants_size;
+	void* d_constants;         /* device staging of the constant block */
+	void* h_constants_pinned;
+	void* d_gbuffer_staging;   /* used by vkr_shading_pass_run_host only */
+	void* d_out_staging;
+	uint64_t kernel_launches;  /* number of kernels this pass has launched so far */
+	float last_kernel_ms;      /* device time of the most recent shading kernel (CUDA events), if timing is enabled */
+	void* event_begin; void* event_end;
+	int timing_enabled;
+} vkr_shading_pass_t;
+
+int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device, const vkr_shading_pass_desc_t* desc);
+void vkr_destroy_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device);
+/* Asynchronous on device->stream. constants: HOST pointer to the block written by vkr_write_constants() (or by the
+   reference's write_constants()). d_gbuffer / d_out_rgba32f: DEVICE pointers (out = width*height float4, rows outside
+   [row_begin,row_end) untouched). */
+int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f);
+/* End-to-end variant with HOST buffers: uploads the G-buffer rows of this stripe, shades, downloads the stripe, waits. */
+int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer, float* out_rgba32f);
+int vkr_shading_pass_wait(vkr_shading_pass_t* pass, const vkr_device_t* device);
+
+/* ---- shadow-ray probe (tests / KATs): rays = {ox,oy,oz,dx,dy,dz,tmin,tmax} per ray on the HOST, out = 1 byte per ray */
+int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, uint32_t ray_count, const float* rays, uint8_t* out_occluded);
+/* ---- sampling probe (tests / KATs): clip + prepare + sample in the polygon's local space on the device */
+int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t vertex_count, const float* vertices_xyz, int biased,
+	uint32_t n, const float* random_numbers, float* out_dirs, float* out_info);
+
+/* ---- BVH builder probe (structural tests on the host; arrays are malloc'ed, release with vkr_bvh_free_probe).
+        nodes: 16 floats per node pair, tris: 12 floats per slot, tri_ids: original index per slot (layout: csrc/vkr_trace.cuh) */
+int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth);
+void vkr_bvh_free_probe(float* nodes, float* tris, uint32_t* tri_ids);
+
+uint32_t vkr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,136 @@
+"""ctypes binding of the CPU oracle (oracle/build/liboracle.so). TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
+
+
+class Config(C.Structure):
+	_fields_ = [(n, C.c_uint32) for n in ("width", "height", "light_count", "max_light_vertex_count", "min_light_vertex_count", "sample_count",
+		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end")]
+
+
+_lib = None
+
+
+def load():
+	global _lib
+	if _lib is None:
+		if not os.path.exists(LIB_PATH):
+			subprocess.check_call(["make", "-C", _HERE])
+		lib = C.CDLL(LIB_PATH)
+		lib.vkr_oracle_light_stride.restype = C.c_size_t
+		lib.vkr_oracle_clip.restype = C.c_uint32
+		_lib = lib
+	return _lib
+
+
+def _p(a):
+	return a.ctypes.data_as(C.c_void_p)
+
+
+def shade(cfg, constants, gbuffer, noise, ltc0, ltc1, tris):
+	"""cfg: dict of Config fields. Returns (rgba float32 [H,W,4], shadow ray count)."""
+	lib = load()
+	c = Config(**cfg)
+	gbuffer = np.ascontiguousarray(gbuffer, dtype=np.float32)
+	noise = np.ascontiguousarray(noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(ltc1, dtype=np.uint16)
+	tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+	out = np.zeros((c.height, c.width, 4), dtype=np.float32)
+	rays = C.c_uint64(0)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_oracle_shade(C.byref(c), cb, _p(gbuffer), _p(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]),
+		_p(ltc0), _p(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), _p(tris), C.c_uint32(len(tris)), _p(out), C.byref(rays))
+	if rc != 0:
+		raise RuntimeError("vkr_oracle_shade failed")
+	return out, rays.value
+
+
+def dequantize_for_bvh(quantized_positions, factor, summand):
+	lib = load()
+	q = np.ascontiguousarray(quantized_positions, dtype=np.uint32).reshape(-1, 2)
+	f = np.ascontiguousarray(factor, dtype=np.float32); s = np.ascontiguousarray(summand, dtype=np.float32)
+	out = np.zeros((len(q), 3), dtype=np.float32)
+	lib.vkr_oracle_dequantize_for_bvh(_p(q), C.c_uint64(len(q)), _p(f), _p(s), _p(out))
+	return out.reshape(-1, 9)
+
+
+def visibility(width, height, constants, quantized_positions):
+	lib = load()
+	q = np.ascontiguousarray(quantized_positions, dtype=np.uint32).reshape(-1, 2)
+	out = np.zeros((height, width), dtype=np.uint32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	lib.vkr_oracle_visibility(C.c_uint32(width), C.c_uint32(height), cb, _p(q), C.c_uint64(len(q) // 3), _p(out))
+	return out
+
+
+def gbuffer(width, height, constants, vis, quantized_positions, normals_and_tex_coords, material_indices, material_params):
+	lib = load()
+	q = np.ascontiguousarray(quantized_positions, dtype=np.uint32); nt = np.ascontiguousarray(normals_and_tex_coords, dtype=np.uint16)
+	mi = np.ascontiguousarray(material_indices, dtype=np.uint8); mp = np.ascontiguousarray(material_params, dtype=np.float32)
+	vis = np.ascontiguousarray(vis, dtype=np.uint32)
+	out = np.zeros((4, height, width, 4), dtype=np.float32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	lib.vkr_oracle_gbuffer(C.c_uint32(width), C.c_uint32(height), cb, _p(vis), _p(q), _p(nt), _p(mi), _p(mp), _p(out))
+	return out
+
+
+def clip(vertex_count, vertices, maxp):
+	lib = load()
+	v = np.zeros((8, 3), dtype=np.float32); v[:len(vertices)] = vertices
+	vc = lib.vkr_oracle_clip(C.c_uint32(vertex_count), _p(v), C.c_uint32(maxp))
+	return vc, v
+
+
+def psa_sample_batch(vertices, maxp, random_numbers, biased=False, do_clip=True):
+	"""Returns (dirs [n,3], errors [n,2], info dict)."""
+	lib = load()
+	vertices = np.asarray(vertices, dtype=np.float32)
+	v = np.zeros((9, 3), dtype=np.float32); v[:len(vertices)] = vertices
+	r = np.ascontiguousarray(random_numbers, dtype=np.float32).reshape(-1, 2)
+	dirs = np.zeros((len(r), 3), dtype=np.float32); err = np.zeros((len(r), 2), dtype=np.float32); info = np.zeros(11, dtype=np.float32)
+	lib.vkr_oracle_psa_sample_batch(C.c_uint32(len(vertices)), _p(v), C.c_uint32(maxp), C.c_int(int(biased)), C.c_int(int(do_clip)), C.c_uint32(len(r)), _p(r), _p(dirs), _p(err), _p(info))
+	return dirs, err, dict(psa=float(info[0]), central=bool(info[1]), vc=int(info[2]), sectors=info[3:].copy())
+
+
+def sort_network(vertices_xy, ellipses_xy, maxp):
+	lib = load()
+	v = np.ascontiguousarray(vertices_xy, dtype=np.float32).copy(); e = np.ascontiguousarray(ellipses_xy, dtype=np.float32).copy()
+	lib.vkr_oracle_sort_network(C.c_uint32(len(v)), C.c_uint32(maxp), _p(v), _p(e))
+	return v, e
+
+
+ELEMENTARY = dict(atan=0, sin=1, cos=2, acos01=3, rsqrt=4, fast_positive_atan=5)
+
+
+def elementary(which, x):
+	lib = load()
+	x = np.ascontiguousarray(x, dtype=np.float32); y = np.zeros_like(x)
+	lib.vkr_oracle_elementary_batch(C.c_int(ELEMENTARY[which]), C.c_uint32(x.size), _p(x), _p(y))
+	return y
+
+
+def kahan(a, b, c, d):
+	lib = load()
+	lib.vkr_oracle_kahan.restype = C.c_float
+	lib.vkr_oracle_kahan.argtypes = [C.c_float] * 4
+	return lib.vkr_oracle_kahan(a, b, c, d)
+
+
+def trace_any(tris, rays, brute=True):
+	lib = load()
+	tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9); rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+	a = np.zeros(len(rays), dtype=np.uint8); b = np.zeros(len(rays), dtype=np.uint8)
+	lib.vkr_oracle_trace_any(_p(tris), C.c_uint32(len(tris)), C.c_uint32(len(rays)), _p(rays), _p(a), _p(b) if brute else None)
+	return a, (b if brute else None)
+
+
+def thread_count():
+	return load().vkr_oracle_thread_count()

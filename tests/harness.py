@@ -1,0 +1,158 @@
+"""Shared test harness: synthetic datasets, an independent numpy reading of the reference's file
+formats for the oracle side, and helpers that run the same frame through the oracle and through
+the CUDA library (C-ABI). Used by tests/, __graft_entry__.smoke() and bench.py's CPU legs only.
+"""
+import ctypes as C
+import os
+import struct
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+import sys
+if ROOT not in sys.path:
+	sys.path.insert(0, ROOT)
+
+from oracle import binding as oracle  # noqa: E402
+from vulkan_renderer_b200 import api, synth  # noqa: E402
+
+_DATA_ROOT = os.environ.get("VKR_TEST_DATA", os.path.join(tempfile.gettempdir(), "vkr_b200_data"))
+_cache = {}
+
+
+def dataset(name, **overrides):
+	"""Builds (once per process and per parameter set) a synthetic dataset on disk."""
+	key = (name, tuple(sorted(overrides.items())))
+	if key not in _cache:
+		tag = name + "".join("_%s%s" % (k, v) for k, v in sorted(overrides.items()))
+		directory = os.path.join(_DATA_ROOT, tag)
+		_cache[key] = synth.build_dataset(directory, name, **overrides)
+	return _cache[key]
+
+
+# ---------------------------------------------------------------------------------------------
+# independent numpy readers of the reference's formats (oracle side; byte/integer work)
+# ---------------------------------------------------------------------------------------------
+
+def read_vks(path):
+	"""src/scene.c:419-483"""
+	with open(path, "rb") as f:
+		marker, version = struct.unpack("<II", f.read(8))
+		assert marker == 0xABCABC and version == 1
+		n_mat, n_tri = struct.unpack("<QQ", f.read(16))
+		factor = np.frombuffer(f.read(12), dtype="<f4").copy(); summand = np.frombuffer(f.read(12), dtype="<f4").copy()
+		names = []
+		for _ in range(n_mat):
+			(length,) = struct.unpack("<Q", f.read(8))
+			names.append(f.read(length + 1)[:-1].decode())
+		positions = np.frombuffer(f.read(8 * 3 * n_tri), dtype="<u4").reshape(-1, 2).copy()
+		normals_uv = np.frombuffer(f.read(8 * 3 * n_tri), dtype="<u2").reshape(-1, 4).copy()
+		material_indices = np.frombuffer(f.read(n_tri), dtype=np.uint8).copy()
+		(eof,) = struct.unpack("<I", f.read(4))
+		assert eof == 0xE0FE0F
+	return dict(triangle_count=n_tri, factor=factor, summand=summand, names=names, positions=positions, normals_uv=normals_uv, material_indices=material_indices)
+
+
+def wang_hash(seed):
+	"""src/math_utilities.h:50-57 on uint32 arrays"""
+	seed = np.asarray(seed, dtype=np.uint32)
+	seed = (seed ^ np.uint32(61)) ^ (seed >> np.uint32(16))
+	seed = seed * np.uint32(9)
+	seed = seed ^ (seed >> np.uint32(4))
+	seed = seed * np.uint32(0x27D4EB2D)
+	seed = seed ^ (seed >> np.uint32(15))
+	return seed
+
+
+def white_noise_table(width=256, height=256, layers=64):
+	"""src/noise_table.c:73-75: RGBA16 [layer][y][x][4]"""
+	n = width * height * layers * 4
+	with np.errstate(over="ignore"):
+		data = (wang_hash(np.arange(n, dtype=np.uint32) + np.uint32(243708)) & np.uint32(0xFFFF)).astype(np.uint16)
+	return data.reshape(layers, height, width, 4)
+
+
+def quantize_ltc(directory, fresnel_count=51):
+	"""src/ltc_table.c:46-116 -> (table0 [F,res,res,4], table1 [F,res,res,2]) uint16"""
+	t0, t1 = [], []
+	for i in range(fresnel_count):
+		with open(os.path.join(directory, "fit%d.dat" % i), "rb") as f:
+			(res,) = struct.unpack("<Q", f.read(8))
+			m = np.frombuffer(f.read(20 * res * res), dtype="<f4").reshape(-1, 5).astype(np.float32)
+		m00, m02, m11, m20, albedo = (m[:, k] for k in range(5))
+		inv = np.stack([m11, -m02 * m11, m00 - m02 * m20, -m11 * m20, m00 * m11], axis=1).astype(np.float32)
+		# the reference scans all nine entries of the 3x3 inverse (zeros included) for the maximum magnitude
+		mx = np.max(np.abs(inv), axis=1, keepdims=True)
+		inv = (inv / mx).astype(np.float32)
+		e = np.stack([inv[:, 0], -inv[:, 1], inv[:, 2], inv[:, 3], inv[:, 4], albedo], axis=1).astype(np.float32)
+		e = np.clip(e, np.float32(0.0), np.float32(1.0))
+		q = (e * np.float32(65535.0) + np.float32(0.5)).astype(np.float32).astype(np.uint16)
+		t0.append(q[:, :4].reshape(res, res, 4)); t1.append(q[:, 4:].reshape(res, res, 2))
+	return np.stack(t0), np.stack(t1)
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-side frame
+# ---------------------------------------------------------------------------------------------
+
+class OracleInputs:
+	"""Everything the oracle needs for one dataset, read independently of the CUDA library's loaders."""
+
+	def __init__(self, info, noise_shape=(256, 256, 64)):
+		self.info = info
+		self.vks = read_vks(info["vks"])
+		self.noise = white_noise_table(*noise_shape)
+		self.ltc0, self.ltc1 = quantize_ltc(info["ltc"])
+		self.material_params = info["material_params"]
+		self._shadow_tris = None
+
+	@property
+	def shadow_tris(self):
+		if self._shadow_tris is None:
+			self._shadow_tris = oracle.dequantize_for_bvh(self.vks["positions"], self.vks["factor"], self.vks["summand"])
+		return self._shadow_tris
+
+	def visibility(self, width, height, constants):
+		return oracle.visibility(width, height, constants, self.vks["positions"])
+
+	def gbuffer(self, width, height, constants, vis):
+		return oracle.gbuffer(width, height, constants, vis, self.vks["positions"], self.vks["normals_uv"], self.vks["material_indices"], self.material_params)
+
+	def shade(self, frame_cfg, constants, gbuffer, row_begin=0, row_end=0):
+		cfg = dict(frame_cfg); cfg["row_begin"] = row_begin; cfg["row_end"] = row_end
+		tris = self.shadow_tris if cfg["trace_shadow_rays"] else np.zeros((0, 9), dtype=np.float32)
+		return oracle.shade(cfg, constants, gbuffer, self.noise, self.ltc0, self.ltc1, tris)
+
+
+def oracle_config(frame, width, height):
+	"""The -D defines of the reference (src/main.c:752-792) as the oracle's config, from a vulkan_renderer_b200.Frame."""
+	s = frame.settings
+	counts = frame.light_vertex_counts() or [3]
+	return dict(width=width, height=height, light_count=frame.light_count, max_light_vertex_count=max(max(counts), 3), min_light_vertex_count=min(counts),
+		sample_count=s.sample_count, sampling_strategies=s.sampling_strategies, mis_heuristic=s.mis_heuristic,
+		biased_sampling=int(s.polygon_sampling_technique == api.TECHNIQUE_PSA_BIASED), trace_shadow_rays=s.trace_shadow_rays, show_polygonal_lights=s.show_polygonal_lights,
+		row_begin=0, row_end=0)
+
+
+def open_frame(info, cuda_device=0, **kw):
+	from vulkan_renderer_b200 import Frame
+	return Frame(info["vks"], info["textures"], info["save"], info["ltc"], cuda_device=cuda_device, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# comparison
+# ---------------------------------------------------------------------------------------------
+
+def compare_radiance(test, ref, rel=1.0e-5, floor=1.0e-6):
+	"""Per-pixel relative error |a-b| / max(|b|, floor) over RGB. Returns dict with the worst pixel and counts."""
+	a = np.asarray(test, dtype=np.float64)[..., :3]; b = np.asarray(ref, dtype=np.float64)[..., :3]
+	nan_mismatch = np.isnan(a) != np.isnan(b)
+	err = np.abs(a - b) / np.maximum(np.abs(b), floor)
+	err = np.where(np.isnan(err), 0.0, err)
+	per_pixel = err.max(axis=-1)
+	bad = per_pixel > rel
+	return dict(max_rel=float(per_pixel.max()) if per_pixel.size else 0.0, bad_pixels=int(bad.sum()), pixels=int(per_pixel.size),
+		bit_exact=bool(np.array_equal(np.asarray(test, dtype=np.float32).view(np.uint32), np.asarray(ref, dtype=np.float32).view(np.uint32))),
+		nan_mismatch=int(nan_mismatch.sum()))

@@ -1,0 +1,151 @@
+"""ctypes binding of libvkr_b200.so (include/vkr_b200.h).
+
+This is the host-side mirror used by tests/, bench.py and smoke(); it adds nothing to the C-ABI.
+The product path is the CUDA library: loading fails loudly when it has not been built, and every
+compute entry point needs a visible CUDA device (vkr_create_device reports the absence).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvkr_b200.so")
+
+# Every symbol include/vkr_b200.h declares
+EXPORTED_SYMBOLS = [
+	"vkr_abi_version", "vkr_create_device", "vkr_destroy_device", "vkr_device_wait_idle",
+	"vkr_load_scene", "vkr_destroy_scene", "vkr_load_ltc_table", "vkr_destroy_ltc_table",
+	"vkr_load_noise_table", "vkr_destroy_noise_table", "vkr_set_noise_constants",
+	"vkr_update_polygonal_light", "vkr_set_polygonal_light_vertex_count", "vkr_destroy_polygonal_light",
+	"vkr_get_world_to_projection_space", "vkr_quick_load", "vkr_quick_save", "vkr_destroy_scene_specification",
+	"vkr_specify_default_render_settings", "vkr_get_constants_size", "vkr_write_constants",
+	"vkr_gbuffer_size", "vkr_run_visibility_pass", "vkr_run_gbuffer_pass",
+	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait",
+	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_free_probe",
+]
+
+# enums (values = the reference's)
+STRATEGY_DIFFUSE_ONLY, STRATEGY_DIFFUSE_GGX_MIS, STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, STRATEGY_DIFFUSE_SPECULAR_MIS, STRATEGY_DIFFUSE_SPECULAR_RANDOM = range(5)
+MIS_BALANCE, MIS_POWER, MIS_WEIGHTED, MIS_OPTIMAL_CLAMPED, MIS_OPTIMAL = range(5)
+TECHNIQUE_PSA, TECHNIQUE_PSA_BIASED = 11, 12
+NOISE_WHITE, NOISE_BLUE, NOISE_AHMED = 0, 1, 2
+
+
+class Device(C.Structure):
+	_fields_ = [("cuda_device", C.c_int), ("sm_count", C.c_int), ("ray_tracing_supported", C.c_int), ("stream", C.c_void_p),
+		("owns_stream", C.c_int), ("name", C.c_char * 64)]
+
+
+class Scene(C.Structure):
+	_fields_ = [("triangle_count", C.c_uint64), ("material_count", C.c_uint64),
+		("dequantization_factor", C.c_float * 3), ("dequantization_summand", C.c_float * 3),
+		("material_names", C.POINTER(C.c_char_p)), ("material_params", C.POINTER(C.c_float)),
+		("d_quantized_positions", C.c_void_p), ("d_normals_and_tex_coords", C.c_void_p), ("d_material_indices", C.c_void_p), ("d_material_params", C.c_void_p),
+		("d_shadow_nodes", C.c_void_p), ("d_shadow_tris", C.c_void_p),
+		("d_primary_nodes", C.c_void_p), ("d_primary_tris", C.c_void_p), ("d_primary_tri_ids", C.c_void_p),
+		("shadow_node_count", C.c_uint64), ("primary_node_count", C.c_uint64),
+		("shadow_max_depth", C.c_uint32), ("primary_max_depth", C.c_uint32), ("build_seconds", C.c_double)]
+
+
+class LtcConstants(C.Structure):
+	_fields_ = [("fresnel_index_factor", C.c_float), ("fresnel_index_summand", C.c_float), ("roughness_factor", C.c_float), ("roughness_summand", C.c_float),
+		("inclination_factor", C.c_float), ("inclination_summand", C.c_float), ("padding", C.c_float * 2)]
+
+
+class LtcTable(C.Structure):
+	_fields_ = [("roughness_count", C.c_uint32), ("inclination_count", C.c_uint32), ("fresnel_count", C.c_uint32),
+		("d_table0", C.c_void_p), ("d_table1", C.c_void_p), ("h_table0", C.POINTER(C.c_uint16)), ("h_table1", C.POINTER(C.c_uint16)),
+		("constants", LtcConstants)]
+
+
+class NoiseTable(C.Structure):
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("layers", C.c_uint32), ("d_noise", C.c_void_p), ("h_noise", C.POINTER(C.c_uint16)), ("random_seed", C.c_uint32)]
+
+
+class Camera(C.Structure):
+	_fields_ = [("position_world_space", C.c_float * 3), ("rotation_z", C.c_float), ("rotation_x", C.c_float), ("vertical_fov", C.c_float),
+		("near_plane", C.c_float), ("far_plane", C.c_float), ("speed", C.c_float), ("rotate_camera", C.c_int), ("rotation_x_0", C.c_float), ("rotation_z_0", C.c_float)]
+
+
+class PolygonalLight(C.Structure):
+	_fields_ = [("rotation_angles", C.c_float * 3), ("scaling_x", C.c_float), ("translation", C.c_float * 3), ("scaling_y", C.c_float),
+		("radiant_flux", C.c_float * 3), ("inv_scaling_x", C.c_float), ("surface_radiance", C.c_float * 3), ("inv_scaling_y", C.c_float),
+		("plane", C.c_float * 4), ("vertex_count", C.c_uint32), ("texturing_technique", C.c_uint32), ("texture_index", C.c_uint32), ("padding_0", C.c_uint32),
+		("rotation", (C.c_float * 4) * 3), ("area", C.c_float), ("rcp_area", C.c_float), ("padding_1", C.c_float * 2),
+		("texture_file_path", C.c_void_p), ("vertices_plane_space", C.POINTER(C.c_float)), ("vertices_world_space", C.POINTER(C.c_float)), ("fan_areas", C.POINTER(C.c_float))]
+
+
+class SceneSpecification(C.Structure):
+	_fields_ = [("camera", Camera), ("polygonal_light_count", C.c_uint32), ("polygonal_lights", C.POINTER(PolygonalLight))]
+
+
+class RenderSettings(C.Structure):
+	_fields_ = [("exposure_factor", C.c_float), ("roughness_factor", C.c_float), ("sample_count", C.c_uint32), ("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int),
+		("mis_visibility_estimate", C.c_float), ("polygon_sampling_technique", C.c_int), ("error_min_exponent", C.c_float),
+		("animate_noise", C.c_int), ("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int)]
+
+
+class ShadingPassDesc(C.Structure):
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("polygonal_light_count", C.c_uint32),
+		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
+		("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int), ("polygon_sampling_technique", C.c_int),
+		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("row_begin", C.c_uint32), ("row_end", C.c_uint32),
+		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable))]
+
+
+class ShadingPass(C.Structure):
+	_fields_ = [("desc", ShadingPassDesc), ("constants_size", C.c_size_t), ("d_constants", C.c_void_p), ("h_constants_pinned", C.c_void_p),
+		("d_gbuffer_staging", C.c_void_p), ("d_out_staging", C.c_void_p), ("kernel_launches", C.c_uint64), ("last_kernel_ms", C.c_float),
+		("event_begin", C.c_void_p), ("event_end", C.c_void_p), ("timing_enabled", C.c_int)]
+
+
+_lib = None
+
+
+def load_library():
+	"""Loads libvkr_b200.so. Raises (never falls back) when the CUDA library is missing."""
+	global _lib
+	if _lib is not None:
+		return _lib
+	if not os.path.exists(LIB_PATH):
+		raise RuntimeError("%s is missing: run `python __graft_entry__.py` (build()) first. There is no CPU fallback." % LIB_PATH)
+	lib = C.CDLL(LIB_PATH)
+	missing = [s for s in EXPORTED_SYMBOLS if not hasattr(lib, s)]
+	if missing:
+		raise RuntimeError("libvkr_b200.so lacks symbols declared in include/vkr_b200.h: %s" % missing)
+	P = C.POINTER
+	lib.vkr_abi_version.restype = C.c_uint32
+	lib.vkr_create_device.argtypes = [P(Device), C.c_int, C.c_void_p]
+	lib.vkr_destroy_device.argtypes = [P(Device)]; lib.vkr_destroy_device.restype = None
+	lib.vkr_device_wait_idle.argtypes = [P(Device)]
+	lib.vkr_load_scene.argtypes = [P(Scene), P(Device), C.c_char_p, C.c_char_p, C.c_int]
+	lib.vkr_destroy_scene.argtypes = [P(Scene), P(Device)]; lib.vkr_destroy_scene.restype = None
+	lib.vkr_load_ltc_table.argtypes = [P(LtcTable), P(Device), C.c_char_p, C.c_uint32]
+	lib.vkr_destroy_ltc_table.argtypes = [P(LtcTable), P(Device)]; lib.vkr_destroy_ltc_table.restype = None
+	lib.vkr_load_noise_table.argtypes = [P(NoiseTable), P(Device), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+	lib.vkr_destroy_noise_table.argtypes = [P(NoiseTable), P(Device)]; lib.vkr_destroy_noise_table.restype = None
+	lib.vkr_set_noise_constants.argtypes = [P(C.c_uint32), P(C.c_uint32), P(C.c_uint32), P(NoiseTable), C.c_int]; lib.vkr_set_noise_constants.restype = None
+	lib.vkr_update_polygonal_light.argtypes = [P(PolygonalLight)]; lib.vkr_update_polygonal_light.restype = None
+	lib.vkr_set_polygonal_light_vertex_count.argtypes = [P(PolygonalLight), C.c_uint32]; lib.vkr_set_polygonal_light_vertex_count.restype = None
+	lib.vkr_destroy_polygonal_light.argtypes = [P(PolygonalLight)]; lib.vkr_destroy_polygonal_light.restype = None
+	lib.vkr_get_world_to_projection_space.argtypes = [C.c_void_p, P(Camera), C.c_float]; lib.vkr_get_world_to_projection_space.restype = None
+	lib.vkr_quick_load.argtypes = [P(SceneSpecification), C.c_char_p]
+	lib.vkr_quick_save.argtypes = [P(SceneSpecification), C.c_char_p]
+	lib.vkr_destroy_scene_specification.argtypes = [P(SceneSpecification)]; lib.vkr_destroy_scene_specification.restype = None
+	lib.vkr_specify_default_render_settings.argtypes = [P(RenderSettings)]; lib.vkr_specify_default_render_settings.restype = None
+	lib.vkr_get_constants_size.argtypes = [P(SceneSpecification)]; lib.vkr_get_constants_size.restype = C.c_size_t
+	lib.vkr_write_constants.argtypes = [C.c_void_p, P(SceneSpecification), P(RenderSettings), P(Scene), P(LtcTable), P(NoiseTable), C.c_uint32, C.c_uint32]
+	lib.vkr_write_constants.restype = C.c_size_t
+	lib.vkr_gbuffer_size.argtypes = [C.c_uint32, C.c_uint32]; lib.vkr_gbuffer_size.restype = C.c_size_t
+	lib.vkr_run_visibility_pass.argtypes = [P(Device), P(Scene), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+	lib.vkr_run_gbuffer_pass.argtypes = [P(Device), P(Scene), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+	lib.vkr_create_shading_pass.argtypes = [P(ShadingPass), P(Device), P(ShadingPassDesc)]
+	lib.vkr_destroy_shading_pass.argtypes = [P(ShadingPass), P(Device)]; lib.vkr_destroy_shading_pass.restype = None
+	lib.vkr_shading_pass_run.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+	lib.vkr_shading_pass_run_host.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+	lib.vkr_shading_pass_wait.argtypes = [P(ShadingPass), P(Device)]
+	lib.vkr_trace_shadow_rays.argtypes = [P(Device), P(Scene), C.c_uint32, C.c_void_p, C.c_void_p]
+	lib.vkr_sample_polygon_batch.argtypes = [P(Device), C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+	lib.vkr_bvh_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
+	lib.vkr_bvh_free_probe.argtypes = [P(C.c_float), P(C.c_float), P(C.c_uint32)]; lib.vkr_bvh_free_probe.restype = None
+	_lib = lib
+	return lib

@@ -1,0 +1,271 @@
+// vkr_api.cu -- frame-side C-ABI: G-buffer producer passes, the shading pass object and the
+// device probes used by the parity tests. Replaces create_shading_pass (src/main.c:598-940), the
+// subpass-1 draw (src/main.c:1429-1434) and the per-frame part of render_frame (src/main.c:2197-2270).
+// Compile with -fmad=false (the probe kernels call the same device math as the megakernel).
+#include "../../include/vkr_b200.h"
+#include "vkr_internal.h"
+#include "vkr_kernels.h"
+#include "vkr_psa.cuh"
+#include "vkr_trace.cuh"
+#include <cstdio>
+#include <cstring>
+
+using namespace vkr;
+
+#define VKR_CUDA_OK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e_)); return 1; } } while (0)
+
+extern "C" size_t vkr_gbuffer_size(uint32_t width, uint32_t height) { return (size_t) width * height * 4 * sizeof(float) * 4; }
+
+// ------------------------------------------------------------------------------------------------
+// G-buffer producer
+// ------------------------------------------------------------------------------------------------
+static int fill_gbuffer_params(gbuffer_kernel_params& p, void** d_constants, const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height) {
+	memset(&p, 0, sizeof(p));
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	VKR_CUDA_OK(cudaMallocAsync(d_constants, 256, stream), "Failed to allocate constants for the G-buffer producer");
+	VKR_CUDA_OK(cudaMemcpyAsync(*d_constants, constants, 256, cudaMemcpyHostToDevice, stream), "Failed to upload constants for the G-buffer producer");
+	p.width = (int) width; p.height = (int) height;
+	p.constants = (const unsigned char*) *d_constants;
+	p.quantized_positions = (const uint2*) scene->d_quantized_positions;
+	p.normals_and_tex_coords = (const ushort4*) scene->d_normals_and_tex_coords;
+	p.material_indices = (const uint8_t*) scene->d_material_indices;
+	p.material_params = (const float*) scene->d_material_params;
+	p.bvh_nodes = (const float4*) scene->d_primary_nodes; p.bvh_tris = (const float4*) scene->d_primary_tris; p.bvh_tri_ids = (const uint32_t*) scene->d_primary_tri_ids;
+	p.tri_count = (uint32_t) scene->triangle_count;
+	return 0;
+}
+
+extern "C" int vkr_run_visibility_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, void* d_visibility) {
+	if (!scene->d_primary_nodes) { printf("Cannot run the visibility pass: the scene was loaded without acceleration structure.\n"); return 1; }
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	gbuffer_kernel_params p; void* d_constants = nullptr;
+	if (fill_gbuffer_params(p, &d_constants, device, scene, constants, width, height)) return 1;
+	p.visibility = (uint32_t*) d_visibility;
+	cudaError_t err = vkr_launch_visibility_kernel(p, (cudaStream_t) device->stream);
+	cudaFreeAsync(d_constants, (cudaStream_t) device->stream);
+	VKR_CUDA_OK(err, "Failed to launch the visibility kernel");
+	return 0;
+}
+
+extern "C" int vkr_run_gbuffer_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, const void* d_visibility, void* d_gbuffer) {
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	gbuffer_kernel_params p; void* d_constants = nullptr;
+	if (fill_gbuffer_params(p, &d_constants, device, scene, constants, width, height)) return 1;
+	p.visibility = (uint32_t*) d_visibility;
+	p.gbuffer = (float4*) d_gbuffer;
+	cudaError_t err = vkr_launch_gbuffer_kernel(p, (cudaStream_t) device->stream);
+	cudaFreeAsync(d_constants, (cudaStream_t) device->stream);
+	VKR_CUDA_OK(err, "Failed to launch the G-buffer kernel");
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading pass
+// ------------------------------------------------------------------------------------------------
+extern "C" void vkr_destroy_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device) {
+	(void) device;
+	if (pass->d_constants) cudaFree(pass->d_constants);
+	if (pass->h_constants_pinned) cudaFreeHost(pass->h_constants_pinned);
+	if (pass->d_gbuffer_staging) cudaFree(pass->d_gbuffer_staging);
+	if (pass->d_out_staging) cudaFree(pass->d_out_staging);
+	if (pass->event_begin) cudaEventDestroy((cudaEvent_t) pass->event_begin);
+	if (pass->event_end) cudaEventDestroy((cudaEvent_t) pass->event_end);
+	memset(pass, 0, sizeof(*pass));
+}
+
+extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device, const vkr_shading_pass_desc_t* desc) {
+	memset(pass, 0, sizeof(*pass));
+	pass->desc = *desc;
+	vkr_shading_pass_desc_t& d = pass->desc;
+	if (d.row_end == 0) d.row_end = d.height;
+	// Legality rules of the reference's settings panel (src/user_interface.cpp:90-180), plus what this library implements
+	if (d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle && d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle_biased) {
+		printf("Failed to create the shading pass: only projected solid angle sampling (technique 11 or 12) is implemented, got %d.\n", (int) d.polygon_sampling_technique);
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if ((int) d.sampling_strategies < 0 || (int) d.sampling_strategies > 4 || (int) d.mis_heuristic < 0 || (int) d.mis_heuristic > 4) {
+		printf("Failed to create the shading pass: invalid sampling strategy or MIS heuristic.\n");
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (d.sampling_strategies == vkr_sampling_strategies_diffuse_ggx_mis && d.mis_heuristic != vkr_mis_heuristic_balance && d.mis_heuristic != vkr_mis_heuristic_power) {
+		printf("Failed to create the shading pass: GGX importance sampling supports the balance and power heuristics only.\n");
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (d.max_polygonal_light_vertex_count < 3 || d.max_polygonal_light_vertex_count > 4 || d.min_polygonal_light_vertex_count < 3 || d.min_polygonal_light_vertex_count > d.max_polygonal_light_vertex_count) {
+		printf("Failed to create the shading pass: polygonal lights must have 3 or 4 vertices (got min %u, max %u).\n", d.min_polygonal_light_vertex_count, d.max_polygonal_light_vertex_count);
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (!d.width || !d.height || d.row_begin >= d.row_end || d.row_end > d.height || !d.sample_count || !d.ltc_table || !d.noise_table || !d.ltc_table->d_table0 || !d.noise_table->d_noise) {
+		printf("Failed to create the shading pass: invalid resolution, row range, sample count or missing LTC / noise tables.\n");
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (d.trace_shadow_rays && (!d.scene || !d.scene->d_shadow_nodes)) {
+		printf("Failed to create the shading pass: shadow rays requested but the scene has no acceleration structure.\n");
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (cudaSetDevice(device->cuda_device) != cudaSuccess) { memset(pass, 0, sizeof(*pass)); return 1; }
+	const uint32_t v = d.max_polygonal_light_vertex_count;
+	pass->constants_size = 256 + (size_t) d.polygonal_light_count * (160 + 16 * (size_t) v * 2 + 16 * (size_t) (v - 2));
+	if (pass->constants_size > 160 * 1024) {
+		printf("Failed to create the shading pass: %u lights do not fit into shared memory.\n", d.polygonal_light_count);
+		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (cudaMalloc(&pass->d_constants, pass->constants_size) != cudaSuccess || cudaMallocHost(&pass->h_constants_pinned, pass->constants_size) != cudaSuccess
+		|| cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+	{
+		printf("Failed to allocate constant buffers for the shading pass.\n");
+		pass->event_begin = e0; pass->event_end = e1;
+		vkr_destroy_shading_pass(pass, device); return 1;
+	}
+	pass->event_begin = e0; pass->event_end = e1;
+	return 0;
+}
+
+static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out) {
+	const vkr_shading_pass_desc_t& d = pass->desc;
+	if (constants_size != pass->constants_size) {
+		printf("The constant block has %llu bytes but the shading pass was created for %llu bytes (%u lights with up to %u vertices).\n",
+			(unsigned long long) constants_size, (unsigned long long) pass->constants_size, d.polygonal_light_count, d.max_polygonal_light_vertex_count);
+		return 1;
+	}
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	memcpy(pass->h_constants_pinned, constants, constants_size);
+	VKR_CUDA_OK(cudaMemcpyAsync(pass->d_constants, pass->h_constants_pinned, constants_size, cudaMemcpyHostToDevice, stream), "Failed to upload the constant block");
+	shading_kernel_params p; memset(&p, 0, sizeof(p));
+	p.width = (int) d.width; p.height = (int) d.height; p.row_begin = (int) d.row_begin; p.row_end = (int) d.row_end;
+	p.gbuffer = (const float4*) d_gbuffer; p.out = (float4*) d_out;
+	p.constants = (const unsigned char*) pass->d_constants;
+	p.constants_bytes = (uint32_t) constants_size;
+	p.constants_smem_bytes = (uint32_t) ((constants_size + 127) / 128 * 128);
+	p.light_count = (int) d.polygonal_light_count; p.max_light_vertex_count = (int) d.max_polygonal_light_vertex_count; p.sample_count = (int) d.sample_count;
+	p.sampling_strategies = (int) d.sampling_strategies; p.mis_heuristic = (int) d.mis_heuristic;
+	p.biased_sampling = d.polygon_sampling_technique == vkr_sample_polygon_projected_solid_angle_biased;
+	p.trace_shadow_rays = d.trace_shadow_rays; p.show_polygonal_lights = d.show_polygonal_lights;
+	p.noise = (const uint16_t*) d.noise_table->d_noise; p.noise_w = (int) d.noise_table->width; p.noise_h = (int) d.noise_table->height; p.noise_layers = (int) d.noise_table->layers;
+	p.ltc0 = (const uint16_t*) d.ltc_table->d_table0; p.ltc1 = (const uint16_t*) d.ltc_table->d_table1;
+	p.ltc_res = (int) d.ltc_table->roughness_count; p.ltc_layers = (int) d.ltc_table->fresnel_count;
+	if (d.trace_shadow_rays) { p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count; }
+	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_begin, stream);
+	cudaError_t err = vkr_launch_shading_kernel(p, stream);
+	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_end, stream);
+	VKR_CUDA_OK(err, "Failed to launch the shading kernel");
+	++pass->kernel_launches;
+	return 0;
+}
+
+extern "C" int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f) {
+	return launch_shading(pass, device, constants, constants_size, d_gbuffer, d_out_rgba32f);
+}
+
+extern "C" int vkr_shading_pass_wait(vkr_shading_pass_t* pass, const vkr_device_t* device) {
+	VKR_CUDA_OK(cudaStreamSynchronize((cudaStream_t) device->stream), "Failed to wait for the shading pass");
+	if (pass->timing_enabled && pass->kernel_launches) {
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, (cudaEvent_t) pass->event_begin, (cudaEvent_t) pass->event_end) == cudaSuccess) pass->last_kernel_ms = ms;
+	}
+	return 0;
+}
+
+extern "C" int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer, float* out_rgba32f) {
+	const vkr_shading_pass_desc_t& d = pass->desc;
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	const size_t plane_bytes = (size_t) d.width * d.height * 16;
+	if (!pass->d_gbuffer_staging) {
+		if (cudaMalloc(&pass->d_gbuffer_staging, 4 * plane_bytes) != cudaSuccess || cudaMalloc(&pass->d_out_staging, plane_bytes) != cudaSuccess) {
+			printf("Failed to allocate device staging buffers for the shading pass.\n");
+			return 1;
+		}
+	}
+	// Upload only the rows of this stripe, plane by plane
+	const size_t row_bytes = (size_t) d.width * 16, stripe_offset = row_bytes * d.row_begin, stripe_bytes = row_bytes * (d.row_end - d.row_begin);
+	for (int k = 0; k != 4; ++k)
+		VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes + stripe_offset, (const char*) gbuffer + k * plane_bytes + stripe_offset, stripe_bytes, cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
+	if (launch_shading(pass, device, constants, constants_size, pass->d_gbuffer_staging, pass->d_out_staging)) return 1;
+	VKR_CUDA_OK(cudaMemcpyAsync((char*) out_rgba32f + stripe_offset, (const char*) pass->d_out_staging + stripe_offset, stripe_bytes, cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
+	return vkr_shading_pass_wait(pass, device);
+}
+
+// ------------------------------------------------------------------------------------------------
+// probes for the parity tests
+// ------------------------------------------------------------------------------------------------
+namespace vkr {
+
+__global__ void __launch_bounds__(128) trace_probe_kernel(bvh_view bvh, uint32_t ray_count, const float* rays, uint8_t* out) {
+	__shared__ int stack[kStackDepth * 128];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= ray_count) return;
+	const float* r = rays + 8 * (size_t) i;
+	out[i] = occluded(bvh, make3(r[0], r[1], r[2]), make3(r[3], r[4], r[5]), r[6], r[7], stack + threadIdx.x, 128) ? 1 : 0;
+}
+
+template <int MAXP, bool BIASED>
+__global__ void sample_probe_kernel(int vertex_count, const float* vertices, uint32_t n, const float* rnd, float* out_dirs, float* out_info) {
+	f3 v[MAXP];
+#pragma unroll
+	for (int i = 0; i != MAXP; ++i) v[i] = (i < vertex_count) ? make3(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]) : make3(0.0f, 0.0f, 0.0f);
+	const int vc = clip_polygon<MAXP>(vertex_count, v);
+	psa_polygon<MAXP> p;
+	p.psa = 0.0f; p.inner_ellipse_0 = make2(0.0f, 0.0f);
+#pragma unroll
+	for (int i = 0; i != MAXP; ++i) p.sector_psa[i] = 0.0f;
+	if (vc) prepare_psa<MAXP, BIASED>(p, vc, v);
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0 && out_info) {
+		out_info[0] = p.psa; out_info[1] = (vc && p.inner_ellipse_0.x > 0.0f) ? 1.0f : 0.0f; out_info[2] = (float) vc;
+#pragma unroll
+		for (int k = 0; k != 8; ++k) out_info[3 + k] = (k < MAXP) ? p.sector_psa[k < MAXP ? k : 0] : 0.0f;
+	}
+	if (i >= n || !vc) return;
+	const f3 d = sample_psa<MAXP, BIASED>(p, make2(rnd[2 * i], rnd[2 * i + 1]));
+	out_dirs[3 * i] = d.x; out_dirs[3 * i + 1] = d.y; out_dirs[3 * i + 2] = d.z;
+}
+
+} // namespace vkr
+
+extern "C" int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, uint32_t ray_count, const float* rays, uint8_t* out_occluded) {
+	if (!scene->d_shadow_nodes) { printf("Cannot trace shadow rays: the scene was loaded without acceleration structure.\n"); return 1; }
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	float* d_rays = nullptr; uint8_t* d_out = nullptr;
+	VKR_CUDA_OK(cudaMalloc(&d_rays, sizeof(float) * 8 * (size_t) (ray_count ? ray_count : 1)), "Failed to allocate rays");
+	if (cudaMalloc(&d_out, ray_count ? ray_count : 1) != cudaSuccess) { cudaFree(d_rays); printf("Failed to allocate ray results.\n"); return 1; }
+	cudaMemcpyAsync(d_rays, rays, sizeof(float) * 8 * (size_t) ray_count, cudaMemcpyHostToDevice, stream);
+	bvh_view bvh; bvh.nodes = (const float4*) scene->d_shadow_nodes; bvh.tris = (const float4*) scene->d_shadow_tris; bvh.tri_ids = nullptr; bvh.tri_count = (uint32_t) scene->triangle_count;
+	if (ray_count) trace_probe_kernel<<<(ray_count + 127) / 128, 128, 0, stream>>>(bvh, ray_count, d_rays, d_out);
+	cudaError_t err = cudaGetLastError();
+	cudaMemcpyAsync(out_occluded, d_out, ray_count, cudaMemcpyDeviceToHost, stream);
+	cudaError_t err2 = cudaStreamSynchronize(stream);
+	cudaFree(d_rays); cudaFree(d_out);
+	VKR_CUDA_OK(err, "Failed to launch the shadow ray probe");
+	VKR_CUDA_OK(err2, "The shadow ray probe failed");
+	return 0;
+}
+
+extern "C" int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t vertex_count, const float* vertices_xyz, int biased, uint32_t n, const float* random_numbers, float* out_dirs, float* out_info) {
+	if (vertex_count != 3 && vertex_count != 4) { printf("The sampling probe supports 3 or 4 vertices.\n"); return 1; }
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	float *d_v = nullptr, *d_r = nullptr, *d_d = nullptr, *d_i = nullptr;
+	const size_t nn = n ? n : 1;
+	if (cudaMalloc(&d_v, sizeof(float) * 12) != cudaSuccess || cudaMalloc(&d_r, sizeof(float) * 2 * nn) != cudaSuccess || cudaMalloc(&d_d, sizeof(float) * 3 * nn) != cudaSuccess || cudaMalloc(&d_i, sizeof(float) * 11) != cudaSuccess) {
+		cudaFree(d_v); cudaFree(d_r); cudaFree(d_d); cudaFree(d_i);
+		printf("Failed to allocate buffers for the sampling probe.\n"); return 1;
+	}
+	cudaMemcpyAsync(d_v, vertices_xyz, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(d_r, random_numbers, sizeof(float) * 2 * (size_t) n, cudaMemcpyHostToDevice, stream);
+	cudaMemsetAsync(d_d, 0, sizeof(float) * 3 * nn, stream);
+	const unsigned blocks = (unsigned) ((nn + 127) / 128);
+	if (vertex_count == 4) { if (biased) sample_probe_kernel<5, true><<<blocks, 128, 0, stream>>>(4, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<5, false><<<blocks, 128, 0, stream>>>(4, d_v, n, d_r, d_d, d_i); }
+	else { if (biased) sample_probe_kernel<4, true><<<blocks, 128, 0, stream>>>(3, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<4, false><<<blocks, 128, 0, stream>>>(3, d_v, n, d_r, d_d, d_i); }
+	cudaError_t err = cudaGetLastError();
+	cudaMemcpyAsync(out_dirs, d_d, sizeof(float) * 3 * (size_t) n, cudaMemcpyDeviceToHost, stream);
+	if (out_info) cudaMemcpyAsync(out_info, d_i, sizeof(float) * 11, cudaMemcpyDeviceToHost, stream);
+	cudaError_t err2 = cudaStreamSynchronize(stream);
+	cudaFree(d_v); cudaFree(d_r); cudaFree(d_d); cudaFree(d_i);
+	VKR_CUDA_OK(err, "Failed to launch the sampling probe");
+	VKR_CUDA_OK(err2, "The sampling probe failed");
+	return 0;
+}

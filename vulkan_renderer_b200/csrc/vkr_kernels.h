@@ -1,0 +1,48 @@
+// vkr_kernels.h -- host-visible launch interface of the CUDA kernels (internal to the library).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// numeric values = the reference's sampling_strategies_t / mis_heuristic_t (src/main.h:45-92)
+enum { VKR_STRATEGY_DIFFUSE_ONLY = 0, VKR_STRATEGY_DIFFUSE_GGX_MIS = 1, VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY = 2,
+	VKR_STRATEGY_DIFFUSE_SPECULAR_MIS = 3, VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM = 4 };
+enum { VKR_MIS_BALANCE = 0, VKR_MIS_POWER = 1, VKR_MIS_WEIGHTED = 2, VKR_MIS_OPTIMAL_CLAMPED = 3, VKR_MIS_OPTIMAL = 4 };
+
+namespace vkr {
+
+struct shading_kernel_params {
+	// frame
+	int width, height;
+	int row_begin, row_end;          // rows [row_begin, row_end) are shaded (multi-GPU stripes)
+	const float4* gbuffer;           // 4 planes of width*height float4
+	float4* out;                     // width*height float4, linear radiance * exposure, alpha 1
+	const unsigned char* constants;  // device copy of the reference's constant block
+	uint32_t constants_bytes;        // 256 + light_count * light_stride (multiple of 16)
+	uint32_t constants_smem_bytes;   // constants_bytes rounded up to 128
+	// what the reference passes as -D defines (src/main.c:752-792)
+	int light_count, max_light_vertex_count, sample_count;
+	int sampling_strategies, mis_heuristic, biased_sampling, trace_shadow_rays, show_polygonal_lights;
+	// tables
+	const uint16_t* noise; int noise_w, noise_h, noise_layers;
+	const uint16_t* ltc0; const uint16_t* ltc1; int ltc_res, ltc_layers;
+	// acceleration structure
+	const float4* bvh_nodes; const float4* bvh_tris; uint32_t tri_count;
+};
+
+struct gbuffer_kernel_params {
+	int width, height;
+	const unsigned char* constants;          // device copy of the 256-byte fixed block
+	const uint2* quantized_positions;        // 3 per triangle (scene.h:56-62)
+	const ushort4* normals_and_tex_coords;   // 3 per triangle
+	const uint8_t* material_indices;         // 1 per triangle
+	const float* material_params;            // 8 floats per material
+	const float4* bvh_nodes; const float4* bvh_tris; const uint32_t* bvh_tri_ids; uint32_t tri_count; // primary-ray BVH (shader-decoded vertices)
+	uint32_t* visibility;                    // width*height primitive indices (0xFFFFFFFF = background)
+	float4* gbuffer;                         // 4 planes
+};
+
+} // namespace vkr
+
+cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_visibility_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_gbuffer_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);

@@ -1,0 +1,365 @@
+"""Seeded synthetic inputs in the reference's own file formats.
+
+The reference ships no data (README.md:8-12), so scenes, material textures, LTC fits and quicksaves
+are synthesised here and written as *.vks / *.vkt / fit*.dat / *.save files that the unchanged
+reference loaders (and this library's loaders) read. Format sources:
+  *.vks   reader src/scene.c:419-483, writer tools/io_export_vulkan_blender28.py:470-531
+  *.vkt   src/textures.c:111-169
+  fit.dat src/ltc_table.c:46-84
+  *.save  src/main.c:49-130
+This is authoring tooling (like the reference's Blender exporter), not part of the timed path.
+"""
+import os
+import struct
+
+import numpy as np
+
+# ---------------------------------------------------------------------------------------------
+# geometry helpers: everything is a list of (triangles[n,3,3], normals[n,3,3], material_id)
+# ---------------------------------------------------------------------------------------------
+
+def _grid_quad(origin, edge_u, edge_v, nu, nv, flip=False):
+	"""Tessellates the parallelogram origin + s*edge_u + t*edge_v into nu*nv*2 triangles."""
+	origin, edge_u, edge_v = (np.asarray(a, dtype=np.float64) for a in (origin, edge_u, edge_v))
+	s = np.linspace(0.0, 1.0, nu + 1)
+	t = np.linspace(0.0, 1.0, nv + 1)
+	S, T = np.meshgrid(s, t, indexing="ij")
+	P = origin[None, None, :] + S[..., None] * edge_u[None, None, :] + T[..., None] * edge_v[None, None, :]
+	p00, p10, p01, p11 = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+	t0 = np.stack([p00, p10, p11], axis=2).reshape(-1, 3, 3)
+	t1 = np.stack([p00, p11, p01], axis=2).reshape(-1, 3, 3)
+	tris = np.concatenate([t0, t1], axis=0)
+	if flip:
+		tris = tris[:, ::-1, :]
+	return tris
+
+
+def _box(lo, hi, n=1, inward=False):
+	"""Axis-aligned box as 6 tessellated faces (n x n quads each); outward normals unless inward."""
+	lo = np.asarray(lo, dtype=np.float64); hi = np.asarray(hi, dtype=np.float64)
+	d = hi - lo
+	ex, ey, ez = np.array([d[0], 0, 0]), np.array([0, d[1], 0]), np.array([0, 0, d[2]])
+	faces = [
+		_grid_quad(lo, ey, ex, n, n),                    # z = lo (normal -z)
+		_grid_quad(lo + ez, ex, ey, n, n),               # z = hi (+z)
+		_grid_quad(lo, ex, ez, n, n),                    # y = lo (-y)
+		_grid_quad(lo + ey, ez, ex, n, n),               # y = hi (+y)
+		_grid_quad(lo, ez, ey, n, n),                    # x = lo (-x)
+		_grid_quad(lo + ex, ey, ez, n, n),               # x = hi (+x)
+	]
+	tris = np.concatenate(faces, axis=0)
+	if inward:
+		tris = tris[:, ::-1, :]
+	return tris
+
+
+def _flat_normals(tris):
+	n = np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])
+	n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+	return np.repeat(n[:, None, :], 3, axis=1)
+
+
+class Mesh:
+	def __init__(self):
+		self.tris, self.mats = [], []
+
+	def add(self, tris, material):
+		self.tris.append(np.asarray(tris, dtype=np.float64))
+		self.mats.append(np.full(len(tris), material, dtype=np.uint8))
+
+	def finish(self):
+		tris = np.concatenate(self.tris, axis=0)
+		mats = np.concatenate(self.mats, axis=0)
+		return tris, _flat_normals(tris), mats
+
+
+# ---------------------------------------------------------------------------------------------
+# scenes
+# ---------------------------------------------------------------------------------------------
+
+def scene_cornell():
+	"""1x1x1 m box open towards -y, two blocks: 5 walls * 2 + 2 boxes * 12 = 34 triangles, 3 materials."""
+	m = Mesh()
+	m.add(_grid_quad([0, 0, 0], [1, 0, 0], [0, 1, 0], 1, 1), 0)            # floor (+z)
+	m.add(_grid_quad([0, 0, 1], [0, 1, 0], [1, 0, 0], 1, 1), 0)            # ceiling (-z)
+	m.add(_grid_quad([0, 1, 0], [1, 0, 0], [0, 0, 1], 1, 1), 0)            # back wall (-y)
+	m.add(_grid_quad([0, 0, 0], [0, 1, 0], [0, 0, 1], 1, 1), 1)            # left wall (+x), red
+	m.add(_grid_quad([1, 0, 0], [0, 0, 1], [0, 1, 0], 1, 1), 2)            # right wall (-x), green
+	m.add(_box([0.15, 0.5, 0.0], [0.45, 0.8, 0.6]), 0)
+	m.add(_box([0.55, 0.2, 0.0], [0.85, 0.5, 0.3]), 0)
+	materials = [
+		dict(name="white", base=(0.73, 0.73, 0.73), roughness=0.7, metal=0.0),
+		dict(name="red", base=(0.65, 0.05, 0.05), roughness=0.7, metal=0.0),
+		dict(name="green", base=(0.12, 0.45, 0.15), roughness=0.7, metal=0.0),
+	]
+	return m.finish(), materials
+
+
+def _city_block(m, rng, x0, y0, size, detail, n_mat):
+	"""One jittered block: building, awning, poles and clutter. detail scales the tessellation."""
+	w = size * rng.uniform(0.45, 0.7); d = size * rng.uniform(0.45, 0.7); h = rng.uniform(4.0, 14.0)
+	bx = x0 + rng.uniform(0.05, 0.25) * size; by = y0 + rng.uniform(0.05, 0.25) * size
+	mat = int(rng.integers(1, n_mat))
+	m.add(_box([bx, by, 0.0], [bx + w, by + d, h], n=max(1, detail)), mat)
+	# awning: a slanted quad in front of the building, double sided
+	a0 = np.array([bx, by - 1.5, 2.6]); au = np.array([w, 0.0, 0.0]); av = np.array([0.0, 1.5, 0.5])
+	na = max(1, detail // 2)
+	m.add(_grid_quad(a0, au, av, na, na), int(rng.integers(1, n_mat)))
+	m.add(_grid_quad(a0, au, av, na, na, flip=True), int(rng.integers(1, n_mat)))
+	# poles
+	for k in range(4):
+		px = x0 + rng.uniform(0.0, size); py = y0 + rng.uniform(0.0, size)
+		m.add(_box([px, py, 0.0], [px + 0.12, py + 0.12, rng.uniform(2.5, 5.0)], n=max(1, detail // 4)), int(rng.integers(1, n_mat)))
+	# clutter: small boxes on the ground and on the roof
+	for k in range(6 * max(1, detail // 2)):
+		cx = x0 + rng.uniform(0.0, size); cy = y0 + rng.uniform(0.0, size); s = rng.uniform(0.15, 0.6)
+		on_roof = bx < cx < bx + w - s and by < cy < by + d - s
+		z = h if on_roof else 0.0
+		m.add(_box([cx, cy, z], [cx + s, cy + s, z + s * rng.uniform(0.5, 2.0)]), int(rng.integers(1, n_mat)))
+
+
+def scene_city(seed=1, blocks=24, extent=200.0, detail=16, ground_cells=256, n_mat=64):
+	"""'bistro_like' stand-in: ground plane + blocks x blocks jittered buildings. Defaults give ~2.8 M triangles."""
+	rng = np.random.default_rng(seed)
+	m = Mesh()
+	m.add(_grid_quad([0, 0, 0], [extent, 0, 0], [0, extent, 0], ground_cells, ground_cells), 0)
+	size = extent / blocks
+	for i in range(blocks):
+		for j in range(blocks):
+			_city_block(m, rng, i * size, j * size, size, detail, n_mat)
+	mrng = np.random.default_rng(seed + 1000)
+	materials = []
+	for k in range(n_mat):
+		materials.append(dict(name="mat%03d" % k, base=tuple(mrng.uniform(0.05, 0.9, 3)), roughness=float(np.sqrt(mrng.uniform(0.1, 0.9))),
+			metal=float(mrng.random() < 0.2)))
+	return m.finish(), materials
+
+
+def scene_room(seed=2, detail=48, clutter=2500, n_mat=32):
+	"""'attic_like' stand-in: closed 12 x 8 x 4 m room with slanted beams and clutter. Defaults give ~1.0 M triangles."""
+	rng = np.random.default_rng(seed)
+	m = Mesh()
+	m.add(_box([0, 0, 0], [12, 8, 4], n=detail, inward=True), 0)
+	for k in range(10):
+		x = 1.0 + k * 1.1
+		m.add(_box([x, 0.0, 3.4], [x + 0.2, 8.0, 3.7], n=max(1, detail // 6)), 1)
+	for k in range(clutter):
+		c = np.array([rng.uniform(0.3, 11.4), rng.uniform(0.3, 7.4), 0.0]); s = rng.uniform(0.1, 0.7)
+		m.add(_box(c, c + np.array([s, s * rng.uniform(0.5, 1.5), s * rng.uniform(0.5, 3.0)]), n=max(1, detail // 12)), int(rng.integers(1, n_mat)))
+	mrng = np.random.default_rng(seed + 1000)
+	materials = [dict(name="room%03d" % k, base=tuple(mrng.uniform(0.05, 0.9, 3)), roughness=float(np.sqrt(mrng.uniform(0.1, 0.9))), metal=float(mrng.random() < 0.2)) for k in range(n_mat)]
+	return m.finish(), materials
+
+
+# ---------------------------------------------------------------------------------------------
+# *.vks writer
+# ---------------------------------------------------------------------------------------------
+
+def _part_1_by_2(x):
+	x = x & 0x3FF
+	x = (x ^ (x << 16)) & 0xFF0000FF
+	x = (x ^ (x << 8)) & 0x0300F00F
+	x = (x ^ (x << 4)) & 0x030C30C3
+	x = (x ^ (x << 2)) & 0x09249249
+	return x
+
+
+def _encode_octahedral(normal):
+	l1 = np.abs(normal).sum(axis=-1, keepdims=True)
+	o = normal[..., 0:2] / np.maximum(l1, 1e-30)
+	sign_not_zero = np.where(o >= 0.0, 1.0, -1.0)
+	o = np.where(normal[..., 2:3] <= 0.0, (1.0 - np.abs(o[..., ::-1])) * sign_not_zero, o)
+	factor = float(2 ** 15 - 1)
+	return np.asarray(o * factor + (factor + 1.5), dtype=np.uint16)
+
+
+def write_vks(path, mesh, materials, sort_triangles=True):
+	tris, normals, mats = mesh
+	n = len(tris)
+	if sort_triangles:
+		centroids = tris.mean(axis=1).astype(np.float32)
+		lo, hi = centroids.min(axis=0), centroids.max(axis=0)
+		q = np.minimum(1023, ((centroids - lo) / np.maximum(hi - lo, 1e-30) * 1024.0).astype(np.uint64)).astype(np.uint64)
+		morton = _part_1_by_2(q[:, 0]) | (_part_1_by_2(q[:, 1]) << np.uint64(1)) | (_part_1_by_2(q[:, 2]) << np.uint64(2))
+		perm = np.argsort(morton, kind="stable")
+		tris, normals, mats = tris[perm], normals[perm], mats[perm]
+	pos = tris.reshape(-1, 3)
+	box_min = pos.min(axis=0); box_max = pos.max(axis=0)
+	span = np.maximum(box_max - box_min, 1e-6)
+	quantization_factor = 2.0 ** 21 / span
+	qp = np.minimum(2 ** 21 - 1, np.asarray(pos * quantization_factor - box_min * quantization_factor, dtype=np.uint32))
+	dequantization_factor = (1.0 / quantization_factor).astype(np.float32)
+	dequantization_summand = (box_min + 0.5 / quantization_factor).astype(np.float32)
+	packed = np.zeros((len(pos), 2), dtype=np.uint32)
+	packed[:, 0] = qp[:, 0] + ((qp[:, 1] & 0x7FF) << 21)
+	packed[:, 1] = ((qp[:, 1] & 0x1FF800) >> 11) + (qp[:, 2] << 10)
+	nuv = np.zeros((len(pos), 4), dtype=np.uint16)
+	nuv[:, 0:2] = _encode_octahedral(normals.reshape(-1, 3))
+	# planar uv: unit square per triangle
+	uv = np.tile(np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0]]), (n, 1))
+	nuv[:, 2:4] = np.clip(uv * ((2.0 ** 16 - 1.0) / 8.0) + 0.5, 0.0, 65535.0).astype(np.uint16)
+	with open(path, "wb") as f:
+		f.write(struct.pack("<II", 0x00ABCABC, 1))
+		f.write(struct.pack("<QQ", len(materials), n))
+		f.write(struct.pack("<fff", *dequantization_factor))
+		f.write(struct.pack("<fff", *dequantization_summand))
+		for mat in materials:
+			name = mat["name"].encode("utf-8")
+			f.write(struct.pack("<Q", len(name))); f.write(name); f.write(b"\0")
+		f.write(packed.astype("<u4").tobytes())
+		f.write(nuv.astype("<u2").tobytes())
+		f.write(mats.astype(np.uint8).tobytes())
+		f.write(struct.pack("<I", 0x00E0FE0F))
+	return dict(triangle_count=n, dequantization_factor=dequantization_factor, dequantization_summand=dequantization_summand,
+		quantized_positions=packed, normals_and_tex_coords=nuv, material_indices=mats.astype(np.uint8))
+
+
+# ---------------------------------------------------------------------------------------------
+# *.vkt constant textures (RGBA16F, 4x4 with a full mip chain)
+# ---------------------------------------------------------------------------------------------
+
+def write_vkt_constant(path, rgba):
+	texel = np.asarray(rgba, dtype=np.float16)
+	mips = [(4, 4), (2, 2), (1, 1)]
+	payload = b""; headers = b""
+	for (w, h) in mips:
+		data = np.tile(texel, w * h).astype("<f2").tobytes()
+		headers += struct.pack("<IIQQ", w, h, len(data), len(payload))
+		payload += data
+	with open(path, "wb") as f:
+		f.write(struct.pack("<IIIIIIQ", 0x00BC1BC1, 1, len(mips), 4, 4, 97, len(payload)))
+		f.write(headers); f.write(payload)
+		f.write(struct.pack("<I", 0x00E0FE0F))
+
+
+def write_material_textures(directory, materials):
+	os.makedirs(directory, exist_ok=True)
+	for m in materials:
+		write_vkt_constant(os.path.join(directory, m["name"] + "_BaseColor.vkt"), list(m["base"]) + [1.0])
+		write_vkt_constant(os.path.join(directory, m["name"] + "_Specular.vkt"), [1.0, m["roughness"], m["metal"], 1.0])
+		write_vkt_constant(os.path.join(directory, m["name"] + "_Normal.vkt"), [0.5, 0.5, 1.0, 1.0])
+
+
+def material_params(materials):
+	"""The 8 floats per material the G-buffer producer consumes, after the RGBA16F round trip of the *.vkt files."""
+	out = np.zeros((len(materials), 8), dtype=np.float32)
+	for i, m in enumerate(materials):
+		h = lambda v: np.float32(np.float16(v))
+		out[i] = [h(m["base"][0]), h(m["base"][1]), h(m["base"][2]), h(m["roughness"]), h(m["metal"]), h(0.5), h(0.5), 0.0]
+	return out
+
+
+# ---------------------------------------------------------------------------------------------
+# LTC fits: a smooth synthetic stand-in, NOT a GGX fit (the real fit*.dat files are not in the repo)
+# ---------------------------------------------------------------------------------------------
+
+def write_ltc_fits(directory, resolution=64, fresnel_count=51):
+	os.makedirs(directory, exist_ok=True)
+	alpha = (np.arange(resolution, dtype=np.float64) / (resolution - 1)) ** 2      # column = sqrt(roughness)
+	incl = np.arange(resolution, dtype=np.float64) / (resolution - 1) * (0.5 * np.pi)  # row = inclination
+	A, I = np.meshgrid(alpha, incl, indexing="xy")
+	for i in range(fresnel_count):
+		f0 = i / (fresnel_count - 1)
+		a = np.clip(A, 0.01, 1.0)
+		m00 = 0.25 + 0.75 * a * (1.0 - 0.3 * np.sin(I))
+		m11 = 0.25 + 0.75 * a
+		m02 = -0.35 * np.sin(I) * (1.0 - a)
+		m20 = 0.15 * np.sin(I) * (1.0 - a) * a
+		albedo = np.clip((0.04 + 0.96 * f0) * (1.0 - 0.5 * a) + 0.3 * (1.0 - f0) * (1.0 - np.cos(I)) ** 3, 0.0, 1.0)
+		data = np.stack([m00, m02, m11, m20, albedo], axis=-1).astype("<f4")
+		with open(os.path.join(directory, "fit%d.dat" % i), "wb") as f:
+			f.write(struct.pack("<Q", resolution))
+			f.write(data.tobytes())
+
+
+# ---------------------------------------------------------------------------------------------
+# quicksaves
+# ---------------------------------------------------------------------------------------------
+
+def make_light(translation, rotation_angles, scaling, flux, vertices_plane_space=None):
+	if vertices_plane_space is None:
+		vertices_plane_space = [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)]
+	return dict(translation=tuple(float(t) for t in translation), rotation_angles=tuple(float(r) for r in rotation_angles),
+		scaling=(float(scaling[0]), float(scaling[1])), flux=tuple(float(f) for f in flux), vertices=[(float(x), float(y)) for x, y in vertices_plane_space])
+
+
+def write_quicksave(path, camera, lights):
+	"""camera: dict(position, rotation_z, rotation_x, vertical_fov, near, far, speed)"""
+	with open(path, "wb") as f:
+		f.write(struct.pack("<3f3f2ffi2f", *camera["position"], camera["rotation_z"], camera["rotation_x"], camera["vertical_fov"],
+			camera["near"], camera["far"], camera.get("speed", 2.0), 0, 0.0, 0.0))
+		f.write(struct.pack("<II", 0, len(lights)))
+		for L in lights:
+			n = len(L["vertices"])
+			# the first 88 bytes of polygonal_light_t: 20 floats + vertex_count + texturing_technique
+			f.write(struct.pack("<3ff3ff3ff3ff4f", *L["rotation_angles"], L["scaling"][0], *L["translation"], L["scaling"][1], *L["flux"], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0))
+			f.write(struct.pack("<II", n, 0))
+			f.write(struct.pack("<Q", 0))        # no texture path
+			f.write(struct.pack("<QQ", 0, 0))    # legacy NULL pointers
+			for (x, y) in L["vertices"]:
+				f.write(struct.pack("<4f", x, y, 0.0, 0.0))
+
+
+def look_at_camera(position, target):
+	"""First-person camera at position looking at target: forward = (-sin z, -cos z) horizontally (camera.c:123-129),
+	rotation_x = angle from straight down (camera.h:28-30)."""
+	d = np.asarray(target, dtype=np.float64) - np.asarray(position, dtype=np.float64)
+	d /= np.linalg.norm(d)
+	return default_camera(position, float(np.arctan2(-d[0], -d[1])), float(np.arccos(np.clip(-d[2], -1.0, 1.0))))
+
+
+def default_camera(position, rotation_z, rotation_x):
+	return dict(position=tuple(float(p) for p in position), rotation_z=float(rotation_z), rotation_x=float(rotation_x), vertical_fov=float(0.33 * np.pi), near=0.05, far=1.0e3, speed=2.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# named configurations (BASELINE.json configs; synthetic stand-ins)
+# ---------------------------------------------------------------------------------------------
+
+def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0), flux=10.0):
+	lights = []
+	for k in range(count):
+		s = rng.uniform(*scale_range, size=2)
+		pos = (rng.uniform(*x_range), rng.uniform(*y_range), rng.uniform(*z_range))
+		# plane normal = rotation column 2; rotate about x by ~pi so that the light faces down, +- 30 degrees
+		angles = (np.pi + rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(0.0, 2.0 * np.pi))
+		lights.append(make_light(pos, angles, s, (flux, flux, flux)))
+	return lights
+
+
+def build_dataset(directory, name, **overrides):
+	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
+	os.makedirs(directory, exist_ok=True)
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3}.get(name, 9))
+	if name == "cornell":
+		mesh, materials = scene_cornell()
+		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
+		lights = [make_light((0.35, 0.35, 0.995), (np.pi, 0.0, 0.0), (0.3, 0.3), (1.0, 1.0, 1.0))]
+		lights[0]["translation"] = (0.35, 0.65, 0.995)
+	elif name == "city":
+		mesh, materials = scene_city(**{k: v for k, v in overrides.items() if k in ("seed", "blocks", "extent", "detail", "ground_cells", "n_mat")})
+		extent = overrides.get("extent", 200.0)
+		camera = look_at_camera((0.5 * extent - 3.0, 0.5 * extent - 34.0, 7.0), (0.5 * extent - 3.0, 0.5 * extent - 10.0, 2.0))
+		n_lights = overrides.get("lights", 8)
+		lights = _ceiling_lights(rng, n_lights, (0.5 * extent - 14.0, 0.5 * extent + 8.0), (0.5 * extent - 24.0, 0.5 * extent - 4.0), (2.0, 4.0))
+	elif name == "mini_city":
+		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
+		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
+		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+	elif name == "room":
+		mesh, materials = scene_room(**{k: v for k, v in overrides.items() if k in ("seed", "detail", "clutter", "n_mat")})
+		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
+		lights = _ceiling_lights(rng, overrides.get("lights", 32), (1.0, 11.0), (1.0, 7.0), (2.4, 3.3), scale_range=(0.3, 1.0))
+	else:
+		raise ValueError(name)
+	vks = os.path.join(directory, name + ".vks")
+	tex = os.path.join(directory, name + "_textures")
+	save = os.path.join(directory, name + ".save")
+	ltc = os.path.join(directory, "ggx_ltc_fit")
+	info = write_vks(vks, mesh, materials)
+	write_material_textures(tex, materials)
+	write_quicksave(save, camera, lights)
+	if not os.path.exists(os.path.join(ltc, "fit50.dat")):
+		write_ltc_fits(ltc)
+	info.update(vks=vks, textures=tex, save=save, ltc=ltc, materials=materials, material_params=material_params(materials), camera=camera, lights=lights)
+	return info
