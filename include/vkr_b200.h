@@ -19,6 +19,7 @@ extern "C" {
 #endif
 
 #define VKR_B200_ABI_VERSION 1
+#define VKR_TILE_ROW_HEIGHT 8 /* pixel rows per screen-tile row (stripe granularity) */
 
 /* ---- enums: numeric values equal the reference's (src/main.h:45-92, src/polygonal_light.h:28-67,
         src/noise_table.h:20-54) so that render_settings_t fields can be passed through unchanged */
@@ -200,8 +201,9 @@ typedef struct vkr_shading_pass_desc_s {
 	vkr_sample_polygon_technique_t polygon_sampling_technique;
 	int trace_shadow_rays;
 	int show_polygonal_lights;
-	/* screen-tile rows this pass instance shades: [row_begin, row_end); row_end = 0 means height (multi-GPU stripes) */
-	uint32_t row_begin, row_end;
+	/* multi-GPU stripes: this pass instance shades the 8-pixel-high screen-tile rows t with t % stripe_count == stripe_index
+	   (interleaved for load balance); stripe_count = 0 or 1 means the whole frame */
+	uint32_t stripe_index, stripe_count;
 	/* resources */
 	const vkr_scene_t* scene;
 	const vkr_ltc_table_t* ltc_table;
@@ -225,7 +227,7 @@ int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device
 void vkr_destroy_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device);
 /* Asynchronous on device->stream. constants: HOST pointer to the block written by vkr_write_constants() (or by the
    reference's write_constants()). d_gbuffer / d_out_rgba32f: DEVICE pointers (out = width*height float4, rows outside
-   [row_begin,row_end) untouched). */
+   this stripe untouched). */
 int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f);
 /* End-to-end variant with HOST buffers: uploads the G-buffer rows of this stripe, shades, downloads the stripe, waits. */
 int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer, float* out_rgba32f);

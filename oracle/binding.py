@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
 
 class Config(C.Structure):
 	_fields_ = [(n, C.c_uint32) for n in ("width", "height", "light_count", "max_light_vertex_count", "min_light_vertex_count", "sample_count",
-		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end")]
+		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride")]
 
 
 _lib = None
@@ -134,3 +134,10 @@ def trace_any(tris, rays, brute=True):
 
 def thread_count():
 	return load().vkr_oracle_thread_count()
+
+
+def last_shade_seconds():
+	"""Wall-clock seconds of the pixel loop of the last shade() call (BVH build excluded)."""
+	lib = load()
+	lib.vkr_oracle_last_shade_seconds.restype = C.c_double
+	return lib.vkr_oracle_last_shade_seconds()

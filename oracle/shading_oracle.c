@@ -569,6 +569,10 @@ static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_
 	c->maxp = V + 1; /* main.c:194-216: PSA techniques clip => one extra vertex */
 }
 
+/* Wall-clock seconds of the pixel loop of the last vkr_oracle_shade call (BVH build excluded), for the CPU baseline */
+static double g_last_shade_seconds = 0.0;
+double vkr_oracle_last_shade_seconds(void) { return g_last_shade_seconds; }
+
 /* shading_pass.frag.glsl:824-866 with the G-buffer standing in for get_shading_data() */
 int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, const float* gbuffer,
 	const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
@@ -590,8 +594,12 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 	const uint32_t y0 = cfg->row_begin, y1 = cfg->row_end ? cfg->row_end : H;
 	const size_t plane = (size_t) W * H * 4;
 	uint64_t total_rays = 0;
+#ifdef _OPENMP
+	const double shade_begin = omp_get_wtime();
+#endif
 	#pragma omp parallel for schedule(dynamic, 1) reduction(+:total_rays)
 	for (uint32_t y = y0; y < y1; ++y) {
+		if (cfg->band_stride && (y - y0) % cfg->band_stride >= cfg->band_height) continue;
 		for (uint32_t x = 0; x != W; ++x) {
 			size_t pi = ((size_t) y * W + x) * 4;
 			uint64_t rays = 0;
@@ -637,6 +645,9 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 			total_rays += rays;
 		}
 	}
+#ifdef _OPENMP
+	g_last_shade_seconds = omp_get_wtime() - shade_begin;
+#endif
 	if (out_ray_count) *out_ray_count = total_rays;
 	obvh_destroy(&bvh);
 	free(c.lights);

@@ -24,6 +24,7 @@ typedef struct {
 	uint32_t trace_shadow_rays;        /* TRACE_SHADOW_RAYS */
 	uint32_t show_polygonal_lights;    /* SHOW_POLYGONAL_LIGHTS */
 	uint32_t row_begin, row_end;       /* shade rows [row_begin,row_end) only; row_end = 0 means height */
+	uint32_t band_height, band_stride; /* if band_stride != 0: of those rows only the ones with (y - row_begin) % band_stride < band_height (bounded CPU samples) */
 } vkr_oracle_config_t;
 
 size_t vkr_oracle_light_stride(uint32_t max_light_vertex_count);
@@ -43,4 +44,5 @@ void vkr_oracle_sort_network(uint32_t vertex_count, uint32_t maxp, float* vertic
 void vkr_oracle_elementary_batch(int which, uint32_t n, const float* x, float* y);
 void vkr_oracle_trace_any(const float* tris, uint32_t tri_count, uint32_t ray_count, const float* rays, uint8_t* out_bvh, uint8_t* out_brute);
 int vkr_oracle_thread_count(void);
+double vkr_oracle_last_shade_seconds(void);
 #endif

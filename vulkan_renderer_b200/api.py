@@ -88,7 +88,7 @@ class ShadingPassDesc(C.Structure):
 	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("polygonal_light_count", C.c_uint32),
 		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
 		("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int), ("polygon_sampling_technique", C.c_int),
-		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("row_begin", C.c_uint32), ("row_end", C.c_uint32),
+		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("stripe_index", C.c_uint32), ("stripe_count", C.c_uint32),
 		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable))]
 
 

@@ -77,7 +77,7 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 	memset(pass, 0, sizeof(*pass));
 	pass->desc = *desc;
 	vkr_shading_pass_desc_t& d = pass->desc;
-	if (d.row_end == 0) d.row_end = d.height;
+	if (d.stripe_count == 0) d.stripe_count = 1;
 	// Legality rules of the reference's settings panel (src/user_interface.cpp:90-180), plus what this library implements
 	if (d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle && d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle_biased) {
 		printf("Failed to create the shading pass: only projected solid angle sampling (technique 11 or 12) is implemented, got %d.\n", (int) d.polygon_sampling_technique);
@@ -95,8 +95,8 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 		printf("Failed to create the shading pass: polygonal lights must have 3 or 4 vertices (got min %u, max %u).\n", d.min_polygonal_light_vertex_count, d.max_polygonal_light_vertex_count);
 		memset(pass, 0, sizeof(*pass)); return 1;
 	}
-	if (!d.width || !d.height || d.row_begin >= d.row_end || d.row_end > d.height || !d.sample_count || !d.ltc_table || !d.noise_table || !d.ltc_table->d_table0 || !d.noise_table->d_noise) {
-		printf("Failed to create the shading pass: invalid resolution, row range, sample count or missing LTC / noise tables.\n");
+	if (!d.width || !d.height || d.stripe_index >= d.stripe_count || !d.sample_count || !d.ltc_table || !d.noise_table || !d.ltc_table->d_table0 || !d.noise_table->d_noise) {
+		printf("Failed to create the shading pass: invalid resolution, stripe, sample count or missing LTC / noise tables.\n");
 		memset(pass, 0, sizeof(*pass)); return 1;
 	}
 	if (d.trace_shadow_rays && (!d.scene || !d.scene->d_shadow_nodes)) {
@@ -134,7 +134,11 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	memcpy(pass->h_constants_pinned, constants, constants_size);
 	VKR_CUDA_OK(cudaMemcpyAsync(pass->d_constants, pass->h_constants_pinned, constants_size, cudaMemcpyHostToDevice, stream), "Failed to upload the constant block");
 	shading_kernel_params p; memset(&p, 0, sizeof(p));
-	p.width = (int) d.width; p.height = (int) d.height; p.row_begin = (int) d.row_begin; p.row_end = (int) d.row_end;
+	p.width = (int) d.width; p.height = (int) d.height; p.tile_row_first = (int) d.stripe_index; p.tile_row_step = (int) d.stripe_count;
+	{
+		const uint32_t tile_rows = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
+		p.tile_row_count = (int) ((tile_rows > d.stripe_index) ? (tile_rows - d.stripe_index + d.stripe_count - 1) / d.stripe_count : 0);
+	}
 	p.gbuffer = (const float4*) d_gbuffer; p.out = (float4*) d_out;
 	p.constants = (const unsigned char*) pass->d_constants;
 	p.constants_bytes = (uint32_t) constants_size;
@@ -179,12 +183,25 @@ extern "C" int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_dev
 			return 1;
 		}
 	}
-	// Upload only the rows of this stripe, plane by plane
-	const size_t row_bytes = (size_t) d.width * 16, stripe_offset = row_bytes * d.row_begin, stripe_bytes = row_bytes * (d.row_end - d.row_begin);
-	for (int k = 0; k != 4; ++k)
-		VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes + stripe_offset, (const char*) gbuffer + k * plane_bytes + stripe_offset, stripe_bytes, cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
+	// Upload only the tile rows of this stripe, plane by plane (a tile row is contiguous inside a plane)
+	const size_t row_bytes = (size_t) d.width * 16;
+	const uint32_t tile_rows = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
+	if (d.stripe_count == 1) {
+		for (int k = 0; k != 4; ++k)
+			VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes, (const char*) gbuffer + k * plane_bytes, plane_bytes, cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
+	}
+	else for (uint32_t t = d.stripe_index; t < tile_rows; t += d.stripe_count) {
+		const uint32_t y0 = t * VKR_TILE_ROW_HEIGHT, y1 = (y0 + VKR_TILE_ROW_HEIGHT < d.height) ? y0 + VKR_TILE_ROW_HEIGHT : d.height;
+		for (int k = 0; k != 4; ++k)
+			VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes + row_bytes * y0, (const char*) gbuffer + k * plane_bytes + row_bytes * y0, row_bytes * (y1 - y0), cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
+	}
 	if (launch_shading(pass, device, constants, constants_size, pass->d_gbuffer_staging, pass->d_out_staging)) return 1;
-	VKR_CUDA_OK(cudaMemcpyAsync((char*) out_rgba32f + stripe_offset, (const char*) pass->d_out_staging + stripe_offset, stripe_bytes, cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
+	if (d.stripe_count == 1)
+		VKR_CUDA_OK(cudaMemcpyAsync(out_rgba32f, pass->d_out_staging, plane_bytes, cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
+	else for (uint32_t t = d.stripe_index; t < tile_rows; t += d.stripe_count) {
+		const uint32_t y0 = t * VKR_TILE_ROW_HEIGHT, y1 = (y0 + VKR_TILE_ROW_HEIGHT < d.height) ? y0 + VKR_TILE_ROW_HEIGHT : d.height;
+		VKR_CUDA_OK(cudaMemcpyAsync((char*) out_rgba32f + row_bytes * y0, (const char*) pass->d_out_staging + row_bytes * y0, row_bytes * (y1 - y0), cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
+	}
 	return vkr_shading_pass_wait(pass, device);
 }
 

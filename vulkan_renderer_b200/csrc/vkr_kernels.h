@@ -13,7 +13,7 @@ namespace vkr {
 struct shading_kernel_params {
 	// frame
 	int width, height;
-	int row_begin, row_end;          // rows [row_begin, row_end) are shaded (multi-GPU stripes)
+	int tile_row_first, tile_row_step, tile_row_count; // 8-pixel tile rows first, first+step, ... are shaded (multi-GPU stripes)
 	const float4* gbuffer;           // 4 planes of width*height float4
 	float4* out;                     // width*height float4, linear radiance * exposure, alpha 1
 	const unsigned char* constants;  // device copy of the reference's constant block

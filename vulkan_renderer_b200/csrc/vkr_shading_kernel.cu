@@ -525,8 +525,8 @@ shading_kernel(const shading_kernel_params p) {
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
 	const int tile = blockIdx.x;
 	const int x = (tile % tiles_x) * kTileW + lx;
-	const int y = p.row_begin + (tile / tiles_x) * kTileH + ly;
-	if (x >= p.width || y >= p.row_end) return;
+	const int y = (p.tile_row_first + (tile / tiles_x) * p.tile_row_step) * kTileH + ly;
+	if (x >= p.width || y >= p.height) return;
 	const size_t pixel = (size_t) y * p.width + x;
 	const size_t plane = (size_t) p.width * p.height;
 	const float4 g0 = __ldg(p.gbuffer + pixel), g1 = __ldg(p.gbuffer + plane + pixel);
@@ -588,7 +588,7 @@ using namespace vkr;
 template <int STRATEGY, int MAXP, bool BIASED>
 static cudaError_t launch_variant(const shading_kernel_params& p, cudaStream_t stream) {
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = (p.row_end - p.row_begin + kTileH - 1) / kTileH;
+	const int tiles_y = p.tile_row_count;
 	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
 	const size_t smem = p.constants_smem_bytes + sizeof(int) * kStackDepth * kThreads;
 	auto kernel = shading_kernel<STRATEGY, MAXP, BIASED>;

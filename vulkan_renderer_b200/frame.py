@@ -67,7 +67,7 @@ class Frame:
 			spec.polygonal_light_count = saved
 		return bytes(buf)
 
-	def pass_desc(self, width, height, row_begin=0, row_end=0):
+	def pass_desc(self, width, height, stripe_index=0, stripe_count=1):
 		s = self.settings
 		counts = self.light_vertex_counts() or [3]
 		d = api.ShadingPassDesc()
@@ -77,13 +77,13 @@ class Frame:
 		d.sample_count = s.sample_count
 		d.sampling_strategies = s.sampling_strategies; d.mis_heuristic = s.mis_heuristic; d.polygon_sampling_technique = s.polygon_sampling_technique
 		d.trace_shadow_rays = s.trace_shadow_rays; d.show_polygonal_lights = s.show_polygonal_lights
-		d.row_begin, d.row_end = row_begin, row_end
+		d.stripe_index, d.stripe_count = stripe_index, stripe_count
 		d.scene = C.pointer(self.scene); d.ltc_table = C.pointer(self.ltc); d.noise_table = C.pointer(self.noise)
 		return d
 
-	def create_pass(self, width, height, row_begin=0, row_end=0, timing=False):
+	def create_pass(self, width, height, stripe_index=0, stripe_count=1, timing=False):
 		p = api.ShadingPass()
-		desc = self.pass_desc(width, height, row_begin, row_end)
+		desc = self.pass_desc(width, height, stripe_index, stripe_count)
 		self._check(self.lib.vkr_create_shading_pass(C.byref(p), C.byref(self.device), C.byref(desc)), "vkr_create_shading_pass")
 		p.timing_enabled = int(timing)
 		self._passes.append(p)
@@ -108,13 +108,14 @@ class Frame:
 			self._check(self.lib.vkr_device_wait_idle(C.byref(self.device)), "vkr_device_wait_idle")
 			return vis.cpu().numpy().view(np.uint32), gb.cpu().numpy()
 
-	def shade_host(self, width, height, gbuffer, row_begin=0, row_end=0):
+	def shade_host(self, width, height, gbuffer, stripe_index=0, stripe_count=1, out=None):
 		"""End-to-end call with host buffers (vkr_shading_pass_run_host). Returns float32 [H, W, 4]."""
-		p = self.create_pass(width, height, row_begin, row_end)
+		p = self.create_pass(width, height, stripe_index, stripe_count)
 		try:
 			constants = self.constants(width, height)
 			gb = np.ascontiguousarray(gbuffer, dtype=np.float32)
-			out = np.zeros((height, width, 4), dtype=np.float32)
+			if out is None:
+				out = np.zeros((height, width, 4), dtype=np.float32)
 			self._check(self.lib.vkr_shading_pass_run_host(C.byref(p), C.byref(self.device), constants, len(constants), gb.ctypes.data, out.ctypes.data), "vkr_shading_pass_run_host")
 		finally:
 			self.destroy_pass(p)

@@ -124,9 +124,29 @@ def scene_city(seed=1, blocks=24, extent=200.0, detail=16, ground_cells=256, n_m
 	m = Mesh()
 	m.add(_grid_quad([0, 0, 0], [extent, 0, 0], [0, extent, 0], ground_cells, ground_cells), 0)
 	size = extent / blocks
+	# an open plaza (the "bistro terrace") in front of the camera: no buildings, but tables, chairs and parasols
+	px0, px1, py0, py1 = 0.5 * extent - 22.0, 0.5 * extent + 16.0, 0.5 * extent - 44.0, 0.5 * extent + 2.0
 	for i in range(blocks):
 		for j in range(blocks):
-			_city_block(m, rng, i * size, j * size, size, detail, n_mat)
+			x0, y0 = i * size, j * size
+			if x0 + size > px0 and x0 < px1 and y0 + size > py0 and y0 < py1:
+				continue
+			_city_block(m, rng, x0, y0, size, detail, n_mat)
+	prng = np.random.default_rng(seed + 500)
+	nd = max(1, detail // 4)
+	for k in range(40 * max(1, detail // 2)):
+		cx = prng.uniform(px0 + 1.0, px1 - 2.0); cy = prng.uniform(py0 + 8.0, py1 - 2.0)
+		kind = k % 3
+		if kind == 0:   # table: top + leg
+			m.add(_box([cx, cy, 0.72], [cx + 0.9, cy + 0.9, 0.78], n=nd), int(prng.integers(1, n_mat)))
+			m.add(_box([cx + 0.4, cy + 0.4, 0.0], [cx + 0.5, cy + 0.5, 0.72], n=nd), int(prng.integers(1, n_mat)))
+		elif kind == 1: # chair: seat + back
+			m.add(_box([cx, cy, 0.42], [cx + 0.45, cy + 0.45, 0.47], n=nd), int(prng.integers(1, n_mat)))
+			m.add(_box([cx, cy, 0.47], [cx + 0.45, cy + 0.05, 0.95], n=nd), int(prng.integers(1, n_mat)))
+		else:           # parasol: pole + slanted canopy
+			m.add(_box([cx, cy, 0.0], [cx + 0.06, cy + 0.06, 2.3], n=nd), int(prng.integers(1, n_mat)))
+			m.add(_grid_quad([cx - 1.2, cy - 1.2, 2.2], [2.4, 0.0, 0.2], [0.0, 2.4, 0.1], 2 * nd, 2 * nd), int(prng.integers(1, n_mat)))
+			m.add(_grid_quad([cx - 1.2, cy - 1.2, 2.2], [2.4, 0.0, 0.2], [0.0, 2.4, 0.1], 2 * nd, 2 * nd, flip=True), int(prng.integers(1, n_mat)))
 	mrng = np.random.default_rng(seed + 1000)
 	materials = []
 	for k in range(n_mat):
@@ -339,9 +359,9 @@ def build_dataset(directory, name, **overrides):
 	elif name == "city":
 		mesh, materials = scene_city(**{k: v for k, v in overrides.items() if k in ("seed", "blocks", "extent", "detail", "ground_cells", "n_mat")})
 		extent = overrides.get("extent", 200.0)
-		camera = look_at_camera((0.5 * extent - 3.0, 0.5 * extent - 34.0, 7.0), (0.5 * extent - 3.0, 0.5 * extent - 10.0, 2.0))
+		camera = look_at_camera((0.5 * extent - 3.0, 0.5 * extent - 42.0, 4.5), (0.5 * extent - 3.0, 0.5 * extent - 18.0, 1.0))
 		n_lights = overrides.get("lights", 8)
-		lights = _ceiling_lights(rng, n_lights, (0.5 * extent - 14.0, 0.5 * extent + 8.0), (0.5 * extent - 24.0, 0.5 * extent - 4.0), (2.0, 4.0))
+		lights = _ceiling_lights(rng, n_lights, (0.5 * extent - 16.0, 0.5 * extent + 10.0), (0.5 * extent - 34.0, 0.5 * extent - 6.0), (2.6, 4.5), flux=60.0)
 	elif name == "mini_city":
 		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
 		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
