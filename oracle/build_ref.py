@@ -1,0 +1,146 @@
+#!/usr/bin/env python3
+"""Compiles the REFERENCE's own shading-pass sources into oracle/_ref/libref_shader.so (TEST INFRASTRUCTURE).
+
+The reference's hot path is GLSL (src/shaders/shading_pass.frag.glsl and its includes). GLSL is close enough
+to C++ that g++ compiles it against oracle/glsl_compat/glsl_compat.hpp after a mechanical syntax pass:
+
+  * '#version' / '#extension' lines dropped, 'layout(...)' qualifiers stripped,
+  * the uniform block 'per_frame_constants { ... }' opened up (its members become globals),
+  * 'inout T x' / 'out T x' parameters become 'T& x' (arrays stay arrays: they decay to pointers),
+  * shader in/out variables become thread_local globals.
+
+No arithmetic is touched. The transformed copies go to oracle/_ref/gen/ (git-ignored, never committed), the
+sources are read where they lie under /root/reference. One translation unit per configuration because the
+reference bakes its settings into the shader as -D defines (src/main.c:752-792).
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SHADERS = "/root/reference/src/shaders"
+OUT = os.path.join(HERE, "_ref")
+GEN = os.path.join(OUT, "gen")
+CXX = "/usr/bin/g++"
+
+STRATEGIES = ["DIFFUSE_ONLY", "DIFFUSE_GGX_MIS", "DIFFUSE_SPECULAR_SEPARATELY", "DIFFUSE_SPECULAR_MIS", "DIFFUSE_SPECULAR_RANDOM"]
+HEURISTICS = ["BALANCE", "POWER", "WEIGHTED", "OPTIMAL_CLAMPED", "OPTIMAL"]
+TECHNIQUES = ["BASELINE", "AREA_TURK", "SOLID_ANGLE_ARVO", "RECTANGLE_SOLID_ANGLE_URENA", "SOLID_ANGLE", "CLIPPED_SOLID_ANGLE", "BILINEAR_COSINE_WARP_HART",
+	"BILINEAR_COSINE_WARP_CLIPPING_HART", "BIQUADRATIC_COSINE_WARP_HART", "BIQUADRATIC_COSINE_WARP_CLIPPING_HART", "PROJECTED_SOLID_ANGLE_ARVO", "PROJECTED_SOLID_ANGLE"]
+
+
+def config_name(c):
+	return "s%d_h%d_b%d_L%d_V%d_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], c["max_vertices"], c["samples"], c["trace"], c["show_lights"], c["materials"])
+
+
+def defines(c):
+	"""The -D list of create_shading_pass (src/main.c:752-792) for one configuration."""
+	d = {
+		"MATERIAL_COUNT": c["materials"], "POLYGONAL_LIGHT_COUNT": c["lights"], "POLYGONAL_LIGHT_ARRAY_SIZE": max(c["lights"], 1),
+		"POLYGONAL_LIGHT_COUNT_CLAMPED": min(c["lights"], 33), "LIGHT_TEXTURE_COUNT": 1,
+		"MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING": c.get("min_vertices", c["max_vertices"]), "MAX_POLYGONAL_LIGHT_VERTEX_COUNT": c["max_vertices"],
+		"MAX_POLYGON_VERTEX_COUNT": c["max_vertices"] + 1, "SAMPLE_COUNT": c["samples"], "SAMPLE_COUNT_CLAMPED": min(c["samples"], 33),
+		"TRACE_SHADOW_RAYS": c["trace"], "SHOW_POLYGONAL_LIGHTS": c["show_lights"],
+		"ERROR_DISPLAY_DIFFUSE": 0, "ERROR_DISPLAY_SPECULAR": 0, "ERROR_INDEX": 0, "OUTPUT_LINEAR_RGB": 1,
+	}
+	for i, s in enumerate(STRATEGIES):
+		d["SAMPLING_STRATEGIES_" + s] = int(c["strategy"] == i)
+	for i, h in enumerate(HEURISTICS):
+		d["MIS_HEURISTIC_" + h] = int(c["heuristic"] == i)
+	for t in TECHNIQUES:
+		d["SAMPLE_POLYGON_" + t] = int(t == "PROJECTED_SOLID_ANGLE")
+	flags = ["-D%s=%s" % kv for kv in d.items()]
+	flags.append("-DUSE_BIASED_PROJECTED_SOLID_ANGLE_SAMPLING" if c["biased"] else "-DDONT_USE_BIASED_PROJECTED_SOLID_ANGLE_SAMPLING")
+	return flags
+
+
+def transform(text):
+	text = re.sub(r"^\s*#(version|extension)[^\n]*\n", "\n", text, flags=re.M)
+	# open up the uniform block: drop its header line and its closing '};'
+	m = re.search(r"layout\s*\([^)]*\)\s*uniform\s+\w+\s*\{", text)
+	if m:
+		depth = 0; i = m.end() - 1
+		while True:
+			if text[i] == "{": depth += 1
+			elif text[i] == "}":
+				depth -= 1
+				if depth == 0: break
+			i += 1
+		close_end = text.index(";", i) + 1
+		text = text[:m.start()] + text[m.end():i] + text[close_end:]
+	# shader stage inputs/outputs -> thread_local globals; resource bindings -> plain globals
+	text = re.sub(r"layout\s*\([^)]*\)\s*in\s+", "thread_local ", text)
+	text = re.sub(r"layout\s*\([^)]*\)\s*out\s+", "thread_local ", text)
+	text = re.sub(r"layout\s*\([^)]*\)\s*uniform\s+", "", text)
+	# parameter qualifiers
+	def param(mm):
+		return "%s %s[" % (mm.group(2), mm.group(3)) if mm.group(4) else "%s& %s" % (mm.group(2), mm.group(3))
+	text = re.sub(r"\b(inout|out)\s+(\w+)\s+(\w+)(\s*\[)?", param, text)
+	return text
+
+
+def generate_sources():
+	os.makedirs(GEN, exist_ok=True)
+	for name in sorted(os.listdir(REF_SHADERS)):
+		if name.endswith(".glsl"):
+			with open(os.path.join(REF_SHADERS, name)) as f:
+				text = f.read()
+			with open(os.path.join(GEN, name), "w") as f:
+				f.write(transform(text))
+
+
+def default_configs():
+	base = dict(strategy=3, heuristic=3, biased=0, lights=3, max_vertices=4, samples=3, trace=1, show_lights=1, materials=8)
+	configs = []
+	for strategy, heuristic in [(0, 0), (1, 0), (1, 1), (2, 0), (3, 0), (3, 1), (3, 2), (3, 3), (3, 4), (4, 0)]:
+		configs.append(dict(base, strategy=strategy, heuristic=heuristic))
+	configs.append(dict(base, biased=1))
+	configs.append(dict(base, samples=40, lights=2))                       # loop instead of unrolled code (SAMPLE_COUNT_CLAMPED = 33)
+	configs.append(dict(base, lights=1, samples=1, trace=0, materials=3, strategy=0, heuristic=3))   # BASELINE config 1 (Cornell)
+	configs.append(dict(base, lights=1, samples=2, trace=1, materials=3))  # Cornell with MIS and rays
+	return configs
+
+
+def build(configs=None, verbose=False):
+	if not os.path.isdir(REF_SHADERS):
+		print("build_ref: /root/reference is not present; keeping the prebuilt oracle/_ref as it is")
+		return None
+	configs = configs or default_configs()
+	generate_sources()
+	compat = os.path.join(HERE, "glsl_compat")
+	common = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-mfma", "-mavx2", "-fopenmp", "-w", "-I", GEN, "-I", compat]
+	objects = []
+	procs = []
+	obj = os.path.join(OUT, "ref_common.o")
+	procs.append(("common", subprocess.Popen([CXX] + common + ["-c", os.path.join(compat, "ref_common.cpp"), "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+	objects.append(obj)
+	names = []
+	for c in configs:
+		name = config_name(c)
+		names.append(dict(c, name=name, entry="ref_shade_" + name))
+		obj = os.path.join(OUT, name + ".o")
+		objects.append(obj)
+		cmd = [CXX] + common + defines(c) + ["-DREF_NS=cfg_" + name, "-DREF_ENTRY=ref_shade_" + name, "-c", os.path.join(compat, "ref_driver.cpp"), "-o", obj]
+		procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+	failed = False
+	for name, p in procs:
+		out, _ = p.communicate()
+		if p.returncode != 0:
+			failed = True
+			sys.stderr.write("---- %s\n%s\n" % (name, out[-6000:]))
+	if failed:
+		raise SystemExit("build_ref: compiling the reference shader as C++ failed")
+	lib = os.path.join(OUT, "libref_shader.so")
+	subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", lib] + objects)
+	with open(os.path.join(OUT, "configs.json"), "w") as f:
+		json.dump(names, f, indent=1)
+	for o in objects:
+		os.remove(o)
+	print("build_ref: %d configurations -> %s" % (len(configs), lib))
+	return lib
+
+
+if __name__ == "__main__":
+	build(verbose="-v" in sys.argv)

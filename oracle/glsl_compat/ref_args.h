@@ -1,0 +1,16 @@
+/* oracle/glsl_compat/ref_args.h -- TEST INFRASTRUCTURE. Argument block of the reference-shader entry points. */
+#ifndef VKR_REF_ARGS_H
+#define VKR_REF_ARGS_H
+#include <stdint.h>
+typedef int (*ref_occluded_hook_t)(const void* user, const float* origin, const float* dir, float tmin, float tmax);
+typedef struct ref_args_s {
+	uint32_t width, height, light_count, sample_count, max_light_vertex_count, material_count;
+	const void* constants;
+	const uint32_t* visibility;
+	const uint32_t* quantized_positions; const uint16_t* normals_and_tex_coords; const uint8_t* material_indices; const float* material_params;
+	const uint16_t* noise; uint32_t noise_w, noise_h, noise_layers;
+	const uint16_t* ltc0; const uint16_t* ltc1; uint32_t ltc_res, ltc_layers;
+	ref_occluded_hook_t occluded_hook; const void* occluded_user;
+	float* out_rgba;
+} ref_args_t;
+#endif

@@ -1,0 +1,69 @@
+"""ctypes binding of oracle/_ref/libref_shader.so: the REFERENCE's shader sources compiled as C++ (TEST INFRASTRUCTURE).
+
+Built by oracle/build_ref.py where /root/reference exists; travels prebuilt to the GPU box (never required there)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_shader.so")
+CONFIGS_PATH = os.path.join(_HERE, "_ref", "configs.json")
+
+HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float)
+
+
+class RefArgs(C.Structure):
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("light_count", C.c_uint32), ("sample_count", C.c_uint32), ("max_light_vertex_count", C.c_uint32), ("material_count", C.c_uint32),
+		("constants", C.c_void_p), ("visibility", C.c_void_p),
+		("quantized_positions", C.c_void_p), ("normals_and_tex_coords", C.c_void_p), ("material_indices", C.c_void_p), ("material_params", C.c_void_p),
+		("noise", C.c_void_p), ("noise_w", C.c_uint32), ("noise_h", C.c_uint32), ("noise_layers", C.c_uint32),
+		("ltc0", C.c_void_p), ("ltc1", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
+		("occluded_hook", C.c_void_p), ("occluded_user", C.c_void_p), ("out_rgba", C.c_void_p)]
+
+
+def available():
+	return os.path.exists(LIB_PATH) and os.path.exists(CONFIGS_PATH)
+
+
+def configs():
+	with open(CONFIGS_PATH) as f:
+		return json.load(f)
+
+
+_lib = None
+
+
+def load():
+	global _lib
+	if _lib is None:
+		_lib = C.CDLL(LIB_PATH)
+		_lib.ref_bvh_create.restype = C.c_void_p
+		_lib.ref_bvh_create.argtypes = [C.c_void_p, C.c_uint32]
+		_lib.ref_bvh_destroy.argtypes = [C.c_void_p]
+	return _lib
+
+
+def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris):
+	"""Runs the reference fragment shader (configuration `entry`) for every pixel. Returns float32 [H, W, 4]."""
+	lib = load()
+	keep = []
+	def arr(a, dtype):
+		a = np.ascontiguousarray(a, dtype=dtype); keep.append(a); return a.ctypes.data
+	out = np.zeros((height, width, 4), dtype=np.float32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	tris = np.ascontiguousarray(shadow_tris, dtype=np.float32).reshape(-1, 9)
+	bvh = lib.ref_bvh_create(tris.ctypes.data, len(tris))
+	a = RefArgs(width=width, height=height, light_count=cfg["lights"], sample_count=cfg["samples"], max_light_vertex_count=cfg["max_vertices"], material_count=len(material_params),
+		constants=C.addressof(cb), visibility=arr(visibility, np.uint32),
+		quantized_positions=arr(vks["positions"], np.uint32), normals_and_tex_coords=arr(vks["normals_uv"], np.uint16), material_indices=arr(vks["material_indices"], np.uint8),
+		material_params=arr(material_params, np.float32), noise=arr(noise, np.uint16), noise_w=noise.shape[2], noise_h=noise.shape[1], noise_layers=noise.shape[0],
+		ltc0=arr(ltc0, np.uint16), ltc1=arr(ltc1, np.uint16), ltc_res=ltc0.shape[1], ltc_layers=ltc0.shape[0],
+		occluded_hook=C.cast(lib.ref_bvh_occluded, C.c_void_p), occluded_user=bvh, out_rgba=out.ctypes.data)
+	fn = getattr(lib, entry)
+	rc = fn(C.byref(a))
+	lib.ref_bvh_destroy(bvh)
+	if rc != 0:
+		raise RuntimeError("%s rejected the arguments (configuration mismatch)" % entry)
+	return out

@@ -78,3 +78,36 @@ def test_config3_like_many_samples():
 	"""8 lights would need the 'city' set; mini_city has 3 quads: 64 spp exercises the noise period (128 fetches/pixel wrap)."""
 	r = _run_both("mini_city", 96, 64, sample_count=64, strategy=api.STRATEGY_DIFFUSE_SPECULAR_MIS, heuristic=api.MIS_OPTIMAL_CLAMPED, trace_shadow_rays=1)
 	_assert_parity(r, "64spp")
+
+
+def _fixture_names():
+	import os
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader.npz"))
+	return sorted({k.split("/")[0] for k in g.files})
+
+
+@pytest.mark.parametrize("name", _fixture_names())
+def test_cuda_path_reproduces_reference_shader_fixture(name):
+	"""CUDA visibility + G-buffer producer + shading megakernel against frames shaded by the REFERENCE's own shader
+	sources (tests/golden/ref_shader.npz, see tests/test_ref_shader.py): bit-identical float32 radiance."""
+	import os
+	from tests.test_ref_shader import _config_from_name
+	from tests.ref_frames import WIDTH, HEIGHT, dataset_for
+	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader.npz"))
+	cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg))
+	frame = H.open_frame(info)
+	try:
+		frame.configure(sample_count=cfg["samples"], strategy=cfg["strategy"], heuristic=cfg["heuristic"],
+			technique=api.TECHNIQUE_PSA_BIASED if cfg["biased"] else api.TECHNIQUE_PSA, trace_shadow_rays=cfg["trace"], show_lights=cfg["show_lights"], light_count=cfg["lights"])
+		constants = frame.constants(WIDTH, HEIGHT)
+		assert constants == bytes(g[name + "/constants"])
+		vis, gb = frame.gbuffer_host(WIDTH, HEIGHT)
+		assert np.array_equal(vis, g[name + "/visibility"])
+		out = frame.shade_host(WIDTH, HEIGHT, gb)
+	finally:
+		frame.close()
+	ref = g[name + "/rgba"]
+	cmp = H.compare_radiance(out, ref, rel=REL_TOL)
+	assert cmp["bad_pixels"] == 0 and cmp["nan_mismatch"] == 0, cmp
+	assert cmp["bit_exact"], cmp

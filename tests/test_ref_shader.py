@@ -1,0 +1,68 @@
+"""Pins the CPU oracle against the REFERENCE's own shader sources.
+
+tests/golden/ref_shader.npz holds frames shaded by src/shaders/shading_pass.frag.glsl (+ includes) compiled as C++
+(oracle/build_ref.py, oracle/glsl_compat/). The oracle must reproduce them bit for bit, for every sampling strategy
+and MIS heuristic of the projected-solid-angle technique. Where oracle/_ref/libref_shader.so is present (build
+container, or shipped prebuilt) the reference shader is also run live and checked against the fixtures.
+"""
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import harness as H
+from tests.ref_frames import WIDTH, HEIGHT, dataset_for, host_constants, oracle_cfg
+from oracle import ref_binding as R
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader.npz")
+
+
+def _golden():
+	return np.load(GOLDEN)
+
+
+def _config_from_name(name):
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)_S(\d+)_t(\d+)_l(\d+)_M(\d+)$", name)
+	s, h, b, L, V, S, t, l, M = (int(x) for x in m.groups())
+	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, samples=S, trace=t, show_lights=l, materials=M)
+
+
+def _names():
+	return sorted({k.split("/")[0] for k in _golden().files})
+
+
+@pytest.mark.parametrize("name", _names())
+def test_oracle_reproduces_reference_shader_bit_for_bit(name):
+	g = _golden(); cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	sha = hashlib.sha256(open(info["vks"], "rb").read()).digest()
+	assert bytes(g[name + "/vks_sha256"]) == sha, "the synthetic scene generator drifted: regenerate with tools/make_ref_golden.py"
+	constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"])
+	assert constants == bytes(g[name + "/constants"]), "the constant block drifted"
+	vis = oi.visibility(WIDTH, HEIGHT, constants)
+	assert np.array_equal(vis, g[name + "/visibility"])
+	gb = oi.gbuffer(WIDTH, HEIGHT, constants, vis)
+	out, _ = oi.shade(oracle_cfg(cfg), constants, gb)
+	ref = g[name + "/rgba"]
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+	assert float(ref[..., :3].max()) > 0.0
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
+def test_live_reference_shader_matches_fixture():
+	g = _golden()
+	live = {c["name"]: c for c in R.configs()}
+	checked = 0
+	for name in _names():
+		if name not in live:
+			continue
+		cfg = live[name]
+		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+		constants = bytes(g[name + "/constants"])
+		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, g[name + "/visibility"], oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris)
+		assert np.array_equal(ref.view(np.uint32), g[name + "/rgba"].view(np.uint32)), name
+		checked += 1
+	assert checked > 0
