@@ -1,0 +1,126 @@
+#!/usr/bin/env python3
+"""Summarises an ncu capture of the shading megakernel into profiles/ (run here, no GPU needed).
+
+  python tools/summarize_ncu.py gpurun_out/r01_prof.ncu-rep gpurun_out/r01_launches.csv profiles/r01_v1
+
+Writes <out>_summary.md: launch list (share of the step per kernel), key metrics of the top kernel (duration, DRAM
+bytes, occupancy, issue utilisation, lanes per instruction), warp stall reasons and the hottest source lines
+(SASS profile joined with nvdisasm line info of the in-tree library).
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+	"sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+	"sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+	"gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic"]
+
+
+def launches(path):
+	rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("=="))]
+	hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value")
+	d = collections.defaultdict(list)
+	for r in rows[1:]:
+		if len(r) > vi:
+			d[r[ki]].append(float(r[vi].replace(",", "")))
+	total = sum(sum(v) for v in d.values())
+	return sorted(((k, len(v), sum(v), sum(v) / total) for k, v in d.items()), key=lambda t: -t[2])
+
+
+def raw_metrics(rep):
+	out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+	rows = list(csv.reader(out.splitlines()))
+	hdr, units, vals = rows[0], rows[1], rows[2]
+	return {h: (vals[i], units[i]) for i, h in enumerate(hdr)}, vals[hdr.index("Kernel Name")]
+
+
+def sass_profile(rep):
+	out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+	rows = list(csv.reader(out.splitlines()))
+	hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+	hdr = rows[hi]
+	idx = {n: hdr.index(n) for n in ("Address", "Instructions Executed", "Thread Instructions Executed", "# Samples")}
+	stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+	prof = []; stall_tot = collections.Counter()
+	for r in rows[hi + 1:]:
+		try:
+			prof.append((int(r[idx["Address"]], 16), float(r[idx["Instructions Executed"]]), float(r[idx["Thread Instructions Executed"]]), float(r[idx["# Samples"]])))
+		except (ValueError, IndexError):
+			continue
+		for i in stalls:
+			try: stall_tot[hdr[i]] += float(r[i])
+			except ValueError: pass
+	return prof, stall_tot
+
+
+def line_info(kernel_mangled_regex):
+	lib = os.path.join(ROOT, "vulkan_renderer_b200", "libvkr_b200.so")
+	tmp = tempfile.mkdtemp()
+	subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+	cubin = os.path.join(tmp, "vkr_shading_kernel.sm_100a.cubin")
+	text = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True).stdout.split("\n")
+	start = [i for i, l in enumerate(text) if re.match(r"\.text\." + kernel_mangled_regex + ":", l)]
+	if not start:
+		return []
+	insts = []; cur = ("?", 0)
+	for l in text[start[0] + 1:]:
+		if l.startswith("\t.section") or l.startswith(".text."):
+			break
+		m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+		if m:
+			cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
+		if re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", l):
+			insts.append(cur)
+	return insts
+
+
+def main():
+	rep, launch_csv, out = sys.argv[1:4]
+	lines = ["# ncu summary: %s" % os.path.basename(rep), ""]
+	lines += ["## Launch list (`--metrics gpu__time_duration.sum --clock-control none`, serialised, cold cache: compare shares)", "", "| kernel | launches | total ns | share |", "|---|---|---|---|"]
+	for k, n, t, s in launches(launch_csv)[:8]:
+		lines.append("| `%s` | %d | %.0f | %.4f |" % (k[:90], n, t, s))
+	m, kernel = raw_metrics(rep)
+	lines += ["", "## Top kernel `%s` (`--set full --clock-control none`)" % kernel, "", "| metric | value | unit |", "|---|---|---|"]
+	for name in METRICS:
+		if name in m:
+			lines.append("| %s | %s | %s |" % (name, m[name][0], m[name][1]))
+	prof, stalls = sass_profile(rep)
+	tot_s = sum(stalls.values())
+	lines += ["", "## Warp stall reasons (share of samples)", "", "| reason | share |", "|---|---|"]
+	for k, v in stalls.most_common(8):
+		lines.append("| %s | %.1f%% |" % (k, 100 * v / tot_s))
+	mm = re.match(r"void vkr::shading_kernel<\(int\)(\d+), \(int\)(\d+), \(bool\)(\d+)>", kernel)
+	insts = line_info(r"_ZN3vkr14shading_kernelILi%sELi%sELb%sEEEvNS_21shading_kernel_paramsE" % mm.groups()) if mm else []
+	if insts and len(insts) == len(prof):
+		by = collections.defaultdict(lambda: [0.0, 0.0, 0.0]); byfile = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+		for (a, c, t, s), key in zip(prof, insts):
+			for d in (by[key], byfile[key[0]]):
+				d[0] += c; d[1] += t; d[2] += s
+		tot = sum(v[0] for v in byfile.values()); tots = sum(v[2] for v in byfile.values())
+		lines += ["", "## Instructions by source file", "", "| file | warp instructions | active lanes / instruction | stall samples |", "|---|---|---|---|"]
+		for f, v in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
+			lines.append("| %s | %.1f%% | %.1f | %.1f%% |" % (f, 100 * v[0] / tot, v[1] / max(v[0], 1), 100 * v[2] / max(tots, 1)))
+		lines += ["", "## Hottest source lines", "", "| share | lanes | where | source |", "|---|---|---|---|"]
+		cache = {}
+		for (f, ln), v in sorted(by.items(), key=lambda kv: -kv[1][0])[:30]:
+			if f not in cache:
+				p = os.path.join(ROOT, "vulkan_renderer_b200", "csrc", f)
+				cache[f] = open(p).read().split("\n") if os.path.exists(p) else []
+			src = cache[f][ln - 1].strip()[:90].replace("|", "\\|") if 0 < ln <= len(cache[f]) else ""
+			lines.append("| %.2f%% | %.1f | %s:%d | `%s` |" % (100 * v[0] / tot, v[1] / max(v[0], 1), f, ln, src))
+	else:
+		lines += ["", "(source correlation skipped: the in-tree library does not match the profiled binary: %d vs %d instructions)" % (len(insts), len(prof))]
+	with open(out + "_summary.md", "w") as f:
+		f.write("\n".join(lines) + "\n")
+	print("\n".join(lines[:40]))
+
+
+if __name__ == "__main__":
+	main()
