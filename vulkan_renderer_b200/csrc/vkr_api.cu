@@ -150,7 +150,11 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	p.noise = (const uint16_t*) d.noise_table->d_noise; p.noise_w = (int) d.noise_table->width; p.noise_h = (int) d.noise_table->height; p.noise_layers = (int) d.noise_table->layers;
 	p.ltc0 = (const uint16_t*) d.ltc_table->d_table0; p.ltc1 = (const uint16_t*) d.ltc_table->d_table1;
 	p.ltc_res = (int) d.ltc_table->roughness_count; p.ltc_layers = (int) d.ltc_table->fresnel_count;
-	if (d.trace_shadow_rays) { p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count; }
+	p.stack_depth = 4;
+	if (d.trace_shadow_rays) {
+		p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count;
+		p.stack_depth = (int) d.scene->shadow_max_depth + 2;
+	}
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_begin, stream);
 	cudaError_t err = vkr_launch_shading_kernel(p, stream);
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_end, stream);
@@ -211,7 +215,7 @@ extern "C" int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_dev
 namespace vkr {
 
 __global__ void __launch_bounds__(128) trace_probe_kernel(bvh_view bvh, uint32_t ray_count, const float* rays, uint8_t* out) {
-	__shared__ int stack[kStackDepth * 128];
+	__shared__ int stack[kMaxStackDepth * 128];
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= ray_count) return;
 	const float* r = rays + 8 * (size_t) i;

@@ -51,7 +51,7 @@ VKR_DEV f3 decode_normal(float ox, float oy) { // mesh_quantization.glsl:19-33
 constexpr int kGTileW = 16, kGTileH = 8, kGThreads = kGTileW * kGTileH;
 
 __global__ void __launch_bounds__(kGThreads) visibility_kernel(const gbuffer_kernel_params p) {
-	__shared__ int stack[kStackDepth * kGThreads];
+	__shared__ int stack[kMaxStackDepth * kGThreads];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
 	const int tiles_x = (p.width + kGTileW - 1) / kGTileW;

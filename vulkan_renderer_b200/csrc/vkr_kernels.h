@@ -27,6 +27,7 @@ struct shading_kernel_params {
 	const uint16_t* ltc0; const uint16_t* ltc1; int ltc_res, ltc_layers;
 	// acceleration structure
 	const float4* bvh_nodes; const float4* bvh_tris; uint32_t tri_count;
+	int stack_depth;                 // traversal stack entries per lane (BVH depth + 2)
 };
 
 struct gbuffer_kernel_params {

@@ -11,8 +11,11 @@
 //           ref >= 0: inner node index; ref < 0: leaf, (ref & 0x7fffffff) = first_triangle << 4 | count
 //   tri   = 48 B = 3 x float4: v0.xyz e1.x | e1.yz e2.xy | e2.z - - -   (e1 = v1 - v0, e2 = v2 - v0)
 //
-// The triangle predicate is the arithmetic contract of DESIGN.md (Moeller-Trumbore, fp32, fixed
-// operation order, no culling, open interval); hit/miss does not depend on traversal order.
+// Arithmetic: the TRIANGLE predicate is part of the parity contract (Moeller-Trumbore,
+// fp32, fixed operation order, no culling, open interval); hit/miss is the OR over all triangles and
+// does not depend on traversal order. The BOX test only has to be conservative: it uses one FFMA
+// per slab plane (plane * 1/d - o/d) and FMNMX min/max; its rounding error is below 1/128 of the
+// padding the builder adds to every box (vkr_bvh.cpp), so no triangle the predicate accepts is culled.
 #pragma once
 #include "vkr_device_math.cuh"
 
@@ -25,7 +28,8 @@ struct bvh_view {
 	uint32_t tri_count;
 };
 
-constexpr int kStackDepth = 64;
+constexpr int kMaxStackDepth = 64;      // the builder guarantees depth < 62 (vkr_host.cpp)
+constexpr int kTraversalDone = 0x7fffffff;
 
 VKR_DEV bool ray_triangle(const float4* __restrict__ tri, f3 o, f3 d, float tmin, float tmax, float* out_t) {
 	const float4 a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
@@ -48,32 +52,95 @@ VKR_DEV bool ray_triangle(const float4* __restrict__ tri, f3 o, f3 d, float tmin
 	return true;
 }
 
-VKR_DEV bool ray_box(float lox, float loy, float loz, float hix, float hiy, float hiz, f3 o, f3 id, float tmin, float tmax) {
-	float t0 = (lox - o.x) * id.x, t1 = (hix - o.x) * id.x;
-	float tn = (t0 < t1) ? t0 : t1, tf = (t0 > t1) ? t0 : t1;
-	float t_near = (tn > tmin) ? tn : tmin, t_far = (tf < tmax) ? tf : tmax;
-	t0 = (loy - o.y) * id.y; t1 = (hiy - o.y) * id.y;
-	tn = (t0 < t1) ? t0 : t1; tf = (t0 > t1) ? t0 : t1;
-	t_near = (tn > t_near) ? tn : t_near; t_far = (tf < t_far) ? tf : t_far;
-	t0 = (loz - o.z) * id.z; t1 = (hiz - o.z) * id.z;
-	tn = (t0 < t1) ? t0 : t1; tf = (t0 > t1) ? t0 : t1;
-	t_near = (tn > t_near) ? tn : t_near; t_far = (tf < t_far) ? tf : t_far;
-	return t_near <= t_far * 1.0000005f;
+// Ray in the form the slab test wants: id = 1/d, oid = o/d
+struct ray_slabs { f3 id, oid; };
+VKR_DEV ray_slabs make_slabs(f3 o, f3 d) {
+	ray_slabs r;
+	r.id = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	r.oid = make3(o.x * r.id.x, o.y * r.id.y, o.z * r.id.z);
+	return r;
 }
 
-// Any-hit query. stack = this thread's column of the CTA's shared-memory stack (stride = blockDim).
+// Conservative slab test (see header). Returns the entry distance in *t_near. NaNs (inf - inf for axis-parallel
+// rays) drop out of fminf/fmaxf, which leaves that slab unconstrained.
+VKR_DEV bool ray_box(float lox, float loy, float loz, float hix, float hiy, float hiz, const ray_slabs& r, float tmin, float tmax, float* t_near) {
+	const float x0 = fmaf(lox, r.id.x, -r.oid.x), x1 = fmaf(hix, r.id.x, -r.oid.x);
+	const float y0 = fmaf(loy, r.id.y, -r.oid.y), y1 = fmaf(hiy, r.id.y, -r.oid.y);
+	const float z0 = fmaf(loz, r.id.z, -r.oid.z), z1 = fmaf(hiz, r.id.z, -r.oid.z);
+	const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
+	const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+	*t_near = tn;
+	return tn <= tf;
+}
+
+// Warp-wide any-hit query: ALL 32 lanes call it together; lanes without a ray pass has_ray = false.
+// Speculative while-while traversal: a lane that reaches a leaf postpones it and keeps descending until it finds a
+// second leaf or runs out of nodes, then the warp tests triangles together (leaf tests used to run at ~4 of 32 lanes).
+// stack = this lane's column of the warp's shared-memory stack (stride in ints between levels).
+VKR_DEV bool occluded_warp(const bvh_view& bvh, bool has_ray, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
+	const unsigned full = 0xffffffffu;
+	const ray_slabs r = make_slabs(o, d);
+	int node = (has_ray && tmax > tmin) ? 0 : kTraversalDone; // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
+	int leaf = 0;      // postponed leaf reference (0 = none; leaf references are negative)
+	int sp = 0;
+	bool hit = false;
+	while (__any_sync(full, node != kTraversalDone || leaf != 0)) {
+		// --- descend until this lane holds two leaves or is out of nodes
+		while (node >= 0 && node != kTraversalDone) {
+			const float4* n = bvh.nodes + 4 * (size_t) node;
+			const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
+			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
+			float tn0, tn1;
+			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
+			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
+			if (h0 && h1) {
+				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
+				node = swap ? ref1 : ref0;
+				stack[sp * stride] = swap ? ref0 : ref1; ++sp;
+			}
+			else if (h0) node = ref0;
+			else if (h1) node = ref1;
+			else if (sp > 0) { --sp; node = stack[sp * stride]; }
+			else node = kTraversalDone;
+			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
+				leaf = node;
+				if (sp > 0) { --sp; node = stack[sp * stride]; }
+				else node = kTraversalDone;
+			}
+		}
+		__syncwarp(full);
+		// --- leaves: `leaf` and possibly `node` (a second leaf)
+		while (leaf != 0) {
+			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
+			float t;
+			for (int i = 0; i != count; ++i)
+				if (ray_triangle(bvh.tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) hit = true;
+			leaf = 0;
+			if (hit) { node = kTraversalDone; sp = 0; }
+			else if (node < 0) {
+				leaf = node;
+				if (sp > 0) { --sp; node = stack[sp * stride]; }
+				else node = kTraversalDone;
+			}
+		}
+		__syncwarp(full);
+	}
+	return hit;
+}
+
+// Per-thread any-hit query (probe kernel); same traversal without warp collectives.
 VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
-	if (!(tmax > tmin)) return false; // undefined in Vulkan; defined as "miss" 
-	const f3 id = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	if (!(tmax > tmin)) return false;
+	const ray_slabs r = make_slabs(o, d);
 	int sp = 0;
 	int node = 0;
-	float t;
+	float t, tn0, tn1;
 	while (true) {
 		const float4* n = bvh.nodes + 4 * (size_t) node;
 		const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
 		const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
-		bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id, tmin, tmax);
-		bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, id, tmin, tmax);
+		bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
+		bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
 		if (h0 && ref0 < 0) {
 			const int first = (ref0 & 0x7fffffff) >> 4, count = ref0 & 15;
 			for (int i = 0; i != count; ++i)
@@ -98,18 +165,19 @@ VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, i
 
 // Closest-hit query, ties in t resolve to the lowest original triangle index (order independent).
 VKR_DEV int closest_hit(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
-	const f3 id = make3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+	const ray_slabs r = make_slabs(o, d);
 	int sp = 0;
 	int node = 0;
 	int best = -1;
 	float best_t = tmax;
-	float t;
+	float t, tn0, tn1;
 	while (true) {
 		const float4* n = bvh.nodes + 4 * (size_t) node;
 		const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
 		const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
-		bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, o, id, tmin, best_t);
-		bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, o, id, tmin, best_t);
+		// closed upper bound so that equal-t candidates are still visited for the tie rule
+		bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, best_t, &tn0);
+		bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, best_t, &tn1);
 #pragma unroll
 		for (int c = 0; c != 2; ++c) {
 			const int ref = c ? ref1 : ref0;
@@ -125,7 +193,10 @@ VKR_DEV int closest_hit(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax,
 				if (c) h1 = false; else h0 = false;
 			}
 		}
-		if (h0 && h1) { stack[sp * stride] = ref1; ++sp; node = ref0; }
+		if (h0 && h1) {
+			const bool swap = tn1 < tn0;
+			stack[sp * stride] = swap ? ref0 : ref1; ++sp; node = swap ? ref1 : ref0;
+		}
 		else if (h0) node = ref0;
 		else if (h1) node = ref1;
 		else {
