@@ -1,0 +1,26 @@
+#!/usr/bin/env python3
+"""Quick kernel timing experiments on the bench scene (developer tool): python tools/quick_time.py [spp] [lights] [rays]"""
+import ctypes as C, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import torch
+from vulkan_renderer_b200 import Frame, api, synth
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+lights = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+rays = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+strategy = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+width, height = 1920, 1080
+info = synth.build_dataset("/tmp/vkr_b200_data/city", "city")
+dev = torch.device("cuda", 0); stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
+frame = Frame(info["vks"], info["textures"], info["save"], info["ltc"], cuda_device=0, stream=stream.cuda_stream)
+frame.configure(sample_count=spp, strategy=strategy, heuristic=api.MIS_OPTIMAL_CLAMPED, trace_shadow_rays=rays, show_lights=1, light_count=lights)
+lib = frame.lib
+constants = frame.constants(width, height)
+vis = torch.empty((height, width), dtype=torch.int32, device=dev); gb = torch.empty((4, height, width, 4), dtype=torch.float32, device=dev); out = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+lib.vkr_run_visibility_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, vis.data_ptr())
+lib.vkr_run_gbuffer_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, vis.data_ptr(), gb.data_ptr())
+p = frame.create_pass(width, height, timing=True)
+for i in range(3):
+	lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr())
+	lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device))
+	print("spp %d lights %d rays %d strategy %d: kernel %.3f ms -> %.1f Msamples/s" % (spp, lights, rays, strategy, p.last_kernel_ms, width * height * spp / p.last_kernel_ms / 1e3), flush=True)
+print("valid fraction", float((gb[1, :, :, 3] != 0).float().mean()), "mean radiance", float(out[..., :3].mean()))

@@ -96,8 +96,12 @@ def main():
 	lines += ["", "## Warp stall reasons (share of samples)", "", "| reason | share |", "|---|---|"]
 	for k, v in stalls.most_common(8):
 		lines.append("| %s | %.1f%% |" % (k, 100 * v / tot_s))
-	mm = re.match(r"void vkr::shading_kernel<\(int\)(\d+), \(int\)(\d+), \(bool\)(\d+)>", kernel)
-	insts = line_info(r"_ZN3vkr14shading_kernelILi%sELi%sELb%sEEEvNS_21shading_kernel_paramsE" % mm.groups()) if mm else []
+	mm = re.search(r"shading_kernel<([^>]*)>", kernel)
+	insts = []
+	if mm:
+		args = re.findall(r"\d+", re.sub(r"\((int|bool)\)", "", mm.group(1)))
+		mangled = "".join("L%s%sE" % ("i" if k < 2 else "b", a) for k, a in enumerate(args))
+		insts = line_info(r"_ZN3vkr14shading_kernelI%sEEvNS_21shading_kernel_paramsE" % mangled)
 	if insts and len(insts) == len(prof):
 		by = collections.defaultdict(lambda: [0.0, 0.0, 0.0]); byfile = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
 		for (a, c, t, s), key in zip(prof, insts):

@@ -23,90 +23,11 @@
 // the floating-point sums identical to the reference's sequential loop.
 // Compile with -fmad=false (see vkr_device_math.cuh).
 #include "vkr_shade_common.cuh"
+#include "vkr_ray_queue.cuh"
 
 namespace vkr {
 
 constexpr int kTileW = 16, kTileH = 8, kThreads = kTileW * kTileH, kWarps = kThreads / 32;
-constexpr int kQueueCapacity = 128;   // rays per warp (power of two); at most 31 left over + 64 new per sample
-constexpr unsigned kFullMask = 0xffffffffu;
-
-// Per-warp ray queue in shared memory (structure of arrays, one ring per warp)
-struct ray_queue {
-	float* dx; float* dy; float* dz; float* tmax;   // [kQueueCapacity]
-	float* cx; float* cy; float* cz;                 // contribution if the ray is unoccluded
-	float* ox_; float* oy_; float* oz_;              // contribution if it is occluded (MIS_HEURISTIC_OPTIMAL only)
-	int* owner;                                      // lane that owns the pixel; bit 31: visibility already known to be false
-	const float* origin;                             // [3 * 32] ray origins = shading positions of the warp's lanes
-	int* stack; int stack_stride;                    // this lane's column of the traversal stack
-	bvh_view bvh;
-	int head, count;                                 // warp-uniform
-	bool enabled;                                    // TRACE_SHADOW_RAYS
-};
-
-constexpr size_t kQueueFloatsPerWarp = 10 * kQueueCapacity + kQueueCapacity /*owner*/ + 96 /*origins*/;
-
-// Traces the n <= 32 oldest rays of the queue and adds the resolved contributions to their owners, oldest first.
-template <bool OPTIMAL>
-VKR_DEV void trace_batch(ray_queue& q, int n, int lane, f3& result) {
-	const bool has = lane < n;
-	const int slot = (q.head + lane) & (kQueueCapacity - 1);
-	int own = 0;
-	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
-	float tmax = 0.0f;
-	if (has) {
-		own = q.owner[slot];
-		const int ol = own & 31;
-		o = make3(q.origin[ol], q.origin[32 + ol], q.origin[64 + ol]);
-		d = make3(q.dx[slot], q.dy[slot], q.dz[slot]);
-		tmax = q.tmax[slot];
-	}
-	const bool known_occluded = own < 0;
-	const bool occ = occluded_warp(q.bvh, has && !known_occluded, o, d, 1.0e-3f, tmax, q.stack, q.stack_stride) || known_occluded;
-	const unsigned occ_mask = __ballot_sync(kFullMask, occ);
-	const int own_lane = own & 31;
-	for (int i = 0; i != n; ++i) {
-		const int ow = __shfl_sync(kFullMask, own_lane, i);
-		if (ow == lane) {
-			const int s = (q.head + i) & (kQueueCapacity - 1);
-			if (!((occ_mask >> i) & 1u)) result = result + make3(q.cx[s], q.cy[s], q.cz[s]);
-			else if (OPTIMAL) result = result + make3(q.ox_[s], q.oy_[s], q.oz_[s]);
-		}
-	}
-	q.head = (q.head + n) & (kQueueCapacity - 1);
-	q.count -= n;
-	__syncwarp(kFullMask);
-}
-
-// Warp-convergent: every lane calls it once per candidate sample. has = this lane contributes something.
-// need_trace = visibility is not known yet (n.w > 0); otherwise the sample is known to be occluded.
-template <bool OPTIMAL>
-VKR_DEV void submit(ray_queue& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, f3& result) {
-	if (!q.enabled) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
-		if (has) {
-			if (need_trace) result = result + c_visible;
-			else if (OPTIMAL) result = result + c_occluded;
-		}
-		return;
-	}
-	const bool push = has && (need_trace || OPTIMAL);
-	const unsigned mask = __ballot_sync(kFullMask, push);
-	if (push) {
-		const int rank = __popc(mask & ((1u << lane) - 1u));
-		const int s = (q.head + q.count + rank) & (kQueueCapacity - 1);
-		q.dx[s] = dir_world.x; q.dy[s] = dir_world.y; q.dz[s] = dir_world.z; q.tmax[s] = tmax;
-		q.cx[s] = c_visible.x; q.cy[s] = c_visible.y; q.cz[s] = c_visible.z;
-		if (OPTIMAL) { q.ox_[s] = c_occluded.x; q.oy_[s] = c_occluded.y; q.oz_[s] = c_occluded.z; }
-		q.owner[s] = need_trace ? lane : (lane | (int) 0x80000000);
-	}
-	q.count += __popc(mask);
-	__syncwarp(kFullMask);
-	while (q.count >= 32) trace_batch<OPTIMAL>(q, 32, lane, result);
-}
-
-template <bool OPTIMAL>
-VKR_DEV void flush(ray_queue& q, int lane, f3& result) {
-	while (q.count > 0) trace_batch<OPTIMAL>(q, q.count < 32 ? q.count : 32, lane, result);
-}
 
 // Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
 VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
@@ -313,7 +234,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 			}
 		}
 	}
-	flush<OPTIMAL>(q, lane, result);
+	drain<OPTIMAL>(q, lane, result);
 	return result * (1.0f / (float) S);
 }
 
@@ -323,7 +244,7 @@ shading_kernel(const shading_kernel_params p) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned char* cb = smem;                                   // constant block incl. lights
 	float* queue_base = reinterpret_cast<float*>(smem + p.constants_smem_bytes);
-	int* stack_base = reinterpret_cast<int*>(queue_base + kQueueFloatsPerWarp * kWarps);
+	int* stack_base = reinterpret_cast<int*>(queue_base + queue_floats_per_warp(OPTIMAL) * kWarps);
 	__shared__ __align__(8) unsigned long long mbar;
 	// --- stage the constant block with one bulk async copy (TMA engine), completion on an mbarrier
 	const uint32_t mbar_addr = (uint32_t) __cvta_generic_to_shared(&mbar);
@@ -384,17 +305,11 @@ shading_kernel(const shading_kernel_params p) {
 	// --- the warp's ray queue and traversal stack
 	ray_queue q;
 	{
-		float* base = queue_base + kQueueFloatsPerWarp * warp;
-		q.dx = base; q.dy = base + kQueueCapacity; q.dz = base + 2 * kQueueCapacity; q.tmax = base + 3 * kQueueCapacity;
-		q.cx = base + 4 * kQueueCapacity; q.cy = base + 5 * kQueueCapacity; q.cz = base + 6 * kQueueCapacity;
-		q.ox_ = base + 7 * kQueueCapacity; q.oy_ = base + 8 * kQueueCapacity; q.oz_ = base + 9 * kQueueCapacity;
-		q.owner = reinterpret_cast<int*>(base + 10 * kQueueCapacity);
-		float* origin = base + 11 * kQueueCapacity;
+		queue_bind(q, queue_base + queue_floats_per_warp(OPTIMAL) * warp, OPTIMAL);
+		float* origin = const_cast<float*>(q.origin);
 		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
-		q.origin = origin;
 		q.stack = stack_base + p.stack_depth * 32 * warp + lane; q.stack_stride = 32;
 		q.bvh.nodes = p.bvh_nodes; q.bvh.tris = p.bvh_tris; q.bvh.tri_ids = nullptr; q.bvh.tri_count = p.tri_count;
-		q.head = 0; q.count = 0;
 		q.enabled = p.trace_shadow_rays != 0 && p.tri_count != 0;
 	}
 	__syncwarp(kFullMask);
@@ -434,11 +349,16 @@ static cudaError_t launch_variant(const shading_kernel_params& p, cudaStream_t s
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
 	const int tiles_y = p.tile_row_count;
 	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
-	const size_t smem = p.constants_smem_bytes + sizeof(float) * kQueueFloatsPerWarp * kWarps + sizeof(int) * (size_t) p.stack_depth * kThreads;
+	const size_t smem = p.constants_smem_bytes + sizeof(float) * queue_floats_per_warp(OPTIMAL) * kWarps + sizeof(int) * (size_t) p.stack_depth * kThreads;
 	auto kernel = shading_kernel<STRATEGY, MAXP, BIASED, OPTIMAL>;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (err != cudaSuccess) return err;
-	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+	// Shared memory for exactly the CTAs the register file admits; the rest of the 228 KB stays L1 for BVH nodes
+	int ctas = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kThreads, smem);
+	if (err != cudaSuccess) return err;
+	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
+	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
 	kernel<<<tiles_x * tiles_y, kThreads, smem, stream>>>(p);
 	return cudaGetLastError();
