@@ -158,26 +158,15 @@ def run_b200(args):
 	f0_lum = (gb[3, :, :, :3] * torch.tensor([0.2126, 0.7152, 0.0722], device=dev)).sum(-1)
 	ltc_layers = int(torch.unique(torch.round(f0_lum[valid].clamp(0, 1) * 50.0)).numel()) if bool(valid.any()) else 0
 	p = frame.create_pass(width, height, stripe_index=rank, stripe_count=world)
-	tile_rows = (height + 7) // 8
-	my_tile_rows = list(range(rank, tile_rows, world))
-	# rows of this rank's stripe, and the gather buffers (every rank contributes the same number of rows; pad with the last)
-	max_rows = 8 * ((tile_rows + world - 1) // world)
-	row_idx = torch.tensor([min(t * 8 + k, height - 1) for t in my_tile_rows for k in range(8)] , dtype=torch.long, device=dev)
-	if row_idx.numel() < max_rows:
-		row_idx = torch.cat([row_idx, row_idx[-1:].expand(max_rows - row_idx.numel())])
-	gathered = torch.empty((world, max_rows, width, 4), dtype=torch.float32, device=dev) if world > 1 else None
-	all_rows = None
-	if world > 1:
-		all_rows = torch.stack([torch.tensor(([min(t * 8 + k, height - 1) for t in range(r, tile_rows, world) for k in range(8)] + [height - 1] * max_rows)[:max_rows], dtype=torch.long, device=dev) for r in range(world)])
+	from vulkan_renderer_b200.stripes import StripeGather, stripe_rows
+	sg = StripeGather(height, width, rank, world, dev)
+	row_idx = sg.my_rows
 	flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
 	def step_device():
 		rc = lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr())
 		assert rc == 0
-		if world > 1:
-			stripe = out.index_select(0, row_idx)
-			dist.all_gather_into_tensor(gathered, stripe)
-			out.index_copy_(0, all_rows.reshape(-1), gathered.reshape(-1, width, 4))
+		sg.gather_frame(out)   # one NCCL all-gather of the HDR stripes (no-op on a single GPU)
 
 	def timed(step_fn, steps, warmup):
 		for _ in range(warmup):
@@ -220,7 +209,8 @@ def run_b200(args):
 	# --- e2e: host buffers in, host buffers out
 	gb_host = torch.empty((4, height, width, 4), dtype=torch.float32).pin_memory(); gb_host.copy_(gb)
 	out_host = torch.zeros((height, width, 4), dtype=torch.float32).pin_memory()
-	stripe_rows = len(my_tile_rows) * 8
+	stripe_row_count = len(stripe_rows(height, rank, world))
+	row_idx_cpu = row_idx.cpu()
 
 	def step_e2e():
 		if world == 1:
@@ -228,14 +218,14 @@ def run_b200(args):
 			assert rc == 0
 		else:
 			# stripe rows host->device, shade, gather over NVLink, rank 0 reads the frame back
-			gb.index_copy_(1, row_idx, gb_host.index_select(1, row_idx.cpu()).to(dev, non_blocking=True))
+			gb.index_copy_(1, row_idx, gb_host.index_select(1, row_idx_cpu).to(dev, non_blocking=True))
 			step_device()
 			if rank == 0:
 				out_host.copy_(out, non_blocking=True)
 	e2e_steps = max(1, min(args.steps, 5)); e2e_warm = max(1, min(args.warmup, 2))
 	e2e_ms = timed(step_e2e, e2e_steps, e2e_warm) / e2e_steps
 	e2e_value = samples / (e2e_ms * 1e-3) / 1e6
-	h2d = (4 * stripe_rows * width * 16) + len(constants) if world > 1 else 4 * height * width * 16 + len(constants)
+	h2d = (4 * stripe_row_count * width * 16) + len(constants) if world > 1 else 4 * height * width * 16 + len(constants)
 	d2h = height * width * 16
 
 	result = None

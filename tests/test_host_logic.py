@@ -1,0 +1,215 @@
+"""CPU tests of the host side of libvkr_b200.so: the C-ABI exports every symbol of include/vkr_b200.h, the loaders
+read the reference's file formats (checked against an independent numpy reading), the constant block has the
+reference's layout, the BVH builder produces a valid tree, and error paths behave like the reference's (int codes,
+zeroed structs). No compute entry point is called here (there is no GPU and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from tests import harness as H
+from vulkan_renderer_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_library):
+	header = open(os.path.join(ROOT, "include", "vkr_b200.h")).read()
+	declared = set(re.findall(r"\b(vkr_[a-z0-9_]+)\s*\(", header))
+	declared -= {n for n in declared if n.endswith("_t")}
+	assert declared, "no declarations parsed"
+	missing = [n for n in sorted(declared) if not hasattr(built_library, n)]
+	assert not missing, missing
+	assert set(api.EXPORTED_SYMBOLS) == declared
+	assert built_library.vkr_abi_version() == 1
+
+
+def test_struct_sizes_match_the_reference_layouts():
+	# src/camera.h:24-44 (48 bytes), src/polygonal_light.h:100-137 (192 bytes, 88-byte quicksave prefix)
+	assert C.sizeof(api.Camera) == 48
+	assert C.sizeof(api.PolygonalLight) == 192
+	assert api.PolygonalLight.vertex_count.offset == 80 and api.PolygonalLight.rotation.offset == 96
+	assert api.PolygonalLight.texture_file_path.offset == 160
+	assert C.sizeof(api.LtcConstants) == 32
+
+
+def _host_objects(info):
+	lib = api.load_library()
+	scene = api.Scene(); ltc = api.LtcTable(); noise = api.NoiseTable(); spec = api.SceneSpecification()
+	assert lib.vkr_load_scene(C.byref(scene), None, info["vks"].encode(), info["textures"].encode(), 1) == 0
+	assert lib.vkr_load_ltc_table(C.byref(ltc), None, info["ltc"].encode(), 51) == 0
+	assert lib.vkr_load_noise_table(C.byref(noise), None, 256, 256, 64, api.NOISE_WHITE) == 0
+	assert lib.vkr_quick_load(C.byref(spec), info["save"].encode()) == 0
+	return lib, scene, ltc, noise, spec
+
+
+def test_loaders_agree_with_independent_numpy_reading():
+	info = H.dataset("mini_city")
+	lib, scene, ltc, noise, spec = _host_objects(info)
+	vks = H.read_vks(info["vks"])
+	assert scene.triangle_count == vks["triangle_count"] == info["triangle_count"]
+	assert np.allclose(list(scene.dequantization_factor), vks["factor"], rtol=0, atol=0)
+	assert np.allclose(list(scene.dequantization_summand), vks["summand"], rtol=0, atol=0)
+	names = [scene.material_names[i].decode() for i in range(scene.material_count)]
+	assert names == vks["names"]
+	mp = np.ctypeslib.as_array(scene.material_params, (scene.material_count, 8))
+	assert np.array_equal(mp, info["material_params"])     # RGBA16F *.vkt round trip
+	t0, t1 = H.quantize_ltc(info["ltc"])
+	assert np.array_equal(np.ctypeslib.as_array(ltc.h_table0, t0.shape), t0)   # src/ltc_table.c:82-116
+	assert np.array_equal(np.ctypeslib.as_array(ltc.h_table1, t1.shape), t1)
+	assert np.array_equal(np.ctypeslib.as_array(noise.h_noise, (64, 256, 256, 4)), H.white_noise_table())   # src/noise_table.c:73-75
+	c = ltc.constants   # src/ltc_table.c:184-191
+	assert c.fresnel_index_factor == 50.0 and c.roughness_summand == np.float32(0.5 / 64) and c.roughness_factor == np.float32(63 / 64)
+	assert spec.polygonal_light_count == len(info["lights"])
+	for i, L in enumerate(info["lights"]):
+		light = spec.polygonal_lights[i]
+		assert light.vertex_count == 4 and np.allclose(list(light.translation), L["translation"])
+	assert abs(spec.camera.vertical_fov - 0.33 * np.pi) < 1e-6
+	lib.vkr_destroy_scene_specification(C.byref(spec)); lib.vkr_destroy_noise_table(C.byref(noise), None); lib.vkr_destroy_ltc_table(C.byref(ltc), None); lib.vkr_destroy_scene(C.byref(scene), None)
+	assert scene.triangle_count == 0 and not scene.material_params    # destroy zeroes the struct (SURVEY 8b conventions)
+
+
+def test_quicksave_round_trip(tmp_path):
+	info = H.dataset("mini_city")
+	lib, scene, ltc, noise, spec = _host_objects(info)
+	path = str(tmp_path / "copy.save").encode()
+	assert lib.vkr_quick_save(C.byref(spec), path) == 0
+	assert open(path, "rb").read() == open(info["save"], "rb").read()   # same bytes as the synthetic writer (layout src/main.c:49-130)
+	assert lib.vkr_quick_load(C.byref(spec), b"/nonexistent/file.save") != 0
+	assert spec.polygonal_light_count == len(info["lights"])            # a failed load leaves the old specification intact
+
+
+def test_constant_block_layout_and_light_maths():
+	info = H.dataset("mini_city")
+	lib, scene, ltc, noise, spec = _host_objects(info)
+	st = api.RenderSettings(); lib.vkr_specify_default_render_settings(C.byref(st))
+	assert (st.exposure_factor, st.sample_count, st.sampling_strategies, st.mis_heuristic, st.mis_visibility_estimate) == (8.0, 1, 3, 3, 0.5)   # src/main.c:232-249
+	st.animate_noise = 0
+	size = lib.vkr_get_constants_size(C.byref(spec))
+	assert size == 256 + 320 * spec.polygonal_light_count                 # quads: 320 bytes per light (src/main.c:334)
+	buf = (C.c_uint8 * size)()
+	assert lib.vkr_write_constants(buf, C.byref(spec), C.byref(st), C.byref(scene), C.byref(ltc), C.byref(noise), 320, 200) == size
+	cb = bytes(buf)
+	f = lambda off, n=1: np.frombuffer(cb[off:off + 4 * n], dtype=np.float32)
+	u = lambda off, n=1: np.frombuffer(cb[off:off + 4 * n], dtype=np.uint32)
+	assert tuple(u(160, 2)) == (320, 200) and f(176)[0] == 8.0 and f(180)[0] == 1.0
+	assert tuple(u(184, 3)) == (255, 255, 63) and tuple(u(208, 4)) == (0, 0x123456, 0x2468AC, 0x369D02)   # src/noise_table.c:161-168
+	assert np.allclose(f(144, 3), info["camera"]["position"])
+	# pixel_to_ray * (w/2 - 0.5, h/2 - 0.5, 1) points along the view direction (camera looks at the dataset's target)
+	p2r = f(96, 12).reshape(3, 4)[:, :3].astype(np.float64)
+	d = p2r @ np.array([159.5, 99.5, 1.0]); d /= np.linalg.norm(d)
+	w2p = f(32, 16).reshape(4, 4).astype(np.float64)
+	target = np.array(info["camera"]["position"]) + d * 3.0
+	clip = w2p @ np.append(target, 1.0)
+	assert abs(clip[0] / clip[3]) < 1e-3 and abs(clip[1] / clip[3]) < 1e-3
+	# light block: plane through the vertices, radiance = flux / (pi * area) (src/polygonal_light.c:46-104)
+	for i in range(spec.polygonal_light_count):
+		p = 256 + 320 * i
+		plane = f(p + 64, 4).astype(np.float64); radiance = f(p + 48, 3); area = f(p + 144)[0]
+		verts = f(p + 160 + 64, 16).reshape(4, 4)[:, :3].astype(np.float64)
+		assert np.allclose(verts @ plane[:3] + plane[3], 0.0, atol=1e-4)
+		assert abs(np.linalg.norm(plane[:3]) - 1.0) < 1e-5
+		sx, sy = info["lights"][i]["scaling"]
+		assert abs(area - sx * sy) < 1e-4 * sx * sy
+		assert np.allclose(radiance, np.array(info["lights"][i]["flux"]) / (np.pi * area), rtol=1e-5)
+		assert u(p + 80)[0] == 4 and u(p + 84)[0] == 0
+
+
+def _probe_bvh(lib, tris):
+	P = C.POINTER
+	nodes = P(C.c_float)(); tri = P(C.c_float)(); ids = P(C.c_uint32)(); nc = C.c_uint64(); md = C.c_uint32()
+	tris = np.ascontiguousarray(tris, dtype=np.float32)
+	assert lib.vkr_bvh_build_probe(tris.ctypes.data, len(tris), C.byref(nodes), C.byref(nc), C.byref(tri), C.byref(ids), C.byref(md)) == 0
+	n = len(tris)
+	out = (np.ctypeslib.as_array(nodes, (nc.value, 16)).copy(), np.ctypeslib.as_array(tri, (max(n, 1), 12)).copy()[:n], np.ctypeslib.as_array(ids, (max(n, 1),)).copy()[:n], md.value)
+	lib.vkr_bvh_free_probe(nodes, tri, ids)
+	return out
+
+
+@pytest.mark.parametrize("name", ["cornell", "mini_city"])
+def test_bvh_builder_structure(name):
+	info = H.dataset(name)
+	lib = api.load_library()
+	vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes, slots, ids, depth = _probe_bvh(lib, tris)
+	n = len(tris)
+	assert sorted(ids.tolist()) == list(range(n))                                   # every triangle exactly once
+	T = tris.reshape(-1, 3, 3)
+	assert np.array_equal(slots[:, 0:3], T[ids][:, 0]) and np.array_equal(slots[:, 3:6], T[ids][:, 1] - T[ids][:, 0]) and np.array_equal(slots[:, 6:9], T[ids][:, 2] - T[ids][:, 0])
+	refs = nodes[:, 12:14].copy().view(np.int32)
+	seen_nodes = np.zeros(len(nodes), dtype=int); seen_slots = np.zeros(n, dtype=int)
+	def walk(k, lo, hi, level):
+		assert level <= depth
+		for c in range(2):
+			clo = nodes[k, 6 * c:6 * c + 3]; chi = nodes[k, 6 * c + 3:6 * c + 6]
+			ref = int(refs[k, c])
+			if ref >= 0:
+				seen_nodes[ref] += 1
+				assert np.all(clo >= lo - 1e-6) and np.all(chi <= hi + 1e-6)       # child boxes nest
+				walk(ref, clo, chi, level + 1)
+			else:
+				first, count = (ref & 0x7FFFFFFF) >> 4, ref & 15
+				assert count <= 4
+				for s in range(first, first + count):
+					seen_slots[s] += 1
+					v = T[ids[s]]
+					assert np.all(v >= clo) and np.all(v <= chi)                    # padded leaf boxes contain their triangles
+	seen_nodes[0] = 1
+	walk(0, np.full(3, -np.inf), np.full(3, np.inf), 1)
+	assert np.all(seen_nodes == 1) and np.all(seen_slots == 1)
+	assert depth < 62
+
+
+def test_bvh_builder_degenerate_inputs():
+	lib = api.load_library()
+	nodes, slots, ids, depth = _probe_bvh(lib, np.zeros((0, 9), dtype=np.float32))          # empty scene
+	assert len(nodes) == 1 and (nodes[0, 12:14].view(np.int32) & 15).tolist() == [0, 0]
+	one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float32)
+	nodes, slots, ids, depth = _probe_bvh(lib, one)                                         # single leaf under the root pair
+	assert len(nodes) == 1 and (int(nodes[0, 12:13].view(np.int32)[0]) & 15) == 1
+	same = np.tile(one, (100, 1))                                                            # 100 coincident triangles: median splits
+	nodes, slots, ids, depth = _probe_bvh(lib, same)
+	assert sorted(ids.tolist()) == list(range(100)) and depth < 62
+
+
+def test_error_paths_return_codes_and_leave_structs_zeroed(tmp_path, capfd):
+	lib = api.load_library()
+	scene = api.Scene()
+	assert lib.vkr_load_scene(C.byref(scene), None, b"/nonexistent.vks", b"/tmp", 1) == 1
+	assert scene.triangle_count == 0
+	bad = tmp_path / "bad.vks"; bad.write_bytes(struct.pack("<II", 0x123, 1) + b"\0" * 64)
+	assert lib.vkr_load_scene(C.byref(scene), None, str(bad).encode(), b"/tmp", 1) == 1          # wrong marker (src/scene.c:423)
+	empty = tmp_path / "empty.vks"; empty.write_bytes(struct.pack("<IIQQ6f", 0xABCABC, 1, 0, 0, 1, 1, 1, 0, 0, 0))
+	assert lib.vkr_load_scene(C.byref(scene), None, str(empty).encode(), b"/tmp", 1) == 1        # zero triangles (src/scene.c:435)
+	info = H.dataset("cornell")
+	trunc = tmp_path / "trunc.vks"; trunc.write_bytes(open(info["vks"], "rb").read()[:-4] + struct.pack("<I", 0))
+	assert lib.vkr_load_scene(C.byref(scene), None, str(trunc).encode(), info["textures"].encode(), 1) == 1   # missing EOF marker (src/scene.c:479)
+	assert lib.vkr_load_scene(C.byref(scene), None, info["vks"].encode(), str(tmp_path).encode(), 1) == 1      # textures missing
+	ltc = api.LtcTable()
+	assert lib.vkr_load_ltc_table(C.byref(ltc), None, str(tmp_path).encode(), 51) == 1 and ltc.roughness_count == 0
+	noise = api.NoiseTable()
+	assert lib.vkr_load_noise_table(C.byref(noise), None, 100, 256, 64, api.NOISE_WHITE) == 1    # not a power of two
+	assert lib.vkr_load_noise_table(C.byref(noise), None, 256, 256, 64, api.NOISE_BLUE) == 1     # data/noise/*.blob absent
+	dev = api.Device()
+	rc = lib.vkr_create_device(C.byref(dev), 0, None)
+	import torch
+	if not torch.cuda.is_available():
+		assert rc == 1 and dev.sm_count == 0      # no CUDA device: fails loudly, no CPU fallback
+	else:
+		lib.vkr_destroy_device(C.byref(dev))
+	assert "Failed" in capfd.readouterr().out     # printf diagnostics like the reference
+
+
+def test_white_noise_and_synthetic_formats_are_what_the_reference_loaders_expect():
+	info = H.dataset("cornell")
+	raw = open(info["vks"], "rb").read()
+	assert struct.unpack_from("<II", raw, 0) == (0xABCABC, 1) and struct.unpack_from("<I", raw, len(raw) - 4)[0] == 0xE0FE0F
+	tex = open(os.path.join(info["textures"], "white_BaseColor.vkt"), "rb").read()
+	marker, version, mips, w, h, fmt, size = struct.unpack_from("<IIIIIIQ", tex, 0)
+	assert (marker, version, mips, w, h, fmt) == (0xBC1BC1, 1, 3, 4, 4, 97) and struct.unpack_from("<I", tex, len(tex) - 4)[0] == 0xE0FE0F
+	fit = open(os.path.join(info["ltc"], "fit0.dat"), "rb").read()
+	assert struct.unpack_from("<Q", fit, 0)[0] == 64 and len(fit) == 8 + 64 * 64 * 20

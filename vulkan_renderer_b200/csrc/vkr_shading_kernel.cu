@@ -239,7 +239,10 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 }
 
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL>
-__global__ void __launch_bounds__(kThreads)
+#ifndef VKR_MIN_CTAS_PER_SM
+#define VKR_MIN_CTAS_PER_SM 3
+#endif
+__global__ void __launch_bounds__(kThreads, VKR_MIN_CTAS_PER_SM)
 shading_kernel(const shading_kernel_params p) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned char* cb = smem;                                   // constant block incl. lights
