@@ -23,6 +23,23 @@ struct psa_polygon {
 	float psa;
 };
 
+// Field-wise select between two register-resident polygons (lets one inlined copy of sample_psa serve both)
+template <int MAXP>
+VKR_DEV psa_polygon<MAXP> select_polygon(bool second, const psa_polygon<MAXP>& a, const psa_polygon<MAXP>& b) {
+	psa_polygon<MAXP> r;
+	r.vertex_count = second ? b.vertex_count : a.vertex_count;
+	r.inner_ellipse_0.x = second ? b.inner_ellipse_0.x : a.inner_ellipse_0.x;
+	r.inner_ellipse_0.y = second ? b.inner_ellipse_0.y : a.inner_ellipse_0.y;
+	r.psa = second ? b.psa : a.psa;
+#pragma unroll
+	for (int i = 0; i != MAXP; ++i) {
+		r.vertices[i].x = second ? b.vertices[i].x : a.vertices[i].x; r.vertices[i].y = second ? b.vertices[i].y : a.vertices[i].y;
+		r.ellipses[i].x = second ? b.ellipses[i].x : a.ellipses[i].x; r.ellipses[i].y = second ? b.ellipses[i].y : a.ellipses[i].y;
+		r.sector_psa[i] = second ? b.sector_psa[i] : a.sector_psa[i];
+	}
+	return r;
+}
+
 // Crossing of segment a->b with the horizon plane z = 0 (polygon_clipping.glsl:19-25)
 VKR_DEV f3 horizon_crossing(f3 a, f3 b) {
 	const float w = a.z / (a.z - b.z);

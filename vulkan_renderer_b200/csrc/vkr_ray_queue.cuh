@@ -58,7 +58,15 @@ VKR_DEV void drain(ray_queue& q, int lane, f3& result) {
 	const float tmin = 1.0e-3f; // shading_pass.frag.glsl:124
 	int next = 0;               // warp-uniform: first entry nobody has taken yet
 	int entry = 0;
-	int node = kTraversalDone, leaf = 0, sp = 0;
+	int node = kTraversalDone, leaf = 0;
+	// The stack is addressed through ONE loop-carried register (shared-memory address of the next free slot, 128 B
+	// between levels = one slot per lane) with a kTraversalDone sentinel at the bottom, so a pop never needs an
+	// "empty" test and the compiler cannot rematerialise base + sp * stride around every push and pop.
+	const uint32_t stack_bottom = (uint32_t) __cvta_generic_to_shared(q.stack);
+	uint32_t top = stack_bottom;
+	const uint32_t level = (uint32_t) q.stack_stride * 4u;
+	auto push = [&](int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"(v) : "memory"); top += level; };
+	auto pop = [&]() { int v; top -= level; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top) : "memory"); return v; };
 	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
 	float tmax = 0.0f;
 	ray_slabs r = make_slabs(o, d);
@@ -80,7 +88,7 @@ VKR_DEV void drain(ray_queue& q, int lane, f3& result) {
 				float t;
 				if (go && q.cached_triangle >= 0 && ray_triangle(q.bvh.tris + 3 * (size_t) q.cached_triangle, o, d, tmin, tmax, &t)) { occ = true; go = false; }
 				q.occluded[entry] = occ ? 1 : 0;
-				if (go) { r = make_slabs(o, d); node = 0; sp = 0; }
+				if (go) { r = make_slabs(o, d); node = 0; top = stack_bottom; push(kTraversalDone); }
 			}
 			next = min(n, next + __popc(idle_mask));
 		}
@@ -96,16 +104,14 @@ VKR_DEV void drain(ray_queue& q, int lane, f3& result) {
 			if (h0 && h1) {
 				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
 				node = swap ? ref1 : ref0;
-				q.stack[sp * q.stack_stride] = swap ? ref0 : ref1; ++sp;
+				push(swap ? ref0 : ref1);
 			}
 			else if (h0) node = ref0;
 			else if (h1) node = ref1;
-			else if (sp > 0) { --sp; node = q.stack[sp * q.stack_stride]; }
-			else node = kTraversalDone;
+			else node = pop();
 			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
 				leaf = node;
-				if (sp > 0) { --sp; node = q.stack[sp * q.stack_stride]; }
-				else node = kTraversalDone;
+				node = pop();
 			}
 		}
 		__syncwarp(kFullMask);
@@ -117,11 +123,10 @@ VKR_DEV void drain(ray_queue& q, int lane, f3& result) {
 			for (int i = 0; i != count; ++i)
 				if (ray_triangle(q.bvh.tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) { hit = true; q.cached_triangle = first + i; }
 			leaf = 0;
-			if (hit) { q.occluded[entry] = 1; node = kTraversalDone; sp = 0; }
+			if (hit) { q.occluded[entry] = 1; node = kTraversalDone; }
 			else if (node < 0) {
 				leaf = node;
-				if (sp > 0) { --sp; node = q.stack[sp * q.stack_stride]; }
-				else node = kTraversalDone;
+				node = pop();
 			}
 		}
 		__syncwarp(kFullMask);
@@ -149,8 +154,10 @@ VKR_DEV void drain(ray_queue& q, int lane, f3& result) {
 
 // Warp-convergent: every lane calls it once per candidate sample. has = this lane contributes something.
 // need_trace = visibility is not known yet (n.w > 0); otherwise the sample is known to be occluded.
+// finish (warp-uniform) = drain even if the queue is not full (end of a light). Keeping the only call of drain() here
+// gives each kernel ONE copy of the traversal loop (instruction-cache footprint).
 template <bool OPTIMAL>
-VKR_DEV void submit(ray_queue& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, f3& result) {
+VKR_DEV void submit(ray_queue& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, f3& result, bool finish) {
 	if (!q.enabled) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
 		if (has) {
 			if (need_trace) result = result + c_visible;
@@ -169,7 +176,7 @@ VKR_DEV void submit(ray_queue& q, int lane, bool has, bool need_trace, f3 dir_wo
 	}
 	q.count += __popc(mask);
 	__syncwarp(kFullMask);
-	if (q.count > kQueueDrainThreshold) drain<OPTIMAL>(q, lane, result);
+	if (q.count > kQueueDrainThreshold || (finish && q.count > 0)) drain<OPTIMAL>(q, lane, result);
 }
 
 } // namespace vkr

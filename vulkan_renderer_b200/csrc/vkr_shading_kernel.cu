@@ -81,7 +81,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 					}
 				}
 			}
-			submit<false>(q, lane, has, pre_vis, w, tmax, c, zero, result);
+			submit<false>(q, lane, has, pre_vis, w, tmax, c, zero, result, false);
 		}
 		if (STRATEGY == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
 			const f3 o_ss = make3(
@@ -108,7 +108,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						}
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result);
+				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 	}
@@ -137,7 +137,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = (light_radiance(light) * evaluate_brdf<true, false>(sp, w)) * pd.psa;
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result);
+				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
 				has = false;
 				if (has_specular) {
 					const f3 dc = sample_psa<MAXP, BIASED>(ps, next_noise_2(ns, p, cb, px, py));
@@ -151,7 +151,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = make3(rtb2.x * dsh.z * ps.psa / ltc_density, rtb2.y * dsh.z * ps.psa / ltc_density, rtb2.z * dsh.z * ps.psa / ltc_density);
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result);
+				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 		else if (STRATEGY == VKR_STRATEGY_DIFFUSE_SPECULAR_MIS) {
@@ -166,44 +166,44 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 			}
 			const float v_est = ldf(cb, OFF_MIS_VIS);
 #pragma unroll 1
-			for (int s = 0; s != S; ++s) {
-				f3 dir_d = zero, dir_s = zero;
-				if (on) {
-					dir_d = sample_psa<MAXP, BIASED>(pd, next_noise_2(ns, p, cb, px, py));
-					if (has_specular) dir_s = normalize(c2s_mul(l, sample_psa<MAXP, BIASED>(ps, next_noise_2(ns, p, cb, px, py))));
-				}
+			// The reference draws the diffuse and the specular sample first and then evaluates both (:610-636); drawing
+			// each sample right before its evaluation consumes the noise stream in the same order. One loop body serves
+			// both techniques and the end-of-light flush (s == S), so the kernel holds one copy of sample_psa and drain.
+			for (int s = 0; s <= S; ++s) {
 #pragma unroll 1
 				for (int j = 0; j != 2; ++j) {
-					const f3 d = (j == 0) ? dir_d : dir_s;
-					bool has = on && (j == 0 || has_specular) && d.z > 0.0f;
+					bool has = on && s != S && (j == 0 || has_specular);
 					bool pre_vis = false; f3 w = zero, c = zero, c_occ = zero; float tmax = 0.0f;
 					if (has) {
-						const float diffuse_density = d.z * rcp_d;
-						const float specular_density = evaluate_ltc_density(l, d, rcp_s);
-						w = shading_to_world(l, sp.normal, flip, d);
-						pre_vis = dot(sp.normal, w) > 0.0f;
-						const bool single = (j == 0) && !has_specular;
-						f3 integrand = zero;
-						if (pre_vis) {
-							tmax = light_plane_distance(sp, light, w);
-							integrand = (light_radiance(light) * evaluate_brdf<true, true>(sp, w)) * d.z;
-						}
-						if (single) {
-							c = integrand * (1.0f / diffuse_density);
-							if (!pre_vis) has = false;
-						}
-						else if (j == 0) {
-							if (pre_vis) c = mis_estimate(p.mis_heuristic, integrand, diffuse_weight, diffuse_density, specular_weight_rgb, specular_density, v_est);
-							if (OPTIMAL) c_occ = mis_estimate(p.mis_heuristic, zero * d.z, diffuse_weight, diffuse_density, specular_weight_rgb, specular_density, v_est);
-						}
-						else {
-							if (pre_vis) c = mis_estimate(p.mis_heuristic, integrand, specular_weight_rgb, specular_density, diffuse_weight, diffuse_density, v_est);
-							if (OPTIMAL) c_occ = mis_estimate(p.mis_heuristic, zero * d.z, specular_weight_rgb, specular_density, diffuse_weight, diffuse_density, v_est);
+						f3 d = sample_psa<MAXP, BIASED>(select_polygon(j != 0, pd, ps), next_noise_2(ns, p, cb, px, py));
+						if (j != 0) d = normalize(c2s_mul(l, d));
+						has = d.z > 0.0f;
+						if (has) {
+							const float diffuse_density = d.z * rcp_d;
+							const float specular_density = evaluate_ltc_density(l, d, rcp_s);
+							w = shading_to_world(l, sp.normal, flip, d);
+							pre_vis = dot(sp.normal, w) > 0.0f;
+							f3 integrand = zero;
+							if (pre_vis) {
+								tmax = light_plane_distance(sp, light, w);
+								integrand = (light_radiance(light) * evaluate_brdf<true, true>(sp, w)) * d.z;
+							}
+							if (j == 0 && !has_specular) { // one technique only: no MIS (:629-631)
+								c = integrand * (1.0f / diffuse_density);
+								has = pre_vis;
+							}
+							else {
+								const f3 w_own = (j == 0) ? diffuse_weight : specular_weight_rgb, w_other = (j == 0) ? specular_weight_rgb : diffuse_weight;
+								const float p_own = (j == 0) ? diffuse_density : specular_density, p_other = (j == 0) ? specular_density : diffuse_density;
+								if (pre_vis) c = mis_estimate(p.mis_heuristic, integrand, w_own, p_own, w_other, p_other, v_est);
+								if (OPTIMAL) c_occ = mis_estimate(p.mis_heuristic, zero * d.z, w_own, p_own, w_other, p_other, v_est);
+							}
 						}
 					}
-					submit<OPTIMAL>(q, lane, has, pre_vis, w, tmax, c, c_occ, result);
+					submit<OPTIMAL>(q, lane, has, pre_vis, w, tmax, c, c_occ, result, s == S);
 				}
 			}
+			return result * (1.0f / (float) S);
 		}
 		else { // VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM
 			const float diffuse_albedo = max_glsl(dot(sp.diffuse_albedo, make3(0.21263901f, 0.71516868f, 0.07219232f)), 0.01f);
@@ -230,7 +230,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = make3(rtb.x * d.z / density, rtb.y * d.z / density, rtb.z * d.z / density);
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result);
+				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 	}
