@@ -139,6 +139,25 @@ def build(configs=None, verbose=False):
 	for o in objects:
 		os.remove(o)
 	print("build_ref: %d configurations -> %s" % (len(configs), lib))
+	build_host()
+	return lib
+
+
+def build_host():
+	"""The reference's UNCHANGED loader / host-maths C files (SURVEY 8b boundary B1), compiled from where they lie
+	against shim/ (a host-memory stand-in for the Vulkan allocation helpers they call) -> oracle/_ref/libref_host.so.
+	tests/test_ref_host.py holds vkr_host.cpp against it byte for byte."""
+	ref_src = "/root/reference/src"
+	if not os.path.isdir(ref_src):
+		return None
+	root = os.path.dirname(HERE)
+	shim = os.path.join(root, "shim")
+	lib = os.path.join(OUT, "libref_host.so")
+	sources = [os.path.join(ref_src, n) for n in ("scene.c", "textures.c", "ltc_table.c", "noise_table.c", "polygonal_light.c", "camera.c")]
+	cmd = ["/usr/bin/gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I", shim, "-I", ref_src,
+		os.path.join(shim, "vkr_shim.c")] + sources + [os.path.join(HERE, "ref_host_probe.c"), "-lm", "-o", lib]
+	subprocess.check_call(cmd)
+	print("build_ref: reference loaders over the shim -> %s" % lib)
 	return lib
 
 

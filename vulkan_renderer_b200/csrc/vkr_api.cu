@@ -129,6 +129,23 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 			(unsigned long long) constants_size, (unsigned long long) pass->constants_size, d.polygonal_light_count, d.max_polygonal_light_vertex_count);
 		return 1;
 	}
+	{ // light blocks must match what the pass was created for (the reference recompiles the shader when they change)
+		const uint32_t v = d.max_polygonal_light_vertex_count;
+		const size_t stride = 160 + 16 * (size_t) v * 2 + 16 * (size_t) (v - 2);
+		for (uint32_t i = 0; i != d.polygonal_light_count; ++i) {
+			uint32_t vertex_count, texturing_technique;
+			memcpy(&vertex_count, (const char*) constants + 256 + stride * i + 80, 4);
+			memcpy(&texturing_technique, (const char*) constants + 256 + stride * i + 84, 4);
+			if (vertex_count < d.min_polygonal_light_vertex_count || vertex_count > v) {
+				printf("Polygonal light %u has %u vertices but the shading pass was created for %u to %u.\n", i, vertex_count, d.min_polygonal_light_vertex_count, v);
+				return 1;
+			}
+			if (texturing_technique != 0) {
+				printf("Polygonal light %u is textured (technique %u); light textures are not supported by this shading pass.\n", i, texturing_technique);
+				return 1;
+			}
+		}
+	}
 	cudaStream_t stream = (cudaStream_t) device->stream;
 	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
 	memcpy(pass->h_constants_pinned, constants, constants_size);
