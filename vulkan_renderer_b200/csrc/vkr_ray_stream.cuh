@@ -1,0 +1,246 @@
+// vkr_ray_stream.cuh -- shadow-ray streams of the warp-specialised shading megakernel.
+//
+// A CTA has two kinds of warps (vkr_shading_kernel.cu): SHADING warps sample the lights and evaluate BRDF and MIS
+// weights for an 8x4 pixel patch, TRACE warps do nothing but BVH traversal. They talk through one ring buffer per
+// shading warp in shared memory:
+//
+//   shading warp (producer)                  ring of kRing entries                     2 trace warps (consumers)
+//   submit(): __ballot_sync compaction  -->  dir, tmax, owner, contribution  -->  every idle LANE draws a ticket
+//   publishes `tail` after every sample      result byte: 0xFF pending / 0 / 1        (atomicAdd on `head`), waits until
+//   resolve(): adds contributions of    <--                                  <--   tail > ticket, traces, stores result
+//   finished entries, oldest first
+//
+// Trace lanes refill themselves individually, so traversal runs at full warp width whatever the ray lengths are and
+// however many pixels of the patch are idle (background, lights below the horizon); a trace warp never waits for the
+// end of a batch. The shading warp only resolves when it needs ring space (or at the end of a light), adding the
+// contributions of its own pixel strictly in submission order, which keeps the floating-point sums identical to the
+// reference's sequential loop (shading_pass.frag.glsl:608-637). Trace warps give their registers to the shading warps
+// (setmaxnreg), which is what lets 24 warps per SM live where the monolithic kernel had 12.
+#pragma once
+#include "vkr_trace.cuh"
+
+namespace vkr {
+
+#ifndef VKR_RING
+#define VKR_RING 256
+#endif
+constexpr int kRing = VKR_RING;              // entries per shading warp (power of two)
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kShadeWarps = 4, kTraceWarps = 8;   // per CTA; trace warp t serves the stream of shading warp t & 3
+constexpr unsigned kPending = 0xffu;
+
+// Shared memory of one stream, as float offsets from its base. 7 (or 10, MIS_HEURISTIC_OPTIMAL) float arrays, owner and
+// result bytes, 96 floats of ray origins, 4 ints of control.
+enum : int {
+	S_DX = 0, S_DY = kRing, S_DZ = 2 * kRing, S_TMAX = 3 * kRing,     // ray direction (world), far end = light plane
+	S_CX = 4 * kRing, S_CY = 5 * kRing, S_CZ = 6 * kRing,              // contribution if the ray is unoccluded
+	S_OX = 7 * kRing, S_OY = 8 * kRing, S_OZ = 9 * kRing               // contribution if it is occluded (OPTIMAL only)
+};
+VKR_DEV constexpr int stream_bytes_at(bool optimal) { return (optimal ? 10 : 7) * kRing; }           // owner[kRing] bytes: lane of the owning pixel; bit 7: known to be occluded (n.w <= 0)
+VKR_DEV constexpr int stream_origin_at(bool optimal) { return stream_bytes_at(optimal) + 2 * kRing / 4; }  // after result[kRing] bytes: kPending / 0 visible / 1 occluded
+VKR_DEV constexpr int stream_control_at(bool optimal) { return stream_origin_at(optimal) + 96; }     // {head: next ticket, tail: entries published, closed: -1 or the final tail, -}
+VKR_DEV constexpr size_t stream_floats_per_warp(bool optimal) { return (size_t) stream_control_at(optimal) + 4; }
+
+VKR_DEV uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+VKR_DEV float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+VKR_DEV void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+VKR_DEV unsigned lds_u8(uint32_t a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+VKR_DEV void sts_u8(uint32_t a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+VKR_DEV int ld_acquire(uint32_t a) { int v; asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+VKR_DEV void st_release(uint32_t a, int v) { asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+VKR_DEV unsigned ld_acquire_u8(uint32_t a) { unsigned v; asm volatile("ld.acquire.cta.shared::cta.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+VKR_DEV void st_release_u8(uint32_t a, unsigned v) { asm volatile("st.release.cta.shared::cta.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+VKR_DEV int atom_add_shared(uint32_t a, int v) { int old; asm volatile("atom.relaxed.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory"); return old; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Producer side (shading warps)
+struct ray_producer {
+	uint32_t base;   // shared-memory address of the stream
+	int fill;        // warp-uniform: entries written and published so far (absolute index; slot = index & (kRing - 1))
+	int resolved;    // warp-uniform: entries below this index have been added to their pixels, their slots are free
+};
+
+// Adds the contributions of entries [q.resolved, min(q.resolved + 32, q.fill)) to their owners, oldest first; waits for
+// the trace warps where results are still pending.
+template <bool OPTIMAL>
+VKR_DEV void resolve_chunk(ray_producer& q, int lane, f3& result) {
+	const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
+	const int first = q.resolved;
+	const int n = min(32, q.fill - first);
+	const uint32_t slot = (uint32_t) (first + lane) & (kRing - 1);
+	const bool valid = lane < n;
+	while (true) {
+		const unsigned r = valid ? ld_acquire_u8(bytes + kRing + slot) : 0u;
+		if (!__any_sync(kFullMask, r == kPending)) break;
+		__nanosleep(64);
+	}
+	const unsigned own = valid ? (lds_u8(bytes + slot) & 31u) : 32u;
+	unsigned mine = __ballot_sync(kFullMask, valid);
+#pragma unroll
+	for (int b = 0; b != 5; ++b) {
+		const unsigned bits = __ballot_sync(kFullMask, (own >> b) & 1u);
+		mine &= ((lane >> b) & 1) ? bits : ~bits;
+	}
+	while (mine) {
+		const uint32_t e = (uint32_t) (first + __ffs(mine) - 1) & (kRing - 1);
+		mine &= mine - 1;
+		const uint32_t a = q.base + 4u * e;
+		if (!lds_u8(bytes + kRing + e)) result = result + make3(lds_f(a + 4u * S_CX), lds_f(a + 4u * S_CY), lds_f(a + 4u * S_CZ));
+		else if (OPTIMAL) result = result + make3(lds_f(a + 4u * S_OX), lds_f(a + 4u * S_OY), lds_f(a + 4u * S_OZ));
+	}
+	q.resolved = first + n;
+	__syncwarp(kFullMask);
+}
+
+// Warp-convergent: every lane calls it once per candidate sample. has = this lane contributes something.
+// need_trace = visibility is not known yet (n.w > 0); otherwise the sample is known to be occluded.
+// finish (warp-uniform) = end of a light: wait until everything submitted so far has been added to `result`.
+template <bool TRACE, bool OPTIMAL>
+VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, f3& result, bool finish) {
+	if (!TRACE) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
+		if (has) {
+			if (need_trace) result = result + c_visible;
+			else if (OPTIMAL) result = result + c_occluded;
+		}
+		return;
+	}
+	const bool push = has && (need_trace || OPTIMAL);
+	const unsigned mask = __ballot_sync(kFullMask, push);
+	if (mask) {
+		const int k = __popc(mask);
+		while (q.fill + k - q.resolved > kRing) resolve_chunk<OPTIMAL>(q, lane, result);
+		if (push) {
+			const uint32_t e = (uint32_t) (q.fill + __popc(mask & ((1u << lane) - 1u))) & (kRing - 1);
+			const uint32_t a = q.base + 4u * e;
+			sts_f(a + 4u * S_DX, dir_world.x); sts_f(a + 4u * S_DY, dir_world.y); sts_f(a + 4u * S_DZ, dir_world.z); sts_f(a + 4u * S_TMAX, tmax);
+			sts_f(a + 4u * S_CX, c_visible.x); sts_f(a + 4u * S_CY, c_visible.y); sts_f(a + 4u * S_CZ, c_visible.z);
+			if (OPTIMAL) { sts_f(a + 4u * S_OX, c_occluded.x); sts_f(a + 4u * S_OY, c_occluded.y); sts_f(a + 4u * S_OZ, c_occluded.z); }
+			const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
+			sts_u8(bytes + e, need_trace ? (unsigned) lane : ((unsigned) lane | 128u));
+			sts_u8(bytes + kRing + e, need_trace ? kPending : 1u);
+		}
+		q.fill += k;
+		__syncwarp(kFullMask);
+		if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 4u, q.fill);
+	}
+	if (finish) while (q.resolved != q.fill) resolve_chunk<OPTIMAL>(q, lane, result);
+}
+
+// End of the tile: everything has been resolved; tells the trace warps that no ticket >= fill will ever be served.
+template <bool OPTIMAL>
+VKR_DEV void close_stream(ray_producer& q, int lane) {
+	__syncwarp(kFullMask);
+	if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 8u, q.fill);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Consumer side (trace warps): runs until the stream is closed and drained. stack = shared-memory address of this
+// lane's column of the warp's traversal stack (128 B between levels = one slot per lane).
+template <bool OPTIMAL>
+VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane) {
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const float tmin = 1.0e-3f; // shading_pass.frag.glsl:124
+	const uint32_t bytes = base + 4u * stream_bytes_at(OPTIMAL);
+	const uint32_t origin = base + 4u * stream_origin_at(OPTIMAL);
+	const uint32_t control = base + 4u * stream_control_at(OPTIMAL);
+	// The stack is addressed through ONE loop-carried register with a kTraversalDone sentinel at the bottom, so a pop
+	// never needs an "empty" test.
+	uint32_t top = stack_bottom;
+	auto push = [&](int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"(v) : "memory"); top += 128u; };
+	auto pop = [&]() { int v; top -= 128u; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top) : "memory"); return v; };
+	int ticket = -1;             // >= 0: index of the entry this lane will trace next, not published yet
+	uint32_t entry = 0;          // slot of the ray in flight
+	bool active = false;         // a ray is in flight
+	bool hit = false;
+	bool finished = false;       // the stream is closed and this lane's ticket lies beyond its end
+	int node = kTraversalDone, leaf = 0;
+	int cached_triangle = -1;    // slot of the last triangle that occluded a ray of this lane
+	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
+	float tmax = 0.0f;
+	ray_slabs r = make_slabs(o, d);
+	while (true) {
+		// --- lanes whose ray has terminated draw a ticket and start on it as soon as it is published
+		const bool wants = !active && ticket < 0 && !finished;
+		const unsigned want = __ballot_sync(kFullMask, wants);
+		if (want) {
+			const int leader = __ffs(want) - 1;
+			int first = 0;
+			if (lane == leader) first = atom_add_shared(control, __popc(want));
+			first = __shfl_sync(kFullMask, first, leader);
+			if (wants) ticket = first + __popc(want & lt_mask);
+		}
+		if (ticket >= 0) {
+			if (ticket < ld_acquire(control + 4u)) {
+				entry = (uint32_t) ticket & (kRing - 1);
+				ticket = -1;
+				const unsigned own = lds_u8(bytes + entry);
+				if (!(own & 128u)) { // entries known to be occluded carry their result already
+					const uint32_t oa = origin + 4u * (own & 31u), ea = base + 4u * entry;
+					o = make3(lds_f(oa), lds_f(oa + 128u), lds_f(oa + 256u));
+					d = make3(lds_f(ea + 4u * S_DX), lds_f(ea + 4u * S_DY), lds_f(ea + 4u * S_DZ));
+					tmax = lds_f(ea + 4u * S_TMAX);
+					active = true;
+					hit = false;
+					node = kTraversalDone; leaf = 0;
+					float t;
+					if (tmax > tmin) { // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
+						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) hit = true;
+						else { r = make_slabs(o, d); node = 0; top = stack_bottom; push(kTraversalDone); }
+					}
+				}
+			}
+			else {
+				const int end = ld_acquire(control + 8u);
+				if (end >= 0 && ticket >= end) { finished = true; ticket = -1; }
+			}
+		}
+		if (!__any_sync(kFullMask, active)) {
+			if (__all_sync(kFullMask, finished)) break;
+			__nanosleep(100); // nothing published yet: leave the issue slots to the other warps
+			continue;
+		}
+		// --- descend until this lane holds two leaves or is out of nodes
+		while (node >= 0 && node != kTraversalDone) {
+			const float4* nd = nodes + 4 * (size_t) node;
+			const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
+			float tn0, tn1;
+			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
+			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
+			if (h0 && h1) {
+				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
+				node = swap ? ref1 : ref0;
+				push(swap ? ref0 : ref1);
+			}
+			else if (h0) node = ref0;
+			else if (h1) node = ref1;
+			else node = pop();
+			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
+				leaf = node;
+				node = pop();
+			}
+		}
+		__syncwarp(kFullMask);
+		// --- leaves: `leaf` and possibly `node` (a second leaf)
+		while (leaf != 0) {
+			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
+			float t;
+			for (int i = 0; i != count; ++i)
+				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) { hit = true; cached_triangle = first + i; }
+			leaf = 0;
+			if (hit) node = kTraversalDone;
+			else if (node < 0) {
+				leaf = node;
+				node = pop();
+			}
+		}
+		// --- a ray ends when it hit something or ran out of nodes
+		if (active && node == kTraversalDone) {
+			st_release_u8(bytes + kRing + entry, hit ? 1u : 0u);
+			active = false;
+		}
+		__syncwarp(kFullMask);
+	}
+}
+
+} // namespace vkr

@@ -13,21 +13,31 @@
 //   - BVH node pairs and triangles along the shadow rays,
 // and writes one float4 of linear radiance per pixel (16 B/pixel).
 //
-// Execution model. Sampling, BRDF and MIS arithmetic run per pixel in registers. Shadow rays do NOT
-// run where they are generated: every lane pushes its rays (direction, light-plane distance, the
-// contribution to add if the ray is unoccluded) into a per-warp ring buffer in shared memory using
-// __ballot_sync compaction; whenever 32 rays are queued the warp traverses them together
-// (occluded_warp, warp-synchronous shared-memory stack), so traversal always runs with full warps
-// even when half the lanes have no ray (samples below the horizon, lights behind the surface,
-// background pixels). Results are added to the owning pixel strictly in submission order, which keeps
-// the floating-point sums identical to the reference's sequential loop.
+// Execution model (warp-specialised). A CTA shades one 16x8 pixel tile with 4 SHADING warps (8x4 pixel patches: sampling,
+// BRDF and MIS arithmetic per pixel in registers) and 8 TRACE warps that only traverse the BVH. Shading lanes push
+// their shadow rays (direction, light-plane distance, the radiance to add if the ray is unoccluded) into a ring buffer
+// in shared memory using __ballot_sync compaction; trace lanes pull rays one at a time as soon as their previous ray
+// has terminated, so traversal runs with full warps although the rays come from lanes that may be idle and although
+// ray lengths differ (vkr_ray_stream.cuh). After the split the trace warps hand most of their registers to the shading
+// warps (setmaxnreg: 48 vs 144 per thread), so 24 warps are resident per SM instead of the 12 a monolithic kernel with
+// 168 registers gets. Results are added to the owning pixel strictly in submission order, which keeps the
+// floating-point sums identical to the reference's sequential loop. Without shadow rays (TRACE = false) the kernel is
+// launched with the shading warps only.
 // Compile with -fmad=false (see vkr_device_math.cuh).
 #include "vkr_shade_common.cuh"
-#include "vkr_ray_queue.cuh"
+#include "vkr_ray_stream.cuh"
 
 namespace vkr {
 
-constexpr int kTileW = 16, kTileH = 8, kThreads = kTileW * kTileH, kWarps = kThreads / 32;
+constexpr int kTileW = 16, kTileH = 8, kShadeThreads = kTileW * kTileH;
+static_assert(kShadeThreads == 32 * kShadeWarps, "one shading warp per 8x4 patch");
+constexpr int kTraceThreads = 32 * kTraceWarps;
+#ifndef VKR_SHADE_REGS
+#define VKR_SHADE_REGS 144
+#endif
+#ifndef VKR_TRACE_REGS
+#define VKR_TRACE_REGS 48
+#endif
 
 // Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
 VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
@@ -39,9 +49,9 @@ VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, 
 
 // One polygonal light for the warp's 32 pixels (shading_pass.frag.glsl:329-711, projected solid angle technique).
 // Control flow is warp-uniform; `on` masks lanes whose pixel is not shaded by this light.
-template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL>
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
 VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
-	const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_queue& q, int lane)
+	const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, int lane)
 {
 	const int S = p.sample_count;
 	const bool flip = dot4_point(light + L_PLANE, sp.position) < 0.0f;
@@ -81,7 +91,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 					}
 				}
 			}
-			submit<false>(q, lane, has, pre_vis, w, tmax, c, zero, result, false);
+			submit<TRACE, false>(q, lane, has, pre_vis, w, tmax, c, zero, result, false);
 		}
 		if (STRATEGY == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
 			const f3 o_ss = make3(
@@ -108,7 +118,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						}
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
+				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 	}
@@ -137,7 +147,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = (light_radiance(light) * evaluate_brdf<true, false>(sp, w)) * pd.psa;
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
+				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
 				has = false;
 				if (has_specular) {
 					const f3 dc = sample_psa<MAXP, BIASED>(ps, next_noise_2(ns, p, cb, px, py));
@@ -151,7 +161,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = make3(rtb2.x * dsh.z * ps.psa / ltc_density, rtb2.y * dsh.z * ps.psa / ltc_density, rtb2.z * dsh.z * ps.psa / ltc_density);
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
+				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 		else if (STRATEGY == VKR_STRATEGY_DIFFUSE_SPECULAR_MIS) {
@@ -200,7 +210,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 							}
 						}
 					}
-					submit<OPTIMAL>(q, lane, has, pre_vis, w, tmax, c, c_occ, result, s == S);
+					submit<TRACE, OPTIMAL>(q, lane, has, pre_vis, w, tmax, c, c_occ, result, s == S);
 				}
 			}
 			return result * (1.0f / (float) S);
@@ -230,25 +240,23 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 						c = make3(rtb.x * d.z / density, rtb.y * d.z / density, rtb.z * d.z / density);
 					}
 				}
-				submit<false>(q, lane, has, true, w, tmax, c, zero, result, false);
+				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
 			}
 		}
 	}
-	drain<OPTIMAL>(q, lane, result);
+	submit<TRACE, OPTIMAL>(q, lane, false, false, zero, 0.0f, zero, zero, result, true);
 	return result * (1.0f / (float) S);
 }
 
-template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL>
-#ifndef VKR_MIN_CTAS_PER_SM
-#define VKR_MIN_CTAS_PER_SM 3
-#endif
-__global__ void __launch_bounds__(kThreads, VKR_MIN_CTAS_PER_SM)
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
+__global__ void __launch_bounds__(TRACE ? kShadeThreads + kTraceThreads : kShadeThreads, TRACE ? 2 : 3)
 shading_kernel(const shading_kernel_params p) {
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned char* cb = smem;                                   // constant block incl. lights
-	float* queue_base = reinterpret_cast<float*>(smem + p.constants_smem_bytes);
-	int* stack_base = reinterpret_cast<int*>(queue_base + queue_floats_per_warp(OPTIMAL) * kWarps);
+	float* stream_base = reinterpret_cast<float*>(smem + p.constants_smem_bytes);
+	int* stack_base = reinterpret_cast<int*>(stream_base + stream_floats_per_warp(OPTIMAL) * kShadeWarps);
 	__shared__ __align__(8) unsigned long long mbar;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	// --- stage the constant block with one bulk async copy (TMA engine), completion on an mbarrier
 	const uint32_t mbar_addr = (uint32_t) __cvta_generic_to_shared(&mbar);
 	const uint32_t cb_addr = (uint32_t) __cvta_generic_to_shared(cb);
@@ -256,7 +264,22 @@ shading_kernel(const shading_kernel_params p) {
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_addr));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if (TRACE && threadIdx.x < kShadeWarps) { // stream control words {head, tail, closed, -}
+		int* control = reinterpret_cast<int*>(stream_base + stream_floats_per_warp(OPTIMAL) * threadIdx.x + stream_control_at(OPTIMAL));
+		control[0] = 0; control[1] = 0; control[2] = -1; control[3] = 0;
+	}
 	__syncthreads();
+	if (TRACE) {
+		// --- role split: from here on the two kinds of warps never meet at a CTA-wide barrier again
+		if (warp >= kShadeWarps) {
+			asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(VKR_TRACE_REGS));
+			const int t = warp - kShadeWarps;
+			trace_stream<OPTIMAL>(smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * (t & (kShadeWarps - 1))), p.bvh_nodes, p.bvh_tris,
+				smem_addr(stack_base + p.stack_depth * 32 * t + lane), lane);
+			return;
+		}
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(VKR_SHADE_REGS));
+	}
 	if (threadIdx.x == 0) {
 		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_addr), "r"(p.constants_bytes) : "memory");
 		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -269,7 +292,6 @@ shading_kernel(const shading_kernel_params p) {
 		}
 	}
 	// --- pixel of this thread: warps cover 8x4 patches of the 16x8 tile
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
 	const int tile = blockIdx.x;
@@ -305,15 +327,12 @@ shading_kernel(const shading_kernel_params p) {
 				color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
 		}
 	}
-	// --- the warp's ray queue and traversal stack
-	ray_queue q;
-	{
-		queue_bind(q, queue_base + queue_floats_per_warp(OPTIMAL) * warp, OPTIMAL);
-		float* origin = const_cast<float*>(q.origin);
+	// --- the warp's ray stream; trace lanes fetch ray origins from it by owner lane
+	ray_producer q;
+	q.base = smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * warp); q.fill = 0; q.resolved = 0;
+	if (TRACE) {
+		float* origin = stream_base + stream_floats_per_warp(OPTIMAL) * warp + stream_origin_at(OPTIMAL);
 		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
-		q.stack = stack_base + p.stack_depth * 32 * warp + lane; q.stack_stride = 32;
-		q.bvh.nodes = p.bvh_nodes; q.bvh.tris = p.bvh_tris; q.bvh.tri_ids = nullptr; q.bvh.tri_count = p.tri_count;
-		q.enabled = p.trace_shadow_rays != 0 && p.tri_count != 0;
 	}
 	__syncwarp(kFullMask);
 	if (__any_sync(kFullMask, valid)) {
@@ -333,10 +352,11 @@ shading_kernel(const shading_kernel_params p) {
 #pragma unroll 1
 		for (int li = 0; li != p.light_count; ++li) {
 			const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
-			const f3 r = shade_light<STRATEGY, MAXP, BIASED, OPTIMAL>(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, lane);
+			const f3 r = shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, lane);
 			if (valid) color = color + r;
 		}
 	}
+	if (TRACE) close_stream<OPTIMAL>(q, lane);
 	if (!in_frame) return;
 	if (isnan(color.x) || isnan(color.y) || isnan(color.z) || isinf(color.x) || isinf(color.y) || isinf(color.z))
 		color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
@@ -347,24 +367,31 @@ shading_kernel(const shading_kernel_params p) {
 
 using namespace vkr;
 
-template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL>
-static cudaError_t launch_variant(const shading_kernel_params& p, cudaStream_t stream) {
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
+static cudaError_t launch_traced(const shading_kernel_params& p, cudaStream_t stream) {
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
 	const int tiles_y = p.tile_row_count;
 	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
-	const size_t smem = p.constants_smem_bytes + sizeof(float) * queue_floats_per_warp(OPTIMAL) * kWarps + sizeof(int) * (size_t) p.stack_depth * kThreads;
-	auto kernel = shading_kernel<STRATEGY, MAXP, BIASED, OPTIMAL>;
+	const int threads = TRACE ? kShadeThreads + kTraceThreads : kShadeThreads;
+	const size_t smem = p.constants_smem_bytes + (TRACE ? sizeof(float) * stream_floats_per_warp(OPTIMAL) * kShadeWarps + sizeof(int) * (size_t) p.stack_depth * kTraceThreads : 0);
+	auto kernel = shading_kernel<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 	if (err != cudaSuccess) return err;
 	// Shared memory for exactly the CTAs the register file admits; the rest of the 228 KB stays L1 for BVH nodes
 	int ctas = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, kThreads, smem);
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, threads, smem);
 	if (err != cudaSuccess) return err;
 	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, kThreads, smem, stream>>>(p);
+	kernel<<<tiles_x * tiles_y, threads, smem, stream>>>(p);
 	return cudaGetLastError();
+}
+
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL>
+static cudaError_t launch_variant(const shading_kernel_params& p, cudaStream_t stream) {
+	if (p.trace_shadow_rays != 0 && p.tri_count != 0) return launch_traced<STRATEGY, MAXP, BIASED, OPTIMAL, true>(p, stream);
+	return launch_traced<STRATEGY, MAXP, BIASED, OPTIMAL, false>(p, stream);
 }
 
 template <int MAXP, bool BIASED>
