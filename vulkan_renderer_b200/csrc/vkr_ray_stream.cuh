@@ -26,8 +26,18 @@ namespace vkr {
 #endif
 constexpr int kRing = VKR_RING;              // entries per shading warp (power of two)
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kShadeWarps = 4, kTraceWarps = 8;   // per CTA; trace warp t serves the stream of shading warp t & 3
+#ifndef VKR_TRACE_GROUPS
+#define VKR_TRACE_GROUPS 2
+#endif
+constexpr int kShadeWarps = 4, kTraceWarps = 4 * VKR_TRACE_GROUPS;   // per CTA; trace warp t serves the stream of shading warp t & 3
 constexpr unsigned kPending = 0xffu;
+#ifndef VKR_NODE_LOOP_MIN_LANES
+#define VKR_NODE_LOOP_MIN_LANES 0
+#endif
+constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
+#ifndef VKR_RESOLVE_SLEEP_NS
+#define VKR_RESOLVE_SLEEP_NS 64
+#endif
 
 // Shared memory of one stream, as float offsets from its base. 7 (or 10, MIS_HEURISTIC_OPTIMAL) float arrays, owner and
 // result bytes, 96 floats of ray origins, 4 ints of control.
@@ -60,10 +70,26 @@ struct ray_producer {
 	int resolved;    // warp-uniform: entries below this index have been added to their pixels, their slots are free
 };
 
+// Radiance sums of one pixel. The reference adds the samples of a light into a per-light sum, scales it by 1/S and
+// adds it to the pixel (shading_pass.frag.glsl:695-711, 853-857). Shadow-ray results arrive late, so the per-light sum
+// is closed lazily: every entry carries the parity of "lights with entries" of its pixel, and when the parity of the
+// next resolved entry differs from that of the previous one, the previous light is complete.
+struct pixel_sum {
+	f3 color;          // pixel radiance so far (all closed lights)
+	f3 light;          // sum over the resolved samples of the light that is currently open
+	float inv_samples; // 1 / S
+	unsigned submit_parity, resolve_parity;  // bit 5 of the owner byte
+	bool pushed;       // this pixel has pushed an entry for the light being sampled
+};
+VKR_DEV void close_light(pixel_sum& acc) {
+	acc.color = acc.color + acc.light * acc.inv_samples;
+	acc.light = make3(0.0f, 0.0f, 0.0f);
+}
+
 // Adds the contributions of entries [q.resolved, min(q.resolved + 32, q.fill)) to their owners, oldest first; waits for
 // the trace warps where results are still pending.
 template <bool OPTIMAL>
-VKR_DEV void resolve_chunk(ray_producer& q, int lane, f3& result) {
+VKR_DEV void resolve_chunk(ray_producer& q, int lane, pixel_sum& acc) {
 	const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
 	const int first = q.resolved;
 	const int n = min(32, q.fill - first);
@@ -72,7 +98,7 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, f3& result) {
 	while (true) {
 		const unsigned r = valid ? ld_acquire_u8(bytes + kRing + slot) : 0u;
 		if (!__any_sync(kFullMask, r == kPending)) break;
-		__nanosleep(64);
+		__nanosleep(VKR_RESOLVE_SLEEP_NS);
 	}
 	const unsigned own = valid ? (lds_u8(bytes + slot) & 31u) : 32u;
 	unsigned mine = __ballot_sync(kFullMask, valid);
@@ -85,8 +111,10 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, f3& result) {
 		const uint32_t e = (uint32_t) (first + __ffs(mine) - 1) & (kRing - 1);
 		mine &= mine - 1;
 		const uint32_t a = q.base + 4u * e;
-		if (!lds_u8(bytes + kRing + e)) result = result + make3(lds_f(a + 4u * S_CX), lds_f(a + 4u * S_CY), lds_f(a + 4u * S_CZ));
-		else if (OPTIMAL) result = result + make3(lds_f(a + 4u * S_OX), lds_f(a + 4u * S_OY), lds_f(a + 4u * S_OZ));
+		const unsigned parity = lds_u8(bytes + e) & 32u;
+		if (parity != acc.resolve_parity) { close_light(acc); acc.resolve_parity = parity; }
+		if (!lds_u8(bytes + kRing + e)) acc.light = acc.light + make3(lds_f(a + 4u * S_CX), lds_f(a + 4u * S_CY), lds_f(a + 4u * S_CZ));
+		else if (OPTIMAL) acc.light = acc.light + make3(lds_f(a + 4u * S_OX), lds_f(a + 4u * S_OY), lds_f(a + 4u * S_OZ));
 	}
 	q.resolved = first + n;
 	__syncwarp(kFullMask);
@@ -94,21 +122,22 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, f3& result) {
 
 // Warp-convergent: every lane calls it once per candidate sample. has = this lane contributes something.
 // need_trace = visibility is not known yet (n.w > 0); otherwise the sample is known to be occluded.
-// finish (warp-uniform) = end of a light: wait until everything submitted so far has been added to `result`.
+// finish (warp-uniform) = end of a light. Nothing waits here: the light's sum is closed when its last entry resolves.
 template <bool TRACE, bool OPTIMAL>
-VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, f3& result, bool finish) {
+VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, pixel_sum& acc, bool finish) {
 	if (!TRACE) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
 		if (has) {
-			if (need_trace) result = result + c_visible;
-			else if (OPTIMAL) result = result + c_occluded;
+			if (need_trace) acc.light = acc.light + c_visible;
+			else if (OPTIMAL) acc.light = acc.light + c_occluded;
 		}
+		if (finish) close_light(acc);
 		return;
 	}
 	const bool push = has && (need_trace || OPTIMAL);
 	const unsigned mask = __ballot_sync(kFullMask, push);
 	if (mask) {
 		const int k = __popc(mask);
-		while (q.fill + k - q.resolved > kRing) resolve_chunk<OPTIMAL>(q, lane, result);
+		while (q.fill + k - q.resolved > kRing) resolve_chunk<OPTIMAL>(q, lane, acc);
 		if (push) {
 			const uint32_t e = (uint32_t) (q.fill + __popc(mask & ((1u << lane) - 1u))) & (kRing - 1);
 			const uint32_t a = q.base + 4u * e;
@@ -116,19 +145,23 @@ VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir
 			sts_f(a + 4u * S_CX, c_visible.x); sts_f(a + 4u * S_CY, c_visible.y); sts_f(a + 4u * S_CZ, c_visible.z);
 			if (OPTIMAL) { sts_f(a + 4u * S_OX, c_occluded.x); sts_f(a + 4u * S_OY, c_occluded.y); sts_f(a + 4u * S_OZ, c_occluded.z); }
 			const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
-			sts_u8(bytes + e, need_trace ? (unsigned) lane : ((unsigned) lane | 128u));
+			sts_u8(bytes + e, (unsigned) lane | acc.submit_parity | (need_trace ? 0u : 128u));
 			sts_u8(bytes + kRing + e, need_trace ? kPending : 1u);
+			acc.pushed = true;
 		}
 		q.fill += k;
 		__syncwarp(kFullMask);
 		if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 4u, q.fill);
 	}
-	if (finish) while (q.resolved != q.fill) resolve_chunk<OPTIMAL>(q, lane, result);
+	if (finish && acc.pushed) { acc.submit_parity ^= 32u; acc.pushed = false; }
 }
 
-// End of the tile: everything has been resolved; tells the trace warps that no ticket >= fill will ever be served.
+// End of the tile: resolves what is still pending, closes the last light and tells the trace warps that no ticket
+// >= fill will ever be served.
 template <bool OPTIMAL>
-VKR_DEV void close_stream(ray_producer& q, int lane) {
+VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc) {
+	while (q.resolved != q.fill) resolve_chunk<OPTIMAL>(q, lane, acc);
+	close_light(acc);
 	__syncwarp(kFullMask);
 	if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 8u, q.fill);
 }
@@ -219,6 +252,9 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 				leaf = node;
 				node = pop();
 			}
+			// lanes that are done or hold two leaves wait at the loop exit: once too few are left descending, let
+			// everybody test triangles and fetch new rays (affects lane utilisation only, not results)
+			if (kNodeLoopMinLanes > 0 && __popc(__activemask()) < kNodeLoopMinLanes) break;
 		}
 		__syncwarp(kFullMask);
 		// --- leaves: `leaf` and possibly `node` (a second leaf)

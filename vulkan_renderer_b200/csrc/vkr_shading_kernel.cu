@@ -50,13 +50,12 @@ VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, 
 // One polygonal light for the warp's 32 pixels (shading_pass.frag.glsl:329-711, projected solid angle technique).
 // Control flow is warp-uniform; `on` masks lanes whose pixel is not shaded by this light.
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
-VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
-	const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, int lane)
+VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
+	const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, pixel_sum& result, int lane)
 {
 	const int S = p.sample_count;
 	const bool flip = dot4_point(light + L_PLANE, sp.position) < 0.0f;
 	const f3 zero = make3(0.0f, 0.0f, 0.0f);
-	f3 result = zero;
 	psa_polygon<MAXP> pd;
 	pd.psa = 0.0f; pd.inner_ellipse_0 = make2(0.0f, 0.0f); pd.vertex_count = 0;
 	if (on) {
@@ -213,7 +212,7 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 					submit<TRACE, OPTIMAL>(q, lane, has, pre_vis, w, tmax, c, c_occ, result, s == S);
 				}
 			}
-			return result * (1.0f / (float) S);
+			return;
 		}
 		else { // VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM
 			const float diffuse_albedo = max_glsl(dot(sp.diffuse_albedo, make3(0.21263901f, 0.71516868f, 0.07219232f)), 0.01f);
@@ -245,7 +244,6 @@ VKR_DEV f3 shade_light(bool on, const shading_point& sp, const ltc_state& l, con
 		}
 	}
 	submit<TRACE, OPTIMAL>(q, lane, false, false, zero, 0.0f, zero, zero, result, true);
-	return result * (1.0f / (float) S);
 }
 
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
@@ -334,6 +332,9 @@ shading_kernel(const shading_kernel_params p) {
 		float* origin = stream_base + stream_floats_per_warp(OPTIMAL) * warp + stream_origin_at(OPTIMAL);
 		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
 	}
+	pixel_sum acc;
+	acc.color = color; acc.light = make3(0.0f, 0.0f, 0.0f); acc.inv_samples = 1.0f / (float) p.sample_count;
+	acc.submit_parity = 0u; acc.resolve_parity = 0u; acc.pushed = false;
 	__syncwarp(kFullMask);
 	if (__any_sync(kFullMask, valid)) {
 		ltc_state l = {};
@@ -352,15 +353,16 @@ shading_kernel(const shading_kernel_params p) {
 #pragma unroll 1
 		for (int li = 0; li != p.light_count; ++li) {
 			const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
-			const f3 r = shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, lane);
-			if (valid) color = color + r;
+			shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, acc, lane);
 		}
 	}
-	if (TRACE) close_stream<OPTIMAL>(q, lane);
+	if (TRACE) close_stream<OPTIMAL>(q, lane, acc);
+	color = acc.color;
 	if (!in_frame) return;
+	f3 final_color = color;
 	if (isnan(color.x) || isnan(color.y) || isnan(color.z) || isinf(color.x) || isinf(color.y) || isinf(color.z))
-		color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
-	p.out[pixel] = make_float4(color.x * exposure, color.y * exposure, color.z * exposure, 1.0f);
+		final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
+	p.out[pixel] = make_float4(final_color.x * exposure, final_color.y * exposure, final_color.z * exposure, 1.0f);
 }
 
 } // namespace vkr
