@@ -32,7 +32,8 @@ TECHNIQUES = ["BASELINE", "AREA_TURK", "SOLID_ANGLE_ARVO", "RECTANGLE_SOLID_ANGL
 
 
 def config_name(c):
-	return "s%d_h%d_b%d_L%d_V%d_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], c["max_vertices"], c["samples"], c["trace"], c["show_lights"], c["materials"])
+	vertices = "%d" % c["max_vertices"] if c.get("min_vertices", c["max_vertices"]) == c["max_vertices"] else "%dm%d" % (c["max_vertices"], c["min_vertices"])
+	return "s%d_h%d_b%d_L%d_V%s_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], vertices, c["samples"], c["trace"], c["show_lights"], c["materials"])
 
 
 def defines(c):
@@ -100,6 +101,10 @@ def default_configs():
 	configs.append(dict(base, samples=40, lights=2))                       # loop instead of unrolled code (SAMPLE_COUNT_CLAMPED = 33)
 	configs.append(dict(base, lights=1, samples=1, trace=0, materials=3, strategy=0, heuristic=3))   # BASELINE config 1 (Cornell)
 	configs.append(dict(base, lights=1, samples=2, trace=1, materials=3))  # Cornell with MIS and rays
+	configs.append(dict(base, max_vertices=3))                             # triangle lights (data set mini_tri)
+	configs.append(dict(base, max_vertices=3, strategy=1, heuristic=0))
+	configs.append(dict(base, max_vertices=4, min_vertices=3))             # triangle, quad, triangle (data set mini_mixed)
+	configs.append(dict(base, max_vertices=4, min_vertices=3, strategy=1, heuristic=1))
 	return configs
 
 

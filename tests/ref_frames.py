@@ -7,7 +7,11 @@ WIDTH, HEIGHT = 64, 48
 
 
 def dataset_for(cfg):
-	return "cornell" if cfg["materials"] == 3 else "mini_city"
+	if cfg["materials"] == 3:
+		return "cornell"
+	if cfg["max_vertices"] == 3:
+		return "mini_tri"
+	return "mini_mixed" if cfg.get("min_vertices", cfg["max_vertices"]) != cfg["max_vertices"] else "mini_city"
 
 
 def host_constants(info, width, height, lights, sample_count=1):
@@ -30,6 +34,6 @@ def host_constants(info, width, height, lights, sample_count=1):
 
 
 def oracle_cfg(cfg, width=WIDTH, height=HEIGHT):
-	return dict(width=width, height=height, light_count=cfg["lights"], max_light_vertex_count=cfg["max_vertices"], min_light_vertex_count=cfg["max_vertices"],
+	return dict(width=width, height=height, light_count=cfg["lights"], max_light_vertex_count=cfg["max_vertices"], min_light_vertex_count=cfg.get("min_vertices", cfg["max_vertices"]),
 		sample_count=cfg["samples"], sampling_strategies=cfg["strategy"], mis_heuristic=cfg["heuristic"], biased_sampling=cfg["biased"],
 		trace_shadow_rays=cfg["trace"], show_polygonal_lights=cfg["show_lights"])

@@ -25,9 +25,10 @@ def _golden():
 
 
 def _config_from_name(name):
-	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)_S(\d+)_t(\d+)_l(\d+)_M(\d+)$", name)
-	s, h, b, L, V, S, t, l, M = (int(x) for x in m.groups())
-	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, samples=S, trace=t, show_lights=l, materials=M)
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)$", name)
+	s, h, b, L, V, Vmin, S, t, l, M = (int(x) if x is not None else None for x in m.groups())
+	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
+		samples=S, trace=t, show_lights=l, materials=M)
 
 
 def _names():

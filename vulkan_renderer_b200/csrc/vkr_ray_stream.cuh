@@ -32,11 +32,11 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kShadeWarps = 4, kTraceWarps = 4 * VKR_TRACE_GROUPS;   // per CTA; trace warp t serves the stream of shading warp t & 3
 constexpr unsigned kPending = 0xffu;
 #ifndef VKR_NODE_LOOP_MIN_LANES
-#define VKR_NODE_LOOP_MIN_LANES 0
+#define VKR_NODE_LOOP_MIN_LANES 16
 #endif
 constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_RESOLVE_SLEEP_NS
-#define VKR_RESOLVE_SLEEP_NS 64
+#define VKR_RESOLVE_SLEEP_NS 512
 #endif
 
 // Shared memory of one stream, as float offsets from its base. 7 (or 10, MIS_HEURISTIC_OPTIMAL) float arrays, owner and

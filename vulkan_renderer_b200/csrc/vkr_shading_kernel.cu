@@ -19,7 +19,7 @@
 // in shared memory using __ballot_sync compaction; trace lanes pull rays one at a time as soon as their previous ray
 // has terminated, so traversal runs with full warps although the rays come from lanes that may be idle and although
 // ray lengths differ (vkr_ray_stream.cuh). After the split the trace warps hand most of their registers to the shading
-// warps (setmaxnreg: 48 vs 144 per thread), so 24 warps are resident per SM instead of the 12 a monolithic kernel with
+// warps (setmaxnreg: 56 vs 128 per thread), so 24 warps are resident per SM instead of the 12 a monolithic kernel with
 // 168 registers gets. Results are added to the owning pixel strictly in submission order, which keeps the
 // floating-point sums identical to the reference's sequential loop. Without shadow rays (TRACE = false) the kernel is
 // launched with the shading warps only.
@@ -33,10 +33,10 @@ constexpr int kTileW = 16, kTileH = 8, kShadeThreads = kTileW * kTileH;
 static_assert(kShadeThreads == 32 * kShadeWarps, "one shading warp per 8x4 patch");
 constexpr int kTraceThreads = 32 * kTraceWarps;
 #ifndef VKR_SHADE_REGS
-#define VKR_SHADE_REGS 144
+#define VKR_SHADE_REGS 128
 #endif
 #ifndef VKR_TRACE_REGS
-#define VKR_TRACE_REGS 48
+#define VKR_TRACE_REGS 56
 #endif
 
 // Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)

@@ -350,7 +350,7 @@ def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0
 def build_dataset(directory, name, **overrides):
 	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
 	os.makedirs(directory, exist_ok=True)
-	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3}.get(name, 9))
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3}.get(name, 9))
 	if name == "cornell":
 		mesh, materials = scene_cornell()
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
@@ -366,6 +366,16 @@ def build_dataset(directory, name, **overrides):
 		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
 		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
 		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+	elif name in ("mini_tri", "mini_mixed"):
+		# the mini_city scene lit by triangles (MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 3) or by a triangle, a quad and a
+		# triangle (MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING = 3 < MAX = 4, main.c:730-732)
+		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
+		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
+		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+		triangle = [(0.0, 0.0), (1.0, 0.0), (0.3, 1.0)]
+		for i, light in enumerate(lights):
+			if name == "mini_tri" or i != 1:
+				light["vertices"] = [(float(x), float(y)) for x, y in triangle]
 	elif name == "room":
 		mesh, materials = scene_room(**{k: v for k, v in overrides.items() if k in ("seed", "detail", "clutter", "n_mat")})
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
