@@ -145,11 +145,12 @@ def test_bvh_builder_structure(name):
 	def walk(k, lo, hi, level):
 		assert level <= depth
 		for c in range(2):
-			clo = nodes[k, 6 * c:6 * c + 3]; chi = nodes[k, 6 * c + 3:6 * c + 6]
+			ctr = nodes[k, 6 * c:6 * c + 3].astype(np.float64); half = nodes[k, 6 * c + 3:6 * c + 6].astype(np.float64)   # centre, half extent
+			clo = ctr - half; chi = ctr + half
 			ref = int(refs[k, c])
 			if ref >= 0:
 				seen_nodes[ref] += 1
-				assert np.all(clo >= lo - 1e-6) and np.all(chi <= hi + 1e-6)       # child boxes nest
+				assert np.all(clo >= lo - 1e-4) and np.all(chi <= hi + 1e-4)       # child boxes nest (up to the rounding of c, h)
 				walk(ref, clo, chi, level + 1)
 			else:
 				first, count = (ref & 0x7FFFFFFF) >> 4, ref & 15

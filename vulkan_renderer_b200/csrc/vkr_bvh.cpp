@@ -6,6 +6,7 @@
 // (every subtree owns a fixed range of the triangle order array; node numbering happens in a
 // serial flattening pass afterwards). Leaf boxes are padded by 2^-16 of the scene extent so that
 // the slab test is conservative w.r.t. the fp32 triangle predicate ("Shadow predicate").
+// Boxes are stored as centre + half extent.
 #include "vkr_bvh.h"
 #include <algorithm>
 #include <cmath>
@@ -157,11 +158,17 @@ void build_bvh(host_bvh& out, const float* vertices, uint64_t triangle_count) {
 	struct item { const build_node* node; uint32_t index; uint32_t depth; };
 	std::vector<item> stack;
 	auto leaf_ref = [](const build_node* nd) { return (int32_t) (0x80000000u | (nd->first << 4) | nd->count); };
+	// Child boxes are stored as centre and half extent (the slab test then needs no per-axis min/max, vkr_trace.cuh).
+	// The half extent is rounded up so that [c - h, c + h] contains the padded box.
 	auto write_child = [&](float* dst, int c, const build_node* nd, int32_t ref) {
-		float lo[3], hi[3];
-		for (int a = 0; a != 3; ++a) { lo[a] = nd ? nd->box.lo[a] - pad : 0.0f; hi[a] = nd ? nd->box.hi[a] + pad : 0.0f; }
-		if (c == 0) { dst[0] = lo[0]; dst[1] = lo[1]; dst[2] = lo[2]; dst[3] = hi[0]; dst[4] = hi[1]; dst[5] = hi[2]; }
-		else { dst[6] = lo[0]; dst[7] = lo[1]; dst[8] = lo[2]; dst[9] = hi[0]; dst[10] = hi[1]; dst[11] = hi[2]; }
+		float ctr[3], half[3];
+		for (int a = 0; a != 3; ++a) {
+			const double lo = nd ? (double) nd->box.lo[a] - (double) pad : 0.0, hi = nd ? (double) nd->box.hi[a] + (double) pad : 0.0;
+			ctr[a] = (float) (0.5 * (lo + hi));
+			half[a] = std::nextafter((float) std::max((double) ctr[a] - lo, hi - (double) ctr[a]), std::numeric_limits<float>::infinity());
+		}
+		float* d = dst + 6 * c;
+		d[0] = ctr[0]; d[1] = ctr[1]; d[2] = ctr[2]; d[3] = half[0]; d[4] = half[1]; d[5] = half[2];
 		dst[12 + c] = as_float(ref);
 	};
 	out.nodes.assign(16, 0.0f);

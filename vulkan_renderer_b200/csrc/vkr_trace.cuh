@@ -6,16 +6,19 @@
 // Layout in HBM (built once on the host, vkr_bvh.cpp):
 //   node  = 64 B = 4 x float4: both children's boxes + both child references ("node pair"),
 //           so one 64-B sector-aligned fetch decides both children.
-//             q0 = (lo0.x, lo0.y, lo0.z, hi0.x)  q1 = (hi0.y, hi0.z, lo1.x, lo1.y)
-//             q2 = (lo1.z, hi1.x, hi1.y, hi1.z)  q3 = (ref0, ref1, -, -) as int bits
+//             q0 = (c0.x, c0.y, c0.z, h0.x)  q1 = (h0.y, h0.z, c1.x, c1.y)
+//             q2 = (c1.z, h1.x, h1.y, h1.z)  q3 = (ref0, ref1, -, -) as int bits
+//           c = box centre, h = half extent (rounded up)
 //           ref >= 0: inner node index; ref < 0: leaf, (ref & 0x7fffffff) = first_triangle << 4 | count
 //   tri   = 48 B = 3 x float4: v0.xyz e1.x | e1.yz e2.xy | e2.z - - -   (e1 = v1 - v0, e2 = v2 - v0)
 //
 // Arithmetic: the TRIANGLE predicate is part of the parity contract (Moeller-Trumbore,
 // fp32, fixed operation order, no culling, open interval); hit/miss is the OR over all triangles and
-// does not depend on traversal order. The BOX test only has to be conservative: it uses one FFMA
-// per slab plane (plane * 1/d - o/d) and FMNMX min/max; its rounding error is below 1/128 of the
-// padding the builder adds to every box (vkr_bvh.cpp), so no triangle the predicate accepts is culled.
+// does not depend on traversal order. The BOX test only has to be conservative. With boxes stored as
+// centre c and half extent h the near/far slab distances are (c - o)/d -+ h/|d|: three FFMAs per axis
+// and no per-axis min/max, which moves the work from the ALU pipe (FMNMX, the busiest pipe of the
+// traversal loop) to the FMA pipe. Its rounding error is below 1/64 of the padding the builder adds
+// to every box (vkr_bvh.cpp), so no triangle the predicate accepts is culled.
 #pragma once
 #include "vkr_device_math.cuh"
 
@@ -61,14 +64,13 @@ VKR_DEV ray_slabs make_slabs(f3 o, f3 d) {
 	return r;
 }
 
-// Conservative slab test (see header). Returns the entry distance in *t_near. NaNs (inf - inf for axis-parallel
-// rays) drop out of fminf/fmaxf, which leaves that slab unconstrained.
-VKR_DEV bool ray_box(float lox, float loy, float loz, float hix, float hiy, float hiz, const ray_slabs& r, float tmin, float tmax, float* t_near) {
-	const float x0 = fmaf(lox, r.id.x, -r.oid.x), x1 = fmaf(hix, r.id.x, -r.oid.x);
-	const float y0 = fmaf(loy, r.id.y, -r.oid.y), y1 = fmaf(hiy, r.id.y, -r.oid.y);
-	const float z0 = fmaf(loz, r.id.z, -r.oid.z), z1 = fmaf(hiz, r.id.z, -r.oid.z);
-	const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), tmin));
-	const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax));
+// Conservative slab test (see header) of the box with centre c and half extent h. Returns the entry distance in
+// *t_near. NaNs (inf - inf for axis-parallel rays) drop out of fminf/fmaxf, which leaves that slab unconstrained.
+VKR_DEV bool ray_box(float cx, float cy, float cz, float hx, float hy, float hz, const ray_slabs& r, float tmin, float tmax, float* t_near) {
+	const float mx = fmaf(cx, r.id.x, -r.oid.x), my = fmaf(cy, r.id.y, -r.oid.y), mz = fmaf(cz, r.id.z, -r.oid.z);
+	const float ax = fabsf(r.id.x), ay = fabsf(r.id.y), az = fabsf(r.id.z);
+	const float tn = fmaxf(fmaxf(fmaf(-hx, ax, mx), fmaf(-hy, ay, my)), fmaxf(fmaf(-hz, az, mz), tmin));
+	const float tf = fminf(fminf(fmaf(hx, ax, mx), fmaf(hy, ay, my)), fminf(fmaf(hz, az, mz), tmax));
 	*t_near = tn;
 	return tn <= tf;
 }
