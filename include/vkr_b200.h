@@ -179,6 +179,9 @@ size_t vkr_get_constants_size(const vkr_scene_specification_t* spec);
 /* Writes the per-frame constants exactly as write_constants() does (src/main.c:2114-2188). Returns bytes written. */
 size_t vkr_write_constants(void* data, const vkr_scene_specification_t* spec, const vkr_render_settings_t* settings,
 	const vkr_scene_t* scene, const vkr_ltc_table_t* ltc, vkr_noise_table_t* noise, uint32_t width, uint32_t height);
+/* HDR screenshots (src/main.c:1702-1750, :2132): write_constants() copies app->screenshot.frame_bits into the block;
+   0 = normal frame, 1 / 2 = the frame carries the low / high bytes of the half-precision colours */
+void vkr_set_frame_bits(void* constants, uint32_t frame_bits);
 
 /* ---- G-buffer producer (stands in for subpass 0 + get_shading_data(), src/main.c:1422-1427,
         src/shaders/shading_pass.frag.glsl:721-822). Layout: 4 planes of width*height float4:
@@ -208,6 +211,11 @@ typedef struct vkr_shading_pass_desc_s {
 	const vkr_scene_t* scene;
 	const vkr_ltc_table_t* ltc_table;
 	const vkr_noise_table_t* noise_table;
+	/* output stage (shading_pass.frag.glsl:866-892): 0 = linear RGB, what the shader writes when the swapchain converts to
+	   sRGB itself (OUTPUT_LINEAR_RGB=1, src/main.c:790); 1 = the shader converts to sRGB (OUTPUT_LINEAR_RGB=0). The
+	   half-bit split for HDR screenshots follows g_frame_bits in the constant block (vkr_set_frame_bits). Output stays
+	   float4: the values the render target receives before its UNORM quantisation. */
+	int output_srgb;
 } vkr_shading_pass_desc_t;
 
 typedef struct vkr_shading_pass_s {

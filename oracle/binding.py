@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
 
 class Config(C.Structure):
 	_fields_ = [(n, C.c_uint32) for n in ("width", "height", "light_count", "max_light_vertex_count", "min_light_vertex_count", "sample_count",
-		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride")]
+		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride", "output_srgb")]
 
 
 _lib = None
@@ -107,7 +107,7 @@ def sort_network(vertices_xy, ellipses_xy, maxp):
 	return v, e
 
 
-ELEMENTARY = dict(atan=0, sin=1, cos=2, acos01=3, rsqrt=4, fast_positive_atan=5)
+ELEMENTARY = dict(atan=0, sin=1, cos=2, acos01=3, rsqrt=4, fast_positive_atan=5, log2=6, exp2=7, linear_to_srgb=8, srgb_to_linear=9, float_to_half=10)
 
 
 def elementary(which, x):

@@ -33,7 +33,10 @@ TECHNIQUES = ["BASELINE", "AREA_TURK", "SOLID_ANGLE_ARVO", "RECTANGLE_SOLID_ANGL
 
 def config_name(c):
 	vertices = "%d" % c["max_vertices"] if c.get("min_vertices", c["max_vertices"]) == c["max_vertices"] else "%dm%d" % (c["max_vertices"], c["min_vertices"])
-	return "s%d_h%d_b%d_L%d_V%s_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], vertices, c["samples"], c["trace"], c["show_lights"], c["materials"])
+	name = "s%d_h%d_b%d_L%d_V%s_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], vertices, c["samples"], c["trace"], c["show_lights"], c["materials"])
+	if c.get("srgb", 0) or c.get("frame_bits", 0):   # output stage: o<srgb><frame_bits>
+		name += "_o%d%d" % (c.get("srgb", 0), c.get("frame_bits", 0))
+	return name
 
 
 def defines(c):
@@ -44,7 +47,7 @@ def defines(c):
 		"MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING": c.get("min_vertices", c["max_vertices"]), "MAX_POLYGONAL_LIGHT_VERTEX_COUNT": c["max_vertices"],
 		"MAX_POLYGON_VERTEX_COUNT": c["max_vertices"] + 1, "SAMPLE_COUNT": c["samples"], "SAMPLE_COUNT_CLAMPED": min(c["samples"], 33),
 		"TRACE_SHADOW_RAYS": c["trace"], "SHOW_POLYGONAL_LIGHTS": c["show_lights"],
-		"ERROR_DISPLAY_DIFFUSE": 0, "ERROR_DISPLAY_SPECULAR": 0, "ERROR_INDEX": 0, "OUTPUT_LINEAR_RGB": 1,
+		"ERROR_DISPLAY_DIFFUSE": 0, "ERROR_DISPLAY_SPECULAR": 0, "ERROR_INDEX": 0, "OUTPUT_LINEAR_RGB": 0 if c.get("srgb", 0) else 1,
 	}
 	for i, s in enumerate(STRATEGIES):
 		d["SAMPLING_STRATEGIES_" + s] = int(c["strategy"] == i)
@@ -105,6 +108,8 @@ def default_configs():
 	configs.append(dict(base, max_vertices=3, strategy=1, heuristic=0))
 	configs.append(dict(base, max_vertices=4, min_vertices=3))             # triangle, quad, triangle (data set mini_mixed)
 	configs.append(dict(base, max_vertices=4, min_vertices=3, strategy=1, heuristic=1))
+	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
+		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs
 
 

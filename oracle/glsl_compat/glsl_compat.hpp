@@ -241,8 +241,8 @@ inline float atan(float y, float x) { // quadrant-corrected, built on the same p
 }
 inline float acos(float x) { return (x >= 0.0f) ? vkr_acos01(vkr_min(x, 1.0f)) : VKR_PI - vkr_acos01(vkr_min(-x, 1.0f)); }
 inline float asin(float x) { return VKR_HALF_PI - acos(x); }
-inline float pow(float x, float y) { return powf(x, y); }
-inline vec3 pow(const vec3& x, const vec3& y) { return vec3(powf(x.x, y.x), powf(x.y, y.y), powf(x.z, y.z)); }
+inline float pow(float x, float y) { return vkr_pow(x, y); }   // the output stage's contract (vkr_math.h); GLSL leaves pow to the driver
+inline vec3 pow(const vec3& x, const vec3& y) { return vec3(vkr_pow(x.x, y.x), vkr_pow(x.y, y.y), vkr_pow(x.z, y.z)); }
 inline float log2(float x) { return log2f(x); }
 inline float exp2(float x) { return exp2f(x); }
 inline float floor(float x) { return floorf(x); }
@@ -253,7 +253,7 @@ inline bool isnan(float x) { return std::isnan(x); }
 inline uint floatBitsToUint(float f) { return f2u(f); }
 inline int floatBitsToInt(float f) { return (int) f2u(f); }
 inline float uintBitsToFloat(uint u) { return u2f(u); }
-inline uint packHalf2x16(const vec2&) { return 0u; } // only reached when g_frame_bits != 0 (HDR screenshots), which the driver never sets
+inline uint packHalf2x16(const vec2& v) { return vkr_pack_half_2x16(v.x, v.y); } // IEEE round to nearest even
 inline bool any(bool b) { return b; }
 struct bvec3 { bool x, y, z; };
 inline bvec3 lessThanEqual(const vec3& a, const vec3& b) { return bvec3{a.x <= b.x, a.y <= b.y, a.z <= b.z}; }

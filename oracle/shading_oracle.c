@@ -638,9 +638,20 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 			}
 			if (isnan(final_color.x) || isnan(final_color.y) || isnan(final_color.z) || isinf(final_color.x) || isinf(final_color.y) || isinf(final_color.z))
 				final_color = mk3(1.0f / c.exposure, 0.0f / c.exposure, 0.8f / c.exposure);
-			out_rgba[pi + 0] = final_color.x * c.exposure;
-			out_rgba[pi + 1] = final_color.y * c.exposure;
-			out_rgba[pi + 2] = final_color.z * c.exposure;
+			v3 out_color = mk3(final_color.x * c.exposure, final_color.y * c.exposure, final_color.z * c.exposure);
+			/* HDR screenshots: two LDR frames hold the low / high bytes of the half-precision colour (shading_pass.frag.glsl:871-887) */
+			const uint32_t frame_bits = rdu(constants, OFF_FRAME_BITS);
+			if (frame_bits > 0) {
+				const uint32_t mask = (frame_bits == 1) ? 0xFFu : 0xFF00u, shift = (frame_bits == 1) ? 0u : 8u;
+				const uint32_t h0 = vkr_pack_half_2x16(out_color.x, out_color.y), h1 = vkr_pack_half_2x16(out_color.z, 1.0f);
+				out_color = mk3((float) ((h0 & mask) >> shift) * (1.0f / 255.0f), (float) ((((h0 & 0xFFFF0000u) >> 16) & mask) >> shift) * (1.0f / 255.0f), (float) ((h1 & mask) >> shift) * (1.0f / 255.0f));
+				if (!cfg->output_srgb) out_color = mk3(vkr_srgb_to_linear(out_color.x), vkr_srgb_to_linear(out_color.y), vkr_srgb_to_linear(out_color.z));
+			}
+			else if (cfg->output_srgb) /* :888-892 */
+				out_color = mk3(vkr_linear_to_srgb(out_color.x), vkr_linear_to_srgb(out_color.y), vkr_linear_to_srgb(out_color.z));
+			out_rgba[pi + 0] = out_color.x;
+			out_rgba[pi + 1] = out_color.y;
+			out_rgba[pi + 2] = out_color.z;
 			out_rgba[pi + 3] = 1.0f;
 			total_rays += rays;
 		}
@@ -852,7 +863,9 @@ float vkr_oracle_acos01(float x) { return vkr_acos01(x); }
 float vkr_oracle_fast_positive_atan(float x) { return psa_fast_positive_atan(x); }
 void vkr_oracle_elementary_batch(int which, uint32_t n, const float* x, float* y) {
 	for (uint32_t i = 0; i != n; ++i)
-		y[i] = (which == 0) ? vkr_atan(x[i]) : (which == 1) ? vkr_sin(x[i]) : (which == 2) ? vkr_cos(x[i]) : (which == 3) ? vkr_acos01(x[i]) : (which == 4) ? vkr_rsqrt(x[i]) : psa_fast_positive_atan(x[i]);
+		y[i] = (which == 0) ? vkr_atan(x[i]) : (which == 1) ? vkr_sin(x[i]) : (which == 2) ? vkr_cos(x[i]) : (which == 3) ? vkr_acos01(x[i]) : (which == 4) ? vkr_rsqrt(x[i])
+			: (which == 6) ? vkr_log2(x[i]) : (which == 7) ? vkr_exp2(x[i]) : (which == 8) ? vkr_linear_to_srgb(x[i]) : (which == 9) ? vkr_srgb_to_linear(x[i])
+			: (which == 10) ? (float) vkr_float_to_half(x[i]) : psa_fast_positive_atan(x[i]);
 }
 
 /* Shadow predicate KATs: per ray {ox,oy,oz,dx,dy,dz,tmin,tmax} -> occluded bit via BVH and (optionally) brute force */

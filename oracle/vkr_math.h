@@ -100,6 +100,61 @@ static inline float vkr_acos01(float x) {
 	return 2.0f * vkr_atan(sqrtf((1.0f - x) / (1.0f + x)));
 }
 
+/* ---- output stage (srgb_utility.glsl, shading_pass.frag.glsl:871-892). GLSL leaves the precision of pow to the driver;
+   this is the contract both sides implement: pow(x, y) = exp2(y * log2(x)) for x > 0, 0 for x <= 0, every step in fp32. */
+static inline float vkr_log2(float x) { /* x > 0, normal; fdlibm's logf kernel, then one fma by 1/ln 2 */
+	uint32_t u = f2u(x) - 0x3f3504f3u;                        /* mantissa in [sqrt(1/2), sqrt(2)) */
+	const float e = (float) ((int32_t) u >> 23);
+	const float f = u2f((u & 0x007fffffu) + 0x3f3504f3u) - 1.0f;
+	const float s = f / (2.0f + f);
+	const float z = s * s, w = z * z;
+	const float t1 = w * fmaf(w, 0.24279078841f, 0.40000972152f);
+	const float t2 = z * fmaf(w, 0.28498786688f, 0.66666662693f);
+	const float hfsq = 0.5f * f * f;
+	const float ln = f - (hfsq - s * (hfsq + (t2 + t1)));
+	return fmaf(ln, 1.44269502162933349609375f, e);
+}
+static inline float vkr_exp2(float x) { /* x in [-126, 127]; smaller x gives 0 */
+	if (!(x >= -126.0f)) return 0.0f;
+	const float n = floorf(x + 0.5f);
+	const float r = x - n;                                        /* [-0.5, 0.5] */
+	float p = 1.52527338e-5f;
+	p = fmaf(p, r, 1.54035304e-4f);
+	p = fmaf(p, r, 1.33335581e-3f);
+	p = fmaf(p, r, 9.61812911e-3f);
+	p = fmaf(p, r, 5.55041087e-2f);
+	p = fmaf(p, r, 2.40226507e-1f);
+	p = fmaf(p, r, 6.93147181e-1f);
+	p = fmaf(p, r, 1.0f);
+	return p * u2f((uint32_t) ((int32_t) n + 127) << 23);
+}
+static inline float vkr_pow(float x, float y) { return (x > 0.0f) ? vkr_exp2(y * vkr_log2(x)) : 0.0f; }
+/* srgb_utility.glsl:21-26 and 44-49 */
+static inline float vkr_linear_to_srgb(float c) {
+	c = vkr_clamp(c, 0.0f, 1.0f);
+	return (c <= 0.0031308f) ? (12.92f * c) : (1.055f * vkr_pow(c, 1.0f / 2.4f) - 0.055f);
+}
+static inline float vkr_srgb_to_linear(float c) {
+	c = vkr_clamp(c, 0.0f, 1.0f);
+	return (c <= 0.04045f) ? ((1.0f / 12.92f) * c) : vkr_pow(fmaf(c, 1.0f / 1.055f, 0.055f / 1.055f), 2.4f);
+}
+/* IEEE binary32 -> binary16, round to nearest even (packHalf2x16) */
+static inline uint32_t vkr_float_to_half(float f) {
+	const uint32_t u = f2u(f), sign = (u >> 16) & 0x8000u, a = u & 0x7fffffffu;
+	if (a > 0x7f800000u) return sign | 0x7e00u;               /* NaN */
+	if (a >= 0x47800000u) return sign | 0x7c00u;              /* >= 65536 (and inf): 65520 <= |f| rounds to inf below */
+	if (a < 0x33000001u) return sign;                         /* <= 2^-25: rounds to zero */
+	uint32_t exponent = a >> 23, mantissa = (a & 0x007fffffu) | 0x00800000u;
+	uint32_t shift, half;
+	if (exponent < 113u) { shift = 126u - exponent; half = 0u; }           /* subnormal half */
+	else { shift = 13u; half = (exponent - 112u) << 10; mantissa &= 0x007fffffu; }
+	const uint32_t kept = mantissa >> shift, rest = mantissa & ((1u << shift) - 1u), halfway = 1u << (shift - 1u);
+	half += kept;
+	if (rest > halfway || (rest == halfway && (half & 1u))) ++half;        /* carries into the exponent (and to inf) correctly */
+	return sign | half;
+}
+static inline uint32_t vkr_pack_half_2x16(float x, float y) { return vkr_float_to_half(x) | (vkr_float_to_half(y) << 16); }
+
 static inline v2 mk2(float x, float y) { v2 r = {x, y}; return r; }
 static inline v3 mk3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
 static inline float dot2(v2 a, v2 b) { return fmaf(a.y, b.y, a.x * b.x); }

@@ -25,6 +25,7 @@ typedef struct {
 	uint32_t show_polygonal_lights;    /* SHOW_POLYGONAL_LIGHTS */
 	uint32_t row_begin, row_end;       /* shade rows [row_begin,row_end) only; row_end = 0 means height */
 	uint32_t band_height, band_stride; /* if band_stride != 0: of those rows only the ones with (y - row_begin) % band_stride < band_height (bounded CPU samples) */
+	uint32_t output_srgb;              /* !OUTPUT_LINEAR_RGB: the shader itself converts to sRGB (UNORM swapchain); the half-bit split follows g_frame_bits in the constant block */
 } vkr_oracle_config_t;
 
 size_t vkr_oracle_light_stride(uint32_t max_light_vertex_count);

@@ -14,7 +14,7 @@ def dataset_for(cfg):
 	return "mini_mixed" if cfg.get("min_vertices", cfg["max_vertices"]) != cfg["max_vertices"] else "mini_city"
 
 
-def host_constants(info, width, height, lights, sample_count=1):
+def host_constants(info, width, height, lights, sample_count=1, frame_bits=0):
 	"""Constant block through the library's host-only loaders (device = NULL)."""
 	lib = api.load_library()
 	scene = api.Scene(); ltc = api.LtcTable(); noise = api.NoiseTable(); spec = api.SceneSpecification(); st = api.RenderSettings()
@@ -28,6 +28,8 @@ def host_constants(info, width, height, lights, sample_count=1):
 	lib.vkr_specify_default_render_settings(C.byref(st)); st.animate_noise = 0; st.exposure_factor = 1.0; st.sample_count = sample_count
 	size = lib.vkr_get_constants_size(C.byref(spec)); buf = (C.c_uint8 * size)()
 	lib.vkr_write_constants(buf, C.byref(spec), C.byref(st), C.byref(scene), C.byref(ltc), C.byref(noise), width, height)
+	if frame_bits:
+		lib.vkr_set_frame_bits(buf, frame_bits)
 	spec.polygonal_light_count = spec_count
 	lib.vkr_destroy_scene_specification(C.byref(spec)); lib.vkr_destroy_noise_table(C.byref(noise), None); lib.vkr_destroy_ltc_table(C.byref(ltc), None); lib.vkr_destroy_scene(C.byref(scene), None)
 	return bytes(buf)
@@ -36,4 +38,4 @@ def host_constants(info, width, height, lights, sample_count=1):
 def oracle_cfg(cfg, width=WIDTH, height=HEIGHT):
 	return dict(width=width, height=height, light_count=cfg["lights"], max_light_vertex_count=cfg["max_vertices"], min_light_vertex_count=cfg.get("min_vertices", cfg["max_vertices"]),
 		sample_count=cfg["samples"], sampling_strategies=cfg["strategy"], mis_heuristic=cfg["heuristic"], biased_sampling=cfg["biased"],
-		trace_shadow_rays=cfg["trace"], show_polygonal_lights=cfg["show_lights"])
+		trace_shadow_rays=cfg["trace"], show_polygonal_lights=cfg["show_lights"], output_srgb=cfg.get("srgb", 0))

@@ -99,7 +99,7 @@ def test_cuda_path_reproduces_reference_shader_fixture(name):
 	frame = H.open_frame(info)
 	try:
 		frame.configure(sample_count=cfg["samples"], strategy=cfg["strategy"], heuristic=cfg["heuristic"],
-			technique=api.TECHNIQUE_PSA_BIASED if cfg["biased"] else api.TECHNIQUE_PSA, trace_shadow_rays=cfg["trace"], show_lights=cfg["show_lights"], light_count=cfg["lights"])
+			technique=api.TECHNIQUE_PSA_BIASED if cfg["biased"] else api.TECHNIQUE_PSA, trace_shadow_rays=cfg["trace"], show_lights=cfg["show_lights"], light_count=cfg["lights"], output_srgb=cfg["srgb"], frame_bits=cfg["frame_bits"])
 		constants = frame.constants(WIDTH, HEIGHT)
 		assert constants == bytes(g[name + "/constants"])
 		vis, gb = frame.gbuffer_host(WIDTH, HEIGHT)

@@ -90,6 +90,35 @@ def test_stripes_tile_the_frame():
 		frame.close()
 
 
+def test_hdr_screenshot_halves_reassemble_to_the_half_precision_frame():
+	"""Output stage (shading_pass.frag.glsl:871-887): the two LDR frames of an HDR screenshot carry the low and the high
+	bytes of packHalf2x16(colour); put together they are the linear frame rounded to binary16, bit for bit."""
+	info = H.dataset("mini_city")
+	oi = H.OracleInputs(info)
+	frame = H.open_frame(info)
+	try:
+		w, h = 160, 96
+		frame.configure(sample_count=4, trace_shadow_rays=1, output_srgb=1, frame_bits=0)
+		constants = frame.constants(w, h)
+		gb = oi.gbuffer(w, h, constants, oi.visibility(w, h, constants))
+		srgb = frame.shade_host(w, h, gb)
+		ref_srgb, _ = oi.shade(H.oracle_config(frame, w, h), constants, gb)
+		assert np.array_equal(srgb.view(np.uint32), ref_srgb.view(np.uint32))
+		frame.configure(output_srgb=0)
+		linear = frame.shade_host(w, h, gb)
+		frame.configure(output_srgb=1, frame_bits=1); low = frame.shade_host(w, h, gb)
+		frame.configure(frame_bits=2); high = frame.shade_host(w, h, gb)
+		ref_high, _ = oi.shade(H.oracle_config(frame, w, h), frame.constants(w, h), gb)
+		assert np.array_equal(high.view(np.uint32), ref_high.view(np.uint32))
+	finally:
+		frame.close()
+	lo = np.rint(low[..., :3] * 255.0).astype(np.uint16); hi = np.rint(high[..., :3] * 255.0).astype(np.uint16)
+	assert np.array_equal(low[..., :3], lo.astype(np.float32) * np.float32(1.0 / 255.0)) and np.array_equal(high[..., :3], hi.astype(np.float32) * np.float32(1.0 / 255.0))
+	halves = (lo | (hi << 8)).astype(np.uint16)
+	assert np.array_equal(halves, linear[..., :3].astype(np.float16).view(np.uint16))
+	assert float(linear[..., :3].max()) > 0.0
+
+
 class _FullSize:
 	"""BASELINE config 3 on the device: 1920x1080, 8 quad lights, 64 spp, clamped optimal MIS, shadow rays on."""
 	W, H_, SPP = 1920, 1080, 64

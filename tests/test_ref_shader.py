@@ -25,10 +25,10 @@ def _golden():
 
 
 def _config_from_name(name):
-	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)$", name)
-	s, h, b, L, V, Vmin, S, t, l, M = (int(x) if x is not None else None for x in m.groups())
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_o(\d)(\d))?$", name)
+	s, h, b, L, V, Vmin, S, t, l, M, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
 	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
-		samples=S, trace=t, show_lights=l, materials=M)
+		samples=S, trace=t, show_lights=l, materials=M, srgb=srgb or 0, frame_bits=frame_bits or 0)
 
 
 def _names():
@@ -41,7 +41,7 @@ def test_oracle_reproduces_reference_shader_bit_for_bit(name):
 	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
 	sha = hashlib.sha256(open(info["vks"], "rb").read()).digest()
 	assert bytes(g[name + "/vks_sha256"]) == sha, "the synthetic scene generator drifted: regenerate with tools/make_ref_golden.py"
-	constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"])
+	constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"], frame_bits=cfg["frame_bits"])
 	assert constants == bytes(g[name + "/constants"]), "the constant block drifted"
 	vis = oi.visibility(WIDTH, HEIGHT, constants)
 	assert np.array_equal(vis, g[name + "/visibility"])

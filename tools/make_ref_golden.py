@@ -31,7 +31,7 @@ def main():
 	for cfg in R.configs():
 		name = dataset_for(cfg)
 		info = H.dataset(name); oi = H.OracleInputs(info)
-		constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"])
+		constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"], frame_bits=cfg.get("frame_bits", 0))
 		vis = oi.visibility(WIDTH, HEIGHT, constants)
 		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris)
 		key = cfg["name"]

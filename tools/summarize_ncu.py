@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarises an ncu capture of the shading megakernel into profiles/ (run here, no GPU needed).
 
-  python tools/summarize_ncu.py gpurun_out/r01_prof.ncu-rep gpurun_out/r01_launches.csv profiles/r01_v1
+  python tools/summarize_ncu.py gpurun_out/r01_prof.ncu-rep gpurun_out/r01_launches.csv profiles/r01_v1 [workload]
 
 Writes <out>_summary.md: launch list (share of the step per kernel), key metrics of the top kernel (duration, DRAM
 bytes, occupancy, issue utilisation, lanes per instruction), warp stall reasons and the hottest source lines
@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
 	"sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
 	"sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-	"gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic"]
+	"gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+	"sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic"]
 
 
 def launches(path):
@@ -123,6 +124,21 @@ def main():
 		lines += ["", "(source correlation skipped: the in-tree library does not match the profiled binary: %d vs %d instructions)" % (len(insts), len(prof))]
 	with open(out + "_summary.md", "w") as f:
 		f.write("\n".join(lines) + "\n")
+	if len(sys.argv) > 4:   # workload name: record the counters bench.py quotes in its roofline object
+		import json
+		def num(name): return float(m[name][0].replace(",", "")) if name in m else None
+		def in_bytes(name):
+			scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+			return num(name) * scale.get(m[name][1], 1.0) if name in m else 0.0
+		path = os.path.join(ROOT, "profiles", "kernel_counters.json")
+		data = json.load(open(path)) if os.path.exists(path) else {}
+		data[sys.argv[4]] = {"source": os.path.basename(out) + "_summary.md (ncu --set full --clock-control none, one launch)",
+			"dram_bytes_per_launch": int(in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")),
+			"issue_active_frac": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0, 4),
+			"l1_data_pipe_frac": round(num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0, 4) if num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") is not None else None,
+			"kernel_ms_under_ncu": round(num("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(m["gpu__time_duration.sum"][1], 1.0), 3)}
+		with open(path, "w") as f:
+			json.dump(data, f, indent=1)
 	print("\n".join(lines[:40]))
 
 

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
 	"vkr_load_noise_table", "vkr_destroy_noise_table", "vkr_set_noise_constants",
 	"vkr_update_polygonal_light", "vkr_set_polygonal_light_vertex_count", "vkr_destroy_polygonal_light",
 	"vkr_get_world_to_projection_space", "vkr_quick_load", "vkr_quick_save", "vkr_destroy_scene_specification",
-	"vkr_specify_default_render_settings", "vkr_get_constants_size", "vkr_write_constants",
+	"vkr_specify_default_render_settings", "vkr_get_constants_size", "vkr_write_constants", "vkr_set_frame_bits",
 	"vkr_gbuffer_size", "vkr_run_visibility_pass", "vkr_run_gbuffer_pass",
 	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait",
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_free_probe",
@@ -89,7 +89,7 @@ class ShadingPassDesc(C.Structure):
 		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
 		("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int), ("polygon_sampling_technique", C.c_int),
 		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("stripe_index", C.c_uint32), ("stripe_count", C.c_uint32),
-		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable))]
+		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable)), ("output_srgb", C.c_int)]
 
 
 class ShadingPass(C.Structure):
@@ -135,6 +135,7 @@ def load_library():
 	lib.vkr_get_constants_size.argtypes = [P(SceneSpecification)]; lib.vkr_get_constants_size.restype = C.c_size_t
 	lib.vkr_write_constants.argtypes = [C.c_void_p, P(SceneSpecification), P(RenderSettings), P(Scene), P(LtcTable), P(NoiseTable), C.c_uint32, C.c_uint32]
 	lib.vkr_write_constants.restype = C.c_size_t
+	lib.vkr_set_frame_bits.argtypes = [C.c_void_p, C.c_uint32]; lib.vkr_set_frame_bits.restype = None
 	lib.vkr_gbuffer_size.argtypes = [C.c_uint32, C.c_uint32]; lib.vkr_gbuffer_size.restype = C.c_size_t
 	lib.vkr_run_visibility_pass.argtypes = [P(Device), P(Scene), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
 	lib.vkr_run_gbuffer_pass.argtypes = [P(Device), P(Scene), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]

@@ -163,7 +163,7 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	p.light_count = (int) d.polygonal_light_count; p.max_light_vertex_count = (int) d.max_polygonal_light_vertex_count; p.sample_count = (int) d.sample_count;
 	p.sampling_strategies = (int) d.sampling_strategies; p.mis_heuristic = (int) d.mis_heuristic;
 	p.biased_sampling = d.polygon_sampling_technique == vkr_sample_polygon_projected_solid_angle_biased;
-	p.trace_shadow_rays = d.trace_shadow_rays; p.show_polygonal_lights = d.show_polygonal_lights;
+	p.trace_shadow_rays = d.trace_shadow_rays; p.show_polygonal_lights = d.show_polygonal_lights; p.output_srgb = d.output_srgb;
 	p.noise = (const uint16_t*) d.noise_table->d_noise; p.noise_w = (int) d.noise_table->width; p.noise_h = (int) d.noise_table->height; p.noise_layers = (int) d.noise_table->layers;
 	p.ltc0 = (const uint16_t*) d.ltc_table->d_table0; p.ltc1 = (const uint16_t*) d.ltc_table->d_table1;
 	p.ltc_res = (int) d.ltc_table->roughness_count; p.ltc_layers = (int) d.ltc_table->fresnel_count;

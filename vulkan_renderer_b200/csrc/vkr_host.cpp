@@ -650,6 +650,10 @@ void invert_4x4(float inverse[4][4], const float matrix[4][4]) {
 }
 }
 
+extern "C" void vkr_set_frame_bits(void* constants, uint32_t frame_bits) {
+	memcpy((char*) constants + 196, &frame_bits, sizeof(frame_bits)); // per_frame_constants_t::frame_bits (main.h:499)
+}
+
 extern "C" size_t vkr_write_constants(void* data, const vkr_scene_specification_t* spec, const vkr_render_settings_t* settings,
 	const vkr_scene_t* scene, const vkr_ltc_table_t* ltc, vkr_noise_table_t* noise, uint32_t width, uint32_t height)
 {

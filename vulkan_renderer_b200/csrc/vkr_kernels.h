@@ -22,6 +22,7 @@ struct shading_kernel_params {
 	// what the reference passes as -D defines (src/main.c:752-792)
 	int light_count, max_light_vertex_count, sample_count;
 	int sampling_strategies, mis_heuristic, biased_sampling, trace_shadow_rays, show_polygonal_lights;
+	int output_srgb;                 // !OUTPUT_LINEAR_RGB (src/main.c:790); the half-bit split follows frame_bits in the constant block
 	// tables
 	const uint16_t* noise; int noise_w, noise_h, noise_layers;
 	const uint16_t* ltc0; const uint16_t* ltc1; int ltc_res, ltc_layers;

@@ -13,7 +13,7 @@ namespace vkr {
 // Byte offsets in the per-frame constant block (src/main.h:488-505, shared_constants.glsl:20-66)
 enum {
 	OFF_PIXEL_TO_RAY = 96, OFF_CAMERA = 144, OFF_MIS_VIS = 156, OFF_EXPOSURE = 176,
-	OFF_NOISE_RES_MASK = 184, OFF_NOISE_LAYER_MASK = 192, OFF_NOISE_RANDOM = 208, OFF_LTC = 224, CONSTANTS_FIXED = 256,
+	OFF_NOISE_RES_MASK = 184, OFF_NOISE_LAYER_MASK = 192, OFF_FRAME_BITS = 196, OFF_NOISE_RANDOM = 208, OFF_LTC = 224, CONSTANTS_FIXED = 256,
 	// inside one light block (polygonal_light_utility.glsl:26-83)
 	L_SURFACE_RADIANCE = 48, L_PLANE = 64, L_VERTEX_COUNT = 80, L_FIXED = 160
 };

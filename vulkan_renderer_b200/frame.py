@@ -32,8 +32,10 @@ class Frame:
 			raise RuntimeError("%s failed with code %d" % (what, code))
 
 	# ---- settings
-	def configure(self, sample_count=None, strategy=None, heuristic=None, technique=None, trace_shadow_rays=None, show_lights=None, light_count=None):
+	def configure(self, sample_count=None, strategy=None, heuristic=None, technique=None, trace_shadow_rays=None, show_lights=None, light_count=None, output_srgb=None, frame_bits=None):
 		s = self.settings
+		if output_srgb is not None: self.output_srgb = int(output_srgb)     # !OUTPUT_LINEAR_RGB (src/main.c:790)
+		if frame_bits is not None: self.frame_bits = int(frame_bits)         # screenshot.frame_bits (src/main.c:2132)
 		if sample_count is not None: s.sample_count = sample_count
 		if strategy is not None: s.sampling_strategies = strategy
 		if heuristic is not None: s.mis_heuristic = heuristic
@@ -63,6 +65,8 @@ class Frame:
 			buf = (C.c_uint8 * size)()
 			written = self.lib.vkr_write_constants(buf, C.byref(spec), C.byref(self.settings), C.byref(self.scene), C.byref(self.ltc), C.byref(self.noise), width, height)
 			assert written == size, (written, size)
+			if getattr(self, "frame_bits", 0):
+				self.lib.vkr_set_frame_bits(buf, self.frame_bits)
 		finally:
 			spec.polygonal_light_count = saved
 		return bytes(buf)
@@ -79,6 +83,7 @@ class Frame:
 		d.trace_shadow_rays = s.trace_shadow_rays; d.show_polygonal_lights = s.show_polygonal_lights
 		d.stripe_index, d.stripe_count = stripe_index, stripe_count
 		d.scene = C.pointer(self.scene); d.ltc_table = C.pointer(self.ltc); d.noise_table = C.pointer(self.noise)
+		d.output_srgb = getattr(self, "output_srgb", 0)
 		return d
 
 	def create_pass(self, width, height, stripe_index=0, stripe_count=1, timing=False):
