@@ -108,6 +108,12 @@ def default_configs():
 	configs.append(dict(base, max_vertices=3, strategy=1, heuristic=0))
 	configs.append(dict(base, max_vertices=4, min_vertices=3))             # triangle, quad, triangle (data set mini_mixed)
 	configs.append(dict(base, max_vertices=4, min_vertices=3, strategy=1, heuristic=1))
+	configs.append(dict(base, lights=32, samples=2))                       # many lights (data set mini_room): the shape of BASELINE config 4
+	configs.append(dict(base, lights=16, samples=1, strategy=1, heuristic=0))
+	configs.append(dict(base, lights=1, samples=256))                      # config 4's sample count: 4 periods of the noise sequence
+	configs.append(dict(base, trace=0))                                    # TRACE_SHADOW_RAYS=0 with the other strategies
+	configs.append(dict(base, trace=0, strategy=1, heuristic=1))
+	configs.append(dict(base, trace=0, heuristic=4))
 	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
 		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs

@@ -9,6 +9,8 @@ WIDTH, HEIGHT = 64, 48
 def dataset_for(cfg):
 	if cfg["materials"] == 3:
 		return "cornell"
+	if cfg["lights"] > 3:
+		return "mini_room"
 	if cfg["max_vertices"] == 3:
 		return "mini_tri"
 	return "mini_mixed" if cfg.get("min_vertices", cfg["max_vertices"]) != cfg["max_vertices"] else "mini_city"

@@ -350,7 +350,7 @@ def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0
 def build_dataset(directory, name, **overrides):
 	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
 	os.makedirs(directory, exist_ok=True)
-	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3}.get(name, 9))
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4}.get(name, 9))
 	if name == "cornell":
 		mesh, materials = scene_cornell()
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
@@ -376,6 +376,11 @@ def build_dataset(directory, name, **overrides):
 		for i, light in enumerate(lights):
 			if name == "mini_tri" or i != 1:
 				light["vertices"] = [(float(x), float(y)) for x, y in triangle]
+	elif name == "mini_room":
+		# small closed room with 32 lights: the many-lights shape of BASELINE config 4 (constant block of 10 KB)
+		mesh, materials = scene_room(seed=4, detail=6, clutter=60, n_mat=8)
+		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
+		lights = _ceiling_lights(rng, overrides.get("lights", 32), (1.0, 11.0), (1.0, 7.0), (2.4, 3.3), scale_range=(0.3, 1.0))
 	elif name == "room":
 		mesh, materials = scene_room(**{k: v for k, v in overrides.items() if k in ("seed", "detail", "clutter", "n_mat")})
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
