@@ -108,6 +108,12 @@ def default_configs():
 	configs.append(dict(base, max_vertices=3, strategy=1, heuristic=0))
 	configs.append(dict(base, max_vertices=4, min_vertices=3))             # triangle, quad, triangle (data set mini_mixed)
 	configs.append(dict(base, max_vertices=4, min_vertices=3, strategy=1, heuristic=1))
+	configs.append(dict(base, max_vertices=7, min_vertices=5))             # pentagon, heptagon, hexagon (data set mini_poly)
+	configs.append(dict(base, max_vertices=7, min_vertices=5, strategy=0, heuristic=0))
+	configs.append(dict(base, max_vertices=7, min_vertices=5, strategy=1, heuristic=0))
+	configs.append(dict(base, max_vertices=5))                             # pentagons (mini_v5)
+	configs.append(dict(base, max_vertices=6, strategy=2, heuristic=0))    # hexagons (mini_v6)
+	configs.append(dict(base, max_vertices=7, strategy=4, heuristic=0))    # heptagons (mini_v7)
 	configs.append(dict(base, lights=32, samples=2))                       # many lights (data set mini_room): the shape of BASELINE config 4
 	configs.append(dict(base, lights=16, samples=1, strategy=1, heuristic=0))
 	configs.append(dict(base, lights=1, samples=256))                      # config 4's sample count: 4 periods of the noise sequence

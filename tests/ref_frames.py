@@ -11,6 +11,9 @@ def dataset_for(cfg):
 		return "cornell"
 	if cfg["lights"] > 3:
 		return "mini_room"
+	if cfg["max_vertices"] >= 5:
+		vmin = cfg.get("min_vertices", cfg["max_vertices"])
+		return "mini_poly" if vmin != cfg["max_vertices"] else "mini_v%d" % cfg["max_vertices"]
 	if cfg["max_vertices"] == 3:
 		return "mini_tri"
 	return "mini_mixed" if cfg.get("min_vertices", cfg["max_vertices"]) != cfg["max_vertices"] else "mini_city"

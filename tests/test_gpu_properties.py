@@ -39,11 +39,11 @@ def test_ragged_frame_sizes(width, height):
 	assert np.array_equal(out_gpu.view(np.uint32), out_cpu.view(np.uint32)), H.compare_radiance(out_gpu, out_cpu)
 
 
-@pytest.mark.parametrize("name", ["mini_tri", "mini_mixed"])
+@pytest.mark.parametrize("name", ["mini_tri", "mini_mixed", "mini_v5", "mini_v6", "mini_v7", "mini_poly"])
 @pytest.mark.parametrize("strategy,heuristic", [(api.STRATEGY_DIFFUSE_ONLY, api.MIS_BALANCE), (api.STRATEGY_DIFFUSE_GGX_MIS, api.MIS_POWER),
 	(api.STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, api.MIS_BALANCE), (api.STRATEGY_DIFFUSE_SPECULAR_MIS, api.MIS_OPTIMAL), (api.STRATEGY_DIFFUSE_SPECULAR_RANDOM, api.MIS_BALANCE)])
 def test_triangle_and_mixed_lights(name, strategy, heuristic):
-	"""MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 3, and lights of 3 and 4 vertices in one frame (MIN < MAX)."""
+	"""MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 3, 5, 6, 7 and lights of different vertex counts in one frame (MIN < MAX)."""
 	out_gpu, out_cpu = _both(name, 96, 64, sample_count=3, strategy=strategy, heuristic=heuristic, trace_shadow_rays=1)
 	assert np.array_equal(out_gpu.view(np.uint32), out_cpu.view(np.uint32)), H.compare_radiance(out_gpu, out_cpu)
 	assert float(out_cpu[..., :3].max()) > 0.0

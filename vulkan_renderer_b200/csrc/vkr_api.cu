@@ -91,8 +91,8 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 		printf("Failed to create the shading pass: GGX importance sampling supports the balance and power heuristics only.\n");
 		memset(pass, 0, sizeof(*pass)); return 1;
 	}
-	if (d.max_polygonal_light_vertex_count < 3 || d.max_polygonal_light_vertex_count > 4 || d.min_polygonal_light_vertex_count < 3 || d.min_polygonal_light_vertex_count > d.max_polygonal_light_vertex_count) {
-		printf("Failed to create the shading pass: polygonal lights must have 3 or 4 vertices (got min %u, max %u).\n", d.min_polygonal_light_vertex_count, d.max_polygonal_light_vertex_count);
+	if (d.max_polygonal_light_vertex_count < 3 || d.max_polygonal_light_vertex_count > 7 || d.min_polygonal_light_vertex_count < 3 || d.min_polygonal_light_vertex_count > d.max_polygonal_light_vertex_count) {
+		printf("Failed to create the shading pass: polygonal lights must have 3 to 7 vertices (got min %u, max %u).\n", d.min_polygonal_light_vertex_count, d.max_polygonal_light_vertex_count);
 		memset(pass, 0, sizeof(*pass)); return 1;
 	}
 	if (!d.width || !d.height || d.stripe_index >= d.stripe_count || !d.sample_count || !d.ltc_table || !d.noise_table || !d.ltc_table->d_table0 || !d.noise_table->d_noise) {
@@ -120,6 +120,17 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 	}
 	pass->event_begin = e0; pass->event_end = e1;
 	return 0;
+}
+
+cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream) {
+	switch (p.max_light_vertex_count) { // MAX_POLYGONAL_LIGHT_VERTEX_COUNT, a compile-time bound of the kernels
+	case 3: return vkr_launch_shading_kernel_maxp4(p, stream);
+	case 4: return vkr_launch_shading_kernel_maxp5(p, stream);
+	case 5: return vkr_launch_shading_kernel_maxp6(p, stream);
+	case 6: return vkr_launch_shading_kernel_maxp7(p, stream);
+	case 7: return vkr_launch_shading_kernel_maxp8(p, stream);
+	default: return cudaErrorInvalidValue;
+	}
 }
 
 static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out) {
@@ -283,7 +294,7 @@ extern "C" int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene
 }
 
 extern "C" int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t vertex_count, const float* vertices_xyz, int biased, uint32_t n, const float* random_numbers, float* out_dirs, float* out_info) {
-	if (vertex_count != 3 && vertex_count != 4) { printf("The sampling probe supports 3 or 4 vertices.\n"); return 1; }
+	if (vertex_count < 3 || vertex_count > 7) { printf("The sampling probe supports 3 to 7 vertices.\n"); return 1; }
 	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
 	cudaStream_t stream = (cudaStream_t) device->stream;
 	float *d_v = nullptr, *d_r = nullptr, *d_d = nullptr, *d_i = nullptr;
@@ -296,8 +307,9 @@ extern "C" int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t ver
 	cudaMemcpyAsync(d_r, random_numbers, sizeof(float) * 2 * (size_t) n, cudaMemcpyHostToDevice, stream);
 	cudaMemsetAsync(d_d, 0, sizeof(float) * 3 * nn, stream);
 	const unsigned blocks = (unsigned) ((nn + 127) / 128);
-	if (vertex_count == 4) { if (biased) sample_probe_kernel<5, true><<<blocks, 128, 0, stream>>>(4, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<5, false><<<blocks, 128, 0, stream>>>(4, d_v, n, d_r, d_d, d_i); }
-	else { if (biased) sample_probe_kernel<4, true><<<blocks, 128, 0, stream>>>(3, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<4, false><<<blocks, 128, 0, stream>>>(3, d_v, n, d_r, d_d, d_i); }
+#define VKR_PROBE(V) case V: if (biased) sample_probe_kernel<V + 1, true><<<blocks, 128, 0, stream>>>(V, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<V + 1, false><<<blocks, 128, 0, stream>>>(V, d_v, n, d_r, d_d, d_i); break;
+	switch (vertex_count) { VKR_PROBE(3) VKR_PROBE(4) VKR_PROBE(5) VKR_PROBE(6) VKR_PROBE(7) default: break; }
+#undef VKR_PROBE
 	cudaError_t err = cudaGetLastError();
 	cudaMemcpyAsync(out_dirs, d_d, sizeof(float) * 3 * (size_t) n, cudaMemcpyDeviceToHost, stream);
 	if (out_info) cudaMemcpyAsync(out_info, d_i, sizeof(float) * 11, cudaMemcpyDeviceToHost, stream);

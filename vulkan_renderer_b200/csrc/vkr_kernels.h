@@ -45,6 +45,11 @@ struct gbuffer_kernel_params {
 
 } // namespace vkr
 
-cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream);   // dispatches on max_light_vertex_count (vkr_api.cu)
+cudaError_t vkr_launch_shading_kernel_maxp4(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_shading_kernel.cu, one object per vertex bound
+cudaError_t vkr_launch_shading_kernel_maxp5(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_shading_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_shading_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_shading_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_visibility_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_gbuffer_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);

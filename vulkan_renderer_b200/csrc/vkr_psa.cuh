@@ -46,12 +46,12 @@ VKR_DEV f3 horizon_crossing(f3 a, f3 b) {
 	return make3(fmaf(w, b.x, fmaf(-w, a.x, a.x)), fmaf(w, b.y, fmaf(-w, a.y, a.y)), 0.0f);
 }
 
-// Clips a convex polygon with n in {3,4} (<= MAXP-1) vertices against z >= 0. The slot each
+// Clips a convex polygon with n in 3..7 (<= MAXP-1) vertices against z >= 0. The slot each
 // output vertex lands in follows the reference (the first vertex defines sector 0 later on).
 // The first output vertex is repeated at index vc when vc < MAXP. Returns vc (0, or 3..n+1).
 template <int MAXP>
 VKR_DEV int clip_polygon(int n, f3 (&v)[MAXP]) {
-	static_assert(MAXP == 4 || MAXP == 5, "light polygons with 3 or 4 vertices");
+	static_assert(MAXP >= 4 && MAXP <= 8, "light polygons with 3 to 7 vertices");
 	f3 in[MAXP - 1];
 #pragma unroll
 	for (int i = 0; i != MAXP - 1; ++i) in[i] = v[i];
@@ -61,26 +61,48 @@ VKR_DEV int clip_polygon(int n, f3 (&v)[MAXP]) {
 	int vc = 0;
 #define P(k) in[k]
 #define OUT(slot, value) v[slot] = (value)
+#define X(k) horizon_crossing(in[k], in[(k + 1) % VKR_CLIP_N])
 	if (n == 3) {
-#define X(k) horizon_crossing(in[k], in[(k + 1) % 3])
 #define VKR_CLIP_N 3
 		switch (bits) {
 #include "vkr_clip_cases.inc"
 		default: vc = 0; break;
 		}
 #undef VKR_CLIP_N
-#undef X
 	}
-	else if (MAXP == 5) {
-#define X(k) horizon_crossing(in[k], in[(k + 1) % (MAXP - 1)])
+	if constexpr (MAXP >= 5) if (n == 4) {
 #define VKR_CLIP_N 4
 		switch (bits) {
 #include "vkr_clip_cases.inc"
 		default: vc = 0; break;
 		}
 #undef VKR_CLIP_N
-#undef X
 	}
+	if constexpr (MAXP >= 6) if (n == 5) {
+#define VKR_CLIP_N 5
+		switch (bits) {
+#include "vkr_clip_cases.inc"
+		default: vc = 0; break;
+		}
+#undef VKR_CLIP_N
+	}
+	if constexpr (MAXP >= 7) if (n == 6) {
+#define VKR_CLIP_N 6
+		switch (bits) {
+#include "vkr_clip_cases.inc"
+		default: vc = 0; break;
+		}
+#undef VKR_CLIP_N
+	}
+	if constexpr (MAXP >= 8) if (n == 7) {
+#define VKR_CLIP_N 7
+		switch (bits) {
+#include "vkr_clip_cases.inc"
+		default: vc = 0; break;
+		}
+#undef VKR_CLIP_N
+	}
+#undef X
 #undef OUT
 #undef P
 #pragma unroll
@@ -184,18 +206,25 @@ VKR_DEV void compare_and_swap(psa_polygon<MAXP>& p) {
 }
 
 template <int MAXP>
-VKR_DEV void sort_convex_polygon_vertices(psa_polygon<MAXP>& p) { // :440-505, networks for <= 5 vertices
+VKR_DEV void sort_convex_polygon_vertices(psa_polygon<MAXP>& p) { // :440-505, one network per vertex count
 	if (p.vertex_count == 3) compare_and_swap<1, 2>(p);
-	else if (MAXP >= 4 && p.vertex_count == 4) compare_and_swap<1, (MAXP >= 4 ? 3 : 0)>(p);
-	else if (MAXP >= 5 && p.vertex_count == 5) {
-		compare_and_swap<(MAXP >= 5 ? 2 : 0), (MAXP >= 5 ? 4 : 1)>(p);
-		compare_and_swap<1, (MAXP >= 5 ? 3 : 0)>(p);
-		compare_and_swap<1, 2>(p);
-		compare_and_swap<0, (MAXP >= 5 ? 3 : 1)>(p);
-		compare_and_swap<(MAXP >= 5 ? 3 : 0), (MAXP >= 5 ? 4 : 1)>(p);
+	if constexpr (MAXP >= 4) if (p.vertex_count == 4) compare_and_swap<1, 3>(p);
+	if constexpr (MAXP >= 5) if (p.vertex_count == 5) {
+		compare_and_swap<2, 4>(p); compare_and_swap<1, 3>(p); compare_and_swap<1, 2>(p); compare_and_swap<0, 3>(p); compare_and_swap<3, 4>(p);
+	}
+	if constexpr (MAXP >= 6) if (p.vertex_count == 6) {
+		compare_and_swap<3, 5>(p); compare_and_swap<2, 4>(p); compare_and_swap<1, 5>(p); compare_and_swap<0, 4>(p); compare_and_swap<4, 5>(p); compare_and_swap<1, 3>(p);
+	}
+	if constexpr (MAXP >= 7) if (p.vertex_count == 7) {
+		compare_and_swap<2, 5>(p); compare_and_swap<1, 6>(p); compare_and_swap<5, 6>(p); compare_and_swap<3, 4>(p); compare_and_swap<0, 4>(p);
+		compare_and_swap<4, 6>(p); compare_and_swap<1, 3>(p); compare_and_swap<3, 5>(p); compare_and_swap<4, 5>(p);
+	}
+	if constexpr (MAXP >= 8) if (p.vertex_count == 8) {
+		compare_and_swap<2, 6>(p); compare_and_swap<3, 7>(p); compare_and_swap<1, 5>(p); compare_and_swap<0, 4>(p); compare_and_swap<4, 6>(p);
+		compare_and_swap<5, 7>(p); compare_and_swap<6, 7>(p); compare_and_swap<4, 5>(p); compare_and_swap<1, 3>(p);
 	}
 	compare_and_swap<0, 2>(p);
-	if (MAXP >= 4 && p.vertex_count >= 4) compare_and_swap<2, (MAXP >= 4 ? 3 : 0)>(p);
+	if constexpr (MAXP >= 4) if (p.vertex_count >= 4) compare_and_swap<2, 3>(p);
 	compare_and_swap<0, 1>(p);
 }
 

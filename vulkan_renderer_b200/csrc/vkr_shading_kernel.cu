@@ -422,11 +422,13 @@ static cudaError_t launch_strategy(const shading_kernel_params& p, cudaStream_t 
 	}
 }
 
-cudaError_t vkr_launch_shading_kernel(const shading_kernel_params& p, cudaStream_t stream) {
+// One translation unit per vertex bound (built with -DVKR_MAXP_TU=4 .. 8, __graft_entry__.py): MAXP = light vertices + 1.
+#ifndef VKR_MAXP_TU
+#error "compile with -DVKR_MAXP_TU=<4..8>"
+#endif
+#define VKR_CONCAT2(a, b) a##b
+#define VKR_CONCAT(a, b) VKR_CONCAT2(a, b)
+cudaError_t VKR_CONCAT(vkr_launch_shading_kernel_maxp, VKR_MAXP_TU)(const shading_kernel_params& p, cudaStream_t stream) {
 	if (p.stack_depth < 2 || p.stack_depth > kMaxStackDepth) return cudaErrorInvalidValue;
-	if (p.max_light_vertex_count == 4)
-		return p.biased_sampling ? launch_strategy<5, true>(p, stream) : launch_strategy<5, false>(p, stream);
-	if (p.max_light_vertex_count == 3)
-		return p.biased_sampling ? launch_strategy<4, true>(p, stream) : launch_strategy<4, false>(p, stream);
-	return cudaErrorInvalidValue;
+	return p.biased_sampling ? launch_strategy<VKR_MAXP_TU, true>(p, stream) : launch_strategy<VKR_MAXP_TU, false>(p, stream);
 }

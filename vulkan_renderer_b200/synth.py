@@ -350,7 +350,7 @@ def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0
 def build_dataset(directory, name, **overrides):
 	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
 	os.makedirs(directory, exist_ok=True)
-	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4}.get(name, 9))
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4, "mini_v5": 3, "mini_v6": 3, "mini_v7": 3, "mini_poly": 3}.get(name, 9))
 	if name == "cornell":
 		mesh, materials = scene_cornell()
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
@@ -376,6 +376,16 @@ def build_dataset(directory, name, **overrides):
 		for i, light in enumerate(lights):
 			if name == "mini_tri" or i != 1:
 				light["vertices"] = [(float(x), float(y)) for x, y in triangle]
+	elif name in ("mini_v5", "mini_v6", "mini_v7", "mini_poly"):
+		# the mini_city scene lit by convex pentagons / hexagons / heptagons (MAX_POLYGONAL_LIGHT_VERTEX_COUNT up to 7), or by
+		# one of each in one frame
+		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
+		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
+		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+		counts = {"mini_v5": [5, 5, 5], "mini_v6": [6, 6, 6], "mini_v7": [7, 7, 7], "mini_poly": [5, 7, 6]}[name]
+		for light, n in zip(lights, counts * (len(lights) // 3 + 1)):
+			phase = 0.3 * n
+			light["vertices"] = [(0.5 + 0.5 * float(np.cos(phase + 2.0 * np.pi * k / n)), 0.5 + 0.5 * float(np.sin(phase + 2.0 * np.pi * k / n))) for k in range(n)]
 	elif name == "mini_room":
 		# small closed room with 32 lights: the many-lights shape of BASELINE config 4 (constant block of 10 KB)
 		mesh, materials = scene_room(seed=4, detail=6, clutter=60, n_mat=8)
