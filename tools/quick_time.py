@@ -26,7 +26,4 @@ for i in range(3):
 	lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr())
 	lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device))
 	print("spp %d lights %d rays %d strategy %d: kernel %.3f ms -> %.1f Msamples/s" % (spp, lights, rays, strategy, p.last_kernel_ms, width * height * spp / p.last_kernel_ms / 1e3), flush=True)
-if hasattr(lib, "vkr_debug_stats"):
-	st = (C.c_ulonglong * 8)(); lib.vkr_debug_stats(st, 1); st = list(st)
-	print("stats over 3 frames: rays %d, from root %.4f, node visits/ray %.2f, cuts %d, entries/cut %.2f, walk levels/cut %.2f" % (st[0], st[1] / max(1, st[0]), st[2] / max(1, st[0]), st[3], st[4] / max(1, st[3]), st[5] / max(1, st[3])))
 print("valid fraction", float((gb[1, :, :, 3] != 0).float().mean()), "mean radiance", float(out[..., :3].mean()))

@@ -60,13 +60,21 @@ def sass_profile(rep):
 	return prof, stall_tot
 
 
-def line_info(kernel_mangled_regex):
-	lib = os.path.join(ROOT, "vulkan_renderer_b200", "libvkr_b200.so")
+def line_info(kernel_mangled_regex, maxp):
+	"""SASS line table of the kernel from the in-tree object of its vertex bound (build/vkr_shading_kernel_maxp<k>.cu.o)."""
+	obj = os.path.join(ROOT, "vulkan_renderer_b200", "build", "vkr_shading_kernel_maxp%s.cu.o" % maxp)
+	if not os.path.exists(obj):
+		return []
 	tmp = tempfile.mkdtemp()
-	subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-	cubin = os.path.join(tmp, "vkr_shading_kernel.sm_100a.cubin")
-	text = subprocess.run(["nvdisasm", "-g", "-c", cubin], stdout=subprocess.PIPE, text=True).stdout.split("\n")
-	start = [i for i, l in enumerate(text) if re.match(r"\.text\." + kernel_mangled_regex + ":", l)]
+	subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+	text, start = [], []
+	for name in sorted(os.listdir(tmp)):
+		if not name.endswith(".cubin"):
+			continue
+		text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, name)], stdout=subprocess.PIPE, text=True).stdout.split("\n")
+		start = [i for i, l in enumerate(text) if re.match(r"\.text\." + kernel_mangled_regex + ":", l)]
+		if start:
+			break
 	if not start:
 		return []
 	insts = []; cur = ("?", 0)
@@ -102,7 +110,7 @@ def main():
 	if mm:
 		args = re.findall(r"\d+", re.sub(r"\((int|bool)\)", "", mm.group(1)))
 		mangled = "".join("L%s%sE" % ("i" if k < 2 else "b", a) for k, a in enumerate(args))
-		insts = line_info(r"_ZN3vkr14shading_kernelI%sEEvNS_21shading_kernel_paramsE" % mangled)
+		insts = line_info(r"_ZN3vkr14shading_kernelI%sEEvNS_21shading_kernel_paramsE" % mangled, args[1])
 	if insts and len(insts) == len(prof):
 		by = collections.defaultdict(lambda: [0.0, 0.0, 0.0]); byfile = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
 		for (a, c, t, s), key in zip(prof, insts):

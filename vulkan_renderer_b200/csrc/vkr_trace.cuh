@@ -75,62 +75,8 @@ VKR_DEV bool ray_box(float cx, float cy, float cz, float hx, float hy, float hz,
 	return tn <= tf;
 }
 
-// Warp-wide any-hit query: ALL 32 lanes call it together; lanes without a ray pass has_ray = false.
-// Speculative while-while traversal: a lane that reaches a leaf postpones it and keeps descending until it finds a
-// second leaf or runs out of nodes, then the warp tests triangles together (leaf tests used to run at ~4 of 32 lanes).
-// stack = this lane's column of the warp's shared-memory stack (stride in ints between levels).
-VKR_DEV bool occluded_warp(const bvh_view& bvh, bool has_ray, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
-	const unsigned full = 0xffffffffu;
-	const ray_slabs r = make_slabs(o, d);
-	int node = (has_ray && tmax > tmin) ? 0 : kTraversalDone; // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
-	int leaf = 0;      // postponed leaf reference (0 = none; leaf references are negative)
-	int sp = 0;
-	bool hit = false;
-	while (__any_sync(full, node != kTraversalDone || leaf != 0)) {
-		// --- descend until this lane holds two leaves or is out of nodes
-		while (node >= 0 && node != kTraversalDone) {
-			const float4* n = bvh.nodes + 4 * (size_t) node;
-			const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3);
-			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
-			float tn0, tn1;
-			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
-			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
-			if (h0 && h1) {
-				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
-				node = swap ? ref1 : ref0;
-				stack[sp * stride] = swap ? ref0 : ref1; ++sp;
-			}
-			else if (h0) node = ref0;
-			else if (h1) node = ref1;
-			else if (sp > 0) { --sp; node = stack[sp * stride]; }
-			else node = kTraversalDone;
-			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
-				leaf = node;
-				if (sp > 0) { --sp; node = stack[sp * stride]; }
-				else node = kTraversalDone;
-			}
-		}
-		__syncwarp(full);
-		// --- leaves: `leaf` and possibly `node` (a second leaf)
-		while (leaf != 0) {
-			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
-			float t;
-			for (int i = 0; i != count; ++i)
-				if (ray_triangle(bvh.tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) hit = true;
-			leaf = 0;
-			if (hit) { node = kTraversalDone; sp = 0; }
-			else if (node < 0) {
-				leaf = node;
-				if (sp > 0) { --sp; node = stack[sp * stride]; }
-				else node = kTraversalDone;
-			}
-		}
-		__syncwarp(full);
-	}
-	return hit;
-}
-
-// Per-thread any-hit query (probe kernel); same traversal without warp collectives.
+// Per-thread any-hit query (probe kernel vkr_trace_shadow_rays); the shading kernel's own traversal loop lives in
+// vkr_ray_stream.cuh (trace warps), built from the same ray_box / ray_triangle.
 VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
 	if (!(tmax > tmin)) return false;
 	const ray_slabs r = make_slabs(o, d);
