@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
 
 class Config(C.Structure):
 	_fields_ = [(n, C.c_uint32) for n in ("width", "height", "light_count", "max_light_vertex_count", "min_light_vertex_count", "sample_count",
-		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride", "output_srgb")]
+		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride", "polygon_sampling_technique", "output_srgb")]
 
 
 _lib = None
@@ -39,7 +39,7 @@ def _p(a):
 def shade(cfg, constants, gbuffer, noise, ltc0, ltc1, tris):
 	"""cfg: dict of Config fields. Returns (rgba float32 [H,W,4], shadow ray count)."""
 	lib = load()
-	c = Config(**cfg)
+	c = Config(**{"polygon_sampling_technique": 11, **cfg})
 	gbuffer = np.ascontiguousarray(gbuffer, dtype=np.float32)
 	noise = np.ascontiguousarray(noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(ltc1, dtype=np.uint16)
 	tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)

@@ -27,13 +27,21 @@ CXX = "/usr/bin/g++"
 
 STRATEGIES = ["DIFFUSE_ONLY", "DIFFUSE_GGX_MIS", "DIFFUSE_SPECULAR_SEPARATELY", "DIFFUSE_SPECULAR_MIS", "DIFFUSE_SPECULAR_RANDOM"]
 HEURISTICS = ["BALANCE", "POWER", "WEIGHTED", "OPTIMAL_CLAMPED", "OPTIMAL"]
-TECHNIQUES = ["BASELINE", "AREA_TURK", "SOLID_ANGLE_ARVO", "RECTANGLE_SOLID_ANGLE_URENA", "SOLID_ANGLE", "CLIPPED_SOLID_ANGLE", "BILINEAR_COSINE_WARP_HART",
+# index = sample_polygon_technique_t (src/polygonal_light.h:30-66); 12 = the biased variant of 11 (c["biased"])
+TECHNIQUES = ["BASELINE", "AREA_TURK", "RECTANGLE_SOLID_ANGLE_URENA", "SOLID_ANGLE_ARVO", "SOLID_ANGLE", "CLIPPED_SOLID_ANGLE", "BILINEAR_COSINE_WARP_HART",
 	"BILINEAR_COSINE_WARP_CLIPPING_HART", "BIQUADRATIC_COSINE_WARP_HART", "BIQUADRATIC_COSINE_WARP_CLIPPING_HART", "PROJECTED_SOLID_ANGLE_ARVO", "PROJECTED_SOLID_ANGLE"]
+CLIPPING_TECHNIQUES = (5, 7, 9, 10, 11)   # get_max_polygon_vertex_count (src/main.c:194-216): clipping may add one vertex
+# error_display_t (src/main.h:95-112) -> (ERROR_DISPLAY_DIFFUSE, ERROR_DISPLAY_SPECULAR, ERROR_INDEX), src/main.c:735-750
+ERROR_DISPLAYS = {0: (0, 0, 0), 1: (1, 0, 0), 2: (1, 0, 1), 3: (1, 0, 2), 4: (0, 1, 0), 5: (0, 1, 1), 6: (0, 1, 2)}
 
 
 def config_name(c):
 	vertices = "%d" % c["max_vertices"] if c.get("min_vertices", c["max_vertices"]) == c["max_vertices"] else "%dm%d" % (c["max_vertices"], c["min_vertices"])
 	name = "s%d_h%d_b%d_L%d_V%s_S%d_t%d_l%d_M%d" % (c["strategy"], c["heuristic"], c["biased"], c["lights"], vertices, c["samples"], c["trace"], c["show_lights"], c["materials"])
+	if c.get("technique", 11) != 11:                 # related-work sampling technique: q<sample_polygon_technique_t>
+		name += "_q%d" % c["technique"]
+	if c.get("error_display", 0):
+		name += "_e%d" % c["error_display"]
 	if c.get("srgb", 0) or c.get("frame_bits", 0):   # output stage: o<srgb><frame_bits>
 		name += "_o%d%d" % (c.get("srgb", 0), c.get("frame_bits", 0))
 	return name
@@ -45,16 +53,17 @@ def defines(c):
 		"MATERIAL_COUNT": c["materials"], "POLYGONAL_LIGHT_COUNT": c["lights"], "POLYGONAL_LIGHT_ARRAY_SIZE": max(c["lights"], 1),
 		"POLYGONAL_LIGHT_COUNT_CLAMPED": min(c["lights"], 33), "LIGHT_TEXTURE_COUNT": 1,
 		"MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING": c.get("min_vertices", c["max_vertices"]), "MAX_POLYGONAL_LIGHT_VERTEX_COUNT": c["max_vertices"],
-		"MAX_POLYGON_VERTEX_COUNT": c["max_vertices"] + 1, "SAMPLE_COUNT": c["samples"], "SAMPLE_COUNT_CLAMPED": min(c["samples"], 33),
+		"MAX_POLYGON_VERTEX_COUNT": c["max_vertices"] + (1 if c.get("technique", 11) in CLIPPING_TECHNIQUES else 0), "SAMPLE_COUNT": c["samples"], "SAMPLE_COUNT_CLAMPED": min(c["samples"], 33),
 		"TRACE_SHADOW_RAYS": c["trace"], "SHOW_POLYGONAL_LIGHTS": c["show_lights"],
-		"ERROR_DISPLAY_DIFFUSE": 0, "ERROR_DISPLAY_SPECULAR": 0, "ERROR_INDEX": 0, "OUTPUT_LINEAR_RGB": 0 if c.get("srgb", 0) else 1,
+		"ERROR_DISPLAY_DIFFUSE": ERROR_DISPLAYS[c.get("error_display", 0)][0], "ERROR_DISPLAY_SPECULAR": ERROR_DISPLAYS[c.get("error_display", 0)][1],
+		"ERROR_INDEX": ERROR_DISPLAYS[c.get("error_display", 0)][2], "OUTPUT_LINEAR_RGB": 0 if c.get("srgb", 0) else 1,
 	}
 	for i, s in enumerate(STRATEGIES):
 		d["SAMPLING_STRATEGIES_" + s] = int(c["strategy"] == i)
 	for i, h in enumerate(HEURISTICS):
 		d["MIS_HEURISTIC_" + h] = int(c["heuristic"] == i)
 	for t in TECHNIQUES:
-		d["SAMPLE_POLYGON_" + t] = int(t == "PROJECTED_SOLID_ANGLE")
+		d["SAMPLE_POLYGON_" + t] = int(t == TECHNIQUES[c.get("technique", 11)])
 	flags = ["-D%s=%s" % kv for kv in d.items()]
 	flags.append("-DUSE_BIASED_PROJECTED_SOLID_ANGLE_SAMPLING" if c["biased"] else "-DDONT_USE_BIASED_PROJECTED_SOLID_ANGLE_SAMPLING")
 	return flags
@@ -120,6 +129,20 @@ def default_configs():
 	configs.append(dict(base, trace=0))                                    # TRACE_SHADOW_RAYS=0 with the other strategies
 	configs.append(dict(base, trace=0, strategy=1, heuristic=1))
 	configs.append(dict(base, trace=0, heuristic=4))
+	# related-work sampling techniques (shading_pass.frag.glsl:332-481), sample_polygon_technique_t 0..10: diffuse only, then GGX MIS
+	# for the techniques the reference's interface allows it with (user_interface.cpp:130-140)
+	for technique in range(0, 11):
+		configs.append(dict(base, strategy=0, heuristic=0, technique=technique))
+	for technique, heuristic in [(2, 0), (3, 1), (4, 0), (5, 1), (10, 0)]:
+		configs.append(dict(base, strategy=1, heuristic=heuristic, technique=technique))
+	for technique in (1, 3, 4, 6, 8):                                        # techniques without clipping: MAX_POLYGON_VERTEX_COUNT = light vertices
+		configs.append(dict(base, strategy=0, heuristic=0, technique=technique, max_vertices=3))
+	for technique in (4, 5, 7, 9, 10):
+		configs.append(dict(base, strategy=0, heuristic=0, technique=technique, max_vertices=7, min_vertices=5))
+	configs.append(dict(base, strategy=0, heuristic=0, technique=1, max_vertices=6))
+	configs.append(dict(base, strategy=0, heuristic=0, technique=10, max_vertices=5, trace=0))
+	configs.append(dict(base, strategy=0, heuristic=0, technique=9, lights=16, samples=1))
+	configs.append(dict(base, strategy=0, heuristic=0, technique=2, lights=1, samples=2, materials=3))   # Cornell box, Urena's rectangle sampling
 	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
 		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs

@@ -234,12 +234,8 @@ inline float sin(float x) { return vkr_sin(x); }
 inline float cos(float x) { return vkr_cos(x); }
 inline float tan(float x) { return vkr_sin(x) / vkr_cos(x); }
 inline float atan(float x) { return vkr_atan(x); }
-inline float atan(float y, float x) { // quadrant-corrected, built on the same polynomial
-	if (x > 0.0f) return vkr_atan(y / x);
-	if (x < 0.0f) return (y >= 0.0f) ? vkr_atan(y / x) + VKR_PI : vkr_atan(y / x) - VKR_PI;
-	return (y > 0.0f) ? VKR_HALF_PI : ((y < 0.0f) ? -VKR_HALF_PI : 0.0f);
-}
-inline float acos(float x) { return (x >= 0.0f) ? vkr_acos01(vkr_min(x, 1.0f)) : VKR_PI - vkr_acos01(vkr_min(-x, 1.0f)); }
+inline float atan(float y, float x) { return vkr_atan2(y, x); }   // quadrant-corrected, built on the same polynomial (vkr_math.h)
+inline float acos(float x) { return vkr_acos(x); }
 inline float asin(float x) { return VKR_HALF_PI - acos(x); }
 inline float pow(float x, float y) { return vkr_pow(x, y); }   // the output stage's contract (vkr_math.h); GLSL leaves pow to the driver
 inline vec3 pow(const vec3& x, const vec3& y) { return vec3(vkr_pow(x.x, y.x), vkr_pow(x.y, y.y), vkr_pow(x.z, y.z)); }

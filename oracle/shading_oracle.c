@@ -5,7 +5,8 @@
  *   src/shaders/ltc_utility.glsl:58-108, brdfs.glsl:42-224, noise_utility.glsl:63-103,
  *   polygonal_light_utility.glsl:93-112, mesh_quantization.glsl:19-45
  * for the projected-solid-angle technique (SAMPLE_POLYGON_PROJECTED_SOLID_ANGLE, incl. the
- * biased variant) and all five sampling strategies. Used ONLY by tests/, by
+ * biased variant) with all five sampling strategies, and for the related-work techniques
+ * (shading_pass.frag.glsl:332-481, related_work_oracle.h) with the two strategies they support. Used ONLY by tests/, by
  * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs.
  *
  * Parity status: the reference ships no golden vectors; texture filtering,
@@ -17,6 +18,7 @@
  * Build: gcc -O2 -ffp-contract=off -mfma -fopenmp -shared -fPIC (oracle/Makefile).
  */
 #include "psa_oracle.h"
+#include "related_work_oracle.h"
 #include "bvh_oracle.h"
 #include "vkr_oracle.h"
 #include <stdio.h>
@@ -31,7 +33,7 @@ enum {
 	OFF_NOISE_RES_MASK = 184, OFF_NOISE_LAYER_MASK = 192, OFF_FRAME_BITS = 196, OFF_NOISE_RANDOM = 208, OFF_LTC = 224,
 	CONSTANTS_FIXED_SIZE = 256,
 	/* polygonal_light_t (polygonal_light_utility.glsl:26-83), offsets inside one light block */
-	L_TRANSLATION = 16, L_SURFACE_RADIANCE = 48, L_PLANE = 64, L_VERTEX_COUNT = 80, L_TEXTURING = 84, L_ROTATION = 96,
+	L_SCALING_X = 12, L_TRANSLATION = 16, L_SCALING_Y = 28, L_SURFACE_RADIANCE = 48, L_PLANE = 64, L_VERTEX_COUNT = 80, L_TEXTURING = 84, L_ROTATION = 96, L_AREA = 144,
 	L_FIXED_SIZE = 160
 };
 
@@ -41,6 +43,10 @@ typedef struct {
 	uint32_t vertex_count;
 	uint32_t texturing_technique;
 	v3 vertices_world_space[PSA_MAXP];
+	/* only the related-work techniques read these (polygonal_light_utility.glsl:26-83) */
+	v3 translation, rotation_cols[3];
+	float scaling_x, scaling_y, area;
+	v2 fan_areas[PSA_MAXP];
 } light_t;
 
 typedef struct {
@@ -394,9 +400,155 @@ static v3 get_polygonal_light_mis_estimate(v3 sampled_dir, float sampled_density
 	return mk3(0.0f, 0.0f, 0.0f);
 }
 
+/* shading_pass.frag.glsl:676-709 for the related-work techniques: GGX sampling with MIS against the polygon density.
+   polygon_density_is_constant: every technique except our projected solid angle sampling passes density_factor as is (:702) */
+static v3 ggx_mis_samples(float density_factor, int density_times_lambert, const shading_data_t* sd, const ltc_t* ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
+	const vkr_oracle_config_t* cfg = c->cfg;
+	v3 result = mk3(0.0f, 0.0f, 0.0f);
+	v3 outgoing_ss = mat43_mul_dir(ltc->world_to_shading, sd->outgoing);
+	outgoing_ss.y = 0.0f;
+	for (uint32_t s = 0; s != cfg->sample_count; ++s) {
+		float ggx_density;
+		v3 dir_ss = sample_ggx_reflected_direction(&ggx_density, outgoing_ss, sd->roughness, get_noise_2(accessor, c));
+		v3 dir_ws = mat43_transpose_mul(ltc->world_to_shading, dir_ss);
+		if (dir_ss.z > 0.0f && polygonal_light_ray_intersection(light, cfg->max_light_vertex_count, sd->position, dir_ws, 0.0f)) {
+			float lambert;
+			v3 rtb = radiance_visibility_brdf_product(&lambert, NULL, dir_ws, sd, light, 1, 1, c, ray_count);
+			float polygon_density = density_times_lambert ? (lambert * density_factor) : density_factor;
+			float w = get_mis_weight_over_density(ggx_density, polygon_density, cfg->mis_heuristic);
+			result.x += rtb.x * lambert * w; result.y += rtb.y * lambert * w; result.z += rtb.z * lambert * w;
+		}
+	}
+	return result;
+}
+
+/* shading_pass.frag.glsl:332-481: the related-work sampling techniques (SAMPLE_POLYGON_BASELINE .. SAMPLE_POLYGON_PROJECTED_SOLID_ANGLE_ARVO),
+   strategies DIFFUSE_ONLY and DIFFUSE_GGX_MIS */
+static v3 evaluate_polygonal_light_shading_related_work(const shading_data_t* sd, ltc_t ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
+	const vkr_oracle_config_t* cfg = c->cfg;
+	const uint32_t S = cfg->sample_count, maxp = c->maxp, maxl = cfg->max_light_vertex_count;
+	const uint32_t technique = cfg->polygon_sampling_technique;
+	const v3 zero = mk3(0.0f, 0.0f, 0.0f);
+	v3 result = zero;
+	float density_factor = 0.0f; /* 1 / solid angle (or 1 / projected solid angle) for the GGX part */
+	if (technique == VKR_TECHNIQUE_BASELINE) { /* :335-345 */
+		v3 corner_offset = sub3(light->translation, sd->position);
+		for (uint32_t s = 0; s != S; ++s) {
+			v2 rnd = get_noise_2(accessor, c);
+			v3 dir = normalize3(add3(add3(corner_offset, scale3(light->rotation_cols[0], rnd.x)), scale3(light->rotation_cols[1], rnd.y)));
+			result = add3(result, get_polygonal_light_mis_estimate(dir, 1.0f, sd, light, c, ray_count));
+		}
+	}
+	else if (technique == VKR_TECHNIQUE_AREA_TURK) { /* :347-353 */
+		for (uint32_t s = 0; s != S; ++s) {
+			v3 light_sample = rw_sample_area_polygon_turk(light->vertex_count, light->vertices_world_space, light->fan_areas, get_noise_2(accessor, c), maxp);
+			v3 dir;
+			float density = rw_get_area_sample_density(&dir, light_sample, sd->position, mk3(light->plane[0], light->plane[1], light->plane[2]), light->area);
+			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+		}
+	}
+	else if (technique == VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA) { /* :355-366 */
+		rw_urena_t squad = rw_prepare_urena(light->translation, light->scaling_x, light->scaling_y, light->rotation_cols, sd->position);
+		for (uint32_t s = 0; s != S; ++s) {
+			v3 dir = rw_sample_urena(&squad, get_noise_2(accessor, c));
+			float density = 1.0f / squad.solid_angle;
+			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+		}
+		density_factor = 1.0f / squad.solid_angle;
+	}
+	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE_ARVO) { /* :368-378 */
+		rw_sa_arvo_t polygon;
+		rw_prepare_sa_arvo(&polygon, light->vertex_count, light->vertices_world_space, sd->position, maxp);
+		for (uint32_t s = 0; s != S; ++s) {
+			v3 dir = rw_sample_sa_arvo(&polygon, get_noise_2(accessor, c), maxp);
+			float density = 1.0f / polygon.solid_angle;
+			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+		}
+		density_factor = 1.0f / polygon.solid_angle;
+	}
+	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE) { /* :380-390 */
+		rw_sa_t polygon;
+		rw_prepare_sa(&polygon, light->vertex_count, light->vertices_world_space, sd->position, maxp, 0);
+		for (uint32_t s = 0; s != S; ++s) {
+			v3 dir = rw_sample_sa(&polygon, get_noise_2(accessor, c), maxp);
+			float density = 1.0f / polygon.solid_angle;
+			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+		}
+		density_factor = 1.0f / polygon.solid_angle;
+	}
+	else if (technique >= VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE && technique <= VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART) { /* :392-437 */
+		v3 verts[PSA_MAXP];
+		memset(verts, 0, sizeof(verts));
+		for (uint32_t i = 0; i != maxl; ++i) verts[i] = mat43_mul_point(ltc.world_to_shading, light->vertices_world_space[i]);
+		uint32_t cvc = light->vertex_count;
+		if (technique != VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART && technique != VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART) {
+			cvc = psa_clip_polygon(light->vertex_count, verts, maxp);
+			if (cvc == 0) return zero;
+		}
+		if (technique == VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE) {
+			rw_sa_t polygon;
+			rw_prepare_sa(&polygon, cvc, verts, zero, maxp, 0);
+			for (uint32_t s = 0; s != S; ++s) {
+				v3 dir = rw_sample_sa(&polygon, get_noise_2(accessor, c), maxp);
+				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
+				float density = 1.0f / polygon.solid_angle;
+				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+			}
+			density_factor = 1.0f / polygon.solid_angle;
+		}
+		else if (technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART || technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART) {
+			rw_bilinear_hart_t polygon;
+			rw_prepare_bilinear_hart(&polygon, cvc, verts, maxp, 0);
+			for (uint32_t s = 0; s != S; ++s) {
+				float density;
+				v3 dir = rw_sample_bilinear_hart(&density, &polygon, get_noise_2(accessor, c), maxp);
+				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
+				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+			}
+		}
+		else {
+			rw_biquadratic_hart_t polygon;
+			rw_prepare_biquadratic_hart(&polygon, cvc, verts, maxp, 0);
+			for (uint32_t s = 0; s != S; ++s) {
+				float density;
+				v3 dir = rw_sample_biquadratic_hart(&density, &polygon, get_noise_2(accessor, c), maxp);
+				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
+				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+			}
+		}
+	}
+	else { /* VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO, :439-481 */
+		float side = fmaf(light->plane[3], 1.0f, fmaf(light->plane[2], sd->position.z, fmaf(light->plane[1], sd->position.y, light->plane[0] * sd->position.x)));
+		for (int i = 0; i != 4; ++i) {
+			ltc.world_to_shading[i][1] = (side < 0.0f) ? -ltc.world_to_shading[i][1] : ltc.world_to_shading[i][1];
+			ltc.world_to_cosine[i][1] = (side < 0.0f) ? -ltc.world_to_cosine[i][1] : ltc.world_to_cosine[i][1];
+		}
+		v3 verts[PSA_MAXP];
+		memset(verts, 0, sizeof(verts));
+		for (uint32_t i = 0; i != maxl; ++i) verts[i] = mat43_mul_point(ltc.world_to_shading, light->vertices_world_space[i]);
+		uint32_t cvc = psa_clip_polygon(light->vertex_count, verts, maxp);
+		if (cvc == 0) return zero;
+		rw_psa_arvo_t polygon;
+		rw_prepare_psa_arvo(&polygon, cvc, verts, maxp);
+		if (polygon.projected_solid_angle <= 0.0f) return zero;
+		for (uint32_t s = 0; s != S; ++s) {
+			v3 dir = rw_sample_psa_arvo(&polygon, get_noise_2(accessor, c), 3, maxp);
+			float density = dir.z / polygon.projected_solid_angle;
+			dir = mat43_transpose_mul(ltc.world_to_shading, dir);
+			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+		}
+		density_factor = 1.0f / polygon.projected_solid_angle;
+	}
+	if (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS)
+		result = add3(result, ggx_mis_samples(density_factor, 0, sd, &ltc, light, accessor, c, ray_count));
+	return scale3(result, 1.0f / (float) S);
+}
+
 /* shading_pass.frag.glsl:329-711, PSA branches (:441-504 and :506-673, :676-709) */
 static v3 evaluate_polygonal_light_shading(const shading_data_t* sd, ltc_t ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
 	const vkr_oracle_config_t* cfg = c->cfg;
+	if (cfg->polygon_sampling_technique != VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE)
+		return evaluate_polygonal_light_shading_related_work(sd, ltc, light, accessor, c, ray_count);
 	const int biased = cfg->biased_sampling;
 	const uint32_t S = cfg->sample_count;
 	const uint32_t maxp = c->maxp;
@@ -565,8 +717,18 @@ static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_
 		L->texturing_technique = rdu(p, L_TEXTURING);
 		const uint8_t* vw = p + L_FIXED_SIZE + 16 * (size_t) V;
 		for (uint32_t i = 0; i != V; ++i) L->vertices_world_space[i] = mk3(rdf(vw, 16 * i), rdf(vw, 16 * i + 4), rdf(vw, 16 * i + 8));
+		L->translation = mk3(rdf(p, L_TRANSLATION), rdf(p, L_TRANSLATION + 4), rdf(p, L_TRANSLATION + 8));
+		L->scaling_x = rdf(p, L_SCALING_X); L->scaling_y = rdf(p, L_SCALING_Y); L->area = rdf(p, L_AREA);
+		for (int col = 0; col != 3; ++col) L->rotation_cols[col] = mk3(rdf(p, L_ROTATION + 4 * col), rdf(p, L_ROTATION + 16 + 4 * col), rdf(p, L_ROTATION + 32 + 4 * col));
+		const uint8_t* fa = vw + 16 * (size_t) V;
+		for (uint32_t i = 0; i + 2 < V; ++i) L->fan_areas[i] = mk2(rdf(fa, 16 * i), rdf(fa, 16 * i + 4));
 	}
-	c->maxp = V + 1; /* main.c:194-216: PSA techniques clip => one extra vertex */
+	/* main.c:194-216: the techniques that clip may gain one vertex */
+	switch (cfg->polygon_sampling_technique) {
+	case VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE: case VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART: case VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART:
+	case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO: case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE: c->maxp = V + 1; break;
+	default: c->maxp = V; break;
+	}
 }
 
 /* Wall-clock seconds of the pixel loop of the last vkr_oracle_shade call (BVH build excluded), for the CPU baseline */
@@ -581,6 +743,16 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 {
 	(void) noise_layers;
 	if (cfg->max_light_vertex_count < 3 || cfg->max_light_vertex_count > 7) return 1;
+	if (cfg->polygon_sampling_technique > VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE) return 1;
+	if (cfg->polygon_sampling_technique != VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE) {
+		/* legality rules of the reference's user interface (user_interface.cpp:90-180) */
+		const uint32_t t = cfg->polygon_sampling_technique;
+		const int ggx_ok = t == VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA || t == VKR_TECHNIQUE_SOLID_ANGLE_ARVO || t == VKR_TECHNIQUE_SOLID_ANGLE || t == VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE || t == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO;
+		if (!(cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_ONLY || (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS && ggx_ok)) || cfg->biased_sampling) {
+			printf("oracle: sampling technique %u does not support sampling strategy %u.\n", t, cfg->sampling_strategies);
+			return 1;
+		}
+	}
 	ctx_t c; memset(&c, 0, sizeof(c));
 	parse_context(&c, cfg, (const uint8_t*) constants);
 	for (uint32_t l = 0; l != cfg->light_count; ++l)

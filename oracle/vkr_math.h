@@ -100,6 +100,15 @@ static inline float vkr_acos01(float x) {
 	return 2.0f * vkr_atan(sqrtf((1.0f - x) / (1.0f + x)));
 }
 
+/* two-argument atan (quadrant-corrected, built on vkr_atan) and acos on [-1,1]: used by the related-work samplers
+   (cubic_solver.glsl:52, polygon_sampling_related_work.glsl:148-151, 764-768) */
+static inline float vkr_atan2(float y, float x) {
+	if (x > 0.0f) return vkr_atan(y / x);
+	if (x < 0.0f) return (y >= 0.0f) ? vkr_atan(y / x) + VKR_PI : vkr_atan(y / x) - VKR_PI;
+	return (y > 0.0f) ? VKR_HALF_PI : ((y < 0.0f) ? -VKR_HALF_PI : 0.0f);
+}
+static inline float vkr_acos(float x) { return (x >= 0.0f) ? vkr_acos01(vkr_min(x, 1.0f)) : VKR_PI - vkr_acos01(vkr_min(-x, 1.0f)); }
+
 /* ---- output stage (srgb_utility.glsl, shading_pass.frag.glsl:871-892). GLSL leaves the precision of pow to the driver;
    this is the contract both sides implement: pow(x, y) = exp2(y * log2(x)) for x > 0, 0 for x <= 0, every step in fp32. */
 static inline float vkr_log2(float x) { /* x > 0, normal; fdlibm's logf kernel, then one fma by 1/ln 2 */

@@ -9,6 +9,11 @@
 /* numeric values = the reference's sampling_strategies_t / mis_heuristic_t (src/main.h:45-92) */
 enum { VKR_STRATEGY_DIFFUSE_ONLY = 0, VKR_STRATEGY_DIFFUSE_GGX_MIS = 1, VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY = 2,
 	VKR_STRATEGY_DIFFUSE_SPECULAR_MIS = 3, VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM = 4 };
+/* sample_polygon_technique_t (src/polygonal_light.h:30-66); the biased variant (12) is technique 11 + biased_sampling */
+enum { VKR_TECHNIQUE_BASELINE = 0, VKR_TECHNIQUE_AREA_TURK = 1, VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA = 2, VKR_TECHNIQUE_SOLID_ANGLE_ARVO = 3,
+	VKR_TECHNIQUE_SOLID_ANGLE = 4, VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE = 5, VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART = 6, VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART = 7,
+	VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART = 8, VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART = 9, VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO = 10,
+	VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE = 11 };
 enum { VKR_MIS_BALANCE = 0, VKR_MIS_POWER = 1, VKR_MIS_WEIGHTED = 2, VKR_MIS_OPTIMAL_CLAMPED = 3, VKR_MIS_OPTIMAL = 4 };
 
 /* What the reference passes as -D defines (src/main.c:752-792) */
@@ -25,6 +30,7 @@ typedef struct {
 	uint32_t show_polygonal_lights;    /* SHOW_POLYGONAL_LIGHTS */
 	uint32_t row_begin, row_end;       /* shade rows [row_begin,row_end) only; row_end = 0 means height */
 	uint32_t band_height, band_stride; /* if band_stride != 0: of those rows only the ones with (y - row_begin) % band_stride < band_height (bounded CPU samples) */
+	uint32_t polygon_sampling_technique; /* SAMPLE_POLYGON_*: VKR_TECHNIQUE_* (the ctypes binding defaults to 11 = projected solid angle) */
 	uint32_t output_srgb;              /* !OUTPUT_LINEAR_RGB: the shader itself converts to sRGB (UNORM swapchain); the half-bit split follows g_frame_bits in the constant block */
 } vkr_oracle_config_t;
 

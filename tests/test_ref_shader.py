@@ -2,7 +2,7 @@
 
 tests/golden/ref_shader.npz holds frames shaded by src/shaders/shading_pass.frag.glsl (+ includes) compiled as C++
 (oracle/build_ref.py, oracle/glsl_compat/). The oracle must reproduce them bit for bit, for every sampling strategy
-and MIS heuristic of the projected-solid-angle technique. Where oracle/_ref/libref_shader.so is present (build
+and MIS heuristic of the projected-solid-angle technique and for the related-work techniques ("_q<technique>": Turk, Urena, Arvo, Hart). Where oracle/_ref/libref_shader.so is present (build
 container, or shipped prebuilt) the reference shader is also run live and checked against the fixtures.
 """
 import hashlib
@@ -25,10 +25,10 @@ def _golden():
 
 
 def _config_from_name(name):
-	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_o(\d)(\d))?$", name)
-	s, h, b, L, V, Vmin, S, t, l, M, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_q(\d+))?(?:_o(\d)(\d))?$", name)
+	s, h, b, L, V, Vmin, S, t, l, M, q, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
 	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
-		samples=S, trace=t, show_lights=l, materials=M, srgb=srgb or 0, frame_bits=frame_bits or 0)
+		samples=S, trace=t, show_lights=l, materials=M, technique=11 if q is None else q, srgb=srgb or 0, frame_bits=frame_bits or 0)
 
 
 def _names():
