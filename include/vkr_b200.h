@@ -36,8 +36,21 @@ typedef enum vkr_mis_heuristic_e {
 	vkr_mis_heuristic_optimal_clamped = 3, vkr_mis_heuristic_optimal = 4
 } vkr_mis_heuristic_t;
 
-/* sample_polygon_technique_t values that this library implements (src/polygonal_light.h:28-67) */
+/* sample_polygon_technique_t (src/polygonal_light.h:28-67). 11 and 12 work with every sampling strategy; the related-work
+   techniques 0..10 with vkr_sampling_strategies_diffuse_only, and 2, 3, 4, 5, 10 also with
+   vkr_sampling_strategies_diffuse_ggx_mis -- the rules of src/user_interface.cpp:124-175 */
 typedef enum vkr_sample_polygon_technique_e {
+	vkr_sample_polygon_baseline = 0,
+	vkr_sample_polygon_area_turk = 1,
+	vkr_sample_polygon_rectangle_solid_angle_urena = 2,
+	vkr_sample_polygon_solid_angle_arvo = 3,
+	vkr_sample_polygon_solid_angle = 4,
+	vkr_sample_polygon_clipped_solid_angle = 5,
+	vkr_sample_polygon_bilinear_cosine_warp_hart = 6,
+	vkr_sample_polygon_bilinear_cosine_warp_clipping_hart = 7,
+	vkr_sample_polygon_biquadratic_cosine_warp_hart = 8,
+	vkr_sample_polygon_biquadratic_cosine_warp_clipping_hart = 9,
+	vkr_sample_polygon_projected_solid_angle_arvo = 10,
 	vkr_sample_polygon_projected_solid_angle = 11,
 	vkr_sample_polygon_projected_solid_angle_biased = 12
 } vkr_sample_polygon_technique_t;

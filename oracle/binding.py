@@ -107,7 +107,7 @@ def sort_network(vertices_xy, ellipses_xy, maxp):
 	return v, e
 
 
-ELEMENTARY = dict(atan=0, sin=1, cos=2, acos01=3, rsqrt=4, fast_positive_atan=5, log2=6, exp2=7, linear_to_srgb=8, srgb_to_linear=9, float_to_half=10)
+ELEMENTARY = dict(atan=0, sin=1, cos=2, acos01=3, rsqrt=4, fast_positive_atan=5, log2=6, exp2=7, linear_to_srgb=8, srgb_to_linear=9, float_to_half=10, acos=11, atan2_pair=12, cbrt_pow=13)
 
 
 def elementary(which, x):
@@ -141,3 +141,20 @@ def last_shade_seconds():
 	lib = load()
 	lib.vkr_oracle_last_shade_seconds.restype = C.c_double
 	return lib.vkr_oracle_last_shade_seconds()
+
+
+def related_work_batch(technique, maxv, light_block, position, frame, random_numbers, symbol_library=None, symbol="vkr_oracle_related_work_batch"):
+	"""One (light, shading point) pair, n samples of a related-work technique. frame = rows x, y, z of world_to_shading_space + translation (12 floats).
+	Returns None if the light is culled, else (dirs [n,3], densities [n], ggx density factor). symbol_library/symbol let the same call run
+	against tests/build/libdevice_on_host.so (the device code compiled for the CPU)."""
+	lib = symbol_library if symbol_library is not None else load()
+	rnd = np.ascontiguousarray(random_numbers, dtype=np.float32).reshape(-1, 2)
+	n = len(rnd)
+	pos = np.ascontiguousarray(position, dtype=np.float32); fr = np.ascontiguousarray(frame, dtype=np.float32).reshape(12)
+	dirs = np.zeros((n, 3), dtype=np.float32); dens = np.zeros(n, dtype=np.float32); ggx = C.c_float(0.0)
+	block = (C.c_uint8 * len(light_block)).from_buffer_copy(light_block)
+	fn = getattr(lib, symbol); fn.restype = C.c_int
+	on = fn(C.c_uint32(technique), C.c_uint32(maxv), block, _p(pos), _p(fr), C.c_uint32(n), _p(rnd), _p(dirs), _p(dens), C.byref(ggx))
+	if on < 0:
+		raise RuntimeError("unsupported technique / vertex bound")
+	return None if on == 0 else (dirs, dens, float(ggx.value))

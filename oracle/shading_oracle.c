@@ -422,126 +422,127 @@ static v3 ggx_mis_samples(float density_factor, int density_times_lambert, const
 	return result;
 }
 
-/* shading_pass.frag.glsl:332-481: the related-work sampling techniques (SAMPLE_POLYGON_BASELINE .. SAMPLE_POLYGON_PROJECTED_SOLID_ANGLE_ARVO),
-   strategies DIFFUSE_ONLY and DIFFUSE_GGX_MIS */
-static v3 evaluate_polygonal_light_shading_related_work(const shading_data_t* sd, ltc_t ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
-	const vkr_oracle_config_t* cfg = c->cfg;
-	const uint32_t S = cfg->sample_count, maxp = c->maxp, maxl = cfg->max_light_vertex_count;
-	const uint32_t technique = cfg->polygon_sampling_technique;
+/* shading_pass.frag.glsl:332-481: the related-work sampling techniques (SAMPLE_POLYGON_BASELINE .. SAMPLE_POLYGON_PROJECTED_SOLID_ANGLE_ARVO)
+   as "prepare once per (pixel, light), then sample": what each #elif branch of evaluate_polygonal_light_shading() does. */
+typedef struct {
+	uint32_t technique, maxp;
+	const light_t* light;
+	v3 position, corner_offset;
+	float world_to_shading[4][3]; /* with the y-row mirrored where the shader does that (:444-449) */
+	rw_urena_t urena;
+	rw_sa_arvo_t sa_arvo;
+	rw_sa_t sa;
+	rw_bilinear_hart_t bilinear;
+	rw_biquadratic_hart_t biquadratic;
+	rw_psa_arvo_t psa_arvo;
+	float ggx_density_factor; /* 1 / solid angle (or 1 / projected solid angle), :683-687 */
+} rw_sampler_t;
+
+/* Returns 0 if the shader returns vec3(0.0f) before sampling (polygon clipped away, empty projected solid angle) */
+static int rw_sampler_prepare(rw_sampler_t* sp, uint32_t technique, uint32_t maxp, uint32_t maxl, const light_t* light, v3 position, const float world_to_shading[4][3]) {
 	const v3 zero = mk3(0.0f, 0.0f, 0.0f);
-	v3 result = zero;
-	float density_factor = 0.0f; /* 1 / solid angle (or 1 / projected solid angle) for the GGX part */
-	if (technique == VKR_TECHNIQUE_BASELINE) { /* :335-345 */
-		v3 corner_offset = sub3(light->translation, sd->position);
-		for (uint32_t s = 0; s != S; ++s) {
-			v2 rnd = get_noise_2(accessor, c);
-			v3 dir = normalize3(add3(add3(corner_offset, scale3(light->rotation_cols[0], rnd.x)), scale3(light->rotation_cols[1], rnd.y)));
-			result = add3(result, get_polygonal_light_mis_estimate(dir, 1.0f, sd, light, c, ray_count));
-		}
+	sp->technique = technique; sp->maxp = maxp; sp->light = light; sp->position = position; sp->ggx_density_factor = 0.0f;
+	memcpy(sp->world_to_shading, world_to_shading, sizeof(sp->world_to_shading));
+	if (technique == VKR_TECHNIQUE_BASELINE) /* :335 */
+		sp->corner_offset = sub3(light->translation, position);
+	else if (technique == VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA) { /* :357-359 */
+		sp->urena = rw_prepare_urena(light->translation, light->scaling_x, light->scaling_y, light->rotation_cols, position);
+		sp->ggx_density_factor = 1.0f / sp->urena.solid_angle;
 	}
-	else if (technique == VKR_TECHNIQUE_AREA_TURK) { /* :347-353 */
-		for (uint32_t s = 0; s != S; ++s) {
-			v3 light_sample = rw_sample_area_polygon_turk(light->vertex_count, light->vertices_world_space, light->fan_areas, get_noise_2(accessor, c), maxp);
-			v3 dir;
-			float density = rw_get_area_sample_density(&dir, light_sample, sd->position, mk3(light->plane[0], light->plane[1], light->plane[2]), light->area);
-			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-		}
+	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE_ARVO) { /* :370-371 */
+		rw_prepare_sa_arvo(&sp->sa_arvo, light->vertex_count, light->vertices_world_space, position, maxp);
+		sp->ggx_density_factor = 1.0f / sp->sa_arvo.solid_angle;
 	}
-	else if (technique == VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA) { /* :355-366 */
-		rw_urena_t squad = rw_prepare_urena(light->translation, light->scaling_x, light->scaling_y, light->rotation_cols, sd->position);
-		for (uint32_t s = 0; s != S; ++s) {
-			v3 dir = rw_sample_urena(&squad, get_noise_2(accessor, c));
-			float density = 1.0f / squad.solid_angle;
-			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-		}
-		density_factor = 1.0f / squad.solid_angle;
+	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE) { /* :382-383 */
+		rw_prepare_sa(&sp->sa, light->vertex_count, light->vertices_world_space, position, maxp, 0);
+		sp->ggx_density_factor = 1.0f / sp->sa.solid_angle;
 	}
-	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE_ARVO) { /* :368-378 */
-		rw_sa_arvo_t polygon;
-		rw_prepare_sa_arvo(&polygon, light->vertex_count, light->vertices_world_space, sd->position, maxp);
-		for (uint32_t s = 0; s != S; ++s) {
-			v3 dir = rw_sample_sa_arvo(&polygon, get_noise_2(accessor, c), maxp);
-			float density = 1.0f / polygon.solid_angle;
-			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+	else if (technique >= VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE && technique <= VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) { /* :392-405, 439-457 */
+		if (technique == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) {
+			float side = fmaf(light->plane[3], 1.0f, fmaf(light->plane[2], position.z, fmaf(light->plane[1], position.y, light->plane[0] * position.x)));
+			for (int i = 0; i != 4; ++i) sp->world_to_shading[i][1] = (side < 0.0f) ? -sp->world_to_shading[i][1] : sp->world_to_shading[i][1];
 		}
-		density_factor = 1.0f / polygon.solid_angle;
-	}
-	else if (technique == VKR_TECHNIQUE_SOLID_ANGLE) { /* :380-390 */
-		rw_sa_t polygon;
-		rw_prepare_sa(&polygon, light->vertex_count, light->vertices_world_space, sd->position, maxp, 0);
-		for (uint32_t s = 0; s != S; ++s) {
-			v3 dir = rw_sample_sa(&polygon, get_noise_2(accessor, c), maxp);
-			float density = 1.0f / polygon.solid_angle;
-			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-		}
-		density_factor = 1.0f / polygon.solid_angle;
-	}
-	else if (technique >= VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE && technique <= VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART) { /* :392-437 */
 		v3 verts[PSA_MAXP];
 		memset(verts, 0, sizeof(verts));
-		for (uint32_t i = 0; i != maxl; ++i) verts[i] = mat43_mul_point(ltc.world_to_shading, light->vertices_world_space[i]);
+		for (uint32_t i = 0; i != maxl; ++i) verts[i] = mat43_mul_point(sp->world_to_shading, light->vertices_world_space[i]);
 		uint32_t cvc = light->vertex_count;
 		if (technique != VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART && technique != VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART) {
 			cvc = psa_clip_polygon(light->vertex_count, verts, maxp);
-			if (cvc == 0) return zero;
+			if (cvc == 0) return 0;
 		}
 		if (technique == VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE) {
-			rw_sa_t polygon;
-			rw_prepare_sa(&polygon, cvc, verts, zero, maxp, 0);
-			for (uint32_t s = 0; s != S; ++s) {
-				v3 dir = rw_sample_sa(&polygon, get_noise_2(accessor, c), maxp);
-				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
-				float density = 1.0f / polygon.solid_angle;
-				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-			}
-			density_factor = 1.0f / polygon.solid_angle;
+			rw_prepare_sa(&sp->sa, cvc, verts, zero, maxp, 0);
+			sp->ggx_density_factor = 1.0f / sp->sa.solid_angle;
 		}
-		else if (technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART || technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART) {
-			rw_bilinear_hart_t polygon;
-			rw_prepare_bilinear_hart(&polygon, cvc, verts, maxp, 0);
-			for (uint32_t s = 0; s != S; ++s) {
-				float density;
-				v3 dir = rw_sample_bilinear_hart(&density, &polygon, get_noise_2(accessor, c), maxp);
-				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
-				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-			}
-		}
+		else if (technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART || technique == VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART)
+			rw_prepare_bilinear_hart(&sp->bilinear, cvc, verts, maxp, 0);
+		else if (technique == VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART || technique == VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART)
+			rw_prepare_biquadratic_hart(&sp->biquadratic, cvc, verts, maxp, 0);
 		else {
-			rw_biquadratic_hart_t polygon;
-			rw_prepare_biquadratic_hart(&polygon, cvc, verts, maxp, 0);
-			for (uint32_t s = 0; s != S; ++s) {
-				float density;
-				v3 dir = rw_sample_biquadratic_hart(&density, &polygon, get_noise_2(accessor, c), maxp);
-				dir = mat43_transpose_mul(ltc.world_to_shading, dir);
-				result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-			}
+			rw_prepare_psa_arvo(&sp->psa_arvo, cvc, verts, maxp);
+			if (sp->psa_arvo.projected_solid_angle <= 0.0f) return 0;
+			sp->ggx_density_factor = 1.0f / sp->psa_arvo.projected_solid_angle;
 		}
 	}
-	else { /* VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO, :439-481 */
-		float side = fmaf(light->plane[3], 1.0f, fmaf(light->plane[2], sd->position.z, fmaf(light->plane[1], sd->position.y, light->plane[0] * sd->position.x)));
-		for (int i = 0; i != 4; ++i) {
-			ltc.world_to_shading[i][1] = (side < 0.0f) ? -ltc.world_to_shading[i][1] : ltc.world_to_shading[i][1];
-			ltc.world_to_cosine[i][1] = (side < 0.0f) ? -ltc.world_to_cosine[i][1] : ltc.world_to_cosine[i][1];
-		}
-		v3 verts[PSA_MAXP];
-		memset(verts, 0, sizeof(verts));
-		for (uint32_t i = 0; i != maxl; ++i) verts[i] = mat43_mul_point(ltc.world_to_shading, light->vertices_world_space[i]);
-		uint32_t cvc = psa_clip_polygon(light->vertex_count, verts, maxp);
-		if (cvc == 0) return zero;
-		rw_psa_arvo_t polygon;
-		rw_prepare_psa_arvo(&polygon, cvc, verts, maxp);
-		if (polygon.projected_solid_angle <= 0.0f) return zero;
-		for (uint32_t s = 0; s != S; ++s) {
-			v3 dir = rw_sample_psa_arvo(&polygon, get_noise_2(accessor, c), 3, maxp);
-			float density = dir.z / polygon.projected_solid_angle;
-			dir = mat43_transpose_mul(ltc.world_to_shading, dir);
-			result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
-		}
-		density_factor = 1.0f / polygon.projected_solid_angle;
+	return 1;
+}
+
+/* One sample: world-space direction and its density with respect to the solid angle measure */
+static v3 rw_sampler_sample(const rw_sampler_t* sp, v2 rnd, float* density) {
+	const light_t* light = sp->light;
+	v3 dir;
+	switch (sp->technique) {
+	case VKR_TECHNIQUE_BASELINE: /* :341-343 */
+		*density = 1.0f;
+		return normalize3(add3(add3(sp->corner_offset, scale3(light->rotation_cols[0], rnd.x)), scale3(light->rotation_cols[1], rnd.y)));
+	case VKR_TECHNIQUE_AREA_TURK: { /* :348-351 */
+		v3 light_sample = rw_sample_area_polygon_turk(light->vertex_count, light->vertices_world_space, light->fan_areas, rnd, sp->maxp);
+		*density = rw_get_area_sample_density(&dir, light_sample, sp->position, mk3(light->plane[0], light->plane[1], light->plane[2]), light->area);
+		return dir;
 	}
-	if (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS)
-		result = add3(result, ggx_mis_samples(density_factor, 0, sd, &ltc, light, accessor, c, ray_count));
-	return scale3(result, 1.0f / (float) S);
+	case VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA: /* :362-363 */
+		*density = 1.0f / sp->urena.solid_angle;
+		return rw_sample_urena(&sp->urena, rnd);
+	case VKR_TECHNIQUE_SOLID_ANGLE_ARVO: /* :374-375 */
+		*density = 1.0f / sp->sa_arvo.solid_angle;
+		return rw_sample_sa_arvo(&sp->sa_arvo, rnd, sp->maxp);
+	case VKR_TECHNIQUE_SOLID_ANGLE: /* :386-387 */
+		*density = 1.0f / sp->sa.solid_angle;
+		return rw_sample_sa(&sp->sa, rnd, sp->maxp);
+	case VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE: /* :412-414 */
+		dir = rw_sample_sa(&sp->sa, rnd, sp->maxp);
+		*density = 1.0f / sp->sa.solid_angle;
+		return mat43_transpose_mul(sp->world_to_shading, dir);
+	case VKR_TECHNIQUE_BILINEAR_COSINE_WARP_HART: case VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART: /* :423-425 */
+		dir = rw_sample_bilinear_hart(density, &sp->bilinear, rnd, sp->maxp);
+		return mat43_transpose_mul(sp->world_to_shading, dir);
+	case VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART: case VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART: /* :433-435 */
+		dir = rw_sample_biquadratic_hart(density, &sp->biquadratic, rnd, sp->maxp);
+		return mat43_transpose_mul(sp->world_to_shading, dir);
+	default: /* VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO, :476-478 */
+		dir = rw_sample_psa_arvo(&sp->psa_arvo, rnd, 3, sp->maxp);
+		*density = dir.z / sp->psa_arvo.projected_solid_angle;
+		return mat43_transpose_mul(sp->world_to_shading, dir);
+	}
+}
+
+/* shading_pass.frag.glsl:332-481 + 676-711 for the related-work techniques, strategies DIFFUSE_ONLY and DIFFUSE_GGX_MIS */
+static v3 evaluate_polygonal_light_shading_related_work(const shading_data_t* sd, ltc_t ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
+	const vkr_oracle_config_t* cfg = c->cfg;
+	rw_sampler_t sampler;
+	if (!rw_sampler_prepare(&sampler, cfg->polygon_sampling_technique, c->maxp, cfg->max_light_vertex_count, light, sd->position, ltc.world_to_shading))
+		return mk3(0.0f, 0.0f, 0.0f);
+	v3 result = mk3(0.0f, 0.0f, 0.0f);
+	for (uint32_t s = 0; s != cfg->sample_count; ++s) {
+		float density;
+		v3 dir = rw_sampler_sample(&sampler, get_noise_2(accessor, c), &density);
+		result = add3(result, get_polygonal_light_mis_estimate(dir, density, sd, light, c, ray_count));
+	}
+	if (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
+		memcpy(ltc.world_to_shading, sampler.world_to_shading, sizeof(ltc.world_to_shading));
+		result = add3(result, ggx_mis_samples(sampler.ggx_density_factor, 0, sd, &ltc, light, accessor, c, ray_count));
+	}
+	return scale3(result, 1.0f / (float) cfg->sample_count);
 }
 
 /* shading_pass.frag.glsl:329-711, PSA branches (:441-504 and :506-673, :676-709) */
@@ -694,6 +695,28 @@ static v3 evaluate_polygonal_light_shading(const shading_data_t* sd, ltc_t ltc, 
 	return scale3(result, 1.0f / (float) S);
 }
 
+static void parse_light(light_t* L, const uint8_t* p, uint32_t V) { /* polygonal_light_utility.glsl:26-83, V = MAX_POLYGONAL_LIGHT_VERTEX_COUNT */
+	L->surface_radiance = mk3(rdf(p, L_SURFACE_RADIANCE), rdf(p, L_SURFACE_RADIANCE + 4), rdf(p, L_SURFACE_RADIANCE + 8));
+	for (int i = 0; i != 4; ++i) L->plane[i] = rdf(p, L_PLANE + 4 * i);
+	L->vertex_count = rdu(p, L_VERTEX_COUNT);
+	L->texturing_technique = rdu(p, L_TEXTURING);
+	const uint8_t* vw = p + L_FIXED_SIZE + 16 * (size_t) V;
+	for (uint32_t i = 0; i != V; ++i) L->vertices_world_space[i] = mk3(rdf(vw, 16 * i), rdf(vw, 16 * i + 4), rdf(vw, 16 * i + 8));
+	L->translation = mk3(rdf(p, L_TRANSLATION), rdf(p, L_TRANSLATION + 4), rdf(p, L_TRANSLATION + 8));
+	L->scaling_x = rdf(p, L_SCALING_X); L->scaling_y = rdf(p, L_SCALING_Y); L->area = rdf(p, L_AREA);
+	for (int col = 0; col != 3; ++col) L->rotation_cols[col] = mk3(rdf(p, L_ROTATION + 4 * col), rdf(p, L_ROTATION + 16 + 4 * col), rdf(p, L_ROTATION + 32 + 4 * col));
+	const uint8_t* fa = vw + 16 * (size_t) V;
+	for (uint32_t i = 0; i + 2 < V; ++i) L->fan_areas[i] = mk2(rdf(fa, 16 * i), rdf(fa, 16 * i + 4));
+}
+
+static uint32_t technique_maxp(uint32_t technique, uint32_t V) { /* get_max_polygon_vertex_count, main.c:194-216: the techniques that clip may gain one vertex */
+	switch (technique) {
+	case VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE: case VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART: case VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART:
+	case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO: case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE: return V + 1;
+	default: return V;
+	}
+}
+
 static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_t* constants) {
 	c->cfg = cfg; c->constants = constants;
 	for (int i = 0; i != 3; ++i) for (int j = 0; j != 4; ++j) c->pixel_to_ray[i][j] = rdf(constants, OFF_PIXEL_TO_RAY + 4 * (4 * i + j));
@@ -710,25 +733,9 @@ static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_
 	c->lights = (light_t*) calloc(cfg->light_count ? cfg->light_count : 1, sizeof(light_t));
 	for (uint32_t l = 0; l != cfg->light_count; ++l) {
 		const uint8_t* p = constants + CONSTANTS_FIXED_SIZE + stride * l;
-		light_t* L = &c->lights[l];
-		L->surface_radiance = mk3(rdf(p, L_SURFACE_RADIANCE), rdf(p, L_SURFACE_RADIANCE + 4), rdf(p, L_SURFACE_RADIANCE + 8));
-		for (int i = 0; i != 4; ++i) L->plane[i] = rdf(p, L_PLANE + 4 * i);
-		L->vertex_count = rdu(p, L_VERTEX_COUNT);
-		L->texturing_technique = rdu(p, L_TEXTURING);
-		const uint8_t* vw = p + L_FIXED_SIZE + 16 * (size_t) V;
-		for (uint32_t i = 0; i != V; ++i) L->vertices_world_space[i] = mk3(rdf(vw, 16 * i), rdf(vw, 16 * i + 4), rdf(vw, 16 * i + 8));
-		L->translation = mk3(rdf(p, L_TRANSLATION), rdf(p, L_TRANSLATION + 4), rdf(p, L_TRANSLATION + 8));
-		L->scaling_x = rdf(p, L_SCALING_X); L->scaling_y = rdf(p, L_SCALING_Y); L->area = rdf(p, L_AREA);
-		for (int col = 0; col != 3; ++col) L->rotation_cols[col] = mk3(rdf(p, L_ROTATION + 4 * col), rdf(p, L_ROTATION + 16 + 4 * col), rdf(p, L_ROTATION + 32 + 4 * col));
-		const uint8_t* fa = vw + 16 * (size_t) V;
-		for (uint32_t i = 0; i + 2 < V; ++i) L->fan_areas[i] = mk2(rdf(fa, 16 * i), rdf(fa, 16 * i + 4));
+		parse_light(&c->lights[l], p, V);
 	}
-	/* main.c:194-216: the techniques that clip may gain one vertex */
-	switch (cfg->polygon_sampling_technique) {
-	case VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE: case VKR_TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART: case VKR_TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART:
-	case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO: case VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE: c->maxp = V + 1; break;
-	default: c->maxp = V; break;
-	}
+	c->maxp = technique_maxp(cfg->polygon_sampling_technique, V);
 }
 
 /* Wall-clock seconds of the pixel loop of the last vkr_oracle_shade call (BVH build excluded), for the CPU baseline */
@@ -987,6 +994,28 @@ int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants_v,
 }
 
 /* ---- small entry points for the known-answer tests */
+/* Probe for tests/test_device_on_host.py: one (light, shading point) pair, n samples of a related-work technique.
+   frame = rows x, y, z of world_to_shading_space and its translation column. Returns 0 if the light is culled. */
+int vkr_oracle_related_work_batch(uint32_t technique, uint32_t maxv, const void* light_block, const float* position, const float* frame,
+	uint32_t n, const float* random_numbers, float* out_dirs, float* out_densities, float* out_ggx_density_factor)
+{
+	light_t light; memset(&light, 0, sizeof(light));
+	parse_light(&light, (const uint8_t*) light_block, maxv);
+	float w2s[4][3];
+	for (int row = 0; row != 3; ++row) {
+		for (int col = 0; col != 3; ++col) w2s[col][row] = frame[3 * row + col];
+		w2s[3][row] = frame[9 + row];
+	}
+	rw_sampler_t sampler;
+	if (!rw_sampler_prepare(&sampler, technique, technique_maxp(technique, maxv), maxv, &light, mk3(position[0], position[1], position[2]), w2s)) return 0;
+	*out_ggx_density_factor = sampler.ggx_density_factor;
+	for (uint32_t i = 0; i != n; ++i) {
+		v3 d = rw_sampler_sample(&sampler, mk2(random_numbers[2 * i], random_numbers[2 * i + 1]), &out_densities[i]);
+		out_dirs[3 * i] = d.x; out_dirs[3 * i + 1] = d.y; out_dirs[3 * i + 2] = d.z;
+	}
+	return 1;
+}
+
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp) {
 	v3 v[PSA_MAXP]; memset(v, 0, sizeof(v));
 	for (uint32_t i = 0; i != maxp; ++i) v[i] = mk3(vertices_xyz[3 * i], vertices_xyz[3 * i + 1], vertices_xyz[3 * i + 2]);
@@ -1037,7 +1066,8 @@ void vkr_oracle_elementary_batch(int which, uint32_t n, const float* x, float* y
 	for (uint32_t i = 0; i != n; ++i)
 		y[i] = (which == 0) ? vkr_atan(x[i]) : (which == 1) ? vkr_sin(x[i]) : (which == 2) ? vkr_cos(x[i]) : (which == 3) ? vkr_acos01(x[i]) : (which == 4) ? vkr_rsqrt(x[i])
 			: (which == 6) ? vkr_log2(x[i]) : (which == 7) ? vkr_exp2(x[i]) : (which == 8) ? vkr_linear_to_srgb(x[i]) : (which == 9) ? vkr_srgb_to_linear(x[i])
-			: (which == 10) ? (float) vkr_float_to_half(x[i]) : psa_fast_positive_atan(x[i]);
+			: (which == 10) ? (float) vkr_float_to_half(x[i]) : (which == 11) ? vkr_acos(x[i]) : (which == 12) ? (vkr_atan2(x[i], 0.5f) + vkr_atan2(0.5f, x[i]))
+			: (which == 13) ? vkr_pow(x[i], 1.0f / 3.0f) : psa_fast_positive_atan(x[i]);
 }
 
 /* Shadow predicate KATs: per ray {ox,oy,oz,dx,dy,dz,tmin,tmax} -> occluded bit via BVH and (optionally) brute force */

@@ -44,6 +44,8 @@ int vkr_oracle_visibility(uint32_t width, uint32_t height, const void* constants
 int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
 	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
 	const float* material_params, float* out_gbuffer);
+int vkr_oracle_related_work_batch(uint32_t technique, uint32_t maxv, const void* light_block, const float* position, const float* frame,
+	uint32_t n, const float* random_numbers, float* out_dirs, float* out_densities, float* out_ggx_density_factor);
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp);
 void vkr_oracle_psa_sample_batch(uint32_t vertex_count, const float* vertices_xyz, uint32_t maxp, int biased, int do_clip,
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_errors, float* out_info);

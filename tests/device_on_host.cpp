@@ -1,0 +1,79 @@
+// tests/device_on_host.cpp -- TEST INFRASTRUCTURE: the product's device sampling headers compiled for the CPU.
+//
+// The related-work samplers (vulkan_renderer_b200/csrc/vkr_related_work.cuh, on top of vkr_psa.cuh and vkr_device_math.cuh)
+// use no warp intrinsics, so g++ can compile the very same source (-ffp-contract=off stands in for nvcc's -fmad=false; the
+// headers are built only from IEEE add/mul/div/sqrt/fma). tests/test_device_on_host.py holds the result bit for bit against
+// the CPU oracle, which in turn is pinned against the reference shader. This catches transcription errors in the device code
+// without a GPU; the -m gpu tests then run the same functions inside the kernel against the reference-shader fixtures.
+// Built by __graft_entry__.build() into tests/build/libdevice_on_host.so. Nothing in the product links against it.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define VKR_DEVICE_CODE_ON_HOST 1
+#define VKR_DEV inline
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+
+#include "vkr_related_work.cuh"
+
+using namespace vkr;
+
+template <int TECHNIQUE, int MAXV>
+static int run(const unsigned char* light_block, const float* position, const float* frame_rows, uint32_t n, const float* rnd, float* out_dirs, float* out_densities, float* out_ggx_density_factor) {
+	rw_light<MAXV> light;
+	rw_load_light<MAXV>(light, light_block);
+	rw_frame frame;
+	frame.rx = make3(frame_rows[0], frame_rows[1], frame_rows[2]); frame.ry = make3(frame_rows[3], frame_rows[4], frame_rows[5]);
+	frame.rz = make3(frame_rows[6], frame_rows[7], frame_rows[8]); frame.t = make3(frame_rows[9], frame_rows[10], frame_rows[11]);
+	rw_sampler<TECHNIQUE, MAXV> sampler;
+	if (!sampler.prepare(light, make3(position[0], position[1], position[2]), frame)) return 0;
+	*out_ggx_density_factor = sampler.ggx_density_factor();
+	for (uint32_t i = 0; i != n; ++i) {
+		const f3 d = sampler.sample(make2(rnd[2 * i], rnd[2 * i + 1]), &out_densities[i]);
+		out_dirs[3 * i] = d.x; out_dirs[3 * i + 1] = d.y; out_dirs[3 * i + 2] = d.z;
+	}
+	return 1;
+}
+
+template <int MAXV>
+static int run_technique(uint32_t technique, const unsigned char* light_block, const float* position, const float* frame, uint32_t n, const float* rnd, float* out_dirs, float* out_densities, float* out_ggx) {
+	switch (technique) {
+#define T(K) case K: return run<K, MAXV>(light_block, position, frame, n, rnd, out_dirs, out_densities, out_ggx);
+	T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10)
+#undef T
+	default: return -1;
+	}
+}
+
+// Same signature and meaning as vkr_oracle_related_work_batch (oracle/vkr_oracle.h)
+extern "C" int vkr_device_on_host_related_work_batch(uint32_t technique, uint32_t maxv, const void* light_block, const float* position, const float* frame,
+	uint32_t n, const float* random_numbers, float* out_dirs, float* out_densities, float* out_ggx_density_factor)
+{
+	const unsigned char* lb = (const unsigned char*) light_block;
+	switch (maxv) {
+	case 3: return run_technique<3>(technique, lb, position, frame, n, random_numbers, out_dirs, out_densities, out_ggx_density_factor);
+	case 4: return run_technique<4>(technique, lb, position, frame, n, random_numbers, out_dirs, out_densities, out_ggx_density_factor);
+	case 5: return run_technique<5>(technique, lb, position, frame, n, random_numbers, out_dirs, out_densities, out_ggx_density_factor);
+	case 6: return run_technique<6>(technique, lb, position, frame, n, random_numbers, out_dirs, out_densities, out_ggx_density_factor);
+	case 7: return run_technique<7>(technique, lb, position, frame, n, random_numbers, out_dirs, out_densities, out_ggx_density_factor);
+	default: return -1;
+	}
+}
+
+// Elementary functions of the device arithmetic contract: 0 atan, 1 sin, 2 cos, 3 acos on [-1,1], 4 atan2(x, 0.5), 5 pow(x, 1/3), 6 fast_positive_atan
+extern "C" void vkr_device_on_host_elementary_batch(int which, uint32_t n, const float* x, float* y) {
+	for (uint32_t i = 0; i != n; ++i) {
+		switch (which) {
+		case 0: y[i] = atan_poly(x[i]); break;
+		case 1: y[i] = sin_cw(x[i]); break;
+		case 2: y[i] = cos_cw(x[i]); break;
+		case 3: y[i] = acos_full(x[i]); break;
+		case 4: y[i] = atan2_poly(x[i], 0.5f) + atan2_poly(0.5f, x[i]); break;
+		case 5: y[i] = pow_contract(x[i], 1.0f / 3.0f); break;
+		default: y[i] = fast_positive_atan(x[i]); break;
+		}
+	}
+}

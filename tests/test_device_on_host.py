@@ -1,0 +1,121 @@
+"""The product's device sampling code, compiled for the CPU, against the oracle (bit for bit).
+
+vulkan_renderer_b200/csrc/vkr_related_work.cuh (with vkr_psa.cuh and vkr_device_math.cuh underneath) uses no warp intrinsics, so
+tests/device_on_host.cpp compiles the same source with g++ -ffp-contract=off. The oracle side (oracle/related_work_oracle.h) is
+pinned against the reference shader (tests/test_ref_shader.py, fixtures "_q<technique>"); this test closes the chain to the
+code the GPU runs for SURVEY 8 row f4 -- the -m gpu tests then exercise it inside the kernel.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import harness as H
+from tests.ref_frames import host_constants
+from oracle import binding as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(ROOT, "tests", "build", "libdevice_on_host.so")
+TECHNIQUES = {0: "baseline", 1: "area (Turk)", 2: "rectangle solid angle (Urena)", 3: "solid angle (Arvo)", 4: "solid angle", 5: "clipped solid angle",
+	6: "bilinear warp (Hart)", 7: "bilinear warp, clipped (Hart)", 8: "biquadratic warp (Hart)", 9: "biquadratic warp, clipped (Hart)", 10: "projected solid angle (Arvo)"}
+DATASETS = {3: "mini_tri", 4: "mini_city", 5: "mini_v5", 6: "mini_v6", 7: "mini_v7"}
+MIXED = {4: "mini_mixed", 7: "mini_poly"}   # lights with fewer vertices than the bound
+
+
+def _lib():
+	if not os.path.exists(LIB_PATH):
+		import __graft_entry__ as G
+		G.build_device_on_host()
+	return C.CDLL(LIB_PATH)
+
+
+def _light_blocks(name, maxv):
+	info = H.dataset(name)
+	constants = host_constants(info, 64, 48, 3)
+	stride = 160 + 16 * maxv * 2 + 16 * (maxv - 2)
+	assert len(constants) == 256 + 3 * stride
+	return [constants[256 + i * stride: 256 + (i + 1) * stride] for i in range(3)]
+
+
+def _scenarios(block, rng, count):
+	"""Shading points around the light with random shading frames: position, rows x/y/z of world_to_shading_space, translation."""
+	b = np.frombuffer(block, dtype=np.float32)
+	centre = b[4:7]
+	out = []
+	for _ in range(count):
+		position = (centre + rng.uniform(-3.0, 3.0, 3)).astype(np.float32)
+		n = rng.normal(size=3); n /= np.linalg.norm(n)
+		x = np.cross(n, rng.normal(size=3)); x /= np.linalg.norm(x)
+		y = np.cross(n, x)
+		rows = np.stack([x, y, n]).astype(np.float32)
+		t = -(rows.astype(np.float64) @ position.astype(np.float64))
+		out.append((position, np.concatenate([rows.reshape(9), t.astype(np.float32)])))
+	return out
+
+
+def _compare(technique, maxv, dataset, seed, points=24, samples=16):
+	lib = _lib()
+	rng = np.random.default_rng(seed)
+	checked = culled = 0
+	for block in _light_blocks(dataset, maxv):
+		for position, frame in _scenarios(block, rng, points):
+			rnd = rng.random((samples, 2)).astype(np.float32)
+			rnd[0] = (0.0, 0.0); rnd[1] = (np.float32(1.0) - np.float32(2.0 ** -24), 0.5)   # the ends of the unit interval
+			ref = O.related_work_batch(technique, maxv, block, position, frame, rnd)
+			dev = O.related_work_batch(technique, maxv, block, position, frame, rnd, symbol_library=lib, symbol="vkr_device_on_host_related_work_batch")
+			assert (ref is None) == (dev is None), "culling differs"
+			if ref is None:
+				culled += 1
+				continue
+			for a, b, what in zip(ref[:2], dev[:2], ("direction", "density")):
+				assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "%s differs: technique %d (%s), %s" % (what, technique, TECHNIQUES[technique], dataset)
+			assert np.float32(ref[2]).view(np.uint32) == np.float32(dev[2]).view(np.uint32)
+			checked += 1
+	return checked, culled
+
+
+@pytest.mark.parametrize("technique", sorted(TECHNIQUES))
+@pytest.mark.parametrize("maxv", sorted(DATASETS))
+def test_device_sampler_matches_oracle(technique, maxv):
+	checked, _ = _compare(technique, maxv, DATASETS[maxv], seed=100 * technique + maxv)
+	assert checked > 0
+
+
+@pytest.mark.parametrize("technique", [3, 4, 5, 7, 9, 10])
+@pytest.mark.parametrize("maxv", sorted(MIXED))
+def test_device_sampler_matches_oracle_with_mixed_vertex_counts(technique, maxv):
+	checked, _ = _compare(technique, maxv, MIXED[maxv], seed=7000 + 100 * technique + maxv)
+	assert checked > 0
+
+
+def test_samples_point_at_the_light_and_densities_integrate():
+	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
+	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""
+	rng = np.random.default_rng(5)
+	block = _light_blocks("mini_city", 4)[0]
+	b = np.frombuffer(block, dtype=np.float32)
+	plane = b[16:20]
+	position, frame = _scenarios(block, rng, 1)[0]
+	rnd = rng.random((4096, 2)).astype(np.float32)
+	solid_angles = {}
+	for technique in (2, 3, 4):
+		dirs, dens, ggx = O.related_work_batch(technique, 4, block, position, frame, rnd)
+		assert np.allclose(np.linalg.norm(dirs, axis=1), 1.0, atol=1e-4)
+		tt = -(plane[:3] @ position + plane[3]) / (dirs @ plane[:3])
+		assert (tt > 0).mean() > 0.999
+		solid_angles[technique] = 1.0 / float(np.median(dens))
+		assert abs(ggx * solid_angles[technique] - 1.0) < 1e-4
+	assert abs(solid_angles[3] / solid_angles[4] - 1.0) < 1e-3
+	assert abs(solid_angles[2] / solid_angles[4] - 1.0) < 1e-3   # the lights of mini_city are rectangles
+
+
+@pytest.mark.parametrize("which_device,which_oracle,lo,hi", [(0, "atan", -50.0, 50.0), (1, "sin", -20.0, 20.0), (2, "cos", -20.0, 20.0), (3, "acos", -1.0, 1.0), (4, "atan2_pair", -4.0, 4.0), (5, "cbrt_pow", 0.0, 30.0), (6, "fast_positive_atan", -8.0, 8.0)])
+def test_device_elementary_functions_match_oracle(which_device, which_oracle, lo, hi):
+	lib = _lib()
+	x = np.random.default_rng(which_device).uniform(lo, hi, 20000).astype(np.float32)
+	y = np.zeros_like(x)
+	lib.vkr_device_on_host_elementary_batch(C.c_int(which_device), C.c_uint32(len(x)), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+	ref = O.elementary(which_oracle, x)
+	assert np.array_equal(y.view(np.uint32), ref.view(np.uint32))

@@ -205,6 +205,29 @@ def test_error_paths_return_codes_and_leave_structs_zeroed(tmp_path, capfd):
 	assert "Failed" in capfd.readouterr().out     # printf diagnostics like the reference
 
 
+def test_shading_pass_rejects_illegal_technique_and_strategy_combinations(capfd):
+	"""The legality rules of the reference's settings panel (src/user_interface.cpp:90-180) are checked before any CUDA call, so they can be
+	tested without a GPU: the related-work techniques sample the diffuse lobe only, GGX MIS needs a stand-alone density."""
+	lib = api.load_library()
+	dev = api.Device()
+	def create(technique, strategy, heuristic=api.MIS_BALANCE):
+		p = api.ShadingPass(); d = api.ShadingPassDesc(width=64, height=32, polygonal_light_count=1, min_polygonal_light_vertex_count=4, max_polygonal_light_vertex_count=4,
+			sample_count=1, sampling_strategies=strategy, mis_heuristic=heuristic, polygon_sampling_technique=technique, stripe_count=1)
+		rc = lib.vkr_create_shading_pass(C.byref(p), C.byref(dev), C.byref(d))
+		assert rc == 1 and p.constants_size == 0 and not p.d_constants     # no LTC / noise tables: every call fails, the message tells why
+		return capfd.readouterr().out
+	for technique in range(11):
+		assert "does not support sampling strategy" in create(technique, api.STRATEGY_DIFFUSE_SPECULAR_MIS)
+		assert "does not support sampling strategy" in create(technique, api.STRATEGY_DIFFUSE_SPECULAR_RANDOM)
+		assert "missing LTC / noise tables" in create(technique, api.STRATEGY_DIFFUSE_ONLY)
+	for technique in (0, 1, 6, 7, 8, 9):
+		assert "does not support sampling strategy" in create(technique, api.STRATEGY_DIFFUSE_GGX_MIS)
+	for technique in (2, 3, 4, 5, 10, 11, 12):
+		assert "missing LTC / noise tables" in create(technique, api.STRATEGY_DIFFUSE_GGX_MIS)
+	assert "balance and power heuristics only" in create(11, api.STRATEGY_DIFFUSE_GGX_MIS, api.MIS_OPTIMAL)
+	assert "unknown polygon sampling technique" in create(13, api.STRATEGY_DIFFUSE_ONLY)
+
+
 def test_white_noise_and_synthetic_formats_are_what_the_reference_loaders_expect():
 	info = H.dataset("cornell")
 	raw = open(info["vks"], "rb").read()

@@ -27,6 +27,10 @@ EXPORTED_SYMBOLS = [
 STRATEGY_DIFFUSE_ONLY, STRATEGY_DIFFUSE_GGX_MIS, STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, STRATEGY_DIFFUSE_SPECULAR_MIS, STRATEGY_DIFFUSE_SPECULAR_RANDOM = range(5)
 MIS_BALANCE, MIS_POWER, MIS_WEIGHTED, MIS_OPTIMAL_CLAMPED, MIS_OPTIMAL = range(5)
 TECHNIQUE_PSA, TECHNIQUE_PSA_BIASED = 11, 12
+# the related-work techniques (sample_polygon_technique_t, src/polygonal_light.h:30-66), SURVEY 8 f4
+(TECHNIQUE_BASELINE, TECHNIQUE_AREA_TURK, TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA, TECHNIQUE_SOLID_ANGLE_ARVO, TECHNIQUE_SOLID_ANGLE, TECHNIQUE_CLIPPED_SOLID_ANGLE,
+	TECHNIQUE_BILINEAR_COSINE_WARP_HART, TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART, TECHNIQUE_BIQUADRATIC_COSINE_WARP_HART,
+	TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART, TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) = range(11)
 NOISE_WHITE, NOISE_BLUE, NOISE_AHMED = 0, 1, 2
 
 

@@ -79,9 +79,19 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 	vkr_shading_pass_desc_t& d = pass->desc;
 	if (d.stripe_count == 0) d.stripe_count = 1;
 	// Legality rules of the reference's settings panel (src/user_interface.cpp:90-180), plus what this library implements
-	if (d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle && d.polygon_sampling_technique != vkr_sample_polygon_projected_solid_angle_biased) {
-		printf("Failed to create the shading pass: only projected solid angle sampling (technique 11 or 12) is implemented, got %d.\n", (int) d.polygon_sampling_technique);
+	const int technique = (int) d.polygon_sampling_technique;
+	if (technique < (int) vkr_sample_polygon_baseline || technique > (int) vkr_sample_polygon_projected_solid_angle_biased) {
+		printf("Failed to create the shading pass: unknown polygon sampling technique %d.\n", technique);
 		memset(pass, 0, sizeof(*pass)); return 1;
+	}
+	if (technique < (int) vkr_sample_polygon_projected_solid_angle) {
+		// the related-work techniques sample the diffuse lobe only; GGX MIS needs a density that can be evaluated on its own
+		const bool ggx_ok = technique == vkr_sample_polygon_rectangle_solid_angle_urena || technique == vkr_sample_polygon_solid_angle_arvo || technique == vkr_sample_polygon_solid_angle
+			|| technique == vkr_sample_polygon_clipped_solid_angle || technique == vkr_sample_polygon_projected_solid_angle_arvo;
+		if (!(d.sampling_strategies == vkr_sampling_strategies_diffuse_only || (d.sampling_strategies == vkr_sampling_strategies_diffuse_ggx_mis && ggx_ok))) {
+			printf("Failed to create the shading pass: polygon sampling technique %d does not support sampling strategy %d.\n", technique, (int) d.sampling_strategies);
+			memset(pass, 0, sizeof(*pass)); return 1;
+		}
 	}
 	if ((int) d.sampling_strategies < 0 || (int) d.sampling_strategies > 4 || (int) d.mis_heuristic < 0 || (int) d.mis_heuristic > 4) {
 		printf("Failed to create the shading pass: invalid sampling strategy or MIS heuristic.\n");
@@ -123,6 +133,16 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 }
 
 cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream) {
+	if (p.polygon_sampling_technique < 11) { // related-work techniques
+		switch (p.max_light_vertex_count) {
+		case 3: return vkr_launch_related_work_kernel_maxv3(p, stream);
+		case 4: return vkr_launch_related_work_kernel_maxv4(p, stream);
+		case 5: return vkr_launch_related_work_kernel_maxv5(p, stream);
+		case 6: return vkr_launch_related_work_kernel_maxv6(p, stream);
+		case 7: return vkr_launch_related_work_kernel_maxv7(p, stream);
+		default: return cudaErrorInvalidValue;
+		}
+	}
 	switch (p.max_light_vertex_count) { // MAX_POLYGONAL_LIGHT_VERTEX_COUNT, a compile-time bound of the kernels
 	case 3: return vkr_launch_shading_kernel_maxp4(p, stream);
 	case 4: return vkr_launch_shading_kernel_maxp5(p, stream);
@@ -174,6 +194,7 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	p.light_count = (int) d.polygonal_light_count; p.max_light_vertex_count = (int) d.max_polygonal_light_vertex_count; p.sample_count = (int) d.sample_count;
 	p.sampling_strategies = (int) d.sampling_strategies; p.mis_heuristic = (int) d.mis_heuristic;
 	p.biased_sampling = d.polygon_sampling_technique == vkr_sample_polygon_projected_solid_angle_biased;
+	p.polygon_sampling_technique = (int) d.polygon_sampling_technique;
 	p.trace_shadow_rays = d.trace_shadow_rays; p.show_polygonal_lights = d.show_polygonal_lights; p.output_srgb = d.output_srgb;
 	p.noise = (const uint16_t*) d.noise_table->d_noise; p.noise_w = (int) d.noise_table->width; p.noise_h = (int) d.noise_table->height; p.noise_layers = (int) d.noise_table->layers;
 	p.ltc0 = (const uint16_t*) d.ltc_table->d_table0; p.ltc1 = (const uint16_t*) d.ltc_table->d_table1;

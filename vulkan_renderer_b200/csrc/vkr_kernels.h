@@ -29,6 +29,7 @@ struct shading_kernel_params {
 	// acceleration structure
 	const float4* bvh_nodes; const float4* bvh_tris; uint32_t tri_count;
 	int stack_depth;                 // traversal stack entries per lane (BVH depth + 2)
+	int polygon_sampling_technique;  // sample_polygon_technique_t (src/polygonal_light.h:30-66); 0..10 run vkr_related_work_kernel.cu
 };
 
 struct gbuffer_kernel_params {
@@ -51,5 +52,10 @@ cudaError_t vkr_launch_shading_kernel_maxp5(const vkr::shading_kernel_params& p,
 cudaError_t vkr_launch_shading_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_related_work_kernel_maxv3(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_related_work_kernel.cu, one object per light vertex bound
+cudaError_t vkr_launch_related_work_kernel_maxv4(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_related_work_kernel_maxv5(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_related_work_kernel_maxv6(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_related_work_kernel_maxv7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_visibility_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_gbuffer_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);

@@ -24,29 +24,9 @@
 // floating-point sums identical to the reference's sequential loop. Without shadow rays (TRACE = false) the kernel is
 // launched with the shading warps only.
 // Compile with -fmad=false (see vkr_device_math.cuh).
-#include <cuda_fp16.h>
-#include "vkr_shade_common.cuh"
-#include "vkr_ray_stream.cuh"
+#include "vkr_shading_tile.cuh"
 
 namespace vkr {
-
-constexpr int kTileW = 16, kTileH = 8, kShadeThreads = kTileW * kTileH;
-static_assert(kShadeThreads == 32 * kShadeWarps, "one shading warp per 8x4 patch");
-constexpr int kTraceThreads = 32 * kTraceWarps;
-#ifndef VKR_SHADE_REGS
-#define VKR_SHADE_REGS 128
-#endif
-#ifndef VKR_TRACE_REGS
-#define VKR_TRACE_REGS 56
-#endif
-
-// Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
-VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
-	const float num = dot4_point(light + L_PLANE, sp.position);
-	const float den = dot(dir_world, make3(ldf(light, L_PLANE), ldf(light, L_PLANE + 4), ldf(light, L_PLANE + 8)));
-	return -num / den;
-}
-VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8)); }
 
 // One polygonal light for the warp's 32 pixels (shading_pass.frag.glsl:329-711, projected solid angle technique).
 // Control flow is warp-uniform; `on` masks lanes whose pixel is not shaded by this light.
@@ -247,134 +227,20 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 	submit<TRACE, OPTIMAL>(q, lane, false, false, zero, 0.0f, zero, zero, result, true);
 }
 
+// The light shader of this translation unit: projected solid angle sampling with the five sampling strategies
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
+struct psa_light_shader {
+	VKR_DEV void operator()(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
+		const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, pixel_sum& result, int lane) const
+	{
+		shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(on, sp, l, light, ns, p, cb, px, py, q, result, lane);
+	}
+};
+
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
 __global__ void __launch_bounds__(TRACE ? kShadeThreads + kTraceThreads : kShadeThreads, TRACE ? 2 : 3)
 shading_kernel(const shading_kernel_params p) {
-	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned char* cb = smem;                                   // constant block incl. lights
-	float* stream_base = reinterpret_cast<float*>(smem + p.constants_smem_bytes);
-	int* stack_base = reinterpret_cast<int*>(stream_base + stream_floats_per_warp(OPTIMAL) * kShadeWarps);
-	__shared__ __align__(8) unsigned long long mbar;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	// --- stage the constant block with one bulk async copy (TMA engine), completion on an mbarrier
-	const uint32_t mbar_addr = (uint32_t) __cvta_generic_to_shared(&mbar);
-	const uint32_t cb_addr = (uint32_t) __cvta_generic_to_shared(cb);
-	if (threadIdx.x == 0) {
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_addr));
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	if (TRACE && threadIdx.x < kShadeWarps) { // stream control words {head, tail, closed, -}
-		int* control = reinterpret_cast<int*>(stream_base + stream_floats_per_warp(OPTIMAL) * threadIdx.x + stream_control_at(OPTIMAL));
-		control[0] = 0; control[1] = 0; control[2] = -1; control[3] = 0;
-	}
-	__syncthreads();
-	if (TRACE) {
-		// --- role split: from here on the two kinds of warps never meet at a CTA-wide barrier again
-		if (warp >= kShadeWarps) {
-			asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(VKR_TRACE_REGS));
-			const int t = warp - kShadeWarps;
-			trace_stream<OPTIMAL>(smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * (t & (kShadeWarps - 1))), p.bvh_nodes, p.bvh_tris,
-				smem_addr(stack_base + p.stack_depth * 32 * t + lane), lane);
-			return;
-		}
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(VKR_SHADE_REGS));
-	}
-	if (threadIdx.x == 0) {
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_addr), "r"(p.constants_bytes) : "memory");
-		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-			:: "r"(cb_addr), "l"(p.constants), "r"(p.constants_bytes), "r"(mbar_addr) : "memory");
-	}
-	{
-		uint32_t done = 0;
-		while (!done) {
-			asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0; selp.u32 %0, 1, 0, q; }" : "=r"(done) : "r"(mbar_addr) : "memory");
-		}
-	}
-	// --- pixel of this thread: warps cover 8x4 patches of the 16x8 tile
-	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tile = blockIdx.x;
-	const int x = (tile % tiles_x) * kTileW + lx;
-	const int y = (p.tile_row_first + (tile / tiles_x) * p.tile_row_step) * kTileH + ly;
-	const bool in_frame = x < p.width && y < p.height;
-	const size_t pixel = in_frame ? ((size_t) y * p.width + x) : 0;
-	const size_t plane = (size_t) p.width * p.height;
-	const float4 g0 = __ldg(p.gbuffer + pixel), g1 = __ldg(p.gbuffer + plane + pixel);
-	const bool valid = in_frame && g1.w != 0.0f;
-	const f3 camera = make3(ldf(cb, OFF_CAMERA), ldf(cb, OFF_CAMERA + 4), ldf(cb, OFF_CAMERA + 8));
-	const float exposure = ldf(cb, OFF_EXPOSURE);
-	f3 color = make3(0.0f, 0.0f, 0.0f);
-	shading_point sp;
-	sp.position = make3(g0.x, g0.y, g0.z);
-	sp.roughness = g0.w;
-	sp.normal = make3(g1.x, g1.y, g1.z);
-	const int light_stride = L_FIXED + 16 * (MAXP - 1) * 2 + 16 * (MAXP - 3);
-	if (p.show_polygonal_lights && in_frame) { // shading_pass.frag.glsl:841-850
-		f3 end; float end_w;
-		if (valid) { end = sp.position; end_w = 1.0f; }
-		else {
-			const float fx = (float) x, fy = (float) y;
-			end = make3(
-				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 8), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 4), fy, ldf(cb, OFF_PIXEL_TO_RAY) * fx)),
-				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 24), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 20), fy, ldf(cb, OFF_PIXEL_TO_RAY + 16) * fx)),
-				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 40), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 36), fy, ldf(cb, OFF_PIXEL_TO_RAY + 32) * fx)));
-			end_w = 0.0f;
-		}
-		for (int li = 0; li != p.light_count; ++li) {
-			const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
-			if (light_ray_intersection<MAXP - 1>(light, camera, end, end_w))
-				color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
-		}
-	}
-	// --- the warp's ray stream; trace lanes fetch ray origins from it by owner lane
-	ray_producer q;
-	q.base = smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * warp); q.fill = 0; q.resolved = 0;
-	if (TRACE) {
-		float* origin = stream_base + stream_floats_per_warp(OPTIMAL) * warp + stream_origin_at(OPTIMAL);
-		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
-	}
-	pixel_sum acc;
-	acc.color = color; acc.light = make3(0.0f, 0.0f, 0.0f); acc.inv_samples = 1.0f / (float) p.sample_count;
-	acc.submit_parity = 0u; acc.resolve_parity = 0u; acc.pushed = false;
-	__syncwarp(kFullMask);
-	if (__any_sync(kFullMask, valid)) {
-		ltc_state l = {};
-		noise_stream ns;
-		ns.z = 0.0f; ns.w = 0.0f; ns.available = 0; ns.sample_index = 0;
-		sp.diffuse_albedo = make3(0.0f, 0.0f, 0.0f); sp.fresnel_0 = make3(0.0f, 0.0f, 0.0f);
-		sp.outgoing = make3(0.0f, 0.0f, 1.0f); sp.lambert_outgoing = 0.0f;
-		if (valid) {
-			const float4 g2 = __ldg(p.gbuffer + 2 * plane + pixel), g3 = __ldg(p.gbuffer + 3 * plane + pixel);
-			sp.diffuse_albedo = make3(g2.x, g2.y, g2.z);
-			sp.fresnel_0 = make3(g3.x, g3.y, g3.z);
-			sp.outgoing = normalize(camera - sp.position);
-			sp.lambert_outgoing = dot(sp.normal, sp.outgoing);
-			get_ltc_coefficients(l, p, cb, sp);
-		}
-#pragma unroll 1
-		for (int li = 0; li != p.light_count; ++li) {
-			const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
-			shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, acc, lane);
-		}
-	}
-	if (TRACE) close_stream<OPTIMAL>(q, lane, acc);
-	color = acc.color;
-	if (!in_frame) return;
-	f3 final_color = color;
-	if (isnan(color.x) || isnan(color.y) || isnan(color.z) || isinf(color.x) || isinf(color.y) || isinf(color.z))
-		final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
-	f3 out_color = make3(final_color.x * exposure, final_color.y * exposure, final_color.z * exposure);
-	// --- output stage (shading_pass.frag.glsl:871-892): half-bit split for HDR screenshots, sRGB conversion
-	const uint32_t frame_bits = ldu(cb, OFF_FRAME_BITS);
-	if (frame_bits > 0u) {
-		const uint32_t mask = (frame_bits == 1u) ? 0xFFu : 0xFF00u, shift = (frame_bits == 1u) ? 0u : 8u;
-		const uint32_t h0 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.x)) | ((uint32_t) __half_as_ushort(__float2half_rn(out_color.y)) << 16);
-		const uint32_t h1 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.z));
-		out_color = make3((float) ((h0 & mask) >> shift) * (1.0f / 255.0f), (float) ((((h0 & 0xFFFF0000u) >> 16) & mask) >> shift) * (1.0f / 255.0f), (float) ((h1 & mask) >> shift) * (1.0f / 255.0f));
-		if (!p.output_srgb) out_color = make3(srgb_to_linear(out_color.x), srgb_to_linear(out_color.y), srgb_to_linear(out_color.z));
-	}
-	else if (p.output_srgb) out_color = make3(linear_to_srgb(out_color.x), linear_to_srgb(out_color.y), linear_to_srgb(out_color.z));
-	p.out[pixel] = make_float4(out_color.x, out_color.y, out_color.z, 1.0f);
+	shade_tile<MAXP, OPTIMAL, TRACE>(p, psa_light_shader<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>());
 }
 
 } // namespace vkr
