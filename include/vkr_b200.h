@@ -254,6 +254,25 @@ int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, c
 int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer, float* out_rgba32f);
 int vkr_shading_pass_wait(vkr_shading_pass_t* pass, const vkr_device_t* device);
 
+/* ---- after the pass: screenshots and frame times (replaces take_screenshot / implement_screenshot,
+        src/main.c:1550-1770, the stb_image_write calls in them and src/frame_timer.c) */
+/* What an 8-bit UNORM render target stores for a float frame: round(clamp(x, 0, 1) * 255) per channel, alpha dropped */
+void vkr_quantize_unorm8(const float* rgba32f, uint32_t width, uint32_t height, uint8_t* out_rgb8);
+/* combine_ldr_screenshots_into_hdr, src/main.c:1696-1707: low / high bytes of half-precision values -> float */
+void vkr_combine_ldr_screenshots_into_hdr(const uint8_t* low_bytes, const uint8_t* high_bytes, size_t entry_count, float* out_hdr);
+/* stbi_write_png / stbi_write_hdr as called at src/main.c:1734, 1755: tightly packed 8-bit RGB / float RGB */
+int vkr_write_png(const char* file_path, uint32_t width, uint32_t height, const uint8_t* rgb8);
+int vkr_write_hdr(const char* file_path, uint32_t width, uint32_t height, const float* rgb32f);
+/* Shades the frame and stores it: *.png (the shader converts to sRGB, 8-bit quantisation) or *.hdr (two frames with the low and
+   high half-float bytes, g_frame_bits = 1 / 2, combined on the host like the reference does). Exactly one path must be given.
+   constants: HOST pointer; d_gbuffer: DEVICE pointer. Synchronous. */
+int vkr_take_screenshot(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer,
+	const char* path_png, const char* path_hdr);
+/* record_frame_time / get_frame_time, src/frame_timer.c:28-75: median of the differences of the last 100 recorded times (seconds) */
+void vkr_record_frame_time(double time_in_seconds);
+float vkr_get_frame_time(void);
+void vkr_reset_frame_times(void);
+
 /* ---- shadow-ray probe (tests / KATs): rays = {ox,oy,oz,dx,dy,dz,tmin,tmax} per ray on the HOST, out = 1 byte per ray */
 int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, uint32_t ray_count, const float* rays, uint8_t* out_occluded);
 /* ---- sampling probe (tests / KATs): clip + prepare + sample in the polygon's local space on the device */
