@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = [
 	"vkr_gbuffer_size", "vkr_run_visibility_pass", "vkr_run_gbuffer_pass",
 	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait",
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_free_probe",
+	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
+	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
 ]
 
 # enums (values = the reference's)

@@ -155,6 +155,42 @@ def scene_city(seed=1, blocks=24, extent=200.0, detail=16, ground_cells=256, n_m
 	return m.finish(), materials
 
 
+def scene_roughness_planes():
+	"""Three 4 m x 4 m planes side by side with roughness 0.15 / 0.4 / 0.8 on a dark floor: the stand-in for the reference's
+	'roughness planes' scene of the timing experiments (src/experiment_list.c:218-409; the asset itself is not in the repository)."""
+	m = Mesh()
+	materials = [dict(name="floor", base=(0.2, 0.2, 0.2), roughness=0.9, metal=0.0)]
+	m.add(_grid_quad([-40.0, -30.0, 0.0], [80.0, 0.0, 0.0], [0.0, 90.0, 0.0], 16, 18), 0)
+	for i, r in enumerate((0.15, 0.4, 0.8)):
+		materials.append(dict(name="plane_%d" % i, base=(0.7, 0.7, 0.7), roughness=r, metal=1.0 if i == 0 else 0.0))
+		m.add(_grid_quad([-6.5 + 4.5 * i, -2.0, 0.05], [4.0, 0.0, 0.0], [0.0, 4.0, 0.0], 8, 8), 1 + i)
+	return m.finish(), materials
+
+
+def roughness_planes_lights(vertex_count, central, light_count):
+	"""Lights of the timing experiments (src/experiment_list.c:366-409): regular polygons with 3 to 7 vertices, either close above the
+	planes and facing down (central: the surface normal passes through the polygon for most pixels) or standing beside them
+	(decentral), one big light or 128 small ones with the same total flux."""
+	rng = np.random.default_rng(1000 * vertex_count + 10 * int(central) + (light_count > 1))
+	polygon = [(0.5 + 0.5 * float(np.cos(0.4 + 2.0 * np.pi * k / vertex_count)), 0.5 + 0.5 * float(np.sin(0.4 + 2.0 * np.pi * k / vertex_count))) for k in range(vertex_count)]
+	lights = []
+	for k in range(light_count):
+		scale = 14.0 if light_count == 1 else 1.6
+		if central:
+			# plane normal = rotation column 2; a rotation about x by pi makes the light face down
+			centre = (0.0, 0.0, 1.2) if light_count == 1 else (rng.uniform(-7.0, 7.0), rng.uniform(-5.0, 5.0), rng.uniform(0.9, 1.5))
+			angles = (np.pi, 0.0, 0.0) if light_count == 1 else (np.pi + rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(0.0, 2.0 * np.pi))
+			translation = (centre[0] - 0.5 * scale, centre[1] + 0.5 * scale, centre[2]) if light_count == 1 else centre
+		else:
+			# a rotation about x by pi/2 turns the normal towards -y: an upright light behind the planes
+			scale = 6.0 if light_count == 1 else 1.2
+			translation = (-3.0, 5.5, 0.3) if light_count == 1 else (rng.uniform(-8.0, 7.0), rng.uniform(4.5, 6.0), rng.uniform(0.2, 3.0))
+			angles = (0.5 * np.pi, 0.0, 0.0) if light_count == 1 else (0.5 * np.pi + rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(-0.3, 0.3))
+		flux = 40.0 / light_count
+		lights.append(make_light(translation, angles, (scale, scale), (flux, flux, flux), polygon))
+	return lights
+
+
 def scene_room(seed=2, detail=48, clutter=2500, n_mat=32):
 	"""'attic_like' stand-in: closed 12 x 8 x 4 m room with slanted beams and clutter. Defaults give ~1.0 M triangles."""
 	rng = np.random.default_rng(seed)
@@ -391,6 +427,11 @@ def build_dataset(directory, name, **overrides):
 		mesh, materials = scene_room(seed=4, detail=6, clutter=60, n_mat=8)
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
 		lights = _ceiling_lights(rng, overrides.get("lights", 32), (1.0, 11.0), (1.0, 7.0), (2.4, 3.3), scale_range=(0.3, 1.0))
+	elif name == "roughness_planes":
+		# scene of the reference's timing experiments; overrides: vertices (3..7), central (0/1), lights (1 or 128)
+		mesh, materials = scene_roughness_planes()
+		camera = look_at_camera((0.0, -6.0, 7.5), (0.0, 0.0, 0.0))
+		lights = roughness_planes_lights(int(overrides.get("vertices", 4)), bool(overrides.get("central", 1)), int(overrides.get("lights", 1)))
 	elif name == "room":
 		mesh, materials = scene_room(**{k: v for k, v in overrides.items() if k in ("seed", "detail", "clutter", "n_mat")})
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
