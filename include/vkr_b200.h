@@ -204,6 +204,23 @@ size_t vkr_gbuffer_size(uint32_t width, uint32_t height);
 int vkr_run_visibility_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, void* d_visibility);
 int vkr_run_gbuffer_pass(const vkr_device_t* device, const vkr_scene_t* scene, const void* constants, uint32_t width, uint32_t height, const void* d_visibility, void* d_gbuffer);
 
+/* ---- render targets (replaces create_render_targets / destroy_render_targets, src/main.c:253-315, and the swapchain image the
+        shading pass writes): device images of one resolution, owned by the library so that a host application needs no CUDA
+        allocator of its own. The reference's depth buffer has no counterpart (visibility comes from primary rays). */
+typedef struct vkr_render_targets_s {
+	uint32_t width, height;
+	void* d_visibility;   /* uint32 per pixel, 0xFFFFFFFF = background (the clear value, src/main.c:1409) */
+	void* d_gbuffer;      /* vkr_gbuffer_size(width, height) bytes */
+	void* d_frame;        /* width * height float4: what the shading pass writes */
+} vkr_render_targets_t;
+int vkr_create_render_targets(vkr_render_targets_t* targets, const vkr_device_t* device, uint32_t width, uint32_t height);
+void vkr_destroy_render_targets(vkr_render_targets_t* targets, const vkr_device_t* device);
+/* Copies the frame (width * height float4) / the G-buffer to HOST memory and waits for it */
+int vkr_download_frame(const vkr_render_targets_t* targets, const vkr_device_t* device, float* out_rgba32f);
+int vkr_download_gbuffer(const vkr_render_targets_t* targets, const vkr_device_t* device, uint32_t* out_visibility, float* out_gbuffer);
+/* Copies a G-buffer from HOST memory into the targets (e.g. one made elsewhere) */
+int vkr_upload_gbuffer(vkr_render_targets_t* targets, const vkr_device_t* device, const float* gbuffer);
+
 /* ---- the shading pass (replaces create_shading_pass src/main.c:598-940, the subpass-1 draw
         src/main.c:1429-1434 and the per-frame part of render_frame src/main.c:2197-2270) */
 typedef struct vkr_shading_pass_desc_s {

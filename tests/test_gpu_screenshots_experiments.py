@@ -18,27 +18,28 @@ pytestmark = pytest.mark.gpu
 
 
 def _frame_and_inputs(width, height):
-	import torch
 	info = H.dataset("mini_city"); oi = H.OracleInputs(info)
 	frame = H.open_frame(info)
 	frame.configure(sample_count=2, strategy=api.STRATEGY_DIFFUSE_SPECULAR_MIS, heuristic=api.MIS_OPTIMAL_CLAMPED, trace_shadow_rays=1, show_lights=1)
 	constants = frame.constants(width, height)
 	vis = oi.visibility(width, height, constants); gb = oi.gbuffer(width, height, constants, vis)
-	d_gb = torch.from_numpy(gb).cuda()
-	return frame, oi, constants, gb, d_gb
+	targets = api.RenderTargets()
+	assert frame.lib.vkr_create_render_targets(C.byref(targets), C.byref(frame.device), width, height) == 0
+	assert frame.lib.vkr_upload_gbuffer(C.byref(targets), C.byref(frame.device), np.ascontiguousarray(gb, dtype=np.float32).ctypes.data_as(C.c_void_p)) == 0
+	return frame, oi, constants, gb, targets
 
 
 def test_png_screenshot_is_the_quantised_srgb_frame(tmp_path):
 	width, height = 96, 56
-	frame, oi, constants, gb, d_gb = _frame_and_inputs(width, height)
+	frame, oi, constants, gb, targets = _frame_and_inputs(width, height)
 	try:
 		p = frame.create_pass(width, height)
 		path = str(tmp_path / "shot.png")
-		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), d_gb.data_ptr(), path.encode(), None) == 0
-		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), d_gb.data_ptr(), path.encode(), path.encode()) == 1   # cannot mix LDR and HDR
+		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), targets.d_gbuffer, path.encode(), None) == 0
+		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), targets.d_gbuffer, path.encode(), path.encode()) == 1   # cannot mix LDR and HDR
 		ref, _ = oi.shade(dict(H.oracle_config(frame, width, height), output_srgb=1), constants, gb)
 	finally:
-		frame.close()
+		frame.lib.vkr_destroy_render_targets(C.byref(targets), C.byref(frame.device)); frame.close()
 	expected = np.floor(np.clip(ref[..., :3], 0.0, 1.0).astype(np.float32) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
 	shot = _read_png(path)
 	assert shot.shape == (height, width, 3) and np.array_equal(shot, expected)
@@ -47,15 +48,15 @@ def test_png_screenshot_is_the_quantised_srgb_frame(tmp_path):
 
 def test_hdr_screenshot_is_the_half_precision_linear_frame(tmp_path):
 	width, height = 96, 56
-	frame, oi, constants, gb, d_gb = _frame_and_inputs(width, height)
+	frame, oi, constants, gb, targets = _frame_and_inputs(width, height)
 	try:
 		p = frame.create_pass(width, height)
 		path = str(tmp_path / "shot.hdr")
-		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), d_gb.data_ptr(), None, path.encode()) == 0
+		assert frame.lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), targets.d_gbuffer, None, path.encode()) == 0
 		assert p.desc.output_srgb == 0                                  # the pass is left as it was
 		ref, _ = oi.shade(H.oracle_config(frame, width, height), constants, gb)
 	finally:
-		frame.close()
+		frame.lib.vkr_destroy_render_targets(C.byref(targets), C.byref(frame.device)); frame.close()
 	half = ref[..., :3].astype(np.float16).astype(np.float64)          # packHalf2x16: round to nearest even
 	shot = _read_hdr(path)
 	peak = half.max(axis=-1, keepdims=True)

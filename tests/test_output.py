@@ -146,3 +146,16 @@ def test_frame_timer_is_the_median_of_recent_frame_times():
 	assert abs(lib.vkr_get_frame_time() - 0.005) < 1e-6
 	lib.vkr_reset_frame_times()
 	assert lib.vkr_get_frame_time() == 0.0
+
+
+def test_render_targets_need_a_gpu_and_say_so(capfd):
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip("covered by the -m gpu tests on a GPU box")
+	lib = _lib()
+	targets = api.RenderTargets(); dev = api.Device()
+	assert lib.vkr_create_render_targets(C.byref(targets), C.byref(dev), 64, 32) == 1
+	assert targets.width == 0 and not targets.d_frame          # zeroed, like the reference's create_* on failure
+	assert lib.vkr_create_render_targets(C.byref(targets), C.byref(dev), 0, 32) == 1
+	assert "Failed to create render targets" in capfd.readouterr().out
+	lib.vkr_destroy_render_targets(C.byref(targets), C.byref(dev))   # tolerates a zeroed object

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_free_probe",
 	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
 	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
+	"vkr_create_render_targets", "vkr_destroy_render_targets", "vkr_download_frame", "vkr_download_gbuffer", "vkr_upload_gbuffer",
 ]
 
 # enums (values = the reference's)
@@ -90,6 +91,10 @@ class RenderSettings(C.Structure):
 		("animate_noise", C.c_int), ("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int)]
 
 
+class RenderTargets(C.Structure):
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("d_visibility", C.c_void_p), ("d_gbuffer", C.c_void_p), ("d_frame", C.c_void_p)]
+
+
 class ShadingPassDesc(C.Structure):
 	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("polygonal_light_count", C.c_uint32),
 		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
@@ -154,5 +159,18 @@ def load_library():
 	lib.vkr_sample_polygon_batch.argtypes = [P(Device), C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
 	lib.vkr_bvh_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
 	lib.vkr_bvh_free_probe.argtypes = [P(C.c_float), P(C.c_float), P(C.c_uint32)]; lib.vkr_bvh_free_probe.restype = None
+	lib.vkr_create_render_targets.argtypes = [P(RenderTargets), P(Device), C.c_uint32, C.c_uint32]
+	lib.vkr_destroy_render_targets.argtypes = [P(RenderTargets), P(Device)]; lib.vkr_destroy_render_targets.restype = None
+	lib.vkr_download_frame.argtypes = [P(RenderTargets), P(Device), C.c_void_p]
+	lib.vkr_download_gbuffer.argtypes = [P(RenderTargets), P(Device), C.c_void_p, C.c_void_p]
+	lib.vkr_upload_gbuffer.argtypes = [P(RenderTargets), P(Device), C.c_void_p]
+	lib.vkr_quantize_unorm8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]; lib.vkr_quantize_unorm8.restype = None
+	lib.vkr_combine_ldr_screenshots_into_hdr.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]; lib.vkr_combine_ldr_screenshots_into_hdr.restype = None
+	lib.vkr_write_png.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+	lib.vkr_write_hdr.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+	lib.vkr_take_screenshot.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_char_p, C.c_char_p]
+	lib.vkr_record_frame_time.argtypes = [C.c_double]; lib.vkr_record_frame_time.restype = None
+	lib.vkr_get_frame_time.argtypes = []; lib.vkr_get_frame_time.restype = C.c_float
+	lib.vkr_reset_frame_times.argtypes = []; lib.vkr_reset_frame_times.restype = None
 	_lib = lib
 	return lib

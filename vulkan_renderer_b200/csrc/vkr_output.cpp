@@ -17,6 +17,56 @@
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Render targets (create_render_targets / destroy_render_targets, src/main.c:253-315)
+extern "C" void vkr_destroy_render_targets(vkr_render_targets_t* targets, const vkr_device_t* device) {
+	(void) device;
+	if (targets->d_visibility) cudaFree(targets->d_visibility);
+	if (targets->d_gbuffer) cudaFree(targets->d_gbuffer);
+	if (targets->d_frame) cudaFree(targets->d_frame);
+	memset(targets, 0, sizeof(*targets));
+}
+
+extern "C" int vkr_create_render_targets(vkr_render_targets_t* targets, const vkr_device_t* device, uint32_t width, uint32_t height) {
+	memset(targets, 0, sizeof(*targets));
+	if (!width || !height) { printf("Failed to create render targets: the resolution is %ux%u.\n", width, height); return 1; }
+	const size_t pixel_count = (size_t) width * height;
+	if (cudaSetDevice(device->cuda_device) != cudaSuccess || cudaMalloc(&targets->d_visibility, sizeof(uint32_t) * pixel_count) != cudaSuccess
+		|| cudaMalloc(&targets->d_gbuffer, vkr_gbuffer_size(width, height)) != cudaSuccess || cudaMalloc(&targets->d_frame, sizeof(float) * 4 * pixel_count) != cudaSuccess)
+	{
+		printf("Failed to create render targets of resolution %ux%u.\n", width, height);
+		vkr_destroy_render_targets(targets, device);
+		return 1;
+	}
+	targets->width = width; targets->height = height;
+	cudaMemsetAsync(targets->d_visibility, 0xFF, sizeof(uint32_t) * pixel_count, (cudaStream_t) device->stream);
+	cudaMemsetAsync(targets->d_frame, 0, sizeof(float) * 4 * pixel_count, (cudaStream_t) device->stream);
+	return 0;
+}
+
+static int copy_and_wait(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, const vkr_device_t* device, const char* what) {
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	if (cudaSetDevice(device->cuda_device) != cudaSuccess || cudaMemcpyAsync(dst, src, bytes, kind, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+		printf("Failed to copy %s: %s\n", what, cudaGetErrorString(cudaGetLastError()));
+		return 1;
+	}
+	return 0;
+}
+
+extern "C" int vkr_download_frame(const vkr_render_targets_t* targets, const vkr_device_t* device, float* out_rgba32f) {
+	return copy_and_wait(out_rgba32f, targets->d_frame, sizeof(float) * 4 * (size_t) targets->width * targets->height, cudaMemcpyDeviceToHost, device, "the frame to the host");
+}
+
+extern "C" int vkr_download_gbuffer(const vkr_render_targets_t* targets, const vkr_device_t* device, uint32_t* out_visibility, float* out_gbuffer) {
+	if (out_visibility && copy_and_wait(out_visibility, targets->d_visibility, sizeof(uint32_t) * (size_t) targets->width * targets->height, cudaMemcpyDeviceToHost, device, "the visibility buffer to the host")) return 1;
+	if (out_gbuffer && copy_and_wait(out_gbuffer, targets->d_gbuffer, vkr_gbuffer_size(targets->width, targets->height), cudaMemcpyDeviceToHost, device, "the G-buffer to the host")) return 1;
+	return 0;
+}
+
+extern "C" int vkr_upload_gbuffer(vkr_render_targets_t* targets, const vkr_device_t* device, const float* gbuffer) {
+	return copy_and_wait(targets->d_gbuffer, gbuffer, vkr_gbuffer_size(targets->width, targets->height), cudaMemcpyHostToDevice, device, "the G-buffer to the device");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // 8-bit render target: UNORM conversion as Vulkan specifies it (round to nearest of clamp(x, 0, 1) * 255); NaN -> 0
 extern "C" void vkr_quantize_unorm8(const float* rgba32f, uint32_t width, uint32_t height, uint8_t* out_rgb8) {
 	const size_t pixel_count = (size_t) width * height;

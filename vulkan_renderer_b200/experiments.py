@@ -83,15 +83,14 @@ def prepare_data(experiment, data_root):
 def run_experiment(experiment, data_root, out_dir=None, frames=12, warmup=3, width=None, height=None, cuda_device=0, screenshot=True):
 	"""Runs one experiment like the application does: set up scene, lights and settings, render `warmup` + `frames` frames, take the
 	median frame time, store the screenshot under its path with the time in milliseconds filled in. Returns the JSON record."""
-	import torch
 	from .frame import Frame
 	info = prepare_data(experiment, data_root)
 	width = width or experiment["width"]; height = height or experiment["height"]
-	dev = torch.device("cuda", cuda_device)
-	frame = Frame(info["vks"], info["textures"], info["save"], info["ltc"], cuda_device=cuda_device, stream=torch.cuda.current_stream(dev).cuda_stream)
+	frame = Frame(info["vks"], info["textures"], info["save"], info["ltc"], cuda_device=cuda_device)
 	lib = frame.lib
 	lib.vkr_get_frame_time.restype = C.c_float
 	lib.vkr_record_frame_time.argtypes = [C.c_double]
+	targets = api.RenderTargets()
 	try:
 		s = experiment["settings"]
 		for key, value in s.items():
@@ -99,16 +98,15 @@ def run_experiment(experiment, data_root, out_dir=None, frames=12, warmup=3, wid
 		if experiment.get("light_count"):
 			frame.configure(light_count=experiment["light_count"])
 		constants = frame.constants(width, height)
-		vis = torch.empty((height, width), dtype=torch.int32, device=dev); gb = torch.empty((4, height, width, 4), dtype=torch.float32, device=dev)
-		out = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
-		frame._check(lib.vkr_run_visibility_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, vis.data_ptr()), "vkr_run_visibility_pass")
-		frame._check(lib.vkr_run_gbuffer_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, vis.data_ptr(), gb.data_ptr()), "vkr_run_gbuffer_pass")
+		frame._check(lib.vkr_create_render_targets(C.byref(targets), C.byref(frame.device), width, height), "vkr_create_render_targets")
+		frame._check(lib.vkr_run_visibility_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, targets.d_visibility), "vkr_run_visibility_pass")
+		frame._check(lib.vkr_run_gbuffer_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, targets.d_visibility, targets.d_gbuffer), "vkr_run_gbuffer_pass")
 		p = frame.create_pass(width, height, timing=True)
 		lib.vkr_reset_frame_times()
 		clock = 1.0   # the frame timer takes time stamps; kernel times from CUDA events are accumulated into one
 		kernel_ms = []
 		for i in range(warmup + frames):
-			frame._check(lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr()), "vkr_shading_pass_run")
+			frame._check(lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), targets.d_gbuffer, targets.d_frame), "vkr_shading_pass_run")
 			frame._check(lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device)), "vkr_shading_pass_wait")
 			if i == warmup:
 				lib.vkr_record_frame_time(clock)
@@ -124,10 +122,11 @@ def run_experiment(experiment, data_root, out_dir=None, frames=12, warmup=3, wid
 			path = os.path.join(out_dir, experiment["screenshot_path"] % frame_time_ms)
 			os.makedirs(os.path.dirname(path), exist_ok=True)
 			hdr = path.endswith(".hdr")
-			frame._check(lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), None if hdr else path.encode(), path.encode() if hdr else None), "vkr_take_screenshot")
+			frame._check(lib.vkr_take_screenshot(C.byref(p), C.byref(frame.device), constants, len(constants), targets.d_gbuffer, None if hdr else path.encode(), path.encode() if hdr else None), "vkr_take_screenshot")
 			record["screenshot"] = path
 		return record
 	finally:
+		lib.vkr_destroy_render_targets(C.byref(targets), C.byref(frame.device))
 		frame.close()
 
 
