@@ -263,7 +263,7 @@ def run_b200(args):
 			"clocks": clocks,
 		}
 		if world == 1 and not args.no_cpu_baseline:
-			result["cpu_baseline"] = cpu_baseline(args, info, width, height, lights, spp, constants, gb.cpu().numpy())
+			result["cpu_baseline"] = cpu_baseline(args, info, width, height, lights, spp, constants, gb.cpu().numpy(), visibility=vis.cpu().numpy().view(np.uint32))
 	frame.destroy_pass(p)
 	frame.close()
 	if world > 1:
@@ -273,29 +273,55 @@ def run_b200(args):
 		print(json.dumps(result), flush=True)
 
 
-def cpu_baseline(args, info, width, height, lights, spp, constants, gbuffer, band_rows=None):
-	"""Times the CPU oracle (scalar fp32 restatement of the reference path, OpenMP over rows) on a bounded sample:
-	8-row bands spread over the frame, full light count and spp."""
+def cpu_baseline(args, info, width, height, lights, spp, constants, gbuffer, band_rows=None, visibility=None):
+	"""Times the reference's path on the host cores on a bounded sample: 8-row bands spread over the frame, full light count and spp.
+	kind "reference": the reference's own shader sources compiled for the CPU (oracle/_ref/libref_shader.so, built by
+	oracle/build_ref.py where /root/reference exists and shipped prebuilt; it starts from the visibility buffer like the
+	shader does, i.e. it includes get_shading_data). kind "port": the C restatement (oracle/) when that library or this
+	configuration is not available. Both use OpenMP over rows with all host threads."""
 	from tests import harness as H
 	from vulkan_renderer_b200 import api
 	oi = H.OracleInputs(info)
-	cfg = dict(width=width, height=height, light_count=lights, max_light_vertex_count=4, min_light_vertex_count=4, sample_count=spp,
-		sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_OPTIMAL_CLAMPED, biased_sampling=0, trace_shadow_rays=1, show_polygonal_lights=1,
-		row_begin=0, row_end=0, band_height=8, band_stride=8 * (args.cpu_band_stride if band_rows is None else band_rows))
-	rows = sum(1 for y in range(height) if y % cfg["band_stride"] < 8)
+	band_stride = 8 * (args.cpu_band_stride if band_rows is None else band_rows)
+	rows = sum(1 for y in range(height) if y % band_stride < 8)
+	ref_cfg = None
+	if not args.cpu_port:
+		try:
+			from oracle import ref_binding as R
+			ref_cfg = R.find_config(strategy=api.STRATEGY_DIFFUSE_SPECULAR_MIS, heuristic=api.MIS_OPTIMAL_CLAMPED, biased=0, lights=lights, max_vertices=4, min_vertices=4,
+				samples=spp, trace=1, show_lights=1, technique=11, srgb=0, frame_bits=0)
+			if ref_cfg is not None and ref_cfg["materials"] < len(oi.material_params):
+				ref_cfg = None
+		except Exception as e:   # a broken prebuilt library must not take the bench down
+			log("[bench] reference shader library unusable (%s); timing the C restatement instead" % e)
+			ref_cfg = None
 	t0 = time.time()
-	_, rays = H.oracle.shade(cfg, constants, gbuffer, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris)
-	seconds = H.oracle.last_shade_seconds()
-	log("[bench] cpu oracle: %d rows in %.2f s (+ %.1f s BVH build), %d shadow rays" % (rows, seconds, time.time() - t0 - seconds, rays))
+	if ref_cfg is not None:
+		if visibility is None:
+			visibility = oi.visibility(width, height, constants)
+		t0 = time.time()
+		R.shade(ref_cfg["entry"], width, height, ref_cfg, constants, visibility, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, band_height=8, band_stride=band_stride)
+		seconds = R.last_shade_seconds(); cores = R.thread_count(); kind = "reference"
+		what = "the reference's shader sources (shading_pass.frag.glsl + includes) compiled as C++ with g++ -O2, fp32, OpenMP, ray queries on a CPU BVH"
+		log("[bench] cpu reference shader: %d rows in %.2f s (+ %.1f s BVH build)" % (rows, seconds, time.time() - t0 - seconds))
+	else:
+		cfg = dict(width=width, height=height, light_count=lights, max_light_vertex_count=4, min_light_vertex_count=4, sample_count=spp,
+			sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_OPTIMAL_CLAMPED, biased_sampling=0, trace_shadow_rays=1, show_polygonal_lights=1,
+			row_begin=0, row_end=0, band_height=8, band_stride=band_stride)
+		_, rays = H.oracle.shade(cfg, constants, gbuffer, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris)
+		seconds = H.oracle.last_shade_seconds(); cores = H.oracle.thread_count(); kind = "port"
+		what = "scalar fp32 C oracle, OpenMP"
+		log("[bench] cpu oracle: %d rows in %.2f s (+ %.1f s BVH build), %d shadow rays" % (rows, seconds, time.time() - t0 - seconds, rays))
 	value = rows * width * spp / seconds / 1e6
-	return {"value": round(value, 4), "unit": "Msamples/s", "cores": H.oracle.thread_count(), "kind": "port",
-		"sample": "%d of %d rows (8-row bands every %d rows), all %d lights, %d spp, scalar fp32 C oracle, OpenMP; BVH build excluded" % (rows, height, cfg["band_stride"], lights, spp),
+	return {"value": round(value, 4), "unit": "Msamples/s", "cores": cores, "kind": kind,
+		"sample": "%d of %d rows (8-row bands every %d rows), all %d lights, %d spp, %s; BVH build excluded" % (rows, height, band_stride, lights, spp, what),
 		"seconds": round(seconds, 3)}
 
 
 def run_reference(args):
-	"""The reference's own implementation of this path is a GLSL fragment shader driven through Vulkan (no ICD, no
-	glslangValidator on this box); its CPU-runnable form is the oracle (kind 'port'). Rank 0 only."""
+	"""The reference's own implementation of this path is a GLSL fragment shader driven through Vulkan (no ICD, no glslangValidator
+	on this box). Its CPU-runnable form is that shader compiled as C++ (oracle/_ref, kind 'reference', see cpu_baseline); without the
+	prebuilt library the C restatement is timed (kind 'port'). Rank 0 only."""
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
 		return
@@ -320,7 +346,7 @@ def run_reference(args):
 	log("[bench] reference arm: oracle G-buffer in %.1f s" % (time.time() - t0))
 	values = []
 	for i in range(args.warmup + args.steps):
-		r = cpu_baseline(args, info, width, height, lights, spp, constants, gb, band_rows=args.cpu_band_stride * 2)
+		r = cpu_baseline(args, info, width, height, lights, spp, constants, gb, band_rows=args.cpu_band_stride * 2, visibility=vis)
 		if i >= args.warmup:
 			values.append(r)
 	seconds = sum(r["seconds"] for r in values)
@@ -332,7 +358,7 @@ def run_reference(args):
 		"higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
 		"config": {"workload": "%s: Bistro-like synthetic city %dx%d, %d quad lights, %d spp, diffuse+specular MIS (clamped optimal), shadow rays on, %d triangles" % (args.workload, width, height, lights, spp, info["triangle_count"]),
 			"note": "each step = a bounded sample of the frame on the host cores; the reference's GLSL/Vulkan path itself cannot run here (no Vulkan ICD / glslangValidator)"},
-		"cpu_baseline": {"value": round(value, 4), "unit": "Msamples/s", "cores": base["cores"], "kind": "port", "sample": base["sample"]},
+		"cpu_baseline": {"value": round(value, 4), "unit": "Msamples/s", "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
 		"e2e": {"value": round(value, 4), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}), flush=True)
@@ -346,6 +372,7 @@ def main():
 	ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
 	ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
 	ap.add_argument("--no-cpu-baseline", action="store_true")
+	ap.add_argument("--cpu-port", action="store_true", help="time the C restatement (oracle/) on the CPU legs even if the compiled reference shader is available")
 	ap.add_argument("--cpu-band-stride", type=int, default=4, help="the CPU sample takes one 8-row band every this many tile rows (the reference arm: twice as many)")
 	args = ap.parse_args()
 	if args.impl == "reference":

@@ -129,6 +129,7 @@ def default_configs():
 	configs.append(dict(base, trace=0))                                    # TRACE_SHADOW_RAYS=0 with the other strategies
 	configs.append(dict(base, trace=0, strategy=1, heuristic=1))
 	configs.append(dict(base, trace=0, heuristic=4))
+	configs.append(dict(base, lights=8, samples=64, materials=64))           # BASELINE config 3 as bench.py runs it (8 quads, 64 spp, clamped optimal MIS, 64 materials): the CPU reference arm
 	# related-work sampling techniques (shading_pass.frag.glsl:332-481), sample_polygon_technique_t 0..10: diffuse only, then GGX MIS
 	# for the techniques the reference's interface allows it with (user_interface.cpp:130-140)
 	for technique in range(0, 11):

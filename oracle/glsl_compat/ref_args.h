@@ -12,5 +12,9 @@ typedef struct ref_args_s {
 	const uint16_t* ltc0; const uint16_t* ltc1; uint32_t ltc_res, ltc_layers;
 	ref_occluded_hook_t occluded_hook; const void* occluded_user;
 	float* out_rgba;
+	/* bounded samples for the CPU baseline (bench.py): rows [row_begin, row_end) (row_end = 0: height); if band_stride != 0 only rows
+	   with (y - row_begin) % band_stride < band_height. shade_seconds: wall clock of the pixel loop (out) */
+	uint32_t row_begin, row_end, band_height, band_stride;
+	double shade_seconds;
 } ref_args_t;
 #endif

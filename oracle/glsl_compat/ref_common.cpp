@@ -2,6 +2,7 @@
 // ray-query hook that routes rayQueryInitializeEXT() to the oracle's BVH (bvh_oracle.h defines the predicate the
 // un-pinned Vulkan driver would otherwise supply).
 #include "glsl_compat.hpp"
+#include <omp.h>
 extern "C" {
 #include "../bvh_oracle.h"
 }
@@ -20,3 +21,4 @@ extern "C" void ref_bvh_destroy(void* bvh) { obvh_destroy((obvh_t*) bvh); free(b
 extern "C" int ref_bvh_occluded(const void* user, const float* o, const float* d, float tmin, float tmax) {
 	return obvh_occluded((const obvh_t*) user, mk3(o[0], o[1], o[2]), mk3(d[0], d[1], d[2]), tmin, tmax);
 }
+extern "C" int ref_thread_count(void) { return omp_get_max_threads(); }

@@ -7,6 +7,7 @@
 // that feeds the uniforms/resources and runs main() for every pixel.
 #include "glsl_compat.hpp"
 #include "ref_args.h"
+#include <omp.h>
 
 #ifndef REF_NS
 #error "build with -DREF_NS=<namespace> -DREF_ENTRY=<symbol>"
@@ -84,11 +85,14 @@ static void set_uniforms(const ref_args_t* a) {
 	g_occluded_hook = a->occluded_hook; g_occluded_user = a->occluded_user;
 }
 
-extern "C" int REF_ENTRY(const ref_args_t* a) {
+extern "C" int REF_ENTRY(ref_args_t* a) {
 	if (a->light_count != POLYGONAL_LIGHT_COUNT || a->sample_count != SAMPLE_COUNT || a->max_light_vertex_count != MAX_POLYGONAL_LIGHT_VERTEX_COUNT || a->material_count > MATERIAL_COUNT) return 1;
 	set_uniforms(a);
+	const uint32_t y0 = a->row_begin, y1 = a->row_end ? a->row_end : a->height;
+	const double begin = omp_get_wtime();
 	#pragma omp parallel for schedule(dynamic, 1)
-	for (uint32_t y = 0; y < a->height; ++y)
+	for (uint32_t y = y0; y < y1; ++y) {
+		if (a->band_stride && (y - y0) % a->band_stride >= a->band_height) continue;
 		for (uint32_t x = 0; x != a->width; ++x) {
 			gl_FragCoord = vec4((float) x + 0.5f, (float) y + 0.5f, 0.5f, 1.0f);
 			g_current_visibility = a->visibility[(size_t) y * a->width + x];
@@ -96,6 +100,8 @@ extern "C" int REF_ENTRY(const ref_args_t* a) {
 			float* o = a->out_rgba + 4 * ((size_t) y * a->width + x);
 			o[0] = g_out_color.x; o[1] = g_out_color.y; o[2] = g_out_color.z; o[3] = g_out_color.w;
 		}
+	}
+	a->shade_seconds = omp_get_wtime() - begin;
 	return 0;
 }
 

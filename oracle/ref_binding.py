@@ -20,7 +20,8 @@ class RefArgs(C.Structure):
 		("quantized_positions", C.c_void_p), ("normals_and_tex_coords", C.c_void_p), ("material_indices", C.c_void_p), ("material_params", C.c_void_p),
 		("noise", C.c_void_p), ("noise_w", C.c_uint32), ("noise_h", C.c_uint32), ("noise_layers", C.c_uint32),
 		("ltc0", C.c_void_p), ("ltc1", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
-		("occluded_hook", C.c_void_p), ("occluded_user", C.c_void_p), ("out_rgba", C.c_void_p)]
+		("occluded_hook", C.c_void_p), ("occluded_user", C.c_void_p), ("out_rgba", C.c_void_p),
+		("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("band_height", C.c_uint32), ("band_stride", C.c_uint32), ("shade_seconds", C.c_double)]
 
 
 def available():
@@ -45,8 +46,33 @@ def load():
 	return _lib
 
 
-def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris):
-	"""Runs the reference fragment shader (configuration `entry`) for every pixel. Returns float32 [H, W, 4]."""
+_last_shade_seconds = 0.0
+
+
+def last_shade_seconds():
+	"""Wall clock of the pixel loop of the last shade() call (BVH build and set-up excluded)."""
+	return _last_shade_seconds
+
+
+def thread_count():
+	return int(load().ref_thread_count())
+
+
+def find_config(**wanted):
+	"""The built configuration whose -D defines equal `wanted` (keys of oracle/build_ref.py), or None."""
+	if not available():
+		return None
+	defaults = dict(technique=11, srgb=0, frame_bits=0, error_display=0)
+	for c in configs():
+		full = dict(defaults, min_vertices=c["max_vertices"]); full.update(c)
+		if all(full.get(k) == v for k, v in wanted.items()):
+			return c
+	return None
+
+
+def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris, row_begin=0, row_end=0, band_height=0, band_stride=0):
+	"""Runs the reference fragment shader (configuration `entry`) for every pixel (or the rows / bands asked for). Returns float32 [H, W, 4]."""
+	global _last_shade_seconds
 	lib = load()
 	keep = []
 	def arr(a, dtype):
@@ -60,10 +86,12 @@ def shade(entry, width, height, cfg, constants, visibility, vks, material_params
 		quantized_positions=arr(vks["positions"], np.uint32), normals_and_tex_coords=arr(vks["normals_uv"], np.uint16), material_indices=arr(vks["material_indices"], np.uint8),
 		material_params=arr(material_params, np.float32), noise=arr(noise, np.uint16), noise_w=noise.shape[2], noise_h=noise.shape[1], noise_layers=noise.shape[0],
 		ltc0=arr(ltc0, np.uint16), ltc1=arr(ltc1, np.uint16), ltc_res=ltc0.shape[1], ltc_layers=ltc0.shape[0],
-		occluded_hook=C.cast(lib.ref_bvh_occluded, C.c_void_p), occluded_user=bvh, out_rgba=out.ctypes.data)
+		occluded_hook=C.cast(lib.ref_bvh_occluded, C.c_void_p), occluded_user=bvh, out_rgba=out.ctypes.data,
+		row_begin=row_begin, row_end=row_end, band_height=band_height, band_stride=band_stride)
 	fn = getattr(lib, entry)
 	rc = fn(C.byref(a))
 	lib.ref_bvh_destroy(bvh)
+	_last_shade_seconds = float(a.shade_seconds)
 	if rc != 0:
 		raise RuntimeError("%s rejected the arguments (configuration mismatch)" % entry)
 	return out
