@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "build", "liboracle.so")
 
 class Config(C.Structure):
 	_fields_ = [(n, C.c_uint32) for n in ("width", "height", "light_count", "max_light_vertex_count", "min_light_vertex_count", "sample_count",
-		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride", "polygon_sampling_technique", "output_srgb")]
+		"sampling_strategies", "mis_heuristic", "biased_sampling", "trace_shadow_rays", "show_polygonal_lights", "row_begin", "row_end", "band_height", "band_stride", "polygon_sampling_technique", "error_display", "output_srgb")]
 
 
 _lib = None

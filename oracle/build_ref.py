@@ -7,7 +7,8 @@ to C++ that g++ compiles it against oracle/glsl_compat/glsl_compat.hpp after a m
   * '#version' / '#extension' lines dropped, 'layout(...)' qualifiers stripped,
   * the uniform block 'per_frame_constants { ... }' opened up (its members become globals),
   * 'inout T x' / 'out T x' parameters become 'T& x' (arrays stay arrays: they decay to pointers),
-  * shader in/out variables become thread_local globals.
+  * shader in/out variables become thread_local globals,
+  * the one float -> int conversion whose NaN case GLSL leaves undefined (error_to_color) goes through glsl_float_to_int().
 
 No arithmetic is touched. The transformed copies go to oracle/_ref/gen/ (git-ignored, never committed), the
 sources are read where they lie under /root/reference. One translation unit per configuration because the
@@ -91,6 +92,9 @@ def transform(text):
 	def param(mm):
 		return "%s %s[" % (mm.group(2), mm.group(3)) if mm.group(4) else "%s& %s" % (mm.group(2), mm.group(3))
 	text = re.sub(r"\b(inout|out)\s+(\w+)\s+(\w+)(\s*\[)?", param, text)
+	# error_to_color() (shading_pass.frag.glsl:114) indexes its colour table with int(color_index); for a NaN error GLSL leaves the
+	# result undefined and a C++ cast reads out of bounds. glsl_float_to_int() maps everything outside the table to its first entry.
+	text = text.replace("tab20b_colors[int(color_index)]", "tab20b_colors[glsl_float_to_int(color_index)]")
 	return text
 
 
@@ -144,6 +148,10 @@ def default_configs():
 	configs.append(dict(base, strategy=0, heuristic=0, technique=10, max_vertices=5, trace=0))
 	configs.append(dict(base, strategy=0, heuristic=0, technique=9, lights=16, samples=1))
 	configs.append(dict(base, strategy=0, heuristic=0, technique=2, lights=1, samples=2, materials=3))   # Cornell box, Urena's rectangle sampling
+	# error display of the sampling procedure (error_display_t 1..6, src/main.h:92-112; shading_pass.frag.glsl:462-481, 549-563)
+	for error_display, extra in [(1, dict(strategy=0, heuristic=0)), (2, dict()), (3, dict(strategy=1, heuristic=0)), (4, dict()), (5, dict(strategy=2, heuristic=0)), (6, dict(strategy=4, heuristic=0)),
+			(1, dict(biased=1)), (4, dict(biased=1)), (3, dict(max_vertices=7, min_vertices=5)), (6, dict(max_vertices=3)), (1, dict(strategy=0, heuristic=0, technique=10)), (2, dict(strategy=0, heuristic=0, technique=10, max_vertices=5))]:
+		configs.append(dict(base, error_display=error_display, **extra))
 	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
 		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs

@@ -239,7 +239,10 @@ inline float acos(float x) { return vkr_acos(x); }
 inline float asin(float x) { return VKR_HALF_PI - acos(x); }
 inline float pow(float x, float y) { return vkr_pow(x, y); }   // the output stage's contract (vkr_math.h); GLSL leaves pow to the driver
 inline vec3 pow(const vec3& x, const vec3& y) { return vec3(vkr_pow(x.x, y.x), vkr_pow(x.y, y.y), vkr_pow(x.z, y.z)); }
-inline float log2(float x) { return log2f(x); }
+// index of error_to_color()'s colour table: valid errors give 0 <= x < 20; what a NaN error turns into is undefined in GLSL (clamp, log2 and int() of
+// NaN) and would read out of bounds here -- defined as the first colour (build_ref.py)
+inline int glsl_float_to_int(float x) { return (x >= 0.0f && x < 20.0f) ? (int) x : 0; }
+inline float log2(float x) { return vkr_log2(x); }   // only error_to_color() uses it; the contract's log2 (vkr_math.h) like pow
 inline float exp2(float x) { return exp2f(x); }
 inline float floor(float x) { return floorf(x); }
 inline float fract(float x) { return x - floorf(x); }

@@ -394,7 +394,7 @@ static inline v3 psa_sample(const psa_polygon_t* polygon, v2 random_numbers, uin
 	return out;
 }
 
-/* :823-883 (error probe; KAT 3 uses component 0 = backward error) */
+/* :823-883: backward error, backward error times projected solid angle, forward error in radians */
 static inline v3 psa_sampling_error(const psa_polygon_t* polygon, v2 random_numbers, v3 sampled_dir, uint32_t maxp, int biased) {
 	float target = random_numbers.x * polygon->projected_solid_angle;
 	if (psa_is_central_case(polygon)) return mk3(0.0f, 0.0f, 0.0f);
@@ -421,7 +421,22 @@ static inline v3 psa_sampling_error(const psa_polygon_t* polygon, v2 random_numb
 		inner_ellipse, psa_get_ellipse_rsqrt_det(inner_ellipse), outer_ellipse, psa_get_ellipse_rsqrt_det(outer_ellipse), dir_0, sxy, biased);
 	float scaled_backward_error = target - sampled_psa;
 	float backward_error = scaled_backward_error / polygon->projected_solid_angle;
-	return mk3(backward_error, scaled_backward_error, 0.0f);
+	/* derivative of the sampled direction with respect to the projected solid angle (:860-875); cm = constraint_matrix before the transpose */
+	v2 inner_dir = psa_ellipse_transform(inner_ellipse, sxy);
+	v2 outer_dir = psa_ellipse_transform(outer_ellipse, sxy);
+	float inner_factor = 1.0f / dot2(sxy, inner_dir);
+	float outer_factor = 1.0f / dot2(sxy, outer_dir);
+	v2 cm0 = scale2(psa_rotate_90(sxy), 0.5f * (inner_factor - outer_factor));
+	v2 cm1 = scale2(inner_dir, (1.0f - random_numbers.y) / (inner_factor * inner_factor));
+	cm1 = add2(cm1, scale2(outer_dir, random_numbers.y / (outer_factor * outer_factor)));
+	/* transpose: t[0] = (cm0.x, cm1.x), t[1] = (cm0.y, cm1.y); determinant(t) = t[0][0] * t[1][1] - t[1][0] * t[0][1] */
+	float rcp_det = 1.0f / (cm0.x * cm1.y - cm0.y * cm1.x);
+	v3 sample_derivative;
+	sample_derivative.x = rcp_det * cm1.y;
+	sample_derivative.y = rcp_det * -cm1.x;
+	sample_derivative.z = -dot2(sxy, mk2(sample_derivative.x, sample_derivative.y)) / sampled_dir.z;
+	float forward_error = sqrtf(dot3(sample_derivative, sample_derivative)) * scaled_backward_error;
+	return mk3(backward_error, scaled_backward_error, forward_error);
 }
 
 #endif

@@ -652,4 +652,38 @@ static inline v3 rw_sample_psa_arvo(const rw_psa_arvo_t* p, v2 rnd, uint32_t ite
 	}
 }
 
+/* :1035-1087: backward error and backward error times projected solid angle of a sample of rw_sample_psa_arvo() */
+static inline v2 rw_psa_arvo_sampling_error(const rw_psa_arvo_t* p, v2 rnd, v3 sampled_dir, uint32_t maxp) {
+	float target = rnd.x * p->projected_solid_angle;
+	if (p->inner_edge_0.cdf_factor > 0.0f) return mk2(0.0f, 0.0f);
+	rw_edge_arvo_t outer_edge;
+	memset(&outer_edge, 0, sizeof(outer_edge));
+	rw_edge_arvo_t inner_edge = p->inner_edge_0;
+	float inner_azimuth = p->vertex_azimuths[0], outer_azimuth = 0.0f, sector_psa = 0.0f, azimuth_0 = 0.0f;
+	for (uint32_t i = 0; i != maxp - 1; ++i) {
+		if ((i > 1 && i + 1 == p->vertex_count) || (i > 0 && target < 0.0f)) break;
+		sector_psa = p->sector_projected_solid_angles[i];
+		target -= sector_psa;
+		rw_edge_arvo_t vertex_edge = p->edges[i];
+		float vertex_azimuth = p->vertex_azimuths[i];
+		if (i == 0) {
+			outer_edge = vertex_edge;
+			outer_azimuth = vertex_azimuth;
+		}
+		else {
+			inner_edge = (vertex_edge.cdf_factor >= 0.0f) ? inner_edge : vertex_edge;
+			inner_azimuth = (vertex_edge.cdf_factor >= 0.0f) ? inner_azimuth : vertex_azimuth;
+			outer_edge = (vertex_edge.cdf_factor >= 0.0f) ? vertex_edge : outer_edge;
+			outer_azimuth = (vertex_edge.cdf_factor >= 0.0f) ? vertex_azimuth : outer_azimuth;
+		}
+		azimuth_0 = p->vertex_azimuths[i];
+	}
+	target += sector_psa;
+	float sampled_azimuth = vkr_atan2(sampled_dir.y, sampled_dir.x);
+	float outer_psa = rw_edge_psa_in_sector_derivative_arvo(&outer_edge, azimuth_0 - outer_azimuth, sampled_azimuth - outer_azimuth).x;
+	float inner_psa = rw_edge_psa_in_sector_derivative_arvo(&inner_edge, azimuth_0 - inner_azimuth, sampled_azimuth - inner_azimuth).x;
+	float sampled_psa = outer_psa + inner_psa;
+	return mk2((target - sampled_psa) / p->projected_solid_angle, target - sampled_psa);
+}
+
 #endif

@@ -54,7 +54,7 @@ typedef struct {
 	const uint8_t* constants;
 	float pixel_to_ray[3][4]; /* row major */
 	v3 camera;
-	float mis_visibility_estimate, exposure, roughness_factor;
+	float mis_visibility_estimate, exposure, roughness_factor, error_factor;
 	uint32_t noise_res_mask[2], noise_layer_mask, noise_random[4];
 	float ltc_c[6];
 	light_t* lights;
@@ -400,6 +400,31 @@ static v3 get_polygonal_light_mis_estimate(v3 sampled_dir, float sampled_density
 	return mk3(0.0f, 0.0f, 0.0f);
 }
 
+/* shading_pass.frag.glsl:80-115: error magnitude -> matplotlib's tab20b colours (the table holds linear Rec. 709 values), one hue per power of ten.
+   pow / log2 follow the arithmetic contract (vkr_math.h); an index outside the table (only a NaN error gets there; undefined in GLSL) selects the first colour */
+static v3 error_to_color(float error, const ctx_t* c) {
+	static const float tab20b_colors[20][3] = {
+		{0.04092f, 0.04374f, 0.19120f}, {0.08438f, 0.08866f, 0.36625f}, {0.14703f, 0.15593f, 0.62396f}, {0.33245f, 0.34191f, 0.73046f},
+		{0.12477f, 0.19120f, 0.04092f}, {0.26225f, 0.36131f, 0.08438f}, {0.46208f, 0.62396f, 0.14703f}, {0.61721f, 0.70838f, 0.33245f},
+		{0.26225f, 0.15293f, 0.03071f}, {0.50888f, 0.34191f, 0.04092f}, {0.79910f, 0.49102f, 0.08438f}, {0.79910f, 0.59720f, 0.29614f},
+		{0.23074f, 0.04519f, 0.04092f}, {0.41789f, 0.06663f, 0.06848f}, {0.67244f, 0.11954f, 0.14703f}, {0.79910f, 0.30499f, 0.33245f},
+		{0.19807f, 0.05286f, 0.17144f}, {0.37626f, 0.08228f, 0.29614f}, {0.61721f, 0.15293f, 0.50888f}, {0.73046f, 0.34191f, 0.67244f},
+	};
+	const float min_exponent = 0.0f, max_exponent = 5.0f;
+	const float min_error = vkr_pow(10.0f, min_exponent);
+	const float max_error = vkr_pow(10.0f, max_exponent - 0.01f);
+	const float color_count = 20.0f;
+	error = vkr_clamp(fabsf(c->error_factor * error), min_error, max_error);
+	float color_index = fmaf(vkr_log2(error), color_count / ((max_exponent - min_exponent) * vkr_log2(10.0f)), color_count * -min_exponent / (max_exponent - min_exponent));
+	int index = (color_index >= 0.0f && color_index < 20.0f) ? (int) color_index : 0;
+	return mk3(tab20b_colors[index][0], tab20b_colors[index][1], tab20b_colors[index][2]);
+}
+static v3 error_display_color(float error, const ctx_t* c) { /* "return error_to_color(error) / g_exposure_factor;" (:472, 493, 553, 560) */
+	v3 color = error_to_color(error, c);
+	return mk3(color.x / c->exposure, color.y / c->exposure, color.z / c->exposure);
+}
+static inline float error_component(v3 e, uint32_t error_display) { uint32_t i = (error_display - 1) % 3; return (i == 0) ? e.x : ((i == 1) ? e.y : e.z); }
+
 /* shading_pass.frag.glsl:676-709 for the related-work techniques: GGX sampling with MIS against the polygon density.
    polygon_density_is_constant: every technique except our projected solid angle sampling passes density_factor as is (:702) */
 static v3 ggx_mis_samples(float density_factor, int density_times_lambert, const shading_data_t* sd, const ltc_t* ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
@@ -532,6 +557,12 @@ static v3 evaluate_polygonal_light_shading_related_work(const shading_data_t* sd
 	rw_sampler_t sampler;
 	if (!rw_sampler_prepare(&sampler, cfg->polygon_sampling_technique, c->maxp, cfg->max_light_vertex_count, light, sd->position, ltc.world_to_shading))
 		return mk3(0.0f, 0.0f, 0.0f);
+	if (cfg->error_display >= 1 && cfg->error_display <= 3 && cfg->polygon_sampling_technique == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) { /* :468-472 */
+		v2 rnd = get_noise_2(accessor, c);
+		v3 sampled_dir = rw_sample_psa_arvo(&sampler.psa_arvo, rnd, 3, c->maxp);
+		v2 e = rw_psa_arvo_sampling_error(&sampler.psa_arvo, rnd, sampled_dir, c->maxp);
+		return error_display_color(error_component(mk3(e.x, e.y, 0.0f), cfg->error_display), c);
+	}
 	v3 result = mk3(0.0f, 0.0f, 0.0f);
 	for (uint32_t s = 0; s != cfg->sample_count; ++s) {
 		float density;
@@ -571,6 +602,11 @@ static v3 evaluate_polygonal_light_shading(const shading_data_t* sd, ltc_t ltc, 
 		if (cvc == 0) return mk3(0.0f, 0.0f, 0.0f);
 		psa_prepare(&polygon_diffuse, cvc, verts, maxp, biased);
 		if (polygon_diffuse.projected_solid_angle <= 0.0f) return mk3(0.0f, 0.0f, 0.0f);
+		if (cfg->error_display >= 1 && cfg->error_display <= 3) { /* ERROR_DISPLAY_DIFFUSE, :489-493 */
+			v2 rnd = get_noise_2(accessor, c);
+			v3 sampled_dir = psa_sample(&polygon_diffuse, rnd, maxp, biased);
+			return error_display_color(error_component(psa_sampling_error(&polygon_diffuse, rnd, sampled_dir, maxp, biased), cfg->error_display), c);
+		}
 		for (uint32_t s = 0; s != S; ++s) {
 			v3 dir = psa_sample(&polygon_diffuse, get_noise_2(accessor, c), maxp, biased);
 			float density = dir.z / polygon_diffuse.projected_solid_angle;
@@ -593,6 +629,17 @@ static v3 evaluate_polygonal_light_shading(const shading_data_t* sd, ltc_t ltc, 
 		if (polygon_diffuse.projected_solid_angle == 0.0f) return mk3(0.0f, 0.0f, 0.0f);
 		float specular_albedo = ltc.albedo;
 		float specular_weight = specular_albedo * polygon_specular.projected_solid_angle;
+		if (cfg->error_display >= 1 && cfg->error_display <= 3) { /* ERROR_DISPLAY_DIFFUSE, :549-553 */
+			v2 rnd = get_noise_2(accessor, c);
+			v3 sampled_dir = psa_sample(&polygon_diffuse, rnd, maxp, biased);
+			return error_display_color(error_component(psa_sampling_error(&polygon_diffuse, rnd, sampled_dir, maxp, biased), cfg->error_display), c);
+		}
+		if (cfg->error_display >= 4) { /* ERROR_DISPLAY_SPECULAR, :555-563 */
+			if (!(polygon_specular.projected_solid_angle > 0.0f)) return mk3(0.0f, 0.0f, 0.0f);
+			v2 rnd = get_noise_2(accessor, c);
+			v3 sampled_dir = psa_sample(&polygon_specular, rnd, maxp, biased);
+			return error_display_color(error_component(psa_sampling_error(&polygon_specular, rnd, sampled_dir, maxp, biased), cfg->error_display), c);
+		}
 		if (strat == VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY) {
 			for (uint32_t s = 0; s != S; ++s) {
 				v3 diffuse_dir = psa_sample(&polygon_diffuse, get_noise_2(accessor, c), maxp, biased);
@@ -723,6 +770,7 @@ static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_
 	c->camera = mk3(rdf(constants, OFF_CAMERA), rdf(constants, OFF_CAMERA + 4), rdf(constants, OFF_CAMERA + 8));
 	c->mis_visibility_estimate = rdf(constants, OFF_MIS_VIS);
 	c->exposure = rdf(constants, OFF_EXPOSURE);
+	c->error_factor = rdf(constants, OFF_ERROR_FACTOR);
 	c->roughness_factor = rdf(constants, OFF_ROUGHNESS_FACTOR);
 	c->noise_res_mask[0] = rdu(constants, OFF_NOISE_RES_MASK); c->noise_res_mask[1] = rdu(constants, OFF_NOISE_RES_MASK + 4);
 	c->noise_layer_mask = rdu(constants, OFF_NOISE_LAYER_MASK);
@@ -757,6 +805,17 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 		const int ggx_ok = t == VKR_TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA || t == VKR_TECHNIQUE_SOLID_ANGLE_ARVO || t == VKR_TECHNIQUE_SOLID_ANGLE || t == VKR_TECHNIQUE_CLIPPED_SOLID_ANGLE || t == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO;
 		if (!(cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_ONLY || (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS && ggx_ok)) || cfg->biased_sampling) {
 			printf("oracle: sampling technique %u does not support sampling strategy %u.\n", t, cfg->sampling_strategies);
+			return 1;
+		}
+	}
+	if (cfg->error_display > 6) return 1;
+	if (cfg->error_display) {
+		/* the shader looks at ERROR_DISPLAY_* in the projected solid angle branches only (:468, 489, 549, 555); Arvo's error has two components */
+		const uint32_t t = cfg->polygon_sampling_technique;
+		const int combined = cfg->sampling_strategies >= VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY;
+		if ((t != VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE && t != VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) || (cfg->error_display >= 4 && !combined)
+			|| (t == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO && cfg->error_display == 3)) {
+			printf("oracle: error display %u is not available with technique %u and strategy %u.\n", cfg->error_display, t, cfg->sampling_strategies);
 			return 1;
 		}
 	}

@@ -31,6 +31,7 @@ typedef struct {
 	uint32_t row_begin, row_end;       /* shade rows [row_begin,row_end) only; row_end = 0 means height */
 	uint32_t band_height, band_stride; /* if band_stride != 0: of those rows only the ones with (y - row_begin) % band_stride < band_height (bounded CPU samples) */
 	uint32_t polygon_sampling_technique; /* SAMPLE_POLYGON_*: VKR_TECHNIQUE_* (the ctypes binding defaults to 11 = projected solid angle) */
+	uint32_t error_display;            /* error_display_t (src/main.h:92-112): 0 none, 1-3 diffuse backward / backward scaled / forward, 4-6 specular */
 	uint32_t output_srgb;              /* !OUTPUT_LINEAR_RGB: the shader itself converts to sRGB (UNORM swapchain); the half-bit split follows g_frame_bits in the constant block */
 } vkr_oracle_config_t;
 

@@ -43,4 +43,4 @@ def host_constants(info, width, height, lights, sample_count=1, frame_bits=0):
 def oracle_cfg(cfg, width=WIDTH, height=HEIGHT):
 	return dict(width=width, height=height, light_count=cfg["lights"], max_light_vertex_count=cfg["max_vertices"], min_light_vertex_count=cfg.get("min_vertices", cfg["max_vertices"]),
 		sample_count=cfg["samples"], sampling_strategies=cfg["strategy"], mis_heuristic=cfg["heuristic"], biased_sampling=cfg["biased"],
-		trace_shadow_rays=cfg["trace"], show_polygonal_lights=cfg["show_lights"], output_srgb=cfg.get("srgb", 0), polygon_sampling_technique=cfg.get("technique", 11))
+		trace_shadow_rays=cfg["trace"], show_polygonal_lights=cfg["show_lights"], output_srgb=cfg.get("srgb", 0), polygon_sampling_technique=cfg.get("technique", 11), error_display=cfg.get("error_display", 0))
