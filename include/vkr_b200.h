@@ -55,6 +55,14 @@ typedef enum vkr_sample_polygon_technique_e {
 	vkr_sample_polygon_projected_solid_angle_biased = 12
 } vkr_sample_polygon_technique_t;
 
+/* error_display_t (src/main.h:92-112): colour-coded error of the first sample of projected solid angle sampling instead of shading.
+   Available with techniques 10 (diffuse, backward errors only), 11 and 12; the specular variants need a diffuse + specular strategy. */
+typedef enum vkr_error_display_e {
+	vkr_error_display_none = 0,
+	vkr_error_display_diffuse_backward = 1, vkr_error_display_diffuse_backward_scaled = 2, vkr_error_display_diffuse_forward = 3,
+	vkr_error_display_specular_backward = 4, vkr_error_display_specular_backward_scaled = 5, vkr_error_display_specular_forward = 6
+} vkr_error_display_t;
+
 typedef enum vkr_noise_type_e { vkr_noise_type_white = 0, vkr_noise_type_blue = 1, vkr_noise_type_ahmed = 2 } vkr_noise_type_t;
 
 /* ---- device (replaces create_vulkan_device, src/vulkan_basics.c:24; device_t, vulkan_basics.h:40-77) */
@@ -246,6 +254,9 @@ typedef struct vkr_shading_pass_desc_s {
 	   half-bit split for HDR screenshots follows g_frame_bits in the constant block (vkr_set_frame_bits). Output stays
 	   float4: the values the render target receives before its UNORM quantisation. */
 	int output_srgb;
+	/* ERROR_DISPLAY_DIFFUSE / ERROR_DISPLAY_SPECULAR / ERROR_INDEX (src/main.c:735-750, 788-790); the scale comes from error_min_exponent
+	   in the render settings via g_error_factor in the constant block */
+	vkr_error_display_t error_display;
 } vkr_shading_pass_desc_t;
 
 typedef struct vkr_shading_pass_s {

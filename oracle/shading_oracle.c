@@ -1075,6 +1075,37 @@ int vkr_oracle_related_work_batch(uint32_t technique, uint32_t maxv, const void*
 	return 1;
 }
 
+/* Probe for tests/test_device_on_host.py: clip + prepare + one sample and its error per random number pair, colour of error component 0 */
+int vkr_oracle_error_display_batch(uint32_t technique, int biased, uint32_t maxv, uint32_t vertex_count, const float* vertices_xyz, uint32_t n, const float* rnd,
+	float error_factor, float* out_errors, float* out_colors)
+{
+	const uint32_t maxp = maxv + 1;
+	v3 verts[PSA_MAXP];
+	memset(verts, 0, sizeof(verts));
+	for (uint32_t i = 0; i != vertex_count; ++i) verts[i] = mk3(vertices_xyz[3 * i], vertices_xyz[3 * i + 1], vertices_xyz[3 * i + 2]);
+	for (uint32_t i = vertex_count; i < maxv; ++i) verts[i] = verts[0];
+	uint32_t cvc = psa_clip_polygon(vertex_count, verts, maxp);
+	if (cvc == 0) return 0;
+	psa_polygon_t polygon; rw_psa_arvo_t arvo;
+	if (technique == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) { rw_prepare_psa_arvo(&arvo, cvc, verts, maxp); if (arvo.projected_solid_angle <= 0.0f) return 0; }
+	else { psa_prepare(&polygon, cvc, verts, maxp, biased); if (polygon.projected_solid_angle <= 0.0f) return 0; }
+	ctx_t c; memset(&c, 0, sizeof(c));
+	c.error_factor = error_factor;
+	for (uint32_t i = 0; i != n; ++i) {
+		v2 r = mk2(rnd[2 * i], rnd[2 * i + 1]);
+		v3 e;
+		if (technique == VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) {
+			v2 e2 = rw_psa_arvo_sampling_error(&arvo, r, rw_sample_psa_arvo(&arvo, r, 3, maxp), maxp);
+			e = mk3(e2.x, e2.y, 0.0f);
+		}
+		else e = psa_sampling_error(&polygon, r, psa_sample(&polygon, r, maxp, biased), maxp, biased);
+		v3 col = error_to_color(e.x, &c);
+		out_errors[3 * i] = e.x; out_errors[3 * i + 1] = e.y; out_errors[3 * i + 2] = e.z;
+		out_colors[3 * i] = col.x; out_colors[3 * i + 1] = col.y; out_colors[3 * i + 2] = col.z;
+	}
+	return 1;
+}
+
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp) {
 	v3 v[PSA_MAXP]; memset(v, 0, sizeof(v));
 	for (uint32_t i = 0; i != maxp; ++i) v[i] = mk3(vertices_xyz[3 * i], vertices_xyz[3 * i + 1], vertices_xyz[3 * i + 2]);

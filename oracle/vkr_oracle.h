@@ -47,6 +47,8 @@ int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants, c
 	const float* material_params, float* out_gbuffer);
 int vkr_oracle_related_work_batch(uint32_t technique, uint32_t maxv, const void* light_block, const float* position, const float* frame,
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_densities, float* out_ggx_density_factor);
+int vkr_oracle_error_display_batch(uint32_t technique, int biased, uint32_t maxv, uint32_t vertex_count, const float* vertices_xyz, uint32_t n, const float* rnd,
+	float error_factor, float* out_errors, float* out_colors);
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp);
 void vkr_oracle_psa_sample_batch(uint32_t vertex_count, const float* vertices_xyz, uint32_t maxp, int biased, int do_clip,
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_errors, float* out_info);

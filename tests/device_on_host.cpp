@@ -63,6 +63,47 @@ extern "C" int vkr_device_on_host_related_work_batch(uint32_t technique, uint32_
 	}
 }
 
+// Error display (shading_pass.frag.glsl:462-493, 549-563): clip + prepare + one sample + its error per random number pair, and the colour of
+// error component 0. technique 10 = Arvo (two error components), 11 = projected solid angle sampling (biased or not).
+template <int MAXV, bool BIASED>
+static int run_error(uint32_t technique, uint32_t vertex_count, const float* vertices_xyz, uint32_t n, const float* rnd, float error_factor, float* out_errors, float* out_colors) {
+	constexpr int MAXP = MAXV + 1;
+	f3 v[MAXP];
+	for (int i = 0; i != MAXP; ++i) v[i] = (i < (int) vertex_count) ? make3(vertices_xyz[3 * i], vertices_xyz[3 * i + 1], vertices_xyz[3 * i + 2]) : make3(0.0f, 0.0f, 0.0f);
+	for (int i = (int) vertex_count; i < MAXV; ++i) v[i] = v[0]; // write_constants() repeats the first vertex (src/main.c:2176)
+	const int vc = clip_polygon<MAXP>((int) vertex_count, v);
+	if (vc == 0) return 0;
+	psa_polygon<MAXP> polygon;
+	psa_arvo_polygon<MAXP> arvo;
+	if (technique == 10) { prepare_psa_arvo<MAXP>(arvo, vc, v); if (arvo.psa <= 0.0f) return 0; }
+	else { prepare_psa<MAXP, BIASED>(polygon, vc, v); if (polygon.psa <= 0.0f) return 0; }
+	for (uint32_t i = 0; i != n; ++i) {
+		const f2 r = make2(rnd[2 * i], rnd[2 * i + 1]);
+		f3 e;
+		if (technique == 10) {
+			const f2 e2 = sampling_error_arvo<MAXP>(arvo, r, sample_psa_arvo<MAXP>(arvo, r, 3));
+			e = make3(e2.x, e2.y, 0.0f);
+		}
+		else e = sampling_error<MAXP, BIASED>(polygon, r, sample_psa<MAXP, BIASED>(polygon, r));
+		const f3 c = error_to_color(e.x, error_factor);
+		out_errors[3 * i] = e.x; out_errors[3 * i + 1] = e.y; out_errors[3 * i + 2] = e.z;
+		out_colors[3 * i] = c.x; out_colors[3 * i + 1] = c.y; out_colors[3 * i + 2] = c.z;
+	}
+	return 1;
+}
+
+// Same signature and meaning as vkr_oracle_error_display_batch (oracle/vkr_oracle.h)
+extern "C" int vkr_device_on_host_error_display_batch(uint32_t technique, int biased, uint32_t maxv, uint32_t vertex_count, const float* vertices_xyz, uint32_t n, const float* rnd,
+	float error_factor, float* out_errors, float* out_colors)
+{
+	switch (maxv) {
+#define V(K) case K: return biased ? run_error<K, true>(technique, vertex_count, vertices_xyz, n, rnd, error_factor, out_errors, out_colors) : run_error<K, false>(technique, vertex_count, vertices_xyz, n, rnd, error_factor, out_errors, out_colors);
+	V(3) V(4) V(5) V(6) V(7)
+#undef V
+	default: return -1;
+	}
+}
+
 // Elementary functions of the device arithmetic contract: 0 atan, 1 sin, 2 cos, 3 acos on [-1,1], 4 atan2(x, 0.5), 5 pow(x, 1/3), 6 fast_positive_atan
 extern "C" void vkr_device_on_host_elementary_batch(int which, uint32_t n, const float* x, float* y) {
 	for (uint32_t i = 0; i != n; ++i) {

@@ -133,7 +133,7 @@ def oracle_config(frame, width, height):
 	return dict(width=width, height=height, light_count=frame.light_count, max_light_vertex_count=max(max(counts), 3), min_light_vertex_count=min(counts),
 		sample_count=s.sample_count, sampling_strategies=s.sampling_strategies, mis_heuristic=s.mis_heuristic,
 		biased_sampling=int(s.polygon_sampling_technique == api.TECHNIQUE_PSA_BIASED), trace_shadow_rays=s.trace_shadow_rays, show_polygonal_lights=s.show_polygonal_lights,
-		row_begin=0, row_end=0, output_srgb=getattr(frame, "output_srgb", 0), polygon_sampling_technique=min(int(s.polygon_sampling_technique), api.TECHNIQUE_PSA))
+		row_begin=0, row_end=0, output_srgb=getattr(frame, "output_srgb", 0), polygon_sampling_technique=min(int(s.polygon_sampling_technique), api.TECHNIQUE_PSA), error_display=getattr(frame, "error_display", 0))
 
 
 def open_frame(info, cuda_device=0, **kw):

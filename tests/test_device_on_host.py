@@ -90,6 +90,41 @@ def test_device_sampler_matches_oracle_with_mixed_vertex_counts(technique, maxv)
 	assert checked > 0
 
 
+def _error_batch(lib, symbol, technique, biased, maxv, vertices, rnd, error_factor):
+	vertices = np.ascontiguousarray(vertices, dtype=np.float32); rnd = np.ascontiguousarray(rnd, dtype=np.float32)
+	n = len(rnd); errors = np.zeros((n, 3), dtype=np.float32); colors = np.zeros((n, 3), dtype=np.float32)
+	fn = getattr(lib, symbol); fn.restype = C.c_int
+	on = fn(C.c_uint32(technique), C.c_int(biased), C.c_uint32(maxv), C.c_uint32(len(vertices)), vertices.ctypes.data_as(C.c_void_p), C.c_uint32(n), rnd.ctypes.data_as(C.c_void_p),
+		C.c_float(error_factor), errors.ctypes.data_as(C.c_void_p), colors.ctypes.data_as(C.c_void_p))
+	assert on >= 0
+	return None if on == 0 else (errors, colors)
+
+
+@pytest.mark.parametrize("technique,biased", [(11, 0), (11, 1), (10, 0)])
+@pytest.mark.parametrize("maxv", [3, 4, 5, 6, 7])
+def test_device_sampling_error_and_error_colours_match_oracle(technique, biased, maxv):
+	"""Error display (ERROR_DISPLAY_*): the sampling error of projected solid angle sampling (ours: three measures, Arvo's: two) and the colour map."""
+	lib = _lib(); oracle = O.load()
+	rng = np.random.default_rng(31 * maxv + technique + biased)
+	checked = 0; colours = set()
+	for trial in range(60):
+		count = maxv if trial % 3 else int(rng.integers(3, maxv + 1))
+		angles = np.sort(rng.uniform(0.0, 2.0 * np.pi, count))
+		centre = rng.normal(size=3) * np.array([1.5, 1.5, 0.8]) + np.array([0.0, 0.0, 0.6])
+		u = rng.normal(size=3); u /= np.linalg.norm(u); w = np.cross(u, rng.normal(size=3)); w /= np.linalg.norm(w)
+		vertices = centre + rng.uniform(0.3, 1.5) * (np.outer(np.cos(angles), u) + np.outer(np.sin(angles), w))
+		rnd = rng.random((24, 2)).astype(np.float32)
+		error_factor = float(10.0 ** rng.uniform(3.0, 8.0))
+		ref = _error_batch(oracle, "vkr_oracle_error_display_batch", technique, biased, maxv, vertices, rnd, error_factor)
+		dev = _error_batch(lib, "vkr_device_on_host_error_display_batch", technique, biased, maxv, vertices, rnd, error_factor)
+		assert (ref is None) == (dev is None)
+		if ref is None:
+			continue
+		assert np.array_equal(ref[0].view(np.uint32), dev[0].view(np.uint32)) and np.array_equal(ref[1].view(np.uint32), dev[1].view(np.uint32))
+		checked += 1; colours |= {tuple(c) for c in ref[1]}
+	assert checked > 10 and len(colours) > 3
+
+
 def test_samples_point_at_the_light_and_densities_integrate():
 	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
 	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""

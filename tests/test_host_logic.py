@@ -226,6 +226,16 @@ def test_shading_pass_rejects_illegal_technique_and_strategy_combinations(capfd)
 		assert "missing LTC / noise tables" in create(technique, api.STRATEGY_DIFFUSE_GGX_MIS)
 	assert "balance and power heuristics only" in create(11, api.STRATEGY_DIFFUSE_GGX_MIS, api.MIS_OPTIMAL)
 	assert "unknown polygon sampling technique" in create(13, api.STRATEGY_DIFFUSE_ONLY)
+	# error display: in the projected solid angle branches of the shader only; the specular variants need a diffuse + specular strategy; Arvo's error has two measures
+	def create_display(technique, strategy, error_display):
+		p = api.ShadingPass(); d = api.ShadingPassDesc(width=64, height=32, polygonal_light_count=1, min_polygonal_light_vertex_count=4, max_polygonal_light_vertex_count=4,
+			sample_count=1, sampling_strategies=strategy, mis_heuristic=api.MIS_BALANCE, polygon_sampling_technique=technique, stripe_count=1, error_display=error_display)
+		assert lib.vkr_create_shading_pass(C.byref(p), C.byref(dev), C.byref(d)) == 1
+		return capfd.readouterr().out
+	for technique, strategy, error_display, legal in [(11, 0, 1, True), (12, 1, 3, True), (11, 3, 2, True), (11, 3, 4, True), (12, 2, 6, True), (10, 0, 1, True), (10, 0, 2, True),
+			(10, 0, 3, False), (11, 0, 4, False), (11, 1, 5, False), (4, 0, 1, False), (10, 3, 4, False), (11, 3, 7, False)]:
+		out = create_display(technique, strategy, error_display)
+		assert ("missing LTC / noise tables" in out) if legal else ("is not available with" in out or "does not support" in out), (technique, strategy, error_display, out)
 
 
 def test_white_noise_and_synthetic_formats_are_what_the_reference_loaders_expect():

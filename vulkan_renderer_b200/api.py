@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = [
 ]
 
 # enums (values = the reference's)
+ERROR_DISPLAY_NONE, ERROR_DISPLAY_DIFFUSE_BACKWARD, ERROR_DISPLAY_DIFFUSE_BACKWARD_SCALED, ERROR_DISPLAY_DIFFUSE_FORWARD, \
+	ERROR_DISPLAY_SPECULAR_BACKWARD, ERROR_DISPLAY_SPECULAR_BACKWARD_SCALED, ERROR_DISPLAY_SPECULAR_FORWARD = range(7)
 STRATEGY_DIFFUSE_ONLY, STRATEGY_DIFFUSE_GGX_MIS, STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, STRATEGY_DIFFUSE_SPECULAR_MIS, STRATEGY_DIFFUSE_SPECULAR_RANDOM = range(5)
 MIS_BALANCE, MIS_POWER, MIS_WEIGHTED, MIS_OPTIMAL_CLAMPED, MIS_OPTIMAL = range(5)
 TECHNIQUE_PSA, TECHNIQUE_PSA_BIASED = 11, 12
@@ -100,7 +102,7 @@ class ShadingPassDesc(C.Structure):
 		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
 		("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int), ("polygon_sampling_technique", C.c_int),
 		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("stripe_index", C.c_uint32), ("stripe_count", C.c_uint32),
-		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable)), ("output_srgb", C.c_int)]
+		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable)), ("output_srgb", C.c_int), ("error_display", C.c_int)]
 
 
 class ShadingPass(C.Structure):

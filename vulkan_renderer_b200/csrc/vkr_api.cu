@@ -93,6 +93,17 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 			memset(pass, 0, sizeof(*pass)); return 1;
 		}
 	}
+	if (d.error_display != vkr_error_display_none) {
+		// the shader evaluates ERROR_DISPLAY_* in its projected solid angle branches only (shading_pass.frag.glsl:468, 489, 549, 555)
+		const int e = (int) d.error_display;
+		const bool combined = (int) d.sampling_strategies >= (int) vkr_sampling_strategies_diffuse_specular_separately;
+		if (e < 0 || e > 6 || technique < (int) vkr_sample_polygon_projected_solid_angle_arvo || (e >= 4 && (!combined || technique == (int) vkr_sample_polygon_projected_solid_angle_arvo))
+			|| (technique == (int) vkr_sample_polygon_projected_solid_angle_arvo && e == (int) vkr_error_display_diffuse_forward))
+		{
+			printf("Failed to create the shading pass: error display %d is not available with polygon sampling technique %d and sampling strategy %d.\n", e, technique, (int) d.sampling_strategies);
+			memset(pass, 0, sizeof(*pass)); return 1;
+		}
+	}
 	if ((int) d.sampling_strategies < 0 || (int) d.sampling_strategies > 4 || (int) d.mis_heuristic < 0 || (int) d.mis_heuristic > 4) {
 		printf("Failed to create the shading pass: invalid sampling strategy or MIS heuristic.\n");
 		memset(pass, 0, sizeof(*pass)); return 1;
@@ -133,7 +144,7 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 }
 
 cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream) {
-	if (p.polygon_sampling_technique < 11) { // related-work techniques
+	if (p.polygon_sampling_technique < 11 || p.error_display != 0) { // related-work techniques and error display
 		switch (p.max_light_vertex_count) {
 		case 3: return vkr_launch_related_work_kernel_maxv3(p, stream);
 		case 4: return vkr_launch_related_work_kernel_maxv4(p, stream);
@@ -195,6 +206,7 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	p.sampling_strategies = (int) d.sampling_strategies; p.mis_heuristic = (int) d.mis_heuristic;
 	p.biased_sampling = d.polygon_sampling_technique == vkr_sample_polygon_projected_solid_angle_biased;
 	p.polygon_sampling_technique = (int) d.polygon_sampling_technique;
+	p.error_display = (int) d.error_display;
 	p.trace_shadow_rays = d.trace_shadow_rays; p.show_polygonal_lights = d.show_polygonal_lights; p.output_srgb = d.output_srgb;
 	p.noise = (const uint16_t*) d.noise_table->d_noise; p.noise_w = (int) d.noise_table->width; p.noise_h = (int) d.noise_table->height; p.noise_layers = (int) d.noise_table->layers;
 	p.ltc0 = (const uint16_t*) d.ltc_table->d_table0; p.ltc1 = (const uint16_t*) d.ltc_table->d_table1;

@@ -419,4 +419,51 @@ VKR_DEV f3 sample_psa(const psa_polygon<MAXP>& p, f2 rnd) {
 	return make3(xy.x, xy.y, sqrtf(max_glsl(0.0f, fmaf(-xy.x, xy.x, fmaf(-xy.y, xy.y, 1.0f)))));
 }
 
+// Error of a sample due to the iterative procedure (:823-883), for the error display modes of the shader (shading_pass.frag.glsl:489-493,
+// 549-563): x = backward error (in the first random number), y = x times the projected solid angle, z = forward error in radians.
+template <int MAXP, bool BIASED>
+VKR_DEV f3 sampling_error(const psa_polygon<MAXP>& p, f2 rnd, f3 sampled_dir) {
+	float target = rnd.x * p.psa;
+	if (p.inner_ellipse_0.x > 0.0f) return make3(0.0f, 0.0f, 0.0f); // the central case is exact up to rounding
+	float sector = 0.0f;
+	f2 outer = make2(0.0f, 0.0f), inner = p.inner_ellipse_0, dir_0 = make2(0.0f, 0.0f);
+	bool go = true;
+#pragma unroll
+	for (int i = 0; i != MAXP - 1; ++i) {
+		go = go && !((i > 1 && i + 1 == p.vertex_count) || (i > 0 && target < 0.0f));
+		if (go) {
+			sector = p.sector_psa[i];
+			target -= sector;
+			const f2 ve = p.ellipses[i];
+			const bool vinner = is_inner_ellipse(ve);
+			if (i == 0) outer = ve;
+			else {
+				inner = vinner ? ve : inner;
+				outer = vinner ? outer : ve;
+			}
+			dir_0 = p.vertices[i];
+		}
+	}
+	target += sector;
+	const f2 sxy = make2(sampled_dir.x, sampled_dir.y);
+	const float sampled_psa = area_between_ellipses_in_sector<BIASED>(inner, ellipse_rsqrt_det(inner), outer, ellipse_rsqrt_det(outer), dir_0, sxy);
+	const float scaled_backward_error = target - sampled_psa;
+	const float backward_error = scaled_backward_error / p.psa;
+	// derivative of the sampled direction with respect to the projected solid angle; cm0 / cm1 = columns of the constraint matrix before its transpose
+	const f2 inner_dir = ellipse_transform(inner, sxy);
+	const f2 outer_dir = ellipse_transform(outer, sxy);
+	const float inner_factor = 1.0f / dot(sxy, inner_dir);
+	const float outer_factor = 1.0f / dot(sxy, outer_dir);
+	const f2 cm0 = rotate_90(sxy) * (0.5f * (inner_factor - outer_factor));
+	f2 cm1 = inner_dir * ((1.0f - rnd.y) / (inner_factor * inner_factor));
+	cm1 = cm1 + outer_dir * (rnd.y / (outer_factor * outer_factor));
+	const float rcp_det = 1.0f / (cm0.x * cm1.y - cm0.y * cm1.x);
+	f3 derivative;
+	derivative.x = rcp_det * cm1.y;
+	derivative.y = rcp_det * -cm1.x;
+	derivative.z = -dot(sxy, make2(derivative.x, derivative.y)) / sampled_dir.z;
+	const float forward_error = sqrtf(dot(derivative, derivative)) * scaled_backward_error;
+	return make3(backward_error, scaled_backward_error, forward_error);
+}
+
 } // namespace vkr

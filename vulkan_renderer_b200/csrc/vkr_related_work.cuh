@@ -740,6 +740,68 @@ VKR_DEV f3 sample_psa_arvo(const psa_arvo_polygon<MAXP>& p, f2 rnd, int iteratio
 	return sample_sector_arvo<true>(rnd, target, inner_edge, inner_azimuth, outer_edge, outer_azimuth, azimuth_0, azimuth_1, iteration_count);
 }
 
+// Backward error of a sample of sample_psa_arvo() and the same times the projected solid angle (:1035-1087)
+template <int MAXP>
+VKR_DEV f2 sampling_error_arvo(const psa_arvo_polygon<MAXP>& p, f2 rnd, f3 sampled_dir) {
+	float target = rnd.x * p.psa;
+	if (p.inner_edge_0.cdf_factor > 0.0f) return make2(0.0f, 0.0f);
+	edge_arvo outer_edge = p.edges[0], inner_edge = p.inner_edge_0;
+	float inner_azimuth = p.azimuths[0], outer_azimuth = 0.0f, sector_psa = 0.0f, azimuth_0 = 0.0f;
+	bool go = true;
+#pragma unroll
+	for (int i = 0; i != MAXP - 1; ++i) {
+		go = go && !((i > 1 && i + 1 >= p.vertex_count) || (i > 0 && target < 0.0f));
+		if (go) {
+			sector_psa = p.sector_psa[i];
+			target -= sector_psa;
+			const edge_arvo vertex_edge = p.edges[i];
+			const float vertex_azimuth = p.azimuths[i];
+			if (i == 0) {
+				outer_edge = vertex_edge;
+				outer_azimuth = vertex_azimuth;
+			}
+			else {
+				const bool outer = vertex_edge.cdf_factor >= 0.0f;
+				inner_edge = select_edge(outer, vertex_edge, inner_edge);
+				inner_azimuth = outer ? inner_azimuth : vertex_azimuth;
+				outer_edge = select_edge(outer, outer_edge, vertex_edge);
+				outer_azimuth = outer ? vertex_azimuth : outer_azimuth;
+			}
+			azimuth_0 = p.azimuths[i];
+		}
+	}
+	target += sector_psa;
+	const float sampled_azimuth = atan2_poly(sampled_dir.y, sampled_dir.x);
+	const float outer_psa = edge_psa_in_sector_derivative_arvo(outer_edge, azimuth_0 - outer_azimuth, sampled_azimuth - outer_azimuth).x;
+	const float inner_psa = edge_psa_in_sector_derivative_arvo(inner_edge, azimuth_0 - inner_azimuth, sampled_azimuth - inner_azimuth).x;
+	const float sampled_psa = outer_psa + inner_psa;
+	return make2((target - sampled_psa) / p.psa, target - sampled_psa);
+}
+
+// Error magnitude -> colour (shading_pass.frag.glsl:80-115): matplotlib's tab20b in linear Rec. 709, one hue per power of ten of
+// error_factor * error. An index outside the table (only a NaN error gets there; undefined in GLSL) selects the first colour.
+VKR_DEV f3 error_to_color(float error, float error_factor) {
+	const float min_exponent = 0.0f, max_exponent = 5.0f;
+	const float min_error = pow_contract(10.0f, min_exponent);
+	const float max_error = pow_contract(10.0f, max_exponent - 0.01f);
+	const float color_count = 20.0f;
+	error = clamp_glsl(fabsf(error_factor * error), min_error, max_error);
+	const float color_index = fmaf(log2_poly(error), color_count / ((max_exponent - min_exponent) * log2_poly(10.0f)), color_count * -min_exponent / (max_exponent - min_exponent));
+	const int index = (color_index >= 0.0f && color_index < 20.0f) ? (int) color_index : 0;
+	float r = 0.04092f, g = 0.04374f, b = 0.19120f;
+	switch (index) {
+#define VKR_COLOR(I, R, G, B) case I: r = R; g = G; b = B; break;
+	VKR_COLOR(1, 0.08438f, 0.08866f, 0.36625f) VKR_COLOR(2, 0.14703f, 0.15593f, 0.62396f) VKR_COLOR(3, 0.33245f, 0.34191f, 0.73046f)
+	VKR_COLOR(4, 0.12477f, 0.19120f, 0.04092f) VKR_COLOR(5, 0.26225f, 0.36131f, 0.08438f) VKR_COLOR(6, 0.46208f, 0.62396f, 0.14703f) VKR_COLOR(7, 0.61721f, 0.70838f, 0.33245f)
+	VKR_COLOR(8, 0.26225f, 0.15293f, 0.03071f) VKR_COLOR(9, 0.50888f, 0.34191f, 0.04092f) VKR_COLOR(10, 0.79910f, 0.49102f, 0.08438f) VKR_COLOR(11, 0.79910f, 0.59720f, 0.29614f)
+	VKR_COLOR(12, 0.23074f, 0.04519f, 0.04092f) VKR_COLOR(13, 0.41789f, 0.06663f, 0.06848f) VKR_COLOR(14, 0.67244f, 0.11954f, 0.14703f) VKR_COLOR(15, 0.79910f, 0.30499f, 0.33245f)
+	VKR_COLOR(16, 0.19807f, 0.05286f, 0.17144f) VKR_COLOR(17, 0.37626f, 0.08228f, 0.29614f) VKR_COLOR(18, 0.61721f, 0.15293f, 0.50888f) VKR_COLOR(19, 0.73046f, 0.34191f, 0.67244f)
+#undef VKR_COLOR
+	default: break;
+	}
+	return make3(r, g, b);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // One interface over all techniques (shading_pass.frag.glsl:332-481).
 //   prepare(): false = this light contributes nothing at this pixel (clipped away / empty projected solid angle)

@@ -32,8 +32,9 @@ class Frame:
 			raise RuntimeError("%s failed with code %d" % (what, code))
 
 	# ---- settings
-	def configure(self, sample_count=None, strategy=None, heuristic=None, technique=None, trace_shadow_rays=None, show_lights=None, light_count=None, output_srgb=None, frame_bits=None):
+	def configure(self, sample_count=None, strategy=None, heuristic=None, technique=None, trace_shadow_rays=None, show_lights=None, light_count=None, output_srgb=None, frame_bits=None, error_display=None):
 		s = self.settings
+		if error_display is not None: self.error_display = int(error_display)   # render_settings_t::error_display (src/main.h:150)
 		if output_srgb is not None: self.output_srgb = int(output_srgb)     # !OUTPUT_LINEAR_RGB (src/main.c:790)
 		if frame_bits is not None: self.frame_bits = int(frame_bits)         # screenshot.frame_bits (src/main.c:2132)
 		if sample_count is not None: s.sample_count = sample_count
@@ -84,6 +85,7 @@ class Frame:
 		d.stripe_index, d.stripe_count = stripe_index, stripe_count
 		d.scene = C.pointer(self.scene); d.ltc_table = C.pointer(self.ltc); d.noise_table = C.pointer(self.noise)
 		d.output_srgb = getattr(self, "output_srgb", 0)
+		d.error_display = getattr(self, "error_display", 0)
 		return d
 
 	def create_pass(self, width, height, stripe_index=0, stripe_count=1, timing=False):
