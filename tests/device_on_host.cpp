@@ -17,7 +17,11 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 
+struct float4 { float x, y, z, w; };
+template <class T> static inline T __ldg(const T* p) { return *p; }
+
 #include "vkr_related_work.cuh"
+#include "vkr_trace.cuh"
 
 using namespace vkr;
 
@@ -101,6 +105,25 @@ extern "C" int vkr_device_on_host_error_display_batch(uint32_t technique, int bi
 	V(3) V(4) V(5) V(6) V(7)
 #undef V
 	default: return -1;
+	}
+}
+
+// The any-hit traversal of the device (vkr_trace.cuh: occluded(), ray_box(), ray_triangle()) over a BVH in the node-pair layout, one ray after
+// the other: rays = {ox, oy, oz, dx, dy, dz, tmin, tmax}. Lets the host-side tests hold every BVH builder against a brute-force loop over all
+// triangles with the very traversal code the GPU runs.
+extern "C" void vkr_device_on_host_trace_any(const float* nodes, const float* tris, uint32_t tri_count, uint32_t ray_count, const float* rays, uint8_t* out_bvh, uint8_t* out_brute) {
+	bvh_view bvh;
+	bvh.nodes = reinterpret_cast<const float4*>(nodes); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = nullptr; bvh.tri_count = tri_count;
+	int stack[kMaxStackDepth + 2];
+	for (uint32_t i = 0; i != ray_count; ++i) {
+		const float* r = rays + 8 * (size_t) i;
+		const f3 o = make3(r[0], r[1], r[2]), d = make3(r[3], r[4], r[5]);
+		out_bvh[i] = occluded(bvh, o, d, r[6], r[7], stack, 1) ? 1 : 0;
+		if (out_brute) {
+			bool hit = false; float t;
+			if (r[7] > r[6]) for (uint32_t k = 0; k != tri_count && !hit; ++k) hit = ray_triangle(bvh.tris + 3 * (size_t) k, o, d, r[6], r[7], &t);
+			out_brute[i] = hit ? 1 : 0;
+		}
 	}
 }
 

@@ -118,24 +118,28 @@ def test_constant_block_layout_and_light_maths():
 		assert u(p + 80)[0] == 4 and u(p + 84)[0] == 0
 
 
-def _probe_bvh(lib, tris):
+BUILDERS = {"sah": 0, "lbvh": 1}   # vkr_bvh.cpp (default), vkr_lbvh.cpp (host reference of the GPU builder)
+
+
+def _probe_bvh(lib, tris, builder=0):
 	P = C.POINTER
 	nodes = P(C.c_float)(); tri = P(C.c_float)(); ids = P(C.c_uint32)(); nc = C.c_uint64(); md = C.c_uint32()
 	tris = np.ascontiguousarray(tris, dtype=np.float32)
-	assert lib.vkr_bvh_build_probe(tris.ctypes.data, len(tris), C.byref(nodes), C.byref(nc), C.byref(tri), C.byref(ids), C.byref(md)) == 0
+	assert lib.vkr_bvh_build_probe_with(builder, tris.ctypes.data, len(tris), C.byref(nodes), C.byref(nc), C.byref(tri), C.byref(ids), C.byref(md)) == 0
 	n = len(tris)
 	out = (np.ctypeslib.as_array(nodes, (nc.value, 16)).copy(), np.ctypeslib.as_array(tri, (max(n, 1), 12)).copy()[:n], np.ctypeslib.as_array(ids, (max(n, 1),)).copy()[:n], md.value)
 	lib.vkr_bvh_free_probe(nodes, tri, ids)
 	return out
 
 
+@pytest.mark.parametrize("builder", sorted(BUILDERS))
 @pytest.mark.parametrize("name", ["cornell", "mini_city"])
-def test_bvh_builder_structure(name):
+def test_bvh_builder_structure(name, builder):
 	info = H.dataset(name)
 	lib = api.load_library()
 	vks = H.read_vks(info["vks"])
 	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
-	nodes, slots, ids, depth = _probe_bvh(lib, tris)
+	nodes, slots, ids, depth = _probe_bvh(lib, tris, BUILDERS[builder])
 	n = len(tris)
 	assert sorted(ids.tolist()) == list(range(n))                                   # every triangle exactly once
 	T = tris.reshape(-1, 3, 3)
@@ -165,16 +169,77 @@ def test_bvh_builder_structure(name):
 	assert depth < 62
 
 
-def test_bvh_builder_degenerate_inputs():
+@pytest.mark.parametrize("builder", sorted(BUILDERS))
+@pytest.mark.parametrize("name", ["cornell", "mini_city", "roughness_planes"])
+def test_bvh_traversal_equals_brute_force_for_every_builder(name, builder):
+	"""The device's any-hit traversal (vkr_trace.cuh, compiled for the CPU by tests/device_on_host.cpp) over the BVH of each builder against a
+	loop over all triangles with the same triangle predicate: the shadow result must not depend on the builder (shadow predicate)."""
+	from tests.test_device_on_host import _lib
+	dev = _lib()
+	info = H.dataset(name); lib = api.load_library()
+	vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes, slots, ids, depth = _probe_bvh(lib, tris, BUILDERS[builder])
+	assert depth + 2 <= 64
+	rng = np.random.default_rng(11)
+	T = tris.reshape(-1, 3, 3); lo = T.reshape(-1, 3).min(0); hi = T.reshape(-1, 3).max(0)
+	n_rays = 1500
+	origins = rng.uniform(lo, hi, (n_rays, 3)); targets = T[rng.integers(0, len(T), n_rays)].mean(1) + rng.normal(scale=0.05, size=(n_rays, 3))
+	d = targets - origins; length = np.linalg.norm(d, axis=1, keepdims=True); d /= length
+	rays = np.concatenate([origins, d, np.full((n_rays, 1), 1e-3), length * rng.uniform(0.3, 1.5, (n_rays, 1))], axis=1).astype(np.float32)
+	rays[:20, 3:6] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 20)]      # axis-parallel directions: the slab test sees infinities
+	rays[20:30, 7] = 0.0                                                     # empty intervals are misses by definition
+	out_bvh = np.zeros(n_rays, dtype=np.uint8); out_brute = np.zeros(n_rays, dtype=np.uint8)
+	nodes = np.ascontiguousarray(nodes, dtype=np.float32); slots = np.ascontiguousarray(slots, dtype=np.float32)
+	dev.vkr_device_on_host_trace_any(nodes.ctypes.data_as(C.c_void_p), slots.ctypes.data_as(C.c_void_p), C.c_uint32(len(slots)), C.c_uint32(n_rays), rays.ctypes.data_as(C.c_void_p),
+		out_bvh.ctypes.data_as(C.c_void_p), out_brute.ctypes.data_as(C.c_void_p))
+	assert np.array_equal(out_bvh, out_brute)
+	assert 0.05 < out_brute.mean() < 0.98 and not out_brute[20:30].any()
+
+
+def test_lbvh_follows_the_morton_order_of_the_centroids():
+	"""What the GPU builder has to reproduce: slots in ascending (Morton code of the centroid, original index) order, leaves of up to four slots."""
 	lib = api.load_library()
-	nodes, slots, ids, depth = _probe_bvh(lib, np.zeros((0, 9), dtype=np.float32))          # empty scene
+	info = H.dataset("mini_city"); vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes, slots, ids, depth = _probe_bvh(lib, tris, BUILDERS["lbvh"])
+	T = tris.reshape(-1, 3, 3)
+	blo = T.min(1); bhi = T.max(1); c = (np.float32(0.5) * (blo + bhi)).astype(np.float32)
+	clo = c.min(0); ext = c.max(0) - clo
+	inv = np.where(ext > 0, np.float32(1.0) / ext, np.float32(0.0)).astype(np.float32)
+	q = np.clip((((c - clo) * inv) * np.float32(2097152.0)).astype(np.float32), 0, 2097151).astype(np.uint64)
+	def expand(v):
+		x = v & np.uint64(0x1fffff)
+		for shift, mask in ((32, 0x1f00000000ffff), (16, 0x1f0000ff0000ff), (8, 0x100f00f00f00f00f), (4, 0x10c30c30c30c30c3), (2, 0x1249249249249249)):
+			x = (x | (x << np.uint64(shift))) & np.uint64(mask)
+		return x
+	code = (expand(q[:, 0]) << np.uint64(2)) | (expand(q[:, 1]) << np.uint64(1)) | expand(q[:, 2])
+	expected = np.lexsort((np.arange(len(code)), code))
+	assert np.array_equal(ids, expected.astype(np.uint32))
+	refs = nodes[:, 12:14].copy().view(np.int32).reshape(-1)
+	counts = refs[refs < 0] & 15
+	assert counts.max() <= 4 and counts.sum() == len(tris) and (counts >= 1).all()
+	sah_nodes, _, _, sah_depth = _probe_bvh(lib, tris, BUILDERS["sah"])
+	assert len(nodes) < 1.3 * len(sah_nodes) + 8 and depth <= 2 * sah_depth + 8   # a comparable tree, not a degenerate one
+
+
+@pytest.mark.parametrize("builder", sorted(BUILDERS))
+def test_bvh_builder_degenerate_inputs(builder):
+	import functools
+	lib = api.load_library()
+	_probe = functools.partial(_probe_bvh, builder=BUILDERS[builder])
+	nodes, slots, ids, depth = _probe(lib, np.zeros((0, 9), dtype=np.float32))              # empty scene
 	assert len(nodes) == 1 and (nodes[0, 12:14].view(np.int32) & 15).tolist() == [0, 0]
 	one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float32)
-	nodes, slots, ids, depth = _probe_bvh(lib, one)                                         # single leaf under the root pair
+	nodes, slots, ids, depth = _probe(lib, one)                                             # single leaf under the root pair
 	assert len(nodes) == 1 and (int(nodes[0, 12:13].view(np.int32)[0]) & 15) == 1
 	same = np.tile(one, (100, 1))                                                            # 100 coincident triangles: median splits
-	nodes, slots, ids, depth = _probe_bvh(lib, same)
+	nodes, slots, ids, depth = _probe(lib, same)                                            # (equal Morton codes: the position breaks the ties)
 	assert sorted(ids.tolist()) == list(range(100)) and depth < 62
+	five = np.tile(one, (5, 1)) + np.arange(5, dtype=np.float32)[:, None]                   # the smallest tree with an inner split
+	nodes, slots, ids, depth = _probe(lib, five)
+	refs = nodes[:, 12:14].copy().view(np.int32).reshape(-1)
+	assert sorted(ids.tolist()) == list(range(5)) and int((refs[refs < 0] & 15).sum()) == 5
 
 
 def test_error_paths_return_codes_and_leave_structs_zeroed(tmp_path, capfd):

@@ -18,4 +18,13 @@ struct host_bvh {
 // vertices: 9 floats per triangle. The result is deterministic for a given input.
 void build_bvh(host_bvh& out, const float* vertices, uint64_t triangle_count);
 
+// Linear BVH (Morton order + Karras' radix tree + leaves of up to four triangles), vkr_lbvh.cpp: the sequential reference of the GPU
+// builder. Same output layout, lower tree quality, identical traversal results.
+void build_lbvh(host_bvh& out, const float* vertices, uint64_t triangle_count);
+uint64_t lbvh_morton_code(const float centroid[3], const float lo[3], const float inv_extent[3]);
+
+enum bvh_builder { bvh_builder_sah = 0, bvh_builder_lbvh = 1, bvh_builder_lbvh_gpu = 2 };
+// VKR_BVH_BUILDER = sah (default) | lbvh | lbvh_gpu
+bvh_builder bvh_builder_from_environment();
+
 } // namespace vkr

@@ -241,7 +241,9 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 			float p[3]; unpack_position(&positions[2 * i], p);
 			for (int j = 0; j != 3; ++j) soup[3 * i + j] = p[j] * scene->dequantization_factor[j] + scene->dequantization_summand[j];
 		}
-		build_bvh(bvh, soup.data(), n);
+		const bvh_builder which = bvh_builder_from_environment();
+		if (which == bvh_builder_lbvh) build_lbvh(bvh, soup.data(), n);
+		if (which != bvh_builder_lbvh || bvh.max_depth >= 62) build_bvh(bvh, soup.data(), n); // default; also the fallback for hostile Morton orders
 		scene->shadow_node_count = bvh.node_count; scene->shadow_max_depth = bvh.max_depth;
 		if (bvh.max_depth >= 62 || upload(&scene->d_shadow_nodes, bvh.nodes.data(), bvh.nodes.size() * 4, device) || upload(&scene->d_shadow_tris, bvh.tris.data(), bvh.tris.size() * 4, device)) {
 			printf("Failed to construct an acceleration structure for the scene file at path %s.\n", file_path);
@@ -720,9 +722,21 @@ extern "C" size_t vkr_write_constants(void* data, const vkr_scene_specification_
 // ------------------------------------------------------------------------------------------------
 // host-side probe of the BVH builder (structural tests without a GPU)
 // ------------------------------------------------------------------------------------------------
-extern "C" int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
+namespace vkr {
+bvh_builder bvh_builder_from_environment() {
+	const char* name = getenv("VKR_BVH_BUILDER");
+	if (name && !strcmp(name, "lbvh")) return bvh_builder_lbvh;
+	if (name && !strcmp(name, "lbvh_gpu")) return bvh_builder_lbvh_gpu;
+	return bvh_builder_sah;
+}
+}
+
+// builder: 0 = binned SAH (vkr_bvh.cpp, what scenes are loaded with by default), 1 = linear BVH (vkr_lbvh.cpp)
+extern "C" int vkr_bvh_build_probe_with(int builder, const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
 	host_bvh bvh;
-	build_bvh(bvh, vertices, triangle_count);
+	if (builder == 1) build_lbvh(bvh, vertices, triangle_count);
+	else if (builder == 0) build_bvh(bvh, vertices, triangle_count);
+	else { printf("The BVH builder probe knows the host builders 0 (SAH) and 1 (linear BVH), not %d.\n", builder); return 1; }
 	*out_nodes = (float*) malloc(sizeof(float) * (bvh.nodes.size() ? bvh.nodes.size() : 1));
 	*out_tris = (float*) malloc(sizeof(float) * (bvh.tris.size() ? bvh.tris.size() : 1));
 	*out_tri_ids = (uint32_t*) malloc(sizeof(uint32_t) * (bvh.tri_ids.size() ? bvh.tri_ids.size() : 1));
@@ -731,5 +745,8 @@ extern "C" int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_coun
 	memcpy(*out_tri_ids, bvh.tri_ids.data(), sizeof(uint32_t) * bvh.tri_ids.size());
 	*out_node_count = bvh.node_count; *out_max_depth = bvh.max_depth;
 	return 0;
+}
+extern "C" int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
+	return vkr_bvh_build_probe_with(0, vertices, triangle_count, out_nodes, out_node_count, out_tris, out_tri_ids, out_max_depth);
 }
 extern "C" void vkr_bvh_free_probe(float* nodes, float* tris, uint32_t* tri_ids) { free(nodes); free(tris); free(tri_ids); }
