@@ -23,6 +23,10 @@ void build_bvh(host_bvh& out, const float* vertices, uint64_t triangle_count);
 void build_lbvh(host_bvh& out, const float* vertices, uint64_t triangle_count);
 uint64_t lbvh_morton_code(const float centroid[3], const float lo[3], const float inv_extent[3]);
 
+// The same builder on the GPU (vkr_lbvh_gpu.cu). vertices: HOST pointer; outputs: device allocations owned by the caller. stream: a cudaStream_t
+// (void* like vkr_device_t::stream, so that this header needs no CUDA headers).
+int build_lbvh_device(const float* vertices, uint64_t triangle_count, void* stream, void** d_nodes, void** d_tris, void** d_tri_ids, uint64_t* node_count, uint32_t* max_depth);
+
 enum bvh_builder { bvh_builder_sah = 0, bvh_builder_lbvh = 1, bvh_builder_lbvh_gpu = 2 };
 // VKR_BVH_BUILDER = sah (default) | lbvh | lbvh_gpu
 bvh_builder bvh_builder_from_environment();

@@ -241,13 +241,27 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 			float p[3]; unpack_position(&positions[2 * i], p);
 			for (int j = 0; j != 3; ++j) soup[3 * i + j] = p[j] * scene->dequantization_factor[j] + scene->dequantization_summand[j];
 		}
+		// Builder: binned SAH on the host by default; VKR_BVH_BUILDER=lbvh / lbvh_gpu select the linear BVH (host reference / GPU). Whatever the
+		// linear builders cannot deliver (too deep a tree for the traversal stack, fewer than five triangles, a CUDA error) is built by the default one.
 		const bvh_builder which = bvh_builder_from_environment();
-		if (which == bvh_builder_lbvh) build_lbvh(bvh, soup.data(), n);
-		if (which != bvh_builder_lbvh || bvh.max_depth >= 62) build_bvh(bvh, soup.data(), n); // default; also the fallback for hostile Morton orders
-		scene->shadow_node_count = bvh.node_count; scene->shadow_max_depth = bvh.max_depth;
-		if (bvh.max_depth >= 62 || upload(&scene->d_shadow_nodes, bvh.nodes.data(), bvh.nodes.size() * 4, device) || upload(&scene->d_shadow_tris, bvh.tris.data(), bvh.tris.size() * 4, device)) {
-			printf("Failed to construct an acceleration structure for the scene file at path %s.\n", file_path);
-			vkr_destroy_scene(scene, device); return 1;
+		bool built_on_device = false;
+		if (which == bvh_builder_lbvh_gpu && cudaSetDevice(device->cuda_device) == cudaSuccess) {
+			void* d_ids = nullptr; uint64_t pairs = 0; uint32_t depth = 0;
+			if (build_lbvh_device(soup.data(), n, device->stream, &scene->d_shadow_nodes, &scene->d_shadow_tris, &d_ids, &pairs, &depth) == 0) {
+				cudaFree(d_ids);
+				if (depth < 62) { built_on_device = true; scene->shadow_node_count = pairs; scene->shadow_max_depth = depth; }
+				else { cudaFree(scene->d_shadow_nodes); cudaFree(scene->d_shadow_tris); scene->d_shadow_nodes = scene->d_shadow_tris = nullptr; }
+			}
+			if (!built_on_device) printf("The GPU BVH builder did not produce a usable tree for %s; building on the host instead.\n", file_path);
+		}
+		if (!built_on_device) {
+			if (which == bvh_builder_lbvh) build_lbvh(bvh, soup.data(), n);
+			if (which != bvh_builder_lbvh || bvh.max_depth >= 62) build_bvh(bvh, soup.data(), n);
+			scene->shadow_node_count = bvh.node_count; scene->shadow_max_depth = bvh.max_depth;
+			if (bvh.max_depth >= 62 || upload(&scene->d_shadow_nodes, bvh.nodes.data(), bvh.nodes.size() * 4, device) || upload(&scene->d_shadow_tris, bvh.tris.data(), bvh.tris.size() * 4, device)) {
+				printf("Failed to construct an acceleration structure for the scene file at path %s.\n", file_path);
+				vkr_destroy_scene(scene, device); return 1;
+			}
 		}
 		// (b) primary rays: vertices as the shaders decode them (fma, mesh_quantization.glsl:38-45)
 		for (uint64_t i = 0; i != 3 * n; ++i) {
@@ -746,6 +760,26 @@ extern "C" int vkr_bvh_build_probe_with(int builder, const float* vertices, uint
 	*out_node_count = bvh.node_count; *out_max_depth = bvh.max_depth;
 	return 0;
 }
+// The GPU builder's output copied to the host in the format of the host probes (tests: array-for-array equality with builder 1)
+extern "C" int vkr_bvh_build_probe_device(const vkr_device_t* device, const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
+	*out_nodes = nullptr; *out_tris = nullptr; *out_tri_ids = nullptr; *out_node_count = 0; *out_max_depth = 0;
+	if (cudaSetDevice(device->cuda_device) != cudaSuccess) { printf("Failed to select the CUDA device for the BVH builder probe.\n"); return 1; }
+	void *d_nodes = nullptr, *d_tris = nullptr, *d_ids = nullptr; uint64_t pairs = 0; uint32_t depth = 0;
+	if (build_lbvh_device(vertices, triangle_count, device->stream, &d_nodes, &d_tris, &d_ids, &pairs, &depth)) {
+		printf("The GPU BVH builder failed for %llu triangles.\n", (unsigned long long) triangle_count); return 1;
+	}
+	*out_nodes = (float*) malloc(sizeof(float) * 16 * (pairs ? pairs : 1));
+	*out_tris = (float*) malloc(sizeof(float) * 12 * triangle_count);
+	*out_tri_ids = (uint32_t*) malloc(sizeof(uint32_t) * triangle_count);
+	const bool ok = cudaMemcpy(*out_nodes, d_nodes, sizeof(float) * 16 * pairs, cudaMemcpyDeviceToHost) == cudaSuccess
+		&& cudaMemcpy(*out_tris, d_tris, sizeof(float) * 12 * triangle_count, cudaMemcpyDeviceToHost) == cudaSuccess
+		&& cudaMemcpy(*out_tri_ids, d_ids, sizeof(uint32_t) * triangle_count, cudaMemcpyDeviceToHost) == cudaSuccess;
+	cudaFree(d_nodes); cudaFree(d_tris); cudaFree(d_ids);
+	if (!ok) { free(*out_nodes); free(*out_tris); free(*out_tri_ids); *out_nodes = nullptr; *out_tris = nullptr; *out_tri_ids = nullptr; printf("Failed to copy the BVH to the host.\n"); return 1; }
+	*out_node_count = pairs; *out_max_depth = depth;
+	return 0;
+}
+
 extern "C" int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
 	return vkr_bvh_build_probe_with(0, vertices, triangle_count, out_nodes, out_node_count, out_tris, out_tri_ids, out_max_depth);
 }
