@@ -30,8 +30,15 @@ def test_timing_matrix_has_the_shape_and_names_of_the_reference_list():
 		assert s["exposure_factor"] == 8.0 / e["light_count"] and not s["trace_shadow_rays"] and not s["show_polygonal_lights"]
 		assert s["polygon_sampling_technique"] == E.SAMPLE_POLYGON_NAME.index(m.group(4))
 	assert (E.SAMPLE_POLYGON_NAME.index("projected_solid_angle_ours"), E.SAMPLE_POLYGON_NAME.index("projected_solid_angle_biased_ours")) == (api.TECHNIQUE_PSA, api.TECHNIQUE_PSA_BIASED)
-	assert E.experiment_list()[0]["name"] == "attic_solid_angle_and_ggx_mis_2spp" and len(E.experiment_list()) == 265
-	assert (E.experiment_list(all_figs=False) == t) and len(E.experiment_list(all_timings=False)) == 5
+	figures = E.experiment_list(all_timings=False)
+	assert figures[0]["name"] == "attic_solid_angle_and_ggx_mis_2spp" and len(figures) == 5 + 2 + 2 * 12 + 8 + 16 + 2 + 2
+	assert len({e["name"] for e in figures}) == len(figures)
+	assert E.experiment_list(all_figs=False) == t and len(E.experiment_list()) == len(figures) + 260
+	by_name = {e["name"]: e for e in figures}
+	assert by_name["error_attic_backward_times_psa"]["settings"]["error_display"] == api.ERROR_DISPLAY_DIFFUSE_BACKWARD_SCALED
+	assert "bistro_tiny_polygon_bilinear_cosine_warp_clipping_hart_1spp" not in by_name and by_name["bistro_small_polygon_reference_128spp"]["settings"]["sample_count"] == 128
+	assert by_name["mis_plane_optimal_ours_2spp"]["settings"]["mis_heuristic"] == api.MIS_OPTIMAL and by_name["shadowed_plane_biased_4096spp"]["settings"]["sample_count"] == 2048
+	assert by_name["cornell_box_projected_solid_angle_arvo_tilted_1spp"]["quick_save_path"] == "data/quicksaves/cornell_box_tilted_light.save"
 
 
 def test_every_experiment_is_a_legal_configuration(capfd):
@@ -41,9 +48,29 @@ def test_every_experiment_is_a_legal_configuration(capfd):
 	for e in E.experiment_list():
 		s = e["settings"]
 		p = api.ShadingPass(); d = api.ShadingPassDesc(width=e["width"], height=e["height"], polygonal_light_count=1, min_polygonal_light_vertex_count=4, max_polygonal_light_vertex_count=4,
-			sample_count=s["sample_count"], sampling_strategies=s["sampling_strategies"], mis_heuristic=s["mis_heuristic"], polygon_sampling_technique=s["polygon_sampling_technique"], stripe_count=1)
+			sample_count=s["sample_count"], sampling_strategies=s["sampling_strategies"], mis_heuristic=s["mis_heuristic"], polygon_sampling_technique=s["polygon_sampling_technique"], stripe_count=1,
+			error_display=s.get("error_display", 0))
 		assert lib.vkr_create_shading_pass(C.byref(p), C.byref(dev), C.byref(d)) == 1
 		assert "missing LTC / noise tables" in capfd.readouterr().out, e["name"]
+
+
+@pytest.mark.parametrize("name", ["mis_plane_weighted_ours_2spp", "cornell_box_projected_solid_angle_arvo_tilted_1spp", "roughness_planes_lambertian_2spp"])
+def test_figure_scene_data_loads_and_is_lit(name):
+	e = [x for x in E.experiment_list(all_timings=False) if x["name"] == name][0]
+	info = H.dataset(e["scene"], **e["scene_parameters"])
+	oi = H.OracleInputs(info)
+	width, height = 64, 48
+	lights = len(info["lights"]); vertices = max(len(l["vertices"]) for l in info["lights"])
+	constants = host_constants(info, width, height, lights)
+	vis = oi.visibility(width, height, constants); gb = oi.gbuffer(width, height, constants, vis)
+	s = e["settings"]
+	cfg = dict(width=width, height=height, light_count=lights, max_light_vertex_count=vertices, min_light_vertex_count=vertices, sample_count=2, sampling_strategies=s["sampling_strategies"],
+		mis_heuristic=s["mis_heuristic"], biased_sampling=0, trace_shadow_rays=1, show_polygonal_lights=1, polygon_sampling_technique=min(s["polygon_sampling_technique"], 11))
+	out, rays = oi.shade(cfg, constants, gb)
+	lit = out[..., :3].sum(-1) > 0
+	assert (vis != 0xFFFFFFFF).mean() > 0.35 and 0.15 < lit.mean() and rays > 0
+	if e["scene"] == "shadowed_plane":
+		assert lit.mean() < (vis != 0xFFFFFFFF).mean()      # something is in shadow or faces away
 
 
 @pytest.mark.parametrize("vertices,central,lights", [(3, 1, 128), (5, 0, 1), (7, 1, 1), (4, 0, 128)])

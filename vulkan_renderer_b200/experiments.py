@@ -7,7 +7,8 @@ file name (advance_experiments, src/main.c:1948-2016; get_frame_time, src/frame_
   * the run-time measurements of the polygon sampling techniques (src/experiment_list.c:366-409): 3 to 7 light vertices x
     central / decentral configuration x (128 lights, 1 sample | 1 light, 128 samples) x the 13 sampling techniques,
     1920x1080, diffuse shading only, shadow rays and light display off,
-  * the attic comparison of sampling strategies (src/experiment_list.c:66-110),
+  * the figure experiments that need no light textures: attic strategies and sampling error (:66-128), small distant lights (:130-168), the MIS
+    heuristics on a shadowed plane (:170-220), the Cornell box with every technique (:222-266), the bias test (:268-292), the roughness planes (:316-339),
 
 on the synthetic stand-ins of the scenes (vulkan_renderer_b200.synth; the reference's assets are not in its repository) and
 runs them through the C-ABI: one shading pass per experiment, frame time = the median of the recorded frame times, kernel
@@ -55,11 +56,14 @@ def timing_experiments():
 	return out
 
 
+def _figure(name, scene, width, height, scene_parameters=None, quick_save_path=None, **settings):
+	return dict(name=name, screenshot_path="data/experiments/%s_%%.3f.png" % name, scene=scene, scene_parameters=scene_parameters or {}, quick_save_path=quick_save_path,
+		width=width, height=height, light_count=None, settings=_settings(**settings))
+
+
 def attic_experiments():
 	"""src/experiment_list.c:66-110: the attic with different sampling strategies (2 samples per pixel in total each) and a reference."""
-	base = dict(scene="room", scene_parameters={}, quick_save_path=None, width=1440, height=1440, light_count=None)
-	def make(name, **kw):
-		return dict(base, name=name, screenshot_path="data/experiments/%s_%%.3f.png" % name, settings=_settings(**kw))
+	make = lambda name, **kw: _figure(name, "room", 1440, 1440, **kw)
 	return [
 		make("attic_solid_angle_and_ggx_mis_2spp", sampling_strategies=api.STRATEGY_DIFFUSE_GGX_MIS, polygon_sampling_technique=api.TECHNIQUE_SOLID_ANGLE),
 		make("attic_projected_solid_angle_ours_and_ggx_mis_2spp", sampling_strategies=api.STRATEGY_DIFFUSE_GGX_MIS),
@@ -69,9 +73,70 @@ def attic_experiments():
 	]
 
 
+def error_experiments():
+	"""src/experiment_list.c:112-128: the sampling error in the attic, colour coded (error_display_t)."""
+	base = dict(trace_shadow_rays=0, show_polygonal_lights=0, mis_heuristic=api.MIS_BALANCE)
+	return [
+		_figure("error_attic_backward", "room", 1440, 1440, error_display=api.ERROR_DISPLAY_DIFFUSE_BACKWARD, **base),
+		_figure("error_attic_backward_times_psa", "room", 1440, 1440, error_display=api.ERROR_DISPLAY_DIFFUSE_BACKWARD_SCALED, **base),
+	]
+
+
+def small_light_experiments():
+	"""src/experiment_list.c:130-168: a small and a tiny distant light in the Bistro, every diffuse technique except Hart's clipping variants."""
+	out = []
+	for size in ("small", "tiny"):
+		save = "data/quicksaves/Bistro_outside_%s_light.save" % size
+		for technique, label in enumerate(SAMPLE_POLYGON_NAME):
+			if technique in (api.TECHNIQUE_BILINEAR_COSINE_WARP_CLIPPING_HART, api.TECHNIQUE_BIQUADRATIC_COSINE_WARP_CLIPPING_HART):
+				continue
+			out.append(_figure("bistro_%s_polygon_%s_1spp" % (size, label), "city", 1920, 1080, dict(light_size=size), save, exposure_factor=14.0, polygon_sampling_technique=technique))
+		out.append(_figure("bistro_%s_polygon_reference_128spp" % size, "city", 1920, 1080, dict(light_size=size), save, exposure_factor=14.0,
+			polygon_sampling_technique=api.TECHNIQUE_AREA_TURK, sample_count=128))
+	return out
+
+
+def mis_plane_experiments():
+	"""src/experiment_list.c:170-220: a shadowed plane with every MIS heuristic, GGX MIS, the one-sample estimator and a reference."""
+	names = ["balance_veach", "power_veach", "weighted_ours", "clamped_optimal_ours", "optimal_ours"]
+	base = dict(sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS)
+	out = [_figure("mis_plane_%s_2spp" % label, "shadowed_plane", 1024, 1024, mis_heuristic=heuristic, **base) for heuristic, label in enumerate(names)]
+	out.append(_figure("mis_plane_solid_angle_and_ggx_balance_veach_2spp", "shadowed_plane", 1024, 1024, sampling_strategies=api.STRATEGY_DIFFUSE_GGX_MIS, mis_heuristic=api.MIS_BALANCE))
+	out.append(_figure("mis_plane_diffuse_and_specular_random_ours_1spp", "shadowed_plane", 1024, 1024, sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_RANDOM))
+	out.append(_figure("mis_plane_reference_128spp", "shadowed_plane", 1024, 1024, mis_heuristic=api.MIS_BALANCE, sample_count=64, **base))
+	return out
+
+
+def cornell_box_experiments():
+	"""src/experiment_list.c:222-266: the Cornell box with every diffuse technique, Arvo's with a tilted light, references."""
+	out = [_figure("cornell_box_%s_1spp" % label, "cornell", 1024, 1024, polygon_sampling_technique=technique) for technique, label in enumerate(SAMPLE_POLYGON_NAME)]
+	tilted = dict(scene_parameters=dict(tilted=1), quick_save_path="data/quicksaves/cornell_box_tilted_light.save")
+	out.append(_figure("cornell_box_projected_solid_angle_arvo_tilted_1spp", "cornell", 1024, 1024, polygon_sampling_technique=api.TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO, **tilted))
+	out.append(_figure("cornell_box_reference_tilted_128spp", "cornell", 1024, 1024, polygon_sampling_technique=api.TECHNIQUE_SOLID_ANGLE, sample_count=128, **tilted))
+	out.append(_figure("cornell_box_reference_128spp", "cornell", 1024, 1024, polygon_sampling_technique=api.TECHNIQUE_SOLID_ANGLE, sample_count=128))
+	return out
+
+
+def shadowed_plane_experiments():
+	"""src/experiment_list.c:268-292: 2048 samples per technique with the unbiased and the biased sampler (the view provokes the bias)."""
+	base = dict(exposure_factor=10.0, sample_count=2048, sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_OPTIMAL_CLAMPED)
+	return [_figure("shadowed_plane_reference_4096spp", "shadowed_plane", 1024, 1024, **base),
+		_figure("shadowed_plane_biased_4096spp", "shadowed_plane", 1024, 1024, polygon_sampling_technique=api.TECHNIQUE_PSA_BIASED, **base)]
+
+
+def roughness_planes_experiments():
+	"""src/experiment_list.c:316-339: three planes of different roughness under a Lambertian emitter (the textured emitter of :341-362 is out of scope)."""
+	base = dict(sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_WEIGHTED)
+	parameters = dict(vertices=4, central=1, lights=1)
+	return [_figure("roughness_planes_lambertian_2spp", "roughness_planes", 2048 + 256, 1024, parameters, **base),
+		_figure("roughness_planes_lambertian_diffuse_only_1spp", "roughness_planes", 2048 + 256, 1024, parameters, **dict(base, sampling_strategies=api.STRATEGY_DIFFUSE_ONLY))]
+
+
 def experiment_list(all_figs=True, all_timings=True):
-	"""create_experiment_list (src/experiment_list.c:25-555) restricted to what runs on untextured polygonal lights."""
-	return (attic_experiments() if all_figs else []) + (timing_experiments() if all_timings else [])
+	"""create_experiment_list (src/experiment_list.c:25-555) in its order, restricted to what runs on untextured polygonal lights: the IES-profile attic
+	(:294-314) and the textured screen (:341-362) are left out, as are the figures for the HTML viewer (html_figs = VK_FALSE in the reference)."""
+	figures = attic_experiments() + error_experiments() + small_light_experiments() + mis_plane_experiments() + cornell_box_experiments() + shadowed_plane_experiments() + roughness_planes_experiments()
+	return (figures if all_figs else []) + (timing_experiments() if all_timings else [])
 
 
 def prepare_data(experiment, data_root):
@@ -94,7 +159,10 @@ def run_experiment(experiment, data_root, out_dir=None, frames=12, warmup=3, wid
 	try:
 		s = experiment["settings"]
 		for key, value in s.items():
-			setattr(frame.settings, key, value)
+			if key == "error_display":
+				frame.configure(error_display=value)   # a pass setting (-D defines), not part of the constant block
+			else:
+				setattr(frame.settings, key, value)
 		if experiment.get("light_count"):
 			frame.configure(light_count=experiment["light_count"])
 		constants = frame.constants(width, height)

@@ -167,6 +167,17 @@ def scene_roughness_planes():
 	return m.finish(), materials
 
 
+def scene_shadowed_plane():
+	"""A ground plane with a bollard and a block that cast shadows: stand-in for the reference's 'mis plane' and 'shadowed plane' scenes
+	(src/experiment_list.c:170-220, 268-292; the assets are not in the repository)."""
+	m = Mesh()
+	materials = [dict(name="ground", base=(0.6, 0.6, 0.6), roughness=0.35, metal=0.0), dict(name="occluder", base=(0.3, 0.25, 0.2), roughness=0.6, metal=0.0)]
+	m.add(_grid_quad([-20.0, -20.0, 0.0], [40.0, 0.0, 0.0], [0.0, 40.0, 0.0], 20, 20), 0)
+	m.add(_box([-0.15, 0.6, 0.0], [0.15, 0.9, 1.1]), 1)
+	m.add(_box([1.2, 1.5, 0.0], [2.0, 2.1, 0.6]), 1)
+	return m.finish(), materials
+
+
 def roughness_planes_lights(vertex_count, central, light_count):
 	"""Lights of the timing experiments (src/experiment_list.c:366-409): regular polygons with 3 to 7 vertices, either close above the
 	planes and facing down (central: the surface normal passes through the polygon for most pixels) or standing beside them
@@ -392,12 +403,17 @@ def build_dataset(directory, name, **overrides):
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
 		lights = [make_light((0.35, 0.35, 0.995), (np.pi, 0.0, 0.0), (0.3, 0.3), (1.0, 1.0, 1.0))]
 		lights[0]["translation"] = (0.35, 0.65, 0.995)
+		if overrides.get("tilted"):   # cornell_box_tilted_light.save (src/experiment_list.c:247-259)
+			lights = [make_light((0.3, 0.75, 0.93), (np.pi + 0.6, 0.25, 0.0), (0.4, 0.3), (1.0, 1.0, 1.0))]
 	elif name == "city":
 		mesh, materials = scene_city(**{k: v for k, v in overrides.items() if k in ("seed", "blocks", "extent", "detail", "ground_cells", "n_mat")})
 		extent = overrides.get("extent", 200.0)
 		camera = look_at_camera((0.5 * extent - 3.0, 0.5 * extent - 42.0, 4.5), (0.5 * extent - 3.0, 0.5 * extent - 18.0, 1.0))
 		n_lights = overrides.get("lights", 8)
 		lights = _ceiling_lights(rng, n_lights, (0.5 * extent - 16.0, 0.5 * extent + 10.0), (0.5 * extent - 34.0, 0.5 * extent - 6.0), (2.6, 4.5), flux=60.0)
+		if overrides.get("light_size"):   # "small" / "tiny": one distant light (the reference's Bistro_outside_<size>_light.save, src/experiment_list.c:129-168)
+			size = {"small": 0.5, "tiny": 0.08}[overrides["light_size"]]
+			lights = [make_light((0.5 * extent - 6.0, 0.5 * extent - 20.0, 9.0), (np.pi + 0.2, 0.1, 0.3), (size, size), (400.0, 400.0, 400.0))]
 	elif name == "mini_city":
 		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
 		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
@@ -427,6 +443,10 @@ def build_dataset(directory, name, **overrides):
 		mesh, materials = scene_room(seed=4, detail=6, clutter=60, n_mat=8)
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
 		lights = _ceiling_lights(rng, overrides.get("lights", 32), (1.0, 11.0), (1.0, 7.0), (2.4, 3.3), scale_range=(0.3, 1.0))
+	elif name == "shadowed_plane":
+		mesh, materials = scene_shadowed_plane()
+		camera = look_at_camera((0.0, -4.0, 2.2), (0.3, 1.0, 0.0))
+		lights = [make_light((-1.0, 3.0, 0.4), (0.5 * np.pi + 0.25, 0.0, 0.0), (2.0, 1.2), (25.0, 25.0, 25.0))]
 	elif name == "roughness_planes":
 		# scene of the reference's timing experiments; overrides: vertices (3..7), central (0/1), lights (1 or 128)
 		mesh, materials = scene_roughness_planes()
