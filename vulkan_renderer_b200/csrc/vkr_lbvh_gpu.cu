@@ -204,11 +204,13 @@ __global__ void __launch_bounds__(kThreads) depth_kernel(uint32_t internal_count
 	atomicMax(max_depth, depth);
 }
 
-struct scratch {
-	void* ptr[16] = {};
+struct scratch { // device allocations that live as long as one build
+	static constexpr int kCapacity = 32;
+	void* ptr[kCapacity] = {};
 	int count = 0;
 	template <class T> bool alloc(T** p, size_t elements) {
-		if (cudaMalloc((void**) p, sizeof(T) * (elements ? elements : 1)) != cudaSuccess) { *p = nullptr; return false; }
+		*p = nullptr;
+		if (count == kCapacity || cudaMalloc((void**) p, sizeof(T) * (elements ? elements : 1)) != cudaSuccess) { *p = nullptr; return false; }
 		ptr[count++] = *p;
 		return true;
 	}
