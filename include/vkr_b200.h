@@ -107,6 +107,18 @@ typedef struct vkr_scene_s {
 int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, const char* file_path, const char* texture_path, int request_acceleration_structure);
 void vkr_destroy_scene(vkr_scene_t* scene, const vkr_device_t* device);
 
+/* ---- material textures (replaces load_2d_textures for *.vkt files, src/textures.c:111-169, and the texture units' format decode):
+        all mip levels decoded to RGBA32F on the host. Formats: R16G16B16(A16)_SFLOAT, R32G32B32(A32)_SFLOAT, R8G8B8A8_UNORM / SRGB,
+        BC1_RGB_UNORM / SRGB, BC5_UNORM (tools/texture_conversion/main.c:27-35). */
+typedef struct vkr_texture_s {
+	uint32_t width, height, mip_count, vk_format;
+	float* h_texels;             /* level 0 first; level l is max(width >> l, 1) x max(height >> l, 1) RGBA32F */
+	uint64_t texel_float_count;
+	int is_constant;             /* every texel of every level has the same value */
+} vkr_texture_t;
+int vkr_load_texture(vkr_texture_t* texture, const char* file_path);
+void vkr_destroy_texture(vkr_texture_t* texture);
+
 /* ---- LTC table (replaces load_ltc_table / destroy_ltc_table, src/ltc_table.h:69-72, ltc_table.c:23-200) */
 typedef struct vkr_ltc_constants_s { /* = ltc_constants_t, src/ltc_table.h:23-35 */
 	float fresnel_index_factor, fresnel_index_summand;

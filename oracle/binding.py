@@ -82,6 +82,27 @@ def gbuffer(width, height, constants, vis, quantized_positions, normals_and_tex_
 	return out
 
 
+def gbuffer_textured(width, height, constants, vis, quantized_positions, normals_and_tex_coords, material_indices, textures):
+	"""textures = (dims uint32 [T,3] {width, height, mips}, offsets uint64 [T], data float32): RGBA32F mip chains, 3 per material."""
+	lib = load()
+	q = np.ascontiguousarray(quantized_positions, dtype=np.uint32); nt = np.ascontiguousarray(normals_and_tex_coords, dtype=np.uint16)
+	mi = np.ascontiguousarray(material_indices, dtype=np.uint8); vis = np.ascontiguousarray(vis, dtype=np.uint32)
+	dims = np.ascontiguousarray(textures[0], dtype=np.uint32); offsets = np.ascontiguousarray(textures[1], dtype=np.uint64); data = np.ascontiguousarray(textures[2], dtype=np.float32)
+	out = np.zeros((4, height, width, 4), dtype=np.float32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_oracle_gbuffer_textured(C.c_uint32(width), C.c_uint32(height), cb, _p(vis), _p(q), _p(nt), _p(mi), C.c_uint32(len(dims)), _p(dims), _p(offsets), _p(data), _p(out))
+	assert rc == 0
+	return out
+
+
+def texture_grad_batch(width, height, mip_count, texels, inputs):
+	lib = load()
+	texels = np.ascontiguousarray(texels, dtype=np.float32); inputs = np.ascontiguousarray(inputs, dtype=np.float32).reshape(-1, 6)
+	out = np.zeros((len(inputs), 4), dtype=np.float32)
+	lib.vkr_oracle_texture_grad_batch(C.c_uint32(width), C.c_uint32(height), C.c_uint32(mip_count), _p(texels), C.c_uint32(len(inputs)), _p(inputs), _p(out))
+	return out
+
+
 def clip(vertex_count, vertices, maxp):
 	lib = load()
 	v = np.zeros((8, 3), dtype=np.float32); v[:len(vertices)] = vertices

@@ -18,6 +18,7 @@
 
 extern "C" {
 #include "../vkr_math.h"
+#include "../texture_filter.h"
 }
 
 typedef unsigned int uint;
@@ -265,7 +266,7 @@ struct textureBuffer { const uint16_t* data; };                  // R16G16B16A16
 struct usubpassInput { int dummy; };
 struct texture2DArray { const uint16_t* data; int w, h, layers; };   // RGBA16_UNORM
 struct sampler2DArray { const uint16_t* data; int res, layers, channels; };
-struct sampler2D { float value[4]; };                            // constant texture
+struct sampler2D { float value[4]; const vkr_texture_view_t* texture; };   // constant texture, or a mip chain filtered as oracle/texture_filter.h defines
 struct accelerationStructureEXT { int dummy; };
 struct rayQueryEXT { bool hit; };
 enum { gl_RayFlagsTerminateOnFirstHitEXT = 4, gl_RayFlagsOpaqueEXT = 1, gl_RayFlagsSkipClosestHitShaderEXT = 8, gl_RayQueryCommittedIntersectionNoneEXT = 0 };
@@ -314,7 +315,12 @@ inline vec4 textureLod(const sampler2DArray& s, const vec3& c, float) {
 	}
 	return out;
 }
-inline vec4 textureGrad(const sampler2D& s, const vec2&, const vec2&, const vec2&) { return vec4(s.value[0], s.value[1], s.value[2], s.value[3]); }
+inline vec4 textureGrad(const sampler2D& s, const vec2& uv, const vec2& ddx, const vec2& ddy) {
+	if (!s.texture) return vec4(s.value[0], s.value[1], s.value[2], s.value[3]);
+	float out[4];
+	vkr_texture_grad(out, s.texture, mk2(uv.x, uv.y), mk2(ddx.x, ddx.y), mk2(ddy.x, ddy.y));
+	return vec4(out[0], out[1], out[2], out[3]);
+}
 inline vec4 textureLod(const sampler2D& s, const vec2&, float) { return vec4(s.value[0], s.value[1], s.value[2], s.value[3]); }
 
 inline void rayQueryInitializeEXT(rayQueryEXT& q, const accelerationStructureEXT&, uint, uint, const vec3& origin, float tmin, const vec3& dir, float tmax) {

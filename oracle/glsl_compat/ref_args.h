@@ -16,5 +16,8 @@ typedef struct ref_args_s {
 	   with (y - row_begin) % band_stride < band_height. shade_seconds: wall clock of the pixel loop (out) */
 	uint32_t row_begin, row_end, band_height, band_stride;
 	double shade_seconds;
+	/* material textures as mip chains (NULL: constant materials from material_params): 3 per material {base colour, specular, normal};
+	   texture_dims = {width, height, mip_count} per texture, texture_offsets = first float of level 0 in texture_data (oracle/texture_filter.h) */
+	const uint32_t* texture_dims; const uint64_t* texture_offsets; const float* texture_data;
 } ref_args_t;
 #endif

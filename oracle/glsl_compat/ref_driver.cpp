@@ -72,12 +72,19 @@ static void set_uniforms(const ref_args_t* a) {
 	g_packed_normals_and_tex_coords.data = a->normals_and_tex_coords;
 	g_material_indices.data = nullptr; g_material_indices.channels = 1;
 	g_material_index_bytes = a->material_indices;
+	static thread_local vkr_texture_view_t views[3 * MATERIAL_COUNT];
 	for (uint32_t m = 0; m != (uint32_t) MATERIAL_COUNT && m != a->material_count; ++m) {
 		const float* mp = a->material_params + 8 * m;
-		sampler2D base = {{mp[0], mp[1], mp[2], 1.0f}}, spec = {{1.0f, mp[3], mp[4], 1.0f}}, nrm = {{mp[5], mp[6], 1.0f, 1.0f}};
+		sampler2D base = {{mp[0], mp[1], mp[2], 1.0f}, nullptr}, spec = {{1.0f, mp[3], mp[4], 1.0f}, nullptr}, nrm = {{mp[5], mp[6], 1.0f, 1.0f}, nullptr};
 		g_material_textures[3 * m + 0] = base; g_material_textures[3 * m + 1] = spec; g_material_textures[3 * m + 2] = nrm;
+		if (a->texture_data) for (uint32_t k = 0; k != 3; ++k) {
+			const uint32_t i = 3 * m + k;
+			views[i].width = a->texture_dims[3 * i]; views[i].height = a->texture_dims[3 * i + 1]; views[i].mip_count = a->texture_dims[3 * i + 2];
+			views[i].texels = a->texture_data + a->texture_offsets[i];
+			g_material_textures[i].texture = &views[i];
+		}
 	}
-	sampler2D white = {{1.0f, 1.0f, 1.0f, 1.0f}};
+	sampler2D white = {{1.0f, 1.0f, 1.0f, 1.0f}, nullptr};
 	for (int i = 0; i != LIGHT_TEXTURE_COUNT; ++i) g_light_textures[i] = white;
 	g_noise_table.data = a->noise; g_noise_table.w = (int) a->noise_w; g_noise_table.h = (int) a->noise_h; g_noise_table.layers = (int) a->noise_layers;
 	g_ltc_tables[0].data = a->ltc0; g_ltc_tables[0].res = (int) a->ltc_res; g_ltc_tables[0].layers = (int) a->ltc_layers; g_ltc_tables[0].channels = 4;

@@ -21,7 +21,8 @@ class RefArgs(C.Structure):
 		("noise", C.c_void_p), ("noise_w", C.c_uint32), ("noise_h", C.c_uint32), ("noise_layers", C.c_uint32),
 		("ltc0", C.c_void_p), ("ltc1", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
 		("occluded_hook", C.c_void_p), ("occluded_user", C.c_void_p), ("out_rgba", C.c_void_p),
-		("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("band_height", C.c_uint32), ("band_stride", C.c_uint32), ("shade_seconds", C.c_double)]
+		("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("band_height", C.c_uint32), ("band_stride", C.c_uint32), ("shade_seconds", C.c_double),
+		("texture_dims", C.c_void_p), ("texture_offsets", C.c_void_p), ("texture_data", C.c_void_p)]
 
 
 def available():
@@ -70,7 +71,7 @@ def find_config(**wanted):
 	return None
 
 
-def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris, row_begin=0, row_end=0, band_height=0, band_stride=0):
+def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris, row_begin=0, row_end=0, band_height=0, band_stride=0, textures=None):
 	"""Runs the reference fragment shader (configuration `entry`) for every pixel (or the rows / bands asked for). Returns float32 [H, W, 4]."""
 	global _last_shade_seconds
 	lib = load()
@@ -88,6 +89,8 @@ def shade(entry, width, height, cfg, constants, visibility, vks, material_params
 		ltc0=arr(ltc0, np.uint16), ltc1=arr(ltc1, np.uint16), ltc_res=ltc0.shape[1], ltc_layers=ltc0.shape[0],
 		occluded_hook=C.cast(lib.ref_bvh_occluded, C.c_void_p), occluded_user=bvh, out_rgba=out.ctypes.data,
 		row_begin=row_begin, row_end=row_end, band_height=band_height, band_stride=band_stride)
+	if textures is not None:   # (dims uint32 [T,3], offsets uint64 [T], data float32): mip chains of 3 textures per material
+		a.texture_dims = arr(textures[0], np.uint32); a.texture_offsets = arr(textures[1], np.uint64); a.texture_data = arr(textures[2], np.float32)
 	fn = getattr(lib, entry)
 	rc = fn(C.byref(a))
 	lib.ref_bvh_destroy(bvh)

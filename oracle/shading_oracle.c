@@ -20,6 +20,7 @@
 #include "psa_oracle.h"
 #include "related_work_oracle.h"
 #include "bvh_oracle.h"
+#include "texture_filter.h"
 #include "vkr_oracle.h"
 #include <stdio.h>
 #ifdef _OPENMP
@@ -969,9 +970,10 @@ int vkr_oracle_visibility(uint32_t width, uint32_t height, const void* constants
 
 /* get_shading_data (shading_pass.frag.glsl:721-822) with constant per-material textures:
    material_params = 8 floats per material {base.rgb, specular.g (linear roughness), specular.b (metalicity), normal.x, normal.y, pad}. */
-int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants_v, const uint32_t* visibility,
+/* textures: NULL (constant materials from material_params) or 3 views per material {base colour, specular, normal}, texture_filter.h */
+static int gbuffer_impl(uint32_t width, uint32_t height, const void* constants_v, const uint32_t* visibility,
 	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
-	const float* material_params, float* out_gbuffer)
+	const float* material_params, const vkr_texture_view_t* textures, float* out_gbuffer)
 {
 	const uint8_t* constants = (const uint8_t*) constants_v;
 	float factor[3], summand[3];
@@ -1018,11 +1020,36 @@ int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants_v,
 				fmaf(bx, normals[0].x, fmaf(by, normals[1].x, bz * normals[2].x)),
 				fmaf(bx, normals[0].y, fmaf(by, normals[1].y, bz * normals[2].y)),
 				fmaf(bx, normals[0].z, fmaf(by, normals[1].z, bz * normals[2].z))));
-			/* constant textures: screen-space derivatives (:755-777) do not influence the fetch */
-			const float* mp = material_params + 8 * (size_t) material_indices[prim];
-			v3 base_color = mk3(mp[0], mp[1], mp[2]);
-			float linear_roughness = mp[3], metalicity = mp[4];
-			v3 nts; nts.x = fmaf(mp[5], 2.0f, -1.0f); nts.y = fmaf(mp[6], 2.0f, -1.0f);
+			float tex_base[4], tex_specular[4], tex_normal[4];
+			const uint32_t material_index = material_indices[prim];
+			if (textures) {
+				/* screen-space derivatives of the barycentrics and the texture coordinate (:754-777), then three textureGrad (:779-783) */
+				v2 tex_coord = mk2(fmaf(bx, tex_coords[0].x, fmaf(by, tex_coords[1].x, bz * tex_coords[2].x)), fmaf(bx, tex_coords[0].y, fmaf(by, tex_coords[1].y, bz * tex_coords[2].y)));
+				v2 tex_coord_derivs[2];
+				for (int i = 0; i != 2; ++i) {
+					v3 ray_direction_deriv = mk3(p2r[0][i], p2r[1][i], p2r[2][i]);
+					v3 ray_cross_edge_1_deriv = cross3(ray_direction_deriv, edges[1]);
+					float rcp_det_deriv = -dot3(edges[0], ray_cross_edge_1_deriv) * rcp_det * rcp_det;
+					float det_0_dir_edge_1_deriv = dot3(ray_to_0, ray_cross_edge_1_deriv);
+					float dy_ = rcp_det_deriv * det_0_dir_edge_1 + rcp_det * det_0_dir_edge_1_deriv;
+					float det_dir_edge_0_0_deriv = dot3(ray_direction_deriv, edge_0_cross_0);
+					float dz_ = -rcp_det_deriv * det_dir_edge_0_0 - rcp_det * det_dir_edge_0_0_deriv;
+					float dx_ = -(dy_ + dz_);
+					v2 d = mk2(0.0f, 0.0f);
+					d = add2(d, scale2(tex_coords[0], dx_)); d = add2(d, scale2(tex_coords[1], dy_)); d = add2(d, scale2(tex_coords[2], dz_));
+					tex_coord_derivs[i] = d;
+				}
+				vkr_texture_grad(tex_base, &textures[3 * material_index + 0], tex_coord, tex_coord_derivs[0], tex_coord_derivs[1]);
+				vkr_texture_grad(tex_specular, &textures[3 * material_index + 1], tex_coord, tex_coord_derivs[0], tex_coord_derivs[1]);
+				vkr_texture_grad(tex_normal, &textures[3 * material_index + 2], tex_coord, tex_coord_derivs[0], tex_coord_derivs[1]);
+			}
+			else { /* constant textures: the derivatives do not influence the fetch */
+				const float* mp = material_params + 8 * (size_t) material_index;
+				tex_base[0] = mp[0]; tex_base[1] = mp[1]; tex_base[2] = mp[2]; tex_specular[1] = mp[3]; tex_specular[2] = mp[4]; tex_normal[0] = mp[5]; tex_normal[1] = mp[6];
+			}
+			v3 base_color = mk3(tex_base[0], tex_base[1], tex_base[2]);
+			float linear_roughness = tex_specular[1], metalicity = tex_specular[2];
+			v3 nts; nts.x = fmaf(tex_normal[0], 2.0f, -1.0f); nts.y = fmaf(tex_normal[1], 2.0f, -1.0f);
 			nts.z = sqrtf(vkr_max(0.0f, fmaf(-nts.x, nts.x, fmaf(-nts.y, nts.y, 1.0f))));
 			v3 diffuse_albedo = mk3(fmaf(base_color.x, -metalicity, base_color.x), fmaf(base_color.y, -metalicity, base_color.y), fmaf(base_color.z, -metalicity, base_color.z));
 			/* mix(x, y, a) = x*(1-a) + y*a */
@@ -1050,6 +1077,37 @@ int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants_v,
 			out_gbuffer[3 * plane + pi + 0] = fresnel_0.x; out_gbuffer[3 * plane + pi + 1] = fresnel_0.y; out_gbuffer[3 * plane + pi + 2] = fresnel_0.z;
 		}
 	return 0;
+}
+
+int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
+	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
+	const float* material_params, float* out_gbuffer)
+{
+	return gbuffer_impl(width, height, constants, visibility, quantized_positions, normals_and_tex_coords, material_indices, material_params, NULL, out_gbuffer);
+}
+
+/* texture_dims: {width, height, mip_count} per texture, texture_offsets: first float of level 0 in texture_data; 3 textures per material */
+int vkr_oracle_gbuffer_textured(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
+	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
+	uint32_t texture_count, const uint32_t* texture_dims, const uint64_t* texture_offsets, const float* texture_data, float* out_gbuffer)
+{
+	vkr_texture_view_t* views = (vkr_texture_view_t*) calloc(texture_count ? texture_count : 1, sizeof(vkr_texture_view_t));
+	for (uint32_t i = 0; i != texture_count; ++i) {
+		views[i].width = texture_dims[3 * i]; views[i].height = texture_dims[3 * i + 1]; views[i].mip_count = texture_dims[3 * i + 2];
+		views[i].texels = texture_data + texture_offsets[i];
+	}
+	int result = gbuffer_impl(width, height, constants, visibility, quantized_positions, normals_and_tex_coords, material_indices, NULL, views, out_gbuffer);
+	free(views);
+	return result;
+}
+
+/* one textureGrad per row of inputs {u, v, dudx, dvdx, dudy, dvdy} (tests) */
+void vkr_oracle_texture_grad_batch(uint32_t width, uint32_t height, uint32_t mip_count, const float* texels, uint32_t n, const float* inputs, float* out_rgba) {
+	vkr_texture_view_t view = { width, height, mip_count, texels };
+	for (uint32_t i = 0; i != n; ++i) {
+		const float* in = inputs + 6 * (size_t) i;
+		vkr_texture_grad(out_rgba + 4 * (size_t) i, &view, mk2(in[0], in[1]), mk2(in[2], in[3]), mk2(in[4], in[5]));
+	}
 }
 
 /* ---- small entry points for the known-answer tests */

@@ -49,6 +49,10 @@ int vkr_oracle_related_work_batch(uint32_t technique, uint32_t maxv, const void*
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_densities, float* out_ggx_density_factor);
 int vkr_oracle_error_display_batch(uint32_t technique, int biased, uint32_t maxv, uint32_t vertex_count, const float* vertices_xyz, uint32_t n, const float* rnd,
 	float error_factor, float* out_errors, float* out_colors);
+int vkr_oracle_gbuffer_textured(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
+	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
+	uint32_t texture_count, const uint32_t* texture_dims, const uint64_t* texture_offsets, const float* texture_data, float* out_gbuffer);
+void vkr_oracle_texture_grad_batch(uint32_t width, uint32_t height, uint32_t mip_count, const float* texels, uint32_t n, const float* inputs, float* out_rgba);
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp);
 void vkr_oracle_psa_sample_batch(uint32_t vertex_count, const float* vertices_xyz, uint32_t maxp, int biased, int do_clip,
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_errors, float* out_info);

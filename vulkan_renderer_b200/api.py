@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_build_probe_with", "vkr_bvh_build_probe_device", "vkr_bvh_free_probe",
 	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
 	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
+	"vkr_load_texture", "vkr_destroy_texture",
 	"vkr_create_render_targets", "vkr_destroy_render_targets", "vkr_download_frame", "vkr_download_gbuffer", "vkr_upload_gbuffer",
 ]
 
@@ -91,6 +92,11 @@ class RenderSettings(C.Structure):
 	_fields_ = [("exposure_factor", C.c_float), ("roughness_factor", C.c_float), ("sample_count", C.c_uint32), ("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int),
 		("mis_visibility_estimate", C.c_float), ("polygon_sampling_technique", C.c_int), ("error_min_exponent", C.c_float),
 		("animate_noise", C.c_int), ("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int)]
+
+
+class Texture(C.Structure):
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("mip_count", C.c_uint32), ("vk_format", C.c_uint32), ("h_texels", C.POINTER(C.c_float)),
+		("texel_float_count", C.c_uint64), ("is_constant", C.c_int)]
 
 
 class RenderTargets(C.Structure):
@@ -163,6 +169,8 @@ def load_library():
 	lib.vkr_bvh_build_probe_with.argtypes = [C.c_int, C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
 	lib.vkr_bvh_build_probe_device.argtypes = [P(Device), C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
 	lib.vkr_bvh_free_probe.argtypes = [P(C.c_float), P(C.c_float), P(C.c_uint32)]; lib.vkr_bvh_free_probe.restype = None
+	lib.vkr_load_texture.argtypes = [P(Texture), C.c_char_p]
+	lib.vkr_destroy_texture.argtypes = [P(Texture)]; lib.vkr_destroy_texture.restype = None
 	lib.vkr_create_render_targets.argtypes = [P(RenderTargets), P(Device), C.c_uint32, C.c_uint32]
 	lib.vkr_destroy_render_targets.argtypes = [P(RenderTargets), P(Device)]; lib.vkr_destroy_render_targets.restype = None
 	lib.vkr_download_frame.argtypes = [P(RenderTargets), P(Device), C.c_void_p]

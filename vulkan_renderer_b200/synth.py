@@ -299,6 +299,73 @@ def write_vkt_constant(path, rgba):
 		f.write(struct.pack("<I", 0x00E0FE0F))
 
 
+def mip_chain(level0):
+	"""Box-filtered mip chain of an [H, W, C] array down to 1x1 (what the reference's converter produces with stb's resizer, in spirit)."""
+	levels = [np.asarray(level0, dtype=np.float32)]
+	while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+		a = levels[-1]; h, w = a.shape[:2]
+		if h > 1: a = 0.5 * (a[0:2 * (h // 2):2] + a[1:2 * (h // 2):2])
+		if w > 1: a = 0.5 * (a[:, 0:2 * (w // 2):2] + a[:, 1:2 * (w // 2):2])
+		levels.append(a.astype(np.float32))
+	return levels
+
+
+def _encode_bc1_block(rgb):
+	"""One 4x4 block [4, 4, 3] in [0,1] -> 8 bytes (4-colour mode: endpoints = the extremes along the main diagonal of the colour box)."""
+	flat = rgb.reshape(16, 3)
+	lo, hi = flat.min(0), flat.max(0)
+	def pack(c): return (int(round(c[0] * 31)) << 11) | (int(round(c[1] * 63)) << 5) | int(round(c[2] * 31))
+	c0, c1 = pack(hi), pack(lo)
+	if c0 == c1:   # one colour: three-colour mode with every index 0
+		return struct.pack("<HHI", c0, c1, 0)
+	if c0 < c1: c0, c1 = c1, c0
+	def unpack(c): return np.array([((c >> 11) & 31) / 31.0, ((c >> 5) & 63) / 63.0, (c & 31) / 31.0])
+	a, b = unpack(c0), unpack(c1)
+	palette = np.stack([a, b, (2 * a + b) / 3, (a + 2 * b) / 3])
+	idx = np.argmin(((flat[:, None, :] - palette[None]) ** 2).sum(-1), axis=1)
+	bits = 0
+	for t in range(16): bits |= int(idx[t]) << (2 * t)
+	return struct.pack("<HHI", c0, c1, bits)
+
+
+def _encode_bc4_block(values):
+	"""One 4x4 block of one channel in [0,1] -> 8 bytes (8-value mode)."""
+	flat = values.reshape(16)
+	r0, r1 = int(round(float(flat.max()) * 255)), int(round(float(flat.min()) * 255))
+	if r0 == r1:
+		return struct.pack("<BB", r0, r1) + bytes(6)
+	palette = np.array([r0, r1] + [((8 - i) * r0 + (i - 1) * r1) / 7.0 for i in range(2, 8)]) / 255.0
+	idx = np.argmin(np.abs(flat[:, None] - palette[None]), axis=1)
+	bits = 0
+	for t in range(16): bits |= int(idx[t]) << (3 * t)
+	return struct.pack("<BB", r0, r1) + bits.to_bytes(6, "little")
+
+
+def write_vkt(path, level0, vk_format=97):
+	"""Writes a *.vkt with a full mip chain (src/textures.c:111-169). level0: [H, W, >=3] floats in [0,1] for the block formats.
+	vk_format: 97 R16G16B16A16_SFLOAT, 109 R32G32B32A32_SFLOAT, 131 BC1_RGB_UNORM, 141 BC5_UNORM."""
+	levels = mip_chain(level0)
+	payload = b""; headers = b""
+	for a in levels:
+		h, w = a.shape[:2]
+		if vk_format in (97, 109):
+			rgba = np.concatenate([a[..., :3], np.ones((h, w, 1), dtype=np.float32) if a.shape[-1] < 4 else a[..., 3:4]], axis=-1)
+			data = rgba.astype("<f2" if vk_format == 97 else "<f4").tobytes()
+		else:
+			pad = np.pad(a, ((0, (-h) % 4), (0, (-w) % 4), (0, 0)), mode="edge")
+			data = b""
+			for by in range(pad.shape[0] // 4):
+				for bx in range(pad.shape[1] // 4):
+					blk = pad[4 * by:4 * by + 4, 4 * bx:4 * bx + 4]
+					data += _encode_bc1_block(blk[..., :3]) if vk_format == 131 else (_encode_bc4_block(blk[..., 0]) + _encode_bc4_block(blk[..., 1]))
+		headers += struct.pack("<IIQQ", w, h, len(data), len(payload))
+		payload += data
+	with open(path, "wb") as f:
+		f.write(struct.pack("<IIIIIIQ", 0x00BC1BC1, 1, len(levels), level0.shape[1], level0.shape[0], vk_format, len(payload)))
+		f.write(headers); f.write(payload)
+		f.write(struct.pack("<I", 0x00E0FE0F))
+
+
 def write_material_textures(directory, materials):
 	os.makedirs(directory, exist_ok=True)
 	for m in materials:
