@@ -98,6 +98,13 @@ typedef struct vkr_scene_s {
 	uint64_t shadow_node_count, primary_node_count;
 	uint32_t shadow_max_depth, primary_max_depth;
 	double build_seconds;
+	/* material textures (src/scene.c:529-540): if any of the 3 * material_count textures is not constant, all of them live on the device as RGBA32F
+	   mip chains and the G-buffer producer filters them (textured = 1); otherwise material_params above is all there is */
+	int textured;
+	void* d_texture_data;      /* float4 per texel, all chains back to back */
+	void* d_texture_dims;      /* uint32[4] per texture: width, height, mip_count, 0; order: material-major, {base colour, specular, normal} */
+	void* d_texture_offsets;   /* uint64 per texture: first texel of level 0 in d_texture_data */
+	uint64_t texture_texel_count;
 } vkr_scene_t;
 
 /* device may be NULL for vkr_load_scene / vkr_load_ltc_table / vkr_load_noise_table: the files are parsed and the host

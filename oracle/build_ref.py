@@ -43,6 +43,8 @@ def config_name(c):
 		name += "_q%d" % c["technique"]
 	if c.get("error_display", 0):
 		name += "_e%d" % c["error_display"]
+	if c.get("textured", 0):                          # same -D defines, material textures that need filtering (data set mini_textured)
+		name += "_x1"
 	if c.get("srgb", 0) or c.get("frame_bits", 0):   # output stage: o<srgb><frame_bits>
 		name += "_o%d%d" % (c.get("srgb", 0), c.get("frame_bits", 0))
 	return name
@@ -152,6 +154,8 @@ def default_configs():
 	for error_display, extra in [(1, dict(strategy=0, heuristic=0)), (2, dict()), (3, dict(strategy=1, heuristic=0)), (4, dict()), (5, dict(strategy=2, heuristic=0)), (6, dict(strategy=4, heuristic=0)),
 			(1, dict(biased=1)), (4, dict(biased=1)), (3, dict(max_vertices=7, min_vertices=5)), (6, dict(max_vertices=3)), (1, dict(strategy=0, heuristic=0, technique=10)), (2, dict(strategy=0, heuristic=0, technique=10, max_vertices=5))]:
 		configs.append(dict(base, error_display=error_display, **extra))
+	configs.append(dict(base, textured=1))                                   # get_shading_data with filtered material textures
+	configs.append(dict(base, textured=1, strategy=1, heuristic=1, trace=0))
 	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
 		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs
@@ -173,6 +177,9 @@ def build(configs=None, verbose=False):
 	names = []
 	for c in configs:
 		name = config_name(c)
+		if c.get("textured", 0):   # textures are inputs, not defines: the entry point of the untextured configuration serves
+			names.append(dict(c, name=name, entry="ref_shade_" + config_name(dict(c, textured=0))))
+			continue
 		names.append(dict(c, name=name, entry="ref_shade_" + name))
 		obj = os.path.join(OUT, name + ".o")
 		objects.append(obj)
@@ -186,6 +193,10 @@ def build(configs=None, verbose=False):
 			sys.stderr.write("---- %s\n%s\n" % (name, out[-6000:]))
 	if failed:
 		raise SystemExit("build_ref: compiling the reference shader as C++ failed")
+	compiled = {n["entry"] for n in names if not n.get("textured", 0)}
+	missing = [n["name"] for n in names if n["entry"] not in compiled]
+	if missing:
+		raise SystemExit("build_ref: textured configurations without an untextured twin: %s" % missing)
 	lib = os.path.join(OUT, "libref_shader.so")
 	subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", lib] + objects)
 	with open(os.path.join(OUT, "configs.json"), "w") as f:

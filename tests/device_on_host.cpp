@@ -18,10 +18,12 @@ static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 
 struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 
 #include "vkr_related_work.cuh"
 #include "vkr_trace.cuh"
+#include "vkr_texture.cuh"
 
 using namespace vkr;
 
@@ -124,6 +126,18 @@ extern "C" void vkr_device_on_host_trace_any(const float* nodes, const float* tr
 			if (r[7] > r[6]) for (uint32_t k = 0; k != tri_count && !hit; ++k) hit = ray_triangle(bvh.tris + 3 * (size_t) k, o, d, r[6], r[7], &t);
 			out_brute[i] = hit ? 1 : 0;
 		}
+	}
+}
+
+// textureGrad as the G-buffer producer defines it (vkr_texture.cuh), one call per row of inputs {u, v, dudx, dvdx, dudy, dvdy}; same signature
+// and meaning as vkr_oracle_texture_grad_batch
+extern "C" void vkr_device_on_host_texture_grad_batch(uint32_t width, uint32_t height, uint32_t mip_count, const float* texels, uint32_t n, const float* inputs, float* out_rgba) {
+	texture_view view;
+	view.width = width; view.height = height; view.mip_count = mip_count; view.texels = reinterpret_cast<const float4*>(texels);
+	for (uint32_t i = 0; i != n; ++i) {
+		const float* in = inputs + 6 * (size_t) i;
+		const float4 c = texture_grad(view, make2(in[0], in[1]), make2(in[2], in[3]), make2(in[4], in[5]));
+		out_rgba[4 * i] = c.x; out_rgba[4 * i + 1] = c.y; out_rgba[4 * i + 2] = c.z; out_rgba[4 * i + 3] = c.w;
 	}
 }
 

@@ -55,6 +55,66 @@ def read_vks(path):
 	return dict(triangle_count=n_tri, factor=factor, summand=summand, names=names, positions=positions, normals_uv=normals_uv, material_indices=material_indices)
 
 
+def read_vkt(path):
+	"""All mip levels of a *.vkt file as RGBA float32 arrays, decoded here in numpy (src/textures.c:111-169; formats of tools/texture_conversion)."""
+	raw = open(path, "rb").read()
+	marker, version, mips, width, height, vk_format, payload_size = struct.unpack_from("<IIIIIIQ", raw, 0)
+	assert marker == 0xBC1BC1 and version == 1
+	headers = [struct.unpack_from("<IIQQ", raw, 32 + 24 * k) for k in range(mips)]
+	base = 32 + 24 * mips
+	assert struct.unpack_from("<I", raw, base + payload_size)[0] == 0xE0FE0F
+	levels = []
+	for (w, h, size, offset) in headers:
+		data = raw[base + offset: base + offset + size]
+		out = np.zeros((h, w, 4), dtype=np.float32); out[..., 3] = 1.0
+		if vk_format in (97, 90):
+			c = 4 if vk_format == 97 else 3
+			out[..., :c] = np.frombuffer(data, dtype="<f2", count=w * h * c).reshape(h, w, c).astype(np.float32)
+		elif vk_format in (109, 106):
+			c = 4 if vk_format == 109 else 3
+			out[..., :c] = np.frombuffer(data, dtype="<f4", count=w * h * c).reshape(h, w, c)
+		elif vk_format == 131:
+			bw = (w + 3) // 4
+			for by in range((h + 3) // 4):
+				for bx in range(bw):
+					c0, c1, bits = struct.unpack_from("<HHI", data, 8 * (by * bw + bx))
+					un = lambda c: np.array([np.float32((c >> 11) & 31) / np.float32(31.0), np.float32((c >> 5) & 63) / np.float32(63.0), np.float32(c & 31) / np.float32(31.0)], dtype=np.float32)
+					a, b = un(c0), un(c1)
+					pal = [a, b, (np.float32(2.0) * a + b) / np.float32(3.0), (a + np.float32(2.0) * b) / np.float32(3.0)] if c0 > c1 else [a, b, np.float32(0.5) * (a + b), np.zeros(3, dtype=np.float32)]
+					for t in range(16):
+						x, y = 4 * bx + (t & 3), 4 * by + (t >> 2)
+						if x < w and y < h: out[y, x, :3] = pal[(bits >> (2 * t)) & 3]
+		elif vk_format == 141:
+			bw = (w + 3) // 4
+			def bc4(off):
+				r0, r1 = np.float32(data[off]) / np.float32(255.0), np.float32(data[off + 1]) / np.float32(255.0)
+				if data[off] > data[off + 1]: pal = [r0, r1] + [(np.float32(8 - i) * r0 + np.float32(i - 1) * r1) / np.float32(7.0) for i in range(2, 8)]
+				else: pal = [r0, r1] + [(np.float32(6 - i) * r0 + np.float32(i - 1) * r1) / np.float32(5.0) for i in range(2, 6)] + [np.float32(0.0), np.float32(1.0)]
+				bits = int.from_bytes(data[off + 2:off + 8], "little")
+				return [pal[(bits >> (3 * t)) & 7] for t in range(16)]
+			for by in range((h + 3) // 4):
+				for bx in range(bw):
+					red, green = bc4(16 * (by * bw + bx)), bc4(16 * (by * bw + bx) + 8)
+					for t in range(16):
+						x, y = 4 * bx + (t & 3), 4 * by + (t >> 2)
+						if x < w and y < h: out[y, x, 0] = red[t]; out[y, x, 1] = green[t]
+		else:
+			raise ValueError("VkFormat %d" % vk_format)
+		levels.append(out)
+	return levels
+
+
+def material_texture_set(info):
+	"""(dims uint32 [T,3], offsets uint64 [T], data float32) of the 3 textures per material, in material order: oracle/texture_filter.h's input."""
+	dims, offsets, chunks, at = [], [], [], 0
+	for m in info["materials"]:
+		for suffix in ("BaseColor", "Specular", "Normal"):
+			levels = read_vkt(os.path.join(info["textures"], "%s_%s.vkt" % (m["name"], suffix)))
+			dims.append((levels[0].shape[1], levels[0].shape[0], len(levels))); offsets.append(at)
+			for l in levels: chunks.append(l.reshape(-1)); at += l.size
+	return np.array(dims, dtype=np.uint32), np.array(offsets, dtype=np.uint64), np.concatenate(chunks).astype(np.float32)
+
+
 def wang_hash(seed):
 	"""src/math_utilities.h:50-57 on uint32 arrays"""
 	seed = np.asarray(seed, dtype=np.uint32)
@@ -106,6 +166,7 @@ class OracleInputs:
 		self.noise = white_noise_table(*noise_shape)
 		self.ltc0, self.ltc1 = quantize_ltc(info["ltc"])
 		self.material_params = info["material_params"]
+		self.textures = material_texture_set(info) if info.get("textured") else None   # mip chains that need filtering, else constant materials
 		self._shadow_tris = None
 
 	@property
@@ -118,6 +179,8 @@ class OracleInputs:
 		return oracle.visibility(width, height, constants, self.vks["positions"])
 
 	def gbuffer(self, width, height, constants, vis):
+		if self.textures is not None:
+			return oracle.gbuffer_textured(width, height, constants, vis, self.vks["positions"], self.vks["normals_uv"], self.vks["material_indices"], self.textures)
 		return oracle.gbuffer(width, height, constants, vis, self.vks["positions"], self.vks["normals_uv"], self.vks["material_indices"], self.material_params)
 
 	def shade(self, frame_cfg, constants, gbuffer, row_begin=0, row_end=0):

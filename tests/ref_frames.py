@@ -7,6 +7,8 @@ WIDTH, HEIGHT = 64, 48
 
 
 def dataset_for(cfg):
+	if cfg.get("textured", 0):
+		return "mini_textured"
 	if cfg["materials"] == 3:
 		return "cornell"
 	if cfg["lights"] > 3:

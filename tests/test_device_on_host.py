@@ -125,6 +125,32 @@ def test_device_sampling_error_and_error_colours_match_oracle(technique, biased,
 	assert checked > 10 and len(colours) > 3
 
 
+@pytest.mark.parametrize("shape", [(64, 64), (32, 16), (5, 7), (1, 1)])
+def test_device_texture_filter_matches_the_definition(shape):
+	"""csrc/vkr_texture.cuh (textureGrad of the G-buffer producer) against oracle/texture_filter.h: magnification, minification over the whole
+	chain, anisotropic footprints in every direction, repeat addressing, degenerate derivatives."""
+	from vulkan_renderer_b200 import synth
+	lib = _lib()
+	h, w = shape
+	rng = np.random.default_rng(w * 100 + h)
+	levels = synth.mip_chain(rng.random((h, w, 4)).astype(np.float32))
+	texels = np.concatenate([l.reshape(-1) for l in levels]).astype(np.float32)
+	n = 4000
+	uv = rng.uniform(-3.0, 4.0, (n, 2))
+	scale = 10.0 ** rng.uniform(-4.0, 0.5, (n, 1))
+	angle = rng.uniform(0.0, 2.0 * np.pi, (n, 1)); stretch = 10.0 ** rng.uniform(0.0, 1.6, (n, 1))
+	ddx = scale * stretch * np.concatenate([np.cos(angle), np.sin(angle)], 1)
+	ddy = scale * np.concatenate([-np.sin(angle), np.cos(angle)], 1) * rng.choice([1.0, 0.3, 3.0], (n, 1))
+	inputs = np.concatenate([uv, ddx, ddy], 1).astype(np.float32)
+	inputs[:8, 2:] = 0.0; inputs[8:12, 2:4] = 0.0; inputs[12, 0] = np.nan; inputs[13, 2] = np.inf; inputs[14, 4] = -np.inf; inputs[15, :2] = 1e30
+	ref = O.texture_grad_batch(w, h, len(levels), texels, inputs)
+	out = np.zeros((n, 4), dtype=np.float32)
+	lib.vkr_device_on_host_texture_grad_batch(C.c_uint32(w), C.c_uint32(h), C.c_uint32(len(levels)), texels.ctypes.data_as(C.c_void_p), C.c_uint32(n),
+		inputs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+	assert np.isfinite(ref[16:]).all()
+
+
 def test_samples_point_at_the_light_and_densities_integrate():
 	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
 	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""

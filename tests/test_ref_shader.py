@@ -25,10 +25,10 @@ def _golden():
 
 
 def _config_from_name(name):
-	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_q(\d+))?(?:_e(\d))?(?:_o(\d)(\d))?$", name)
-	s, h, b, L, V, Vmin, S, t, l, M, q, e, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
-	return dict(name=name, entry="ref_shade_" + name, strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
-		samples=S, trace=t, show_lights=l, materials=M, technique=11 if q is None else q, error_display=e or 0, srgb=srgb or 0, frame_bits=frame_bits or 0)
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_q(\d+))?(?:_e(\d))?(?:_x(\d))?(?:_o(\d)(\d))?$", name)
+	s, h, b, L, V, Vmin, S, t, l, M, q, e, x, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
+	return dict(name=name, entry="ref_shade_" + name.replace("_x1", ""), strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
+		samples=S, trace=t, show_lights=l, materials=M, technique=11 if q is None else q, error_display=e or 0, textured=x or 0, srgb=srgb or 0, frame_bits=frame_bits or 0)
 
 
 def _names():
@@ -63,7 +63,7 @@ def test_live_reference_shader_matches_fixture():
 		cfg = live[name]
 		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
 		constants = bytes(g[name + "/constants"])
-		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, g[name + "/visibility"], oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris)
+		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, g[name + "/visibility"], oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures)
 		assert np.array_equal(ref.view(np.uint32), g[name + "/rgba"].view(np.uint32)), name
 		checked += 1
 	assert checked > 0

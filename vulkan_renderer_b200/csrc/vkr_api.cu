@@ -30,6 +30,9 @@ static int fill_gbuffer_params(gbuffer_kernel_params& p, void** d_constants, con
 	p.normals_and_tex_coords = (const ushort4*) scene->d_normals_and_tex_coords;
 	p.material_indices = (const uint8_t*) scene->d_material_indices;
 	p.material_params = (const float*) scene->d_material_params;
+	if (scene->textured) {
+		p.texture_data = (const float4*) scene->d_texture_data; p.texture_dims = (const uint4*) scene->d_texture_dims; p.texture_offsets = (const unsigned long long*) scene->d_texture_offsets;
+	}
 	p.bvh_nodes = (const float4*) scene->d_primary_nodes; p.bvh_tris = (const float4*) scene->d_primary_tris; p.bvh_tri_ids = (const uint32_t*) scene->d_primary_tri_ids;
 	p.tri_count = (uint32_t) scene->triangle_count;
 	return 0;

@@ -4,10 +4,13 @@
 //     (src/shaders/visibility_pass.vert.glsl:27-33, src/main.c:1422-1427): closest hit of the
 //     primary ray through each pixel centre, against the shader-decoded (fma) vertices.
 // (2) gbuffer kernel: the reference's get_shading_data() (src/shaders/shading_pass.frag.glsl:721-822)
-//     with constant material textures, writing the 64 B/pixel G-buffer the shading megakernel reads.
+//     writing the 64 B/pixel G-buffer the shading megakernel reads. Materials whose textures are constant take one
+//     texel (TEXTURED = false); otherwise the three material textures are filtered with screen-space derivatives as the
+//     shader does (textureGrad at :779-783, filter definition in vkr_texture.cuh).
 // A visibility buffer produced elsewhere (e.g. by a rasteriser) can be fed to (2) directly.
 // Compile with -fmad=false.
 #include "vkr_trace.cuh"
+#include "vkr_texture.cuh"
 #include "vkr_kernels.h"
 
 namespace vkr {
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(kGThreads) visibility_kernel(const gbuffer_ker
 	p.visibility[(size_t) y * p.width + x] = (hit < 0) ? 0xFFFFFFFFu : (uint32_t) hit;
 }
 
+template <bool TEXTURED>
 __global__ void __launch_bounds__(128) gbuffer_kernel(const gbuffer_kernel_params p) {
 	const size_t pixel = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
 	const size_t plane = (size_t) p.width * p.height;
@@ -105,11 +109,48 @@ __global__ void __launch_bounds__(128) gbuffer_kernel(const gbuffer_kernel_param
 		fmaf(bx, nrm[0].x, fmaf(by, nrm[1].x, bz * nrm[2].x)),
 		fmaf(bx, nrm[0].y, fmaf(by, nrm[1].y, bz * nrm[2].y)),
 		fmaf(bx, nrm[0].z, fmaf(by, nrm[1].z, bz * nrm[2].z))));
-	const float* mp = p.material_params + 8 * (size_t) __ldg(p.material_indices + prim);
-	const f3 base = make3(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2));
-	const float linear_roughness = __ldg(mp + 3), metalicity = __ldg(mp + 4);
+	const uint32_t material_index = __ldg(p.material_indices + prim);
+	f3 base; float linear_roughness, metalicity; f2 normal_texel;
+	if (TEXTURED) {
+		// screen-space derivatives of the barycentrics and of the texture coordinate (:754-777), then three textureGrad (:779-783)
+		const f2 tex_coord = make2(fmaf(bx, uv[0].x, fmaf(by, uv[1].x, bz * uv[2].x)), fmaf(bx, uv[0].y, fmaf(by, uv[1].y, bz * uv[2].y)));
+		const float det_0_dir_edge_1 = dot(ray_to_0, ray_cross_e1), det_dir_edge_0_0 = dot(ray, e0_cross_0);
+		f2 tex_coord_derivs[2];
+#pragma unroll
+		for (int i = 0; i != 2; ++i) {
+			const f3 ray_deriv = make3(gldf(cb, G_OFF_PIXEL_TO_RAY + 4 * i), gldf(cb, G_OFF_PIXEL_TO_RAY + 16 + 4 * i), gldf(cb, G_OFF_PIXEL_TO_RAY + 32 + 4 * i));
+			const f3 ray_cross_e1_deriv = cross(ray_deriv, e1);
+			const float rcp_det_deriv = -dot(e0, ray_cross_e1_deriv) * rcp_det * rcp_det;
+			const float det_0_dir_edge_1_deriv = dot(ray_to_0, ray_cross_e1_deriv);
+			const float dby = rcp_det_deriv * det_0_dir_edge_1 + rcp_det * det_0_dir_edge_1_deriv;
+			const float det_dir_edge_0_0_deriv = dot(ray_deriv, e0_cross_0);
+			const float dbz = -rcp_det_deriv * det_dir_edge_0_0 - rcp_det * det_dir_edge_0_0_deriv;
+			const float dbx = -(dby + dbz);
+			f2 d = make2(0.0f, 0.0f);
+			d = d + uv[0] * dbx; d = d + uv[1] * dby; d = d + uv[2] * dbz;
+			tex_coord_derivs[i] = d;
+		}
+		float4 texel[3];
+#pragma unroll
+		for (int k = 0; k != 3; ++k) {
+			const uint4 dims = __ldg(p.texture_dims + 3 * material_index + k);
+			texture_view view;
+			view.width = dims.x; view.height = dims.y; view.mip_count = dims.z;
+			view.texels = p.texture_data + __ldg(p.texture_offsets + 3 * material_index + k);
+			texel[k] = texture_grad(view, tex_coord, tex_coord_derivs[0], tex_coord_derivs[1]);
+		}
+		base = make3(texel[0].x, texel[0].y, texel[0].z);
+		linear_roughness = texel[1].y; metalicity = texel[1].z;
+		normal_texel = make2(texel[2].x, texel[2].y);
+	}
+	else {
+		const float* mp = p.material_params + 8 * (size_t) material_index;
+		base = make3(__ldg(mp), __ldg(mp + 1), __ldg(mp + 2));
+		linear_roughness = __ldg(mp + 3); metalicity = __ldg(mp + 4);
+		normal_texel = make2(__ldg(mp + 5), __ldg(mp + 6));
+	}
 	f3 nts;
-	nts.x = fmaf(__ldg(mp + 5), 2.0f, -1.0f); nts.y = fmaf(__ldg(mp + 6), 2.0f, -1.0f);
+	nts.x = fmaf(normal_texel.x, 2.0f, -1.0f); nts.y = fmaf(normal_texel.y, 2.0f, -1.0f);
 	nts.z = sqrtf(max_glsl(0.0f, fmaf(-nts.x, nts.x, fmaf(-nts.y, nts.y, 1.0f))));
 	const f3 diffuse = make3(fmaf(base.x, -metalicity, base.x), fmaf(base.y, -metalicity, base.y), fmaf(base.z, -metalicity, base.z));
 	const float om = 1.0f - metalicity;
@@ -148,6 +189,7 @@ cudaError_t vkr_launch_visibility_kernel(const vkr::gbuffer_kernel_params& p, cu
 cudaError_t vkr_launch_gbuffer_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream) {
 	const size_t pixels = (size_t) p.width * p.height;
 	if (!pixels) return cudaSuccess;
-	vkr::gbuffer_kernel<<<(unsigned) ((pixels + 127) / 128), 128, 0, stream>>>(p);
+	if (p.texture_data) vkr::gbuffer_kernel<true><<<(unsigned) ((pixels + 127) / 128), 128, 0, stream>>>(p);
+	else vkr::gbuffer_kernel<false><<<(unsigned) ((pixels + 127) / 128), 128, 0, stream>>>(p);
 	return cudaGetLastError();
 }

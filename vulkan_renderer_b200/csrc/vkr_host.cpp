@@ -167,7 +167,8 @@ extern "C" void vkr_destroy_scene(vkr_scene_t* scene, const vkr_device_t* device
 	}
 	free(scene->material_params);
 	void* dev_ptrs[] = { scene->d_quantized_positions, scene->d_normals_and_tex_coords, scene->d_material_indices, scene->d_material_params,
-		scene->d_shadow_nodes, scene->d_shadow_tris, scene->d_primary_nodes, scene->d_primary_tris, scene->d_primary_tri_ids };
+		scene->d_shadow_nodes, scene->d_shadow_tris, scene->d_primary_nodes, scene->d_primary_tris, scene->d_primary_tri_ids,
+		scene->d_texture_data, scene->d_texture_dims, scene->d_texture_offsets };
 	for (void* p : dev_ptrs) if (p) cudaFree(p);
 	memset(scene, 0, sizeof(*scene));
 }
@@ -297,6 +298,35 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 	if (upload(&scene->d_material_params, scene->material_params, sizeof(float) * 8 * scene->material_count, device)) {
 		printf("Failed to upload materials of the scene %s.\n", file_path);
 		vkr_destroy_scene(scene, device); return 1;
+	}
+	// Textures that need filtering: every mip level as RGBA32F on the device (vkr_textures.cpp, vkr_texture.cuh)
+	if (device && scene->material_count) {
+		std::vector<vkr_texture_t> textures(3 * (size_t) scene->material_count);
+		bool failed = false, any_pattern = false;
+		for (uint64_t i = 0; i != scene->material_count && !failed; ++i)
+			for (int j = 0; j != 3 && !failed; ++j) {
+				const std::string path = std::string(texture_path) + "/" + scene->material_names[i] + "_" + suffixes[j] + ".vkt";
+				failed = vkr_load_texture(&textures[3 * i + j], path.c_str()) != 0;
+				any_pattern = any_pattern || (!failed && !textures[3 * i + j].is_constant);
+			}
+		if (!failed && any_pattern) {
+			std::vector<uint32_t> dims(4 * textures.size()); std::vector<uint64_t> offsets(textures.size());
+			uint64_t texel_count = 0;
+			for (size_t k = 0; k != textures.size(); ++k) {
+				dims[4 * k] = textures[k].width; dims[4 * k + 1] = textures[k].height; dims[4 * k + 2] = textures[k].mip_count; dims[4 * k + 3] = 0;
+				offsets[k] = texel_count; texel_count += textures[k].texel_float_count / 4;
+			}
+			std::vector<float> data(4 * (size_t) texel_count);
+			for (size_t k = 0; k != textures.size(); ++k) memcpy(&data[4 * (size_t) offsets[k]], textures[k].h_texels, sizeof(float) * (size_t) textures[k].texel_float_count);
+			failed = upload(&scene->d_texture_data, data.data(), data.size() * 4, device) || upload(&scene->d_texture_dims, dims.data(), dims.size() * 4, device)
+				|| upload(&scene->d_texture_offsets, offsets.data(), offsets.size() * 8, device);
+			scene->textured = 1; scene->texture_texel_count = texel_count;
+		}
+		for (vkr_texture_t& t : textures) vkr_destroy_texture(&t);
+		if (failed) {
+			printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);
+			vkr_destroy_scene(scene, device); return 1;
+		}
 	}
 	return 0;
 }

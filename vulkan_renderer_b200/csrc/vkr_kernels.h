@@ -39,10 +39,12 @@ struct gbuffer_kernel_params {
 	const uint2* quantized_positions;        // 3 per triangle (scene.h:56-62)
 	const ushort4* normals_and_tex_coords;   // 3 per triangle
 	const uint8_t* material_indices;         // 1 per triangle
-	const float* material_params;            // 8 floats per material
+	const float* material_params;            // 8 floats per material (materials whose textures are constant)
 	const float4* bvh_nodes; const float4* bvh_tris; const uint32_t* bvh_tri_ids; uint32_t tri_count; // primary-ray BVH (shader-decoded vertices)
 	uint32_t* visibility;                    // width*height primitive indices (0xFFFFFFFF = background)
 	float4* gbuffer;                         // 4 planes
+	// material textures that need filtering (vkr_texture.cuh), 3 per material {base colour, specular, normal}; null for constant materials
+	const float4* texture_data; const uint4* texture_dims; const unsigned long long* texture_offsets; // dims = {width, height, mip_count, -}, offsets in texels
 };
 
 } // namespace vkr

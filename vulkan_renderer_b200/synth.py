@@ -374,6 +374,25 @@ def write_material_textures(directory, materials):
 		write_vkt_constant(os.path.join(directory, m["name"] + "_Normal.vkt"), [0.5, 0.5, 1.0, 1.0])
 
 
+def write_patterned_material_textures(directory, materials, seed=5):
+	"""Material textures that are not constant, in the formats real assets use (tools/texture_conversion: BC1 base colour, BC5 normals; the
+	specular texture as RGBA16F and not square): tiles in the base colour, roughness stripes, a metallic checker for some materials, bumps."""
+	os.makedirs(directory, exist_ok=True)
+	rng = np.random.default_rng(seed)
+	for k, m in enumerate(materials):
+		yy, xx = np.mgrid[0:64, 0:64]
+		tiles = (((xx // 8) + (yy // 8)) % 2).astype(np.float32)
+		base = np.clip(np.asarray(m["base"], dtype=np.float32)[None, None, :] * (0.55 + 0.6 * tiles[..., None]) + 0.05 * rng.random((64, 64, 3)), 0.0, 1.0)
+		write_vkt(os.path.join(directory, m["name"] + "_BaseColor.vkt"), base.astype(np.float32), 131)
+		yy, xx = np.mgrid[0:16, 0:32]
+		roughness = np.clip(m["roughness"] * (0.6 + 0.8 * ((xx // 4) % 2)), 0.05, 1.0)
+		metal = ((xx // 8 + yy // 8) % 2) * (1.0 if k % 3 == 0 else 0.0)
+		write_vkt(os.path.join(directory, m["name"] + "_Specular.vkt"), np.stack([np.ones((16, 32)), roughness, metal], -1).astype(np.float32), 97)
+		yy, xx = np.mgrid[0:32, 0:32]
+		normal = np.stack([0.5 + 0.25 * np.sin(xx * 2.0 * np.pi / 8.0), 0.5 + 0.25 * np.cos(yy * 2.0 * np.pi / 16.0), np.ones((32, 32))], -1)
+		write_vkt(os.path.join(directory, m["name"] + "_Normal.vkt"), normal.astype(np.float32), 141)
+
+
 def material_params(materials):
 	"""The 8 floats per material the G-buffer producer consumes, after the RGBA16F round trip of the *.vkt files."""
 	out = np.zeros((len(materials), 8), dtype=np.float32)
@@ -464,7 +483,7 @@ def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0
 def build_dataset(directory, name, **overrides):
 	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
 	os.makedirs(directory, exist_ok=True)
-	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4, "mini_v5": 3, "mini_v6": 3, "mini_v7": 3, "mini_poly": 3}.get(name, 9))
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_textured": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4, "mini_v5": 3, "mini_v6": 3, "mini_v7": 3, "mini_poly": 3}.get(name, 9))
 	if name == "cornell":
 		mesh, materials = scene_cornell()
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
@@ -482,6 +501,11 @@ def build_dataset(directory, name, **overrides):
 			size = {"small": 0.5, "tiny": 0.08}[overrides["light_size"]]
 			lights = [make_light((0.5 * extent - 6.0, 0.5 * extent - 20.0, 9.0), (np.pi + 0.2, 0.1, 0.3), (size, size), (400.0, 400.0, 400.0))]
 	elif name == "mini_city":
+		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
+		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
+		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+	elif name == "mini_textured":
+		# the mini_city scene with material textures that need filtering: BC1 base colour, RGBA16F specular, BC5 normals
 		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
 		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
 		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
@@ -530,9 +554,10 @@ def build_dataset(directory, name, **overrides):
 	save = os.path.join(directory, name + ".save")
 	ltc = os.path.join(directory, "ggx_ltc_fit")
 	info = write_vks(vks, mesh, materials)
-	write_material_textures(tex, materials)
+	if name == "mini_textured": write_patterned_material_textures(tex, materials)
+	else: write_material_textures(tex, materials)
 	write_quicksave(save, camera, lights)
 	if not os.path.exists(os.path.join(ltc, "fit50.dat")):
 		write_ltc_fits(ltc)
-	info.update(vks=vks, textures=tex, save=save, ltc=ltc, materials=materials, material_params=material_params(materials), camera=camera, lights=lights)
+	info.update(textured=(name == "mini_textured"), vks=vks, textures=tex, save=save, ltc=ltc, materials=materials, material_params=material_params(materials), camera=camera, lights=lights)
 	return info
