@@ -67,3 +67,24 @@ def test_live_reference_shader_matches_fixture():
 		assert np.array_equal(ref.view(np.uint32), g[name + "/rgba"].view(np.uint32)), name
 		checked += 1
 	assert checked > 0
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
+@pytest.mark.parametrize("width,height", [(40, 30), (97, 41)])
+def test_oracle_follows_the_live_reference_shader_at_other_resolutions(width, height):
+	"""The fixtures are 64x48; other resolutions move every pixel ray, sample and noise fetch. A spread of configurations (every strategy,
+	related-work techniques, error display, textures) is shaded by the reference shader and by the oracle: bit-identical again."""
+	picks = ["s0_h0_b0_L3_V4_S3_t1_l1_M8", "s1_h1_b0_L3_V4_S3_t1_l1_M8", "s2_h0_b0_L3_V4_S3_t1_l1_M8", "s3_h3_b0_L3_V4_S3_t1_l1_M8", "s4_h0_b0_L3_V4_S3_t1_l1_M8",
+		"s3_h4_b0_L3_V4_S3_t1_l1_M8", "s3_h3_b1_L3_V4_S3_t1_l1_M8", "s3_h3_b0_L3_V7m5_S3_t1_l1_M8", "s3_h3_b0_L32_V4_S2_t1_l1_M8",
+		"s0_h0_b0_L3_V4_S3_t1_l1_M8_q3", "s0_h0_b0_L3_V4_S3_t1_l1_M8_q9", "s1_h0_b0_L3_V4_S3_t1_l1_M8_q10", "s0_h0_b0_L3_V7m5_S3_t1_l1_M8_q7",
+		"s3_h3_b0_L3_V4_S3_t1_l1_M8_e4", "s3_h3_b0_L3_V4_S3_t1_l1_M8_x1"]
+	live = {c["name"]: c for c in R.configs()}
+	for name in picks:
+		cfg = live[name]
+		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+		constants = host_constants(info, width, height, cfg["lights"])
+		vis = oi.visibility(width, height, constants)
+		ref = R.shade(cfg["entry"], width, height, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures)
+		gb = oi.gbuffer(width, height, constants, vis)
+		out, _ = oi.shade(oracle_cfg(cfg, width, height), constants, gb)
+		assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), (name, H.compare_radiance(out, ref))
