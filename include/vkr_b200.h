@@ -332,6 +332,9 @@ int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t vertex_count, 
 int vkr_bvh_build_probe_with(int builder, const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth);
 /* the linear BVH built on the GPU (vkr_lbvh_gpu.cu; VKR_BVH_BUILDER=lbvh_gpu), copied to the host: must equal builder 1 array for array */
 int vkr_bvh_build_probe_device(const vkr_device_t* device, const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth);
+/* builder 0's tree collapsed into 4-wide nodes (32 floats each; layout: csrc/vkr_bvh.h) -- groundwork for a 4-wide trace loop, not used by the kernels yet */
+int vkr_bvh4_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes4, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth,
+	uint64_t* out_bvh2_node_count, uint32_t* out_bvh2_max_depth);
 int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth);
 void vkr_bvh_free_probe(float* nodes, float* tris, uint32_t* tri_ids);
 

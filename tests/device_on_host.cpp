@@ -141,6 +141,25 @@ extern "C" void vkr_device_on_host_texture_grad_batch(uint32_t width, uint32_t h
 	}
 }
 
+// The same rays through the binary tree and through its 4-wide collapse (vkr_trace.cuh: occluded4): answers and nodes fetched per ray
+extern "C" void vkr_device_on_host_trace_any_wide(const float* nodes2, const float* nodes4, const float* tris, uint32_t ray_count, const float* rays, uint8_t* out2, uint8_t* out4,
+	uint64_t* out_steps2, uint64_t* out_steps4)
+{
+	bvh_view bvh;
+	bvh.nodes = reinterpret_cast<const float4*>(nodes2); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = nullptr; bvh.tri_count = 0;
+	int stack[4 * kMaxStackDepth];
+	*out_steps2 = *out_steps4 = 0;
+	for (uint32_t i = 0; i != ray_count; ++i) {
+		const float* r = rays + 8 * (size_t) i;
+		const f3 o = make3(r[0], r[1], r[2]), d = make3(r[3], r[4], r[5]);
+		out2[i] = occluded(bvh, o, d, r[6], r[7], stack, 1) ? 1 : 0;
+		int steps = 0;
+		out4[i] = occluded4(reinterpret_cast<const float4*>(nodes4), bvh.tris, o, d, r[6], r[7], stack, 1, &steps) ? 1 : 0;
+		*out_steps4 += (uint64_t) steps;
+	}
+	(void) out_steps2;
+}
+
 // Elementary functions of the device arithmetic contract: 0 atan, 1 sin, 2 cos, 3 acos on [-1,1], 4 atan2(x, 0.5), 5 pow(x, 1/3), 6 fast_positive_atan
 extern "C" void vkr_device_on_host_elementary_batch(int which, uint32_t n, const float* x, float* y) {
 	for (uint32_t i = 0; i != n; ++i) {

@@ -197,6 +197,49 @@ def test_bvh_traversal_equals_brute_force_for_every_builder(name, builder):
 	assert 0.05 < out_brute.mean() < 0.98 and not out_brute[20:30].any()
 
 
+def _probe_bvh4(lib, tris):
+	P = C.POINTER
+	nodes4 = P(C.c_float)(); tri = P(C.c_float)(); ids = P(C.c_uint32)(); nc = C.c_uint64(); md = C.c_uint32(); nc2 = C.c_uint64(); md2 = C.c_uint32()
+	tris = np.ascontiguousarray(tris, dtype=np.float32)
+	assert lib.vkr_bvh4_build_probe(tris.ctypes.data, len(tris), C.byref(nodes4), C.byref(nc), C.byref(tri), C.byref(ids), C.byref(md), C.byref(nc2), C.byref(md2)) == 0
+	n = len(tris)
+	out = (np.ctypeslib.as_array(nodes4, (nc.value, 32)).copy(), np.ctypeslib.as_array(tri, (max(n, 1), 12)).copy()[:n], md.value, nc2.value, md2.value)
+	lib.vkr_bvh_free_probe(nodes4, tri, ids)
+	return out
+
+
+@pytest.mark.parametrize("name", ["cornell", "mini_city", "roughness_planes"])
+def test_four_wide_collapse_keeps_the_tree_and_the_answers(name):
+	"""Groundwork for a 4-wide trace loop: the collapse of the SAH tree into 128-byte nodes references every leaf of the binary tree exactly once,
+	roughly halves the depth, and the per-thread 4-wide traversal (vkr_trace.cuh: occluded4, compiled for the CPU) answers like the binary one."""
+	from tests.test_device_on_host import _lib
+	dev = _lib(); lib = api.load_library()
+	info = H.dataset(name); vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes2, slots, ids, depth2 = _probe_bvh(lib, tris, BUILDERS["sah"])
+	nodes4, slots4, depth4, count2, d2 = _probe_bvh4(lib, tris)
+	assert np.array_equal(slots, slots4) and count2 == len(nodes2) and d2 == depth2
+	refs2 = nodes2[:, 12:14].copy().view(np.int32).reshape(-1); refs4 = nodes4[:, 24:28].copy().view(np.int32).reshape(-1)
+	leaves2 = sorted(int(r) for r in refs2 if r < 0 and (r & 15)); leaves4 = sorted(int(r) for r in refs4 if r < 0 and (r & 15))
+	assert leaves2 == leaves4                                                   # the same leaves, each once
+	inner4 = sorted(int(r) for r in refs4 if r >= 0)
+	assert inner4 == list(range(1, len(nodes4))) and len(nodes4) < 0.75 * len(nodes2) + 2 and depth4 <= (depth2 + 1) // 2 + 2
+	empty = refs4[(refs4 < 0) & ((refs4 & 15) == 0)]
+	assert (nodes4.reshape(-1, 32)[:, 3:24:6][refs4.reshape(-1, 4) == -2147483648] == -1.0).all() or len(empty) == 0   # unused children cannot be hit
+	rng = np.random.default_rng(5)
+	T = tris.reshape(-1, 3, 3); lo = T.reshape(-1, 3).min(0); hi = T.reshape(-1, 3).max(0)
+	n_rays = 3000
+	origins = rng.uniform(lo, hi, (n_rays, 3)); targets = T[rng.integers(0, len(T), n_rays)].mean(1) + rng.normal(scale=0.05, size=(n_rays, 3))
+	d = targets - origins; length = np.linalg.norm(d, axis=1, keepdims=True); d /= length
+	rays = np.concatenate([origins, d, np.full((n_rays, 1), 1e-3), length * rng.uniform(0.3, 1.5, (n_rays, 1))], axis=1).astype(np.float32)
+	rays[:20, 3:6] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 20)]
+	out2 = np.zeros(n_rays, dtype=np.uint8); out4 = np.zeros(n_rays, dtype=np.uint8); s2 = C.c_uint64(); s4 = C.c_uint64()
+	n2 = np.ascontiguousarray(nodes2, dtype=np.float32); n4 = np.ascontiguousarray(nodes4, dtype=np.float32); sl = np.ascontiguousarray(slots, dtype=np.float32)
+	dev.vkr_device_on_host_trace_any_wide(n2.ctypes.data_as(C.c_void_p), n4.ctypes.data_as(C.c_void_p), sl.ctypes.data_as(C.c_void_p), C.c_uint32(n_rays), rays.ctypes.data_as(C.c_void_p),
+		out2.ctypes.data_as(C.c_void_p), out4.ctypes.data_as(C.c_void_p), C.byref(s2), C.byref(s4))
+	assert np.array_equal(out2, out4) and 0.02 < out2.mean() < 0.99
+
+
 def test_lbvh_follows_the_morton_order_of_the_centroids():
 	"""What the GPU builder has to reproduce: slots in ascending (Morton code of the centroid, original index) order, leaves of up to four slots."""
 	lib = api.load_library()

@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
 	"vkr_specify_default_render_settings", "vkr_get_constants_size", "vkr_write_constants", "vkr_set_frame_bits",
 	"vkr_gbuffer_size", "vkr_run_visibility_pass", "vkr_run_gbuffer_pass",
 	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait",
-	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_build_probe_with", "vkr_bvh_build_probe_device", "vkr_bvh_free_probe",
+	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_build_probe_with", "vkr_bvh_build_probe_device", "vkr_bvh4_build_probe", "vkr_bvh_free_probe",
 	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
 	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
 	"vkr_load_texture", "vkr_destroy_texture",
@@ -169,6 +169,7 @@ def load_library():
 	lib.vkr_bvh_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
 	lib.vkr_bvh_build_probe_with.argtypes = [C.c_int, C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
 	lib.vkr_bvh_build_probe_device.argtypes = [P(Device), C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]
+	lib.vkr_bvh4_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32), P(C.c_uint64), P(C.c_uint32)]
 	lib.vkr_bvh_free_probe.argtypes = [P(C.c_float), P(C.c_float), P(C.c_uint32)]; lib.vkr_bvh_free_probe.restype = None
 	lib.vkr_load_texture.argtypes = [P(Texture), C.c_char_p]
 	lib.vkr_destroy_texture.argtypes = [P(Texture)]; lib.vkr_destroy_texture.restype = None

@@ -202,4 +202,57 @@ void build_bvh(host_bvh& out, const float* vertices, uint64_t triangle_count) {
 	out.node_count = next;
 }
 
+// Collapses node pairs into 4-wide nodes: starting from the two children of a pair, the inner child with the largest surface area is
+// replaced by its own two children until there are four (or only leaves are left). Boxes are copied as they are (already padded and
+// rounded outwards), so the 4-wide tree is exactly as conservative as the binary one. Deterministic; nodes are numbered depth first.
+void build_bvh4_from_bvh2(host_bvh4& out, const host_bvh& in) {
+	out = host_bvh4();
+	struct child { float box[6]; int32_t ref; };
+	auto load = [&](uint32_t pair, int c) {
+		child ch;
+		const float* src = &in.nodes[16 * (size_t) pair];
+		std::memcpy(ch.box, src + 6 * c, sizeof(ch.box));
+		std::memcpy(&ch.ref, src + 12 + c, 4);
+		return ch;
+	};
+	auto area = [](const child& ch) { return ch.box[3] * ch.box[4] + ch.box[4] * ch.box[5] + ch.box[5] * ch.box[3]; };
+	struct item { uint32_t pair, index, depth; };
+	std::vector<item> stack;
+	out.nodes.assign(32, 0.0f);
+	uint32_t next = 1;
+	stack.push_back({0, 0, 1});
+	while (!stack.empty()) {
+		const item it = stack.back(); stack.pop_back();
+		out.max_depth = std::max(out.max_depth, it.depth);
+		child children[4]; int count = 2;
+		children[0] = load(it.pair, 0); children[1] = load(it.pair, 1);
+		while (count < 4) {
+			int widest = -1;
+			for (int c = 0; c != count; ++c)
+				if (children[c].ref >= 0 && (widest < 0 || area(children[c]) > area(children[widest]))) widest = c;
+			if (widest < 0) break;
+			const uint32_t pair = (uint32_t) children[widest].ref;
+			children[widest] = load(pair, 0);
+			children[count++] = load(pair, 1);
+		}
+		int32_t refs[4];
+		for (int c = 0; c != 4; ++c) {
+			if (c >= count) { refs[c] = (int32_t) 0x80000000u; continue; }
+			if (children[c].ref >= 0) {
+				refs[c] = (int32_t) next++;
+				out.nodes.resize(32 * (size_t) next, 0.0f);
+				stack.push_back({(uint32_t) children[c].ref, (uint32_t) refs[c], it.depth + 1});
+			}
+			else refs[c] = children[c].ref;
+		}
+		float* dst = &out.nodes[32 * (size_t) it.index];
+		for (int c = 0; c != 4; ++c) {
+			if (c < count) std::memcpy(dst + 6 * c, children[c].box, sizeof(children[c].box));
+			else { dst[6 * c] = dst[6 * c + 1] = dst[6 * c + 2] = 0.0f; dst[6 * c + 3] = dst[6 * c + 4] = dst[6 * c + 5] = -1.0f; }
+			dst[24 + c] = as_float(refs[c]);
+		}
+	}
+	out.node_count = next;
+}
+
 } // namespace vkr

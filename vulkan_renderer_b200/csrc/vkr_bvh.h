@@ -27,6 +27,16 @@ uint64_t lbvh_morton_code(const float centroid[3], const float lo[3], const floa
 // (void* like vkr_device_t::stream, so that this header needs no CUDA headers).
 int build_lbvh_device(const float* vertices, uint64_t triangle_count, void* stream, void** d_nodes, void** d_tris, void** d_tri_ids, uint64_t* node_count, uint32_t* max_depth);
 
+// 4-wide nodes collapsed from a BVH2 (vkr_bvh.cpp: build_bvh4_from_bvh2): groundwork for a traversal with half as many, fatter steps
+// (DESIGN.md section 7). node = 128 B = 8 x float4: child c has centre and half extent at floats [6c, 6c + 6), its reference (same
+// encoding as in the node pairs) as int bits at float 24 + c; unused children are empty leaves with a negative half extent.
+struct host_bvh4 {
+	std::vector<float> nodes;   // 32 floats per node
+	uint32_t max_depth = 0;
+	uint64_t node_count = 0;
+};
+void build_bvh4_from_bvh2(host_bvh4& out, const host_bvh& in);
+
 enum bvh_builder { bvh_builder_sah = 0, bvh_builder_lbvh = 1, bvh_builder_lbvh_gpu = 2 };
 // VKR_BVH_BUILDER = sah (default) | lbvh | lbvh_gpu
 bvh_builder bvh_builder_from_environment();

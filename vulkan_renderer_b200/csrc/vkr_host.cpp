@@ -810,6 +810,24 @@ extern "C" int vkr_bvh_build_probe_device(const vkr_device_t* device, const floa
 	return 0;
 }
 
+// The 4-wide collapse of builder 0's tree (vkr_bvh.h: host_bvh4): nodes4 = 32 floats per node, tris / tri_ids as in the other probes
+extern "C" int vkr_bvh4_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes4, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth,
+	uint64_t* out_bvh2_node_count, uint32_t* out_bvh2_max_depth)
+{
+	host_bvh bvh; host_bvh4 wide;
+	build_bvh(bvh, vertices, triangle_count);
+	build_bvh4_from_bvh2(wide, bvh);
+	*out_nodes4 = (float*) malloc(sizeof(float) * wide.nodes.size());
+	*out_tris = (float*) malloc(sizeof(float) * (bvh.tris.size() ? bvh.tris.size() : 1));
+	*out_tri_ids = (uint32_t*) malloc(sizeof(uint32_t) * (bvh.tri_ids.size() ? bvh.tri_ids.size() : 1));
+	memcpy(*out_nodes4, wide.nodes.data(), sizeof(float) * wide.nodes.size());
+	memcpy(*out_tris, bvh.tris.data(), sizeof(float) * bvh.tris.size());
+	memcpy(*out_tri_ids, bvh.tri_ids.data(), sizeof(uint32_t) * bvh.tri_ids.size());
+	*out_node_count = wide.node_count; *out_max_depth = wide.max_depth;
+	*out_bvh2_node_count = bvh.node_count; *out_bvh2_max_depth = bvh.max_depth;
+	return 0;
+}
+
 extern "C" int vkr_bvh_build_probe(const float* vertices, uint64_t triangle_count, float** out_nodes, uint64_t* out_node_count, float** out_tris, uint32_t** out_tri_ids, uint32_t* out_max_depth) {
 	return vkr_bvh_build_probe_with(0, vertices, triangle_count, out_nodes, out_node_count, out_tris, out_tri_ids, out_max_depth);
 }
