@@ -105,6 +105,7 @@ typedef struct vkr_scene_s {
 	void* d_texture_dims;      /* uint32[4] per texture: width, height, mip_count, 0; order: material-major, {base colour, specular, normal} */
 	void* d_texture_offsets;   /* uint64 per texture: first texel of level 0 in d_texture_data */
 	uint64_t texture_texel_count;
+	uint32_t shadow_bvh_width;  /* children per node of d_shadow_nodes: 2 (64-byte node pairs); 4 only with VKR_BVH_WIDTH=4 in the environment, for the experimental kernel variant */
 } vkr_scene_t;
 
 /* device may be NULL for vkr_load_scene / vkr_load_ltc_table / vkr_load_noise_table: the files are parsed and the host

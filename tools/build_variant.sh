@@ -8,8 +8,8 @@ name=$1; flags=$2
 out=vulkan_renderer_b200/build/variants; mkdir -p $out
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
 	-ccbin /usr/bin/g++ -Xcompiler -fPIC -I include -DVKR_MAXP_TU=5 $flags -c vulkan_renderer_b200/csrc/vkr_shading_kernel.cu -o $out/$name.o
-b=vulkan_renderer_b200/build   # only the quad-light kernels (vertex bound 5) are rebuilt; the other bounds come from the in-tree objects
-nvcc -shared -o $out/libvkr_$name.so $out/$name.o $b/vkr_shading_kernel_maxp4.cu.o $b/vkr_shading_kernel_maxp6.cu.o $b/vkr_shading_kernel_maxp7.cu.o $b/vkr_shading_kernel_maxp8.cu.o \
-	$b/vkr_gbuffer_kernel.cu.o $b/vkr_api.cu.o $b/vkr_host.cpp.o $b/vkr_bvh.cpp.o -ccbin /usr/bin/g++ -Xcompiler -fopenmp -lgomp -cudart static
+b=vulkan_renderer_b200/build   # only the quad-light kernels (vertex bound 5) are rebuilt; everything else comes from the in-tree objects
+others=$(ls $b/*.o | grep -v vkr_shading_kernel_maxp5)
+nvcc -shared -o $out/libvkr_$name.so $out/$name.o $others -ccbin /usr/bin/g++ -Xcompiler -fopenmp -lgomp -cudart static
 rm $out/$name.o
 echo built $out/libvkr_$name.so

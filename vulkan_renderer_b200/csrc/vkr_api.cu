@@ -218,6 +218,7 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	if (d.trace_shadow_rays) {
 		p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count;
 		p.stack_depth = (int) d.scene->shadow_max_depth + 2;
+		p.bvh_width = d.scene->shadow_bvh_width ? (int) d.scene->shadow_bvh_width : 2;
 	}
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_begin, stream);
 	cudaError_t err = vkr_launch_shading_kernel(p, stream);
@@ -312,6 +313,7 @@ __global__ void sample_probe_kernel(int vertex_count, const float* vertices, uin
 
 extern "C" int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, uint32_t ray_count, const float* rays, uint8_t* out_occluded) {
 	if (!scene->d_shadow_nodes) { printf("Cannot trace shadow rays: the scene was loaded without acceleration structure.\n"); return 1; }
+	if (scene->shadow_bvh_width == 4) { printf("The shadow-ray probe walks node pairs; the scene was loaded with 4-wide nodes (VKR_BVH_WIDTH=4).\n"); return 1; }
 	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
 	cudaStream_t stream = (cudaStream_t) device->stream;
 	float* d_rays = nullptr; uint8_t* d_out = nullptr;

@@ -250,15 +250,25 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 			void* d_ids = nullptr; uint64_t pairs = 0; uint32_t depth = 0;
 			if (build_lbvh_device(soup.data(), n, device->stream, &scene->d_shadow_nodes, &scene->d_shadow_tris, &d_ids, &pairs, &depth) == 0) {
 				cudaFree(d_ids);
-				if (depth < 62) { built_on_device = true; scene->shadow_node_count = pairs; scene->shadow_max_depth = depth; }
+				if (depth < 62) { built_on_device = true; scene->shadow_node_count = pairs; scene->shadow_max_depth = depth; scene->shadow_bvh_width = 2; }
 				else { cudaFree(scene->d_shadow_nodes); cudaFree(scene->d_shadow_tris); scene->d_shadow_nodes = scene->d_shadow_tris = nullptr; }
 			}
 			if (!built_on_device) printf("The GPU BVH builder did not produce a usable tree for %s; building on the host instead.\n", file_path);
 		}
 		if (!built_on_device) {
+			scene->shadow_bvh_width = 2;
 			if (which == bvh_builder_lbvh) build_lbvh(bvh, soup.data(), n);
 			if (which != bvh_builder_lbvh || bvh.max_depth >= 62) build_bvh(bvh, soup.data(), n);
 			scene->shadow_node_count = bvh.node_count; scene->shadow_max_depth = bvh.max_depth;
+			const char* width = getenv("VKR_BVH_WIDTH");
+			host_bvh4 wide;
+			if (width && !strcmp(width, "4") && bvh.max_depth < 62) { // experimental: 4-wide nodes for the kernel variant built with -DVKR_BVH_WIDTH=4 (up to 3 pushes per level)
+				build_bvh4_from_bvh2(wide, bvh);
+				if (3 * wide.max_depth + 2 <= 64) {
+					bvh.nodes = wide.nodes;
+					scene->shadow_node_count = wide.node_count; scene->shadow_max_depth = 3 * wide.max_depth; scene->shadow_bvh_width = 4;
+				}
+			}
 			if (bvh.max_depth >= 62 || upload(&scene->d_shadow_nodes, bvh.nodes.data(), bvh.nodes.size() * 4, device) || upload(&scene->d_shadow_tris, bvh.tris.data(), bvh.tris.size() * 4, device)) {
 				printf("Failed to construct an acceleration structure for the scene file at path %s.\n", file_path);
 				vkr_destroy_scene(scene, device); return 1;

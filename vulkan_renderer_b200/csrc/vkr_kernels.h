@@ -30,6 +30,7 @@ struct shading_kernel_params {
 	const float4* bvh_nodes; const float4* bvh_tris; uint32_t tri_count;
 	int stack_depth;                 // traversal stack entries per lane (BVH depth + 2)
 	int polygon_sampling_technique;  // sample_polygon_technique_t (src/polygonal_light.h:30-66); 0..10 run vkr_related_work_kernel.cu
+	int bvh_width;                   // children per node of bvh_nodes: 2 (node pairs, default) or 4 (experimental, must equal the kernels' VKR_BVH_WIDTH)
 	int error_display;               // error_display_t (src/main.h:92-112); != 0 runs error_display_kernel (vkr_related_work_kernel.cu)
 };
 

@@ -257,6 +257,7 @@ cudaError_t VKR_CONCAT(vkr_launch_related_work_kernel_maxv, VKR_MAXV_TU)(const s
 		return launch_error_display<VKR_MAXV_TU>(p, stream);
 	}
 	if (p.stack_depth < 2 || p.stack_depth > kMaxStackDepth) return cudaErrorInvalidValue;
+	if (p.trace_shadow_rays != 0 && p.tri_count != 0 && p.bvh_width != VKR_BVH_WIDTH) return cudaErrorInvalidValue;
 	if (p.polygon_sampling_technique < VKR_TECHNIQUE_BASELINE || p.polygon_sampling_technique > VKR_TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO) return cudaErrorInvalidValue;
 	switch (p.sampling_strategies) {
 	case VKR_STRATEGY_DIFFUSE_ONLY: return launch_related_work_traced<VKR_STRATEGY_DIFFUSE_ONLY, VKR_MAXV_TU>(p, stream);

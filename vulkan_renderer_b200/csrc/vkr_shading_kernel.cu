@@ -296,5 +296,6 @@ static cudaError_t launch_strategy(const shading_kernel_params& p, cudaStream_t 
 #define VKR_CONCAT(a, b) VKR_CONCAT2(a, b)
 cudaError_t VKR_CONCAT(vkr_launch_shading_kernel_maxp, VKR_MAXP_TU)(const shading_kernel_params& p, cudaStream_t stream) {
 	if (p.stack_depth < 2 || p.stack_depth > kMaxStackDepth) return cudaErrorInvalidValue;
+	if (p.trace_shadow_rays != 0 && p.tri_count != 0 && p.bvh_width != VKR_BVH_WIDTH) return cudaErrorInvalidValue; // the scene's BVH layout must be the one these kernels walk
 	return p.biased_sampling ? launch_strategy<VKR_MAXP_TU, true>(p, stream) : launch_strategy<VKR_MAXP_TU, false>(p, stream);
 }
