@@ -17,13 +17,20 @@ static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); re
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 
+// the CUDA vector types the headers use, laid out as on the device
 struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct ushort4 { uint16_t x, y, z, w; };
+typedef int cudaError_t;
+typedef void* cudaStream_t;
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 
 #include "vkr_related_work.cuh"
 #include "vkr_trace.cuh"
 #include "vkr_texture.cuh"
+#include "vkr_gbuffer.cuh"
 
 using namespace vkr;
 
@@ -158,6 +165,26 @@ extern "C" void vkr_device_on_host_trace_any_wide(const float* nodes2, const flo
 		*out_steps4 += (uint64_t) steps;
 	}
 	(void) out_steps2;
+}
+
+// The body of the G-buffer kernel (vkr_gbuffer.cuh: shade_gbuffer_pixel) for every pixel, on host arrays laid out like the device buffers.
+// texture_dims = uint32[4] per texture, texture_offsets in texels, texture_data = RGBA32F texels; all three null for constant materials.
+extern "C" void vkr_device_on_host_gbuffer(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility, const uint32_t* quantized_positions,
+	const uint16_t* normals_and_tex_coords, const uint8_t* material_indices, const float* material_params, const uint32_t* texture_dims, const uint64_t* texture_offsets,
+	const float* texture_data, float* out_gbuffer)
+{
+	gbuffer_kernel_params p;
+	memset(&p, 0, sizeof(p));
+	p.width = (int) width; p.height = (int) height; p.constants = (const unsigned char*) constants;
+	p.quantized_positions = reinterpret_cast<const uint2*>(quantized_positions); p.normals_and_tex_coords = reinterpret_cast<const ushort4*>(normals_and_tex_coords);
+	p.material_indices = material_indices; p.material_params = material_params;
+	p.visibility = const_cast<uint32_t*>(visibility); p.gbuffer = reinterpret_cast<float4*>(out_gbuffer);
+	p.texture_data = reinterpret_cast<const float4*>(texture_data); p.texture_dims = reinterpret_cast<const uint4*>(texture_dims);
+	p.texture_offsets = reinterpret_cast<const unsigned long long*>(texture_offsets);
+	for (size_t pixel = 0; pixel != (size_t) width * height; ++pixel) {
+		if (texture_data) shade_gbuffer_pixel<true>(p, pixel);
+		else shade_gbuffer_pixel<false>(p, pixel);
+	}
 }
 
 // Elementary functions of the device arithmetic contract: 0 atan, 1 sin, 2 cos, 3 acos on [-1,1], 4 atan2(x, 0.5), 5 pow(x, 1/3), 6 fast_positive_atan

@@ -151,6 +151,33 @@ def test_device_texture_filter_matches_the_definition(shape):
 	assert np.isfinite(ref[16:]).all()
 
 
+@pytest.mark.parametrize("name", ["mini_city", "mini_textured", "cornell"])
+def test_gbuffer_kernel_body_matches_the_oracle(name):
+	"""The whole per-pixel body of the G-buffer kernel (csrc/vkr_gbuffer.cuh: triangle decode, barycentrics, screen-space derivatives, three textureGrad over
+	BC1 / RGBA16F / BC5 mip chains, normal mapping) run on the CPU for every pixel of a frame, against get_shading_data() of the oracle: bit-identical."""
+	lib = _lib()
+	width, height = 120, 68
+	info = H.dataset(name); oi = H.OracleInputs(info)
+	constants = host_constants(info, width, height, len(info["lights"]))
+	vis = oi.visibility(width, height, constants)
+	ref = oi.gbuffer(width, height, constants, vis)
+	out = np.zeros((4, height, width, 4), dtype=np.float32)
+	q = np.ascontiguousarray(oi.vks["positions"], dtype=np.uint32); nt = np.ascontiguousarray(oi.vks["normals_uv"], dtype=np.uint16)
+	mi = np.ascontiguousarray(oi.vks["material_indices"], dtype=np.uint8); mp = np.ascontiguousarray(oi.material_params, dtype=np.float32)
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	if oi.textures is not None:
+		dims3, offsets, data = oi.textures
+		dims = np.zeros((len(dims3), 4), dtype=np.uint32); dims[:, :3] = dims3
+		offsets_texels = (offsets // 4).astype(np.uint64)
+		tex = (P(dims), P(offsets_texels), P(data))
+	else:
+		tex = (None, None, None)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	lib.vkr_device_on_host_gbuffer(C.c_uint32(width), C.c_uint32(height), cb, P(vis), P(q), P(nt), P(mi), P(mp), tex[0], tex[1], tex[2], P(out))
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+	assert (vis != 0xFFFFFFFF).mean() > 0.3
+
+
 def test_samples_point_at_the_light_and_densities_integrate():
 	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
 	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""

@@ -1,6 +1,8 @@
 // vkr_kernels.h -- host-visible launch interface of the CUDA kernels (internal to the library).
 #pragma once
+#ifndef VKR_DEVICE_CODE_ON_HOST   // tests/device_on_host.cpp supplies the few CUDA types itself
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 // numeric values = the reference's sampling_strategies_t / mis_heuristic_t (src/main.h:45-92)
