@@ -31,6 +31,9 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 #include "vkr_trace.cuh"
 #include "vkr_texture.cuh"
 #include "vkr_gbuffer.cuh"
+#include <algorithm>
+using std::min; using std::max;   // the integer min / max of the device headers
+#include "vkr_error_display.cuh"
 
 using namespace vkr;
 
@@ -184,6 +187,83 @@ extern "C" void vkr_device_on_host_gbuffer(uint32_t width, uint32_t height, cons
 	for (size_t pixel = 0; pixel != (size_t) width * height; ++pixel) {
 		if (texture_data) shade_gbuffer_pixel<true>(p, pixel);
 		else shade_gbuffer_pixel<false>(p, pixel);
+	}
+}
+
+// One frame of the error display modes on the CPU: per pixel the prologue and epilogue of the shading tile (csrc/vkr_shading_tile.cuh: G-buffer read, light
+// display, LTC set-up, noise stream, NaN -> pink, exposure; restated here because that file is warp-level code) around the product's per-light function
+// error_display_of_light() (csrc/vkr_error_display.cuh). Linear output, g_frame_bits = 0.
+template <int MAXV>
+static void error_display_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+	const unsigned char* cb = p.constants;
+	const size_t plane = (size_t) p.width * p.height;
+	const int light_stride = L_FIXED + 16 * MAXV * 2 + 16 * (MAXV - 2);
+	const f3 camera = make3(ldf(cb, OFF_CAMERA), ldf(cb, OFF_CAMERA + 4), ldf(cb, OFF_CAMERA + 8));
+	const float exposure = ldf(cb, OFF_EXPOSURE);
+	for (int y = 0; y != p.height; ++y) for (int x = 0; x != p.width; ++x) {
+		const size_t pixel = (size_t) y * p.width + x;
+		const float4 g0 = p.gbuffer[pixel], g1 = p.gbuffer[plane + pixel];
+		const bool valid = g1.w != 0.0f;
+		f3 color = make3(0.0f, 0.0f, 0.0f);
+		shading_point sp;
+		sp.position = make3(g0.x, g0.y, g0.z); sp.roughness = g0.w; sp.normal = make3(g1.x, g1.y, g1.z);
+		if (show_lights) {
+			f3 end; float end_w;
+			if (valid) { end = sp.position; end_w = 1.0f; }
+			else {
+				const float fx = (float) x, fy = (float) y;
+				end = make3(
+					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 8), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 4), fy, ldf(cb, OFF_PIXEL_TO_RAY) * fx)),
+					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 24), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 20), fy, ldf(cb, OFF_PIXEL_TO_RAY + 16) * fx)),
+					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 40), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 36), fy, ldf(cb, OFF_PIXEL_TO_RAY + 32) * fx)));
+				end_w = 0.0f;
+			}
+			for (int li = 0; li != p.light_count; ++li) {
+				const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
+				if (light_ray_intersection<MAXV>(light, camera, end, end_w))
+					color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
+			}
+		}
+		if (valid) {
+			const float4 g2 = p.gbuffer[2 * plane + pixel], g3 = p.gbuffer[3 * plane + pixel];
+			sp.diffuse_albedo = make3(g2.x, g2.y, g2.z); sp.fresnel_0 = make3(g3.x, g3.y, g3.z);
+			sp.outgoing = normalize(camera - sp.position);
+			sp.lambert_outgoing = dot(sp.normal, sp.outgoing);
+			ltc_state l = {};
+			get_ltc_coefficients(l, p, cb, sp);
+			noise_stream ns;
+			ns.z = 0.0f; ns.w = 0.0f; ns.available = 0; ns.sample_index = 0;
+			for (int li = 0; li != p.light_count; ++li) {
+				f3 contribution;
+				if (error_display_of_light<MAXV>(&contribution, sp, l, cb + CONSTANTS_FIXED + li * light_stride, ns, p, cb, (uint32_t) x, (uint32_t) y)) color = color + contribution;
+			}
+		}
+		f3 final_color = color;
+		if (std::isnan(color.x) || std::isnan(color.y) || std::isnan(color.z) || std::isinf(color.x) || std::isinf(color.y) || std::isinf(color.z))
+			final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
+		float* o = out_rgba + 4 * pixel;
+		o[0] = final_color.x * exposure; o[1] = final_color.y * exposure; o[2] = final_color.z * exposure; o[3] = 1.0f;
+	}
+}
+
+extern "C" int vkr_device_on_host_error_display_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t technique, uint32_t error_display, int show_lights,
+	const void* constants, const float* gbuffer, const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers, float* out_rgba)
+{
+	shading_kernel_params p;
+	memset(&p, 0, sizeof(p));
+	p.width = (int) width; p.height = (int) height; p.gbuffer = reinterpret_cast<const float4*>(gbuffer); p.constants = (const unsigned char*) constants;
+	p.light_count = (int) light_count; p.max_light_vertex_count = (int) maxv; p.sample_count = 1;
+	p.polygon_sampling_technique = (int) (technique == 12 ? 11 : technique); p.biased_sampling = technique == 12; p.error_display = (int) error_display;
+	p.noise = noise; p.noise_w = (int) noise_w; p.noise_h = (int) noise_h; p.noise_layers = (int) noise_layers;
+	p.ltc0 = ltc0; p.ltc1 = ltc1; p.ltc_res = (int) ltc_res; p.ltc_layers = (int) ltc_layers;
+	switch (maxv) {
+	case 3: error_display_frame<3>(p, show_lights, out_rgba); return 0;
+	case 4: error_display_frame<4>(p, show_lights, out_rgba); return 0;
+	case 5: error_display_frame<5>(p, show_lights, out_rgba); return 0;
+	case 6: error_display_frame<6>(p, show_lights, out_rgba); return 0;
+	case 7: error_display_frame<7>(p, show_lights, out_rgba); return 0;
+	default: return 1;
 	}
 }
 

@@ -178,6 +178,39 @@ def test_gbuffer_kernel_body_matches_the_oracle(name):
 	assert (vis != 0xFFFFFFFF).mean() > 0.3
 
 
+def _error_display_fixture_names():
+	import os
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	return sorted({k.split("/")[0] for k in g.files if "_e" in k.split("/")[0]})
+
+
+@pytest.mark.parametrize("name", _error_display_fixture_names())
+def test_error_display_light_shader_reproduces_the_reference_shader_fixtures(name):
+	"""csrc/vkr_error_display.cuh -- what error_display_kernel runs per (pixel, light): clipping in shading / cosine space, preparation, the one sample, its
+	error, the colour map, noise consumption across lights -- executed on the CPU for whole frames, against the frames of the reference's own shader compiled
+	with ERROR_DISPLAY_* (fixtures "_e<n>"). Bit-identical, pink pixels included."""
+	import os
+	from tests.test_ref_shader import _config_from_name
+	from tests.ref_frames import WIDTH, HEIGHT, dataset_for
+	lib = _lib()
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	constants = bytes(g[name + "/constants"])
+	gb = np.ascontiguousarray(oi.gbuffer(WIDTH, HEIGHT, constants, g[name + "/visibility"]), dtype=np.float32)
+	out = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
+	technique = cfg["technique"] if cfg["technique"] != 11 else (12 if cfg["biased"] else 11)
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	noise = np.ascontiguousarray(oi.noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(oi.ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(oi.ltc1, dtype=np.uint16)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_device_on_host_error_display_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(technique),
+		C.c_uint32(cfg["error_display"]), C.c_int(cfg["show_lights"]), cb, P(gb), P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]),
+		P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), P(out))
+	assert rc == 0
+	ref = g[name + "/rgba"]
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+
+
 def test_samples_point_at_the_light_and_densities_integrate():
 	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
 	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""
