@@ -26,6 +26,11 @@ typedef int cudaError_t;
 typedef void* cudaStream_t;
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+// what the builder's per-element functions use; the emulation below runs one element after the other, so plain reads and writes do
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p += v; return old; }
+static inline void __threadfence() {}
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long) x) : 64; }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 
 #include "vkr_related_work.cuh"
 #include "vkr_trace.cuh"
@@ -34,6 +39,8 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 #include <algorithm>
 using std::min; using std::max;   // the integer min / max of the device headers
 #include "vkr_error_display.cuh"
+#include "vkr_lbvh.cuh"
+#include <vector>
 
 using namespace vkr;
 
@@ -265,6 +272,52 @@ extern "C" int vkr_device_on_host_error_display_frame(uint32_t width, uint32_t h
 	case 7: error_display_frame<7>(p, show_lights, out_rgba); return 0;
 	default: return 1;
 	}
+}
+
+// The GPU linear-BVH builder (csrc/vkr_lbvh_gpu.cu) with every kernel launch replaced by a loop over its elements and the two library calls by their
+// definitions (cub::DeviceRadixSort::SortPairs = stable sort by key, cub::DeviceScan::ExclusiveSum = running sum): the per-element device functions of
+// csrc/vkr_lbvh.cuh do all the work. Output as the host probes deliver it; must equal builder 1 (csrc/vkr_lbvh.cpp) array for array.
+extern "C" int vkr_device_on_host_lbvh(const float* vertices, uint64_t triangle_count, float* out_nodes, uint64_t* out_node_count, float* out_tris, uint32_t* out_tri_ids, uint32_t* out_max_depth) {
+	if (triangle_count <= (uint64_t) kLbvhLeafSize) return 1;
+	const uint32_t n = (uint32_t) triangle_count, internal_count = n - 1;
+	std::vector<float> box_lo(3 * (size_t) n), box_hi(3 * (size_t) n), centroid(3 * (size_t) n);
+	uint32_t keys[12]; // scene lo/hi, centroid lo/hi as ordered keys, reduced with min / max like the atomics do
+	for (int a = 0; a != 3; ++a) { keys[a] = keys[6 + a] = 0xffffffffu; keys[3 + a] = keys[9 + a] = 0u; }
+	for (uint32_t t = 0; t != n; ++t) {
+		lbvh_triangle_bounds(vertices, t, &box_lo[3 * (size_t) t], &box_hi[3 * (size_t) t], &centroid[3 * (size_t) t]);
+		for (int a = 0; a != 3; ++a) {
+			keys[a] = std::min(keys[a], float_to_ordered(box_lo[3 * (size_t) t + a])); keys[3 + a] = std::max(keys[3 + a], float_to_ordered(box_hi[3 * (size_t) t + a]));
+			keys[6 + a] = std::min(keys[6 + a], float_to_ordered(centroid[3 * (size_t) t + a])); keys[9 + a] = std::max(keys[9 + a], float_to_ordered(centroid[3 * (size_t) t + a]));
+		}
+	}
+	float extent = 0.0f, lo[3], inv[3];
+	for (int a = 0; a != 3; ++a) {
+		extent = fmaxf(extent, fmaxf(fabsf(ordered_to_float(keys[a])), fabsf(ordered_to_float(keys[3 + a]))));
+		lo[a] = ordered_to_float(keys[6 + a]);
+		const float e = ordered_to_float(keys[9 + a]) - lo[a];
+		inv[a] = (e > 0.0f) ? 1.0f / e : 0.0f;
+	}
+	const float pad = extent * (1.0f / 65536.0f);
+	std::vector<uint64_t> codes_in(n), codes(n); std::vector<uint32_t> order(n);
+	for (uint32_t t = 0; t != n; ++t) { codes_in[t] = lbvh_morton(&centroid[3 * (size_t) t], make3(lo[0], lo[1], lo[2]), make3(inv[0], inv[1], inv[2])); order[t] = t; }
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t l, uint32_t r) { return codes_in[l] < codes_in[r]; });
+	for (uint32_t s2 = 0; s2 != n; ++s2) codes[s2] = codes_in[order[s2]];
+	for (uint32_t s2 = 0; s2 != n; ++s2) { lbvh_slot(vertices, order[s2], out_tris + 12 * (size_t) s2); out_tri_ids[s2] = order[s2]; }
+	std::vector<int32_t> first(internal_count), last(internal_count), split(internal_count), parent(internal_count, -1), leaf_parent(n, -1);
+	for (int64_t i = 0; i != (int64_t) internal_count; ++i) lbvh_radix_tree_node(codes.data(), n, i, first.data(), last.data(), split.data(), parent.data(), leaf_parent.data());
+	std::vector<float> node_lo(3 * (size_t) internal_count), node_hi(3 * (size_t) internal_count); std::vector<uint32_t> arrivals(internal_count, 0u), used(internal_count), rank(internal_count);
+	for (uint32_t s2 = 0; s2 != n; ++s2) lbvh_refit_from_leaf(s2, order.data(), box_lo.data(), box_hi.data(), first.data(), last.data(), split.data(), parent.data(), leaf_parent.data(), node_lo.data(), node_hi.data(), arrivals.data());
+	for (uint32_t i = 0; i != internal_count; ++i) if (arrivals[i] != 2u) return 2; // every internal node is reached by both subtrees
+	uint32_t used_count = 0;
+	for (uint32_t i = 0; i != internal_count; ++i) { used[i] = lbvh_is_used(first[i], last[i]); rank[i] = used_count; used_count += used[i]; }
+	uint32_t depth = 0;
+	for (uint32_t i = 0; i != internal_count; ++i) {
+		if (!used[i]) continue;
+		lbvh_emit_pair(i, order.data(), box_lo.data(), box_hi.data(), node_lo.data(), node_hi.data(), first.data(), last.data(), split.data(), used.data(), rank.data(), pad, out_nodes + 16 * (size_t) rank[i]);
+		depth = std::max(depth, lbvh_depth(i, parent.data()));
+	}
+	*out_node_count = used_count; *out_max_depth = depth;
+	return 0;
 }
 
 // Elementary functions of the device arithmetic contract: 0 atan, 1 sin, 2 cos, 3 acos on [-1,1], 4 atan2(x, 0.5), 5 pow(x, 1/3), 6 fast_positive_atan

@@ -240,6 +240,32 @@ def test_four_wide_collapse_keeps_the_tree_and_the_answers(name):
 	assert np.array_equal(out2, out4) and 0.02 < out2.mean() < 0.99
 
 
+@pytest.mark.parametrize("source", ["cornell", "mini_city", "roughness_planes", "soup_5", "soup_4097", "soup_60000"])
+def test_gpu_builder_steps_reproduce_the_reference_on_the_cpu(source):
+	"""csrc/vkr_lbvh.cuh -- the per-element functions the GPU builder's kernels call -- run on the CPU with every launch replaced by a loop (tests/device_on_host.cpp)
+	against the sequential reference csrc/vkr_lbvh.cpp: node pairs, slots, order and depth equal array for array. What this leaves to the GPU tests are the
+	launches themselves, the warp-reduced bounds and the two cub calls."""
+	from tests.test_device_on_host import _lib
+	dev = _lib(); lib = api.load_library()
+	if source.startswith("soup_"):
+		n = int(source.split("_")[1]); rng = np.random.default_rng(7)
+		centres = rng.uniform(-50.0, 50.0, (n, 1, 3)) * np.array([1.0, 1.0, 0.1])
+		tris = (centres + rng.normal(scale=0.3, size=(n, 3, 3))).astype(np.float32).reshape(n, 9)
+		tris[: n // 50] = tris[0]
+	else:
+		info = H.dataset(source); vks = H.read_vks(info["vks"])
+		tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	tris = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+	ref_nodes, ref_slots, ref_ids, ref_depth = _probe_bvh(lib, tris, BUILDERS["lbvh"])
+	n = len(tris)
+	nodes = np.zeros((n, 16), dtype=np.float32); slots = np.zeros((n, 12), dtype=np.float32); ids = np.zeros(n, dtype=np.uint32); count = C.c_uint64(); depth = C.c_uint32()
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	assert dev.vkr_device_on_host_lbvh(P(tris), C.c_uint64(n), P(nodes), C.byref(count), P(slots), P(ids), C.byref(depth)) == 0
+	assert count.value == len(ref_nodes) and depth.value == ref_depth
+	assert np.array_equal(ids, ref_ids) and np.array_equal(slots.view(np.uint32), ref_slots.view(np.uint32))
+	assert np.array_equal(nodes[:count.value].view(np.uint32), ref_nodes.view(np.uint32))
+
+
 def test_lbvh_follows_the_morton_order_of_the_centroids():
 	"""What the GPU builder has to reproduce: slots in ascending (Morton code of the centroid, original index) order, leaves of up to four slots."""
 	lib = api.load_library()
