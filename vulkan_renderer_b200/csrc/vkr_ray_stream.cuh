@@ -239,28 +239,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 #if VKR_BVH_WIDTH == 4
 		// EXPERIMENTAL variant (tools/build_variant.sh ... "-DVKR_BVH_WIDTH=4" with VKR_BVH_WIDTH=4 in the environment when the scene is loaded): 128-byte
 		// nodes with four children (vkr_bvh.h: host_bvh4), half as many steps per ray. The nearest hit child is entered, the others go on the stack
-		// (leaves too: pop() hands them back like any reference). Written without GPU access; the per-thread form occluded4() is tested on the CPU.
+		// (leaves too: pop() hands them back like any reference). The node step is bvh4_descend_step() of vkr_trace.cuh, shared with occluded4(), which is tested
+		// on the CPU; this warp loop around it was written without GPU access.
 		while (node >= 0 && node != kTraversalDone) {
-			const float4* nd = nodes + 8 * (size_t) node;
-			const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4), q5 = __ldg(nd + 5), q6 = __ldg(nd + 6);
-			const int ref0 = __float_as_int(q6.x), ref1 = __float_as_int(q6.y), ref2 = __float_as_int(q6.z), ref3 = __float_as_int(q6.w);
-			float tn0, tn1, tn2, tn3;
-			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
-			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
-			const bool h2 = ray_box(q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, r, tmin, tmax, &tn2);
-			const bool h3 = ray_box(q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, r, tmin, tmax, &tn3);
-			const float inf = __int_as_float(0x7f800000);
-			const float d0 = h0 ? tn0 : inf, d1 = h1 ? tn1 : inf, d2 = h2 ? tn2 : inf, d3 = h3 ? tn3 : inf;
-			int best = -1; float best_t = inf;
-			if (h0) { best = 0; best_t = d0; }
-			if (h1 && d1 < best_t) { best = 1; best_t = d1; }
-			if (h2 && d2 < best_t) { best = 2; best_t = d2; }
-			if (h3 && d3 < best_t) { best = 3; best_t = d3; }
-			if (h0 && best != 0) push(ref0);
-			if (h1 && best != 1) push(ref1);
-			if (h2 && best != 2) push(ref2);
-			if (h3 && best != 3) push(ref3);
-			node = (best < 0) ? pop() : ((best == 0) ? ref0 : ((best == 1) ? ref1 : ((best == 2) ? ref2 : ref3)));
+			node = bvh4_descend_step(nodes, node, r, tmin, tmax, push); // nearest hit child; the other hit children are on the stack now
+			if (node == kTraversalDone) node = pop();
 			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
 				leaf = node;
 				node = pop();

@@ -111,35 +111,53 @@ VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, i
 	}
 }
 
-// Any-hit query over 4-wide nodes (vkr_bvh.h: host_bvh4; 8 x float4 per node). Same predicate, same answer as occluded(); the node test
-// decides four children at once, so a ray takes about half as many steps. Groundwork for a 4-wide trace loop;
-// `steps` counts the nodes fetched (statistics for the tests, may be null).
+// One step through a 4-wide node (vkr_bvh.h: host_bvh4; 8 x float4 per node: child c has centre and half extent at floats [6c, 6c + 6), the four
+// references as int bits in the seventh float4). Tests the four boxes, returns the reference of the nearest hit child and hands the other hit
+// children (inner nodes and leaves alike) to push(); returns kTraversalDone if no child is hit. Shared by occluded4() below (tested on the CPU)
+// and by the experimental 4-wide form of the trace warps' loop (vkr_ray_stream.cuh, VKR_BVH_WIDTH == 4).
+template <class Push>
+VKR_DEV int bvh4_descend_step(const float4* __restrict__ nodes4, int node, const ray_slabs& r, float tmin, float tmax, Push&& push) {
+	const float4* nd = nodes4 + 8 * (size_t) node;
+	const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4), q5 = __ldg(nd + 5), q6 = __ldg(nd + 6);
+	const int ref0 = __float_as_int(q6.x), ref1 = __float_as_int(q6.y), ref2 = __float_as_int(q6.z), ref3 = __float_as_int(q6.w);
+	float tn0, tn1, tn2, tn3;
+	const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
+	const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
+	const bool h2 = ray_box(q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, r, tmin, tmax, &tn2);
+	const bool h3 = ray_box(q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, r, tmin, tmax, &tn3);
+	int best = -1; float best_t = 0.0f;
+	if (h0) { best = 0; best_t = tn0; }
+	if (h1 && (best < 0 || tn1 < best_t)) { best = 1; best_t = tn1; }
+	if (h2 && (best < 0 || tn2 < best_t)) { best = 2; best_t = tn2; }
+	if (h3 && (best < 0 || tn3 < best_t)) { best = 3; best_t = tn3; }
+	if (h0 && best != 0) push(ref0);
+	if (h1 && best != 1) push(ref1);
+	if (h2 && best != 2) push(ref2);
+	if (h3 && best != 3) push(ref3);
+	return (best < 0) ? kTraversalDone : ((best == 0) ? ref0 : ((best == 1) ? ref1 : ((best == 2) ? ref2 : ref3)));
+}
+
+// Any-hit query over 4-wide nodes. Same predicate, same answer as occluded(); a step decides four children at once, so a ray takes about half as
+// many steps. `steps` counts the nodes fetched (statistics for the tests, may be null).
 VKR_DEV bool occluded4(const float4* __restrict__ nodes4, const float4* __restrict__ tris, f3 o, f3 d, float tmin, float tmax, int* stack, int stride, int* steps) {
 	if (!(tmax > tmin)) return false;
 	const ray_slabs r = make_slabs(o, d);
 	int sp = 0;
 	int node = 0;
-	float t, tn;
+	float t;
+	auto push = [&](int ref) { stack[sp * stride] = ref; ++sp; };
 	while (true) {
-		if (steps) ++*steps;
-		const float4* n = nodes4 + 8 * (size_t) node;
-		const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2), q3 = __ldg(n + 3), q4 = __ldg(n + 4), q5 = __ldg(n + 5), q6 = __ldg(n + 6);
-		const float b[24] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w };
-		const int refs[4] = { __float_as_int(q6.x), __float_as_int(q6.y), __float_as_int(q6.z), __float_as_int(q6.w) };
-		int next = kTraversalDone;
-#pragma unroll
-		for (int c = 0; c != 4; ++c) {
-			if (!ray_box(b[6 * c], b[6 * c + 1], b[6 * c + 2], b[6 * c + 3], b[6 * c + 4], b[6 * c + 5], r, tmin, tmax, &tn)) continue;
-			if (refs[c] < 0) {
-				const int first = (refs[c] & 0x7fffffff) >> 4, count = refs[c] & 15;
-				for (int i = 0; i != count; ++i)
-					if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) return true;
-			}
-			else if (next == kTraversalDone) next = refs[c];
-			else { stack[sp * stride] = refs[c]; ++sp; }
+		if (node < 0) { // a leaf
+			const int first = (node & 0x7fffffff) >> 4, count = node & 15;
+			for (int i = 0; i != count; ++i)
+				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) return true;
+			node = kTraversalDone;
 		}
-		if (next != kTraversalDone) node = next;
 		else {
+			if (steps) ++*steps;
+			node = bvh4_descend_step(nodes4, node, r, tmin, tmax, push);
+		}
+		if (node == kTraversalDone) {
 			if (sp == 0) return false;
 			--sp; node = stack[sp * stride];
 		}
