@@ -76,87 +76,6 @@ int upload(void** d_ptr, const void* src, size_t bytes, const vkr_device_t* devi
 }
 
 // ------------------------------------------------------------------------------------------------
-// *.vkt material textures (format: src/textures.c:111-169). Only one texel per texture is used:
-// materials are treated as constant (the smallest mip level = the texture average), SURVEY 8d.
-// ------------------------------------------------------------------------------------------------
-static float half_to_float_bits(uint16_t h) {
-	const uint32_t sign = (uint32_t) (h & 0x8000u) << 16;
-	uint32_t exp = (h >> 10) & 31u, man = h & 1023u, bits;
-	if (exp == 0) {
-		if (man == 0) bits = sign;
-		else { int e = -1; do { ++e; man <<= 1; } while (!(man & 1024u)); bits = sign | ((uint32_t) (127 - 15 - e) << 23) | ((man & 1023u) << 13); }
-	}
-	else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
-	else bits = sign | ((exp + 112u) << 23) | (man << 13);
-	float f; memcpy(&f, &bits, 4); return f;
-}
-static float srgb_to_linear(float c) { return (c <= 0.04045f) ? (c / 12.92f) : powf((c + 0.055f) / 1.055f, 2.4f); }
-
-// Returns the first texel of the smallest mip level as 4 floats
-static int read_vkt_constant(float out[4], const char* path) {
-	FILE* file = fopen(path, "rb");
-	if (!file) { printf("Failed to open the texture file at path %s.\n", path); return 1; }
-	uint32_t marker = 0, version = 0, mips = 0, res[2] = {0, 0}, format = 0; uint64_t size = 0;
-	fread(&marker, 4, 1, file); fread(&version, 4, 1, file);
-	if (marker != 0xbc1bc1 || version != 1) { printf("The texture at path %s does not have the *.vkt format. Aborting.\n", path); fclose(file); return 1; }
-	fread(&mips, 4, 1, file); fread(res, 4, 2, file); fread(&format, 4, 1, file); fread(&size, 8, 1, file);
-	if (mips == 0 || mips > 32) { fclose(file); return 1; }
-	uint64_t last_size = 0, last_offset = 0;
-	for (uint32_t k = 0; k != mips; ++k) {
-		uint32_t r[2]; uint64_t s, o;
-		fread(r, 4, 2, file); fread(&s, 8, 1, file); fread(&o, 8, 1, file);
-		last_size = s; last_offset = o;
-	}
-	const long payload = ftell(file);
-	uint8_t texel[16] = {0};
-	fseek(file, payload + (long) last_offset, SEEK_SET);
-	fread(texel, 1, last_size < 16 ? (size_t) last_size : 16, file);
-	fseek(file, payload + (long) size, SEEK_SET);
-	uint32_t eof_marker = 0; fread(&eof_marker, 4, 1, file);
-	fclose(file);
-	if (eof_marker != 0xE0FE0F) { printf("The texture file at path %s seems to be invalid. The texture data is not followed by the expected end of file marker.\n", path); return 1; }
-	out[0] = out[1] = out[2] = 0.0f; out[3] = 1.0f;
-	switch (format) {
-	case 97: { uint16_t h[4]; memcpy(h, texel, 8); for (int i = 0; i != 4; ++i) out[i] = half_to_float_bits(h[i]); break; }   // R16G16B16A16_SFLOAT
-	case 90: { uint16_t h[3]; memcpy(h, texel, 6); for (int i = 0; i != 3; ++i) out[i] = half_to_float_bits(h[i]); break; }   // R16G16B16_SFLOAT
-	case 109: memcpy(out, texel, 16); break;                                                                                   // R32G32B32A32_SFLOAT
-	case 106: memcpy(out, texel, 12); break;                                                                                   // R32G32B32_SFLOAT
-	case 37: for (int i = 0; i != 4; ++i) out[i] = texel[i] / 255.0f; break;                                                   // R8G8B8A8_UNORM
-	case 43: for (int i = 0; i != 3; ++i) out[i] = srgb_to_linear(texel[i] / 255.0f); out[3] = texel[3] / 255.0f; break;       // R8G8B8A8_SRGB
-	case 131: case 132: { // BC1: texel (0,0) of the first block
-		uint16_t c0, c1; memcpy(&c0, texel, 2); memcpy(&c1, texel + 2, 2);
-		const uint32_t idx = texel[4] & 3u;
-		float a[3] = { ((c0 >> 11) & 31) / 31.0f, ((c0 >> 5) & 63) / 63.0f, (c0 & 31) / 31.0f };
-		float b[3] = { ((c1 >> 11) & 31) / 31.0f, ((c1 >> 5) & 63) / 63.0f, (c1 & 31) / 31.0f };
-		for (int i = 0; i != 3; ++i) {
-			float v;
-			if (idx == 0) v = a[i]; else if (idx == 1) v = b[i];
-			else if (c0 > c1) v = (idx == 2) ? (2.0f * a[i] + b[i]) / 3.0f : (a[i] + 2.0f * b[i]) / 3.0f;
-			else v = (idx == 2) ? 0.5f * (a[i] + b[i]) : 0.0f;
-			out[i] = (format == 132) ? srgb_to_linear(v) : v;
-		}
-		break; }
-	case 141: { // BC5: two BC4 blocks, texel (0,0)
-		for (int ch = 0; ch != 2; ++ch) {
-			const uint8_t* blk = texel + 8 * ch;
-			const float r0 = blk[0] / 255.0f, r1 = blk[1] / 255.0f;
-			const uint32_t idx = blk[2] & 7u;
-			float v;
-			if (idx == 0) v = r0; else if (idx == 1) v = r1;
-			else if (blk[0] > blk[1]) v = ((8 - idx) * r0 + (idx - 1) * r1) / 7.0f;
-			else if (idx < 6) v = ((6 - idx) * r0 + (idx - 1) * r1) / 5.0f;
-			else v = (idx == 6) ? 0.0f : 1.0f;
-			out[ch] = v;
-		}
-		break; }
-	default:
-		printf("The texture at path %s has VkFormat %u, which this library cannot read.\n", path, format);
-		return 1;
-	}
-	return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // scene (*.vks reader: src/scene.c:419-483; acceleration structure input: src/scene.c:175-187)
 // ------------------------------------------------------------------------------------------------
 extern "C" void vkr_destroy_scene(vkr_scene_t* scene, const vkr_device_t* device) {
@@ -288,55 +207,49 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 		}
 	}
 	scene->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-	// Materials: <texture_path>/<material>_{BaseColor,Specular,Normal}.vkt (scene.c:24-31, 529-533)
+	// Materials: <texture_path>/<material>_{BaseColor,Specular,Normal}.vkt (scene.c:24-31, 529-533), every mip level decoded to RGBA32F (vkr_textures.cpp).
+	// material_params holds the first texel of the smallest mip level (the texture average): all there is to a constant texture. If any texture is
+	// not constant, the chains go to the device and the G-buffer producer filters them (vkr_texture.cuh).
 	scene->material_params = (float*) calloc(8 * (scene->material_count ? scene->material_count : 1), sizeof(float));
 	static const char* suffixes[3] = { "BaseColor", "Specular", "Normal" };
-	for (uint64_t i = 0; i != scene->material_count; ++i) {
+	std::vector<vkr_texture_t> textures(3 * (size_t) scene->material_count);
+	bool failed = false, any_pattern = false;
+	for (uint64_t i = 0; i != scene->material_count && !failed; ++i) {
 		float tex[3][4];
-		for (int j = 0; j != 3; ++j) {
+		for (int j = 0; j != 3 && !failed; ++j) {
 			const std::string path = std::string(texture_path) + "/" + scene->material_names[i] + "_" + suffixes[j] + ".vkt";
-			if (read_vkt_constant(tex[j], path.c_str())) {
-				printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);
-				vkr_destroy_scene(scene, device); return 1;
-			}
+			vkr_texture_t& t = textures[3 * i + j];
+			failed = vkr_load_texture(&t, path.c_str()) != 0;
+			if (failed) break;
+			any_pattern = any_pattern || !t.is_constant;
+			const uint32_t last = t.mip_count - 1;
+			const uint64_t last_texels = (uint64_t) ((t.width >> last) ? (t.width >> last) : 1) * ((t.height >> last) ? (t.height >> last) : 1);
+			memcpy(tex[j], t.h_texels + (t.texel_float_count - 4 * last_texels), sizeof(tex[j]));
 		}
+		if (failed) break;
 		float* mp = scene->material_params + 8 * i;
 		mp[0] = tex[0][0]; mp[1] = tex[0][1]; mp[2] = tex[0][2];
 		mp[3] = tex[1][1]; mp[4] = tex[1][2];
 		mp[5] = tex[2][0]; mp[6] = tex[2][1]; mp[7] = 0.0f;
 	}
-	if (upload(&scene->d_material_params, scene->material_params, sizeof(float) * 8 * scene->material_count, device)) {
-		printf("Failed to upload materials of the scene %s.\n", file_path);
-		vkr_destroy_scene(scene, device); return 1;
+	if (!failed) failed = upload(&scene->d_material_params, scene->material_params, sizeof(float) * 8 * scene->material_count, device) != 0;
+	if (!failed && device && any_pattern) {
+		std::vector<uint32_t> dims(4 * textures.size()); std::vector<uint64_t> offsets(textures.size());
+		uint64_t texel_count = 0;
+		for (size_t k = 0; k != textures.size(); ++k) {
+			dims[4 * k] = textures[k].width; dims[4 * k + 1] = textures[k].height; dims[4 * k + 2] = textures[k].mip_count; dims[4 * k + 3] = 0;
+			offsets[k] = texel_count; texel_count += textures[k].texel_float_count / 4;
+		}
+		std::vector<float> data(4 * (size_t) texel_count);
+		for (size_t k = 0; k != textures.size(); ++k) memcpy(&data[4 * (size_t) offsets[k]], textures[k].h_texels, sizeof(float) * (size_t) textures[k].texel_float_count);
+		failed = upload(&scene->d_texture_data, data.data(), data.size() * 4, device) || upload(&scene->d_texture_dims, dims.data(), dims.size() * 4, device)
+			|| upload(&scene->d_texture_offsets, offsets.data(), offsets.size() * 8, device);
+		scene->textured = 1; scene->texture_texel_count = texel_count;
 	}
-	// Textures that need filtering: every mip level as RGBA32F on the device (vkr_textures.cpp, vkr_texture.cuh)
-	if (device && scene->material_count) {
-		std::vector<vkr_texture_t> textures(3 * (size_t) scene->material_count);
-		bool failed = false, any_pattern = false;
-		for (uint64_t i = 0; i != scene->material_count && !failed; ++i)
-			for (int j = 0; j != 3 && !failed; ++j) {
-				const std::string path = std::string(texture_path) + "/" + scene->material_names[i] + "_" + suffixes[j] + ".vkt";
-				failed = vkr_load_texture(&textures[3 * i + j], path.c_str()) != 0;
-				any_pattern = any_pattern || (!failed && !textures[3 * i + j].is_constant);
-			}
-		if (!failed && any_pattern) {
-			std::vector<uint32_t> dims(4 * textures.size()); std::vector<uint64_t> offsets(textures.size());
-			uint64_t texel_count = 0;
-			for (size_t k = 0; k != textures.size(); ++k) {
-				dims[4 * k] = textures[k].width; dims[4 * k + 1] = textures[k].height; dims[4 * k + 2] = textures[k].mip_count; dims[4 * k + 3] = 0;
-				offsets[k] = texel_count; texel_count += textures[k].texel_float_count / 4;
-			}
-			std::vector<float> data(4 * (size_t) texel_count);
-			for (size_t k = 0; k != textures.size(); ++k) memcpy(&data[4 * (size_t) offsets[k]], textures[k].h_texels, sizeof(float) * (size_t) textures[k].texel_float_count);
-			failed = upload(&scene->d_texture_data, data.data(), data.size() * 4, device) || upload(&scene->d_texture_dims, dims.data(), dims.size() * 4, device)
-				|| upload(&scene->d_texture_offsets, offsets.data(), offsets.size() * 8, device);
-			scene->textured = 1; scene->texture_texel_count = texel_count;
-		}
-		for (vkr_texture_t& t : textures) vkr_destroy_texture(&t);
-		if (failed) {
-			printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);
-			vkr_destroy_scene(scene, device); return 1;
-		}
+	for (vkr_texture_t& t : textures) vkr_destroy_texture(&t);
+	if (failed) {
+		printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);
+		vkr_destroy_scene(scene, device); return 1;
 	}
 	return 0;
 }
