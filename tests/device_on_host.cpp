@@ -32,6 +32,10 @@ static inline void __threadfence() {}
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long) x) : 64; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 
+// warp-level intrinsics: declared so that the ray-stream header parses; the TRACE = false instantiations used here never call them
+unsigned __ballot_sync(unsigned, int); int __any_sync(unsigned, int); int __all_sync(unsigned, int); void __syncwarp(unsigned); int __popc(unsigned); int __ffs(unsigned);
+void __nanosleep(unsigned); unsigned __activemask(); int __shfl_sync(unsigned, int, int); size_t __cvta_generic_to_shared(const void*);
+
 #include "vkr_related_work.cuh"
 #include "vkr_trace.cuh"
 #include "vkr_texture.cuh"
@@ -39,6 +43,7 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 #include <algorithm>
 using std::min; using std::max;   // the integer min / max of the device headers
 #include "vkr_error_display.cuh"
+#include "vkr_shade_light.cuh"
 #include "vkr_lbvh.cuh"
 #include <vector>
 
@@ -200,8 +205,9 @@ extern "C" void vkr_device_on_host_gbuffer(uint32_t width, uint32_t height, cons
 // One frame of the error display modes on the CPU: per pixel the prologue and epilogue of the shading tile (csrc/vkr_shading_tile.cuh: G-buffer read, light
 // display, LTC set-up, noise stream, NaN -> pink, exposure; restated here because that file is warp-level code) around the product's per-light function
 // error_display_of_light() (csrc/vkr_error_display.cuh). Linear output, g_frame_bits = 0.
-template <int MAXV>
-static void error_display_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+// light(sp, l, light_block, ns, x, y, acc): one light for one pixel; acc is the pixel's pixel_sum (vkr_ray_stream.cuh)
+template <int MAXV, class Light>
+static void tile_frame(const shading_kernel_params& p, int show_lights, const Light& light_fn, float* out_rgba) {
 	const unsigned char* cb = p.constants;
 	const size_t plane = (size_t) p.width * p.height;
 	const int light_stride = L_FIXED + 16 * MAXV * 2 + 16 * (MAXV - 2);
@@ -231,6 +237,9 @@ static void error_display_frame(const shading_kernel_params& p, int show_lights,
 					color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
 			}
 		}
+		pixel_sum acc;
+		acc.color = color; acc.light = make3(0.0f, 0.0f, 0.0f); acc.inv_samples = 1.0f / (float) p.sample_count;
+		acc.submit_parity = 0u; acc.resolve_parity = 0u; acc.pushed = false;
 		if (valid) {
 			const float4 g2 = p.gbuffer[2 * plane + pixel], g3 = p.gbuffer[3 * plane + pixel];
 			sp.diffuse_albedo = make3(g2.x, g2.y, g2.z); sp.fresnel_0 = make3(g3.x, g3.y, g3.z);
@@ -240,16 +249,66 @@ static void error_display_frame(const shading_kernel_params& p, int show_lights,
 			get_ltc_coefficients(l, p, cb, sp);
 			noise_stream ns;
 			ns.z = 0.0f; ns.w = 0.0f; ns.available = 0; ns.sample_index = 0;
-			for (int li = 0; li != p.light_count; ++li) {
-				f3 contribution;
-				if (error_display_of_light<MAXV>(&contribution, sp, l, cb + CONSTANTS_FIXED + li * light_stride, ns, p, cb, (uint32_t) x, (uint32_t) y)) color = color + contribution;
-			}
+			for (int li = 0; li != p.light_count; ++li) light_fn(sp, l, cb + CONSTANTS_FIXED + li * light_stride, ns, (uint32_t) x, (uint32_t) y, acc);
 		}
+		color = acc.color;
 		f3 final_color = color;
 		if (std::isnan(color.x) || std::isnan(color.y) || std::isnan(color.z) || std::isinf(color.x) || std::isinf(color.y) || std::isinf(color.z))
 			final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
 		float* o = out_rgba + 4 * pixel;
 		o[0] = final_color.x * exposure; o[1] = final_color.y * exposure; o[2] = final_color.z * exposure; o[3] = 1.0f;
+	}
+}
+
+template <int MAXV>
+static void error_display_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+	tile_frame<MAXV>(p, show_lights, [&](const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns, uint32_t x, uint32_t y, pixel_sum& acc) {
+		f3 contribution;
+		if (error_display_of_light<MAXV>(&contribution, sp, l, light, ns, p, p.constants, x, y)) acc.color = acc.color + contribution;
+	}, out_rgba);
+}
+
+// The shading pass without shadow rays (TRACE = false: every candidate sample is added in place) with the product's shade_light() (csrc/vkr_shade_light.cuh)
+template <int STRATEGY, int MAXV, bool BIASED, bool OPTIMAL>
+static void shading_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+	tile_frame<MAXV>(p, show_lights, [&](const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns, uint32_t x, uint32_t y, pixel_sum& acc) {
+		ray_producer q; q.base = 0; q.fill = 0; q.resolved = 0;
+		shade_light<STRATEGY, MAXV + 1, BIASED, OPTIMAL, false>(true, sp, l, light, ns, p, p.constants, x, y, q, acc, 0);
+	}, out_rgba);
+}
+
+template <int MAXV, bool BIASED>
+static int shading_frame_strategy(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+	switch (p.sampling_strategies) {
+	case VKR_STRATEGY_DIFFUSE_ONLY: shading_frame<VKR_STRATEGY_DIFFUSE_ONLY, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_GGX_MIS: shading_frame<VKR_STRATEGY_DIFFUSE_GGX_MIS, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_SPECULAR_MIS:
+		if (p.mis_heuristic == VKR_MIS_OPTIMAL) shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, true>(p, show_lights, out_rgba);
+		else shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, false>(p, show_lights, out_rgba);
+		return 0;
+	case VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	default: return 1;
+	}
+}
+
+// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0.
+extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t strategy, uint32_t heuristic, int biased, uint32_t sample_count, int show_lights,
+	const void* constants, const float* gbuffer, const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers, float* out_rgba)
+{
+	shading_kernel_params p;
+	memset(&p, 0, sizeof(p));
+	p.width = (int) width; p.height = (int) height; p.gbuffer = reinterpret_cast<const float4*>(gbuffer); p.constants = (const unsigned char*) constants;
+	p.light_count = (int) light_count; p.max_light_vertex_count = (int) maxv; p.sample_count = (int) sample_count;
+	p.sampling_strategies = (int) strategy; p.mis_heuristic = (int) heuristic; p.biased_sampling = biased; p.polygon_sampling_technique = biased ? 12 : 11;
+	p.noise = noise; p.noise_w = (int) noise_w; p.noise_h = (int) noise_h; p.noise_layers = (int) noise_layers;
+	p.ltc0 = ltc0; p.ltc1 = ltc1; p.ltc_res = (int) ltc_res; p.ltc_layers = (int) ltc_layers;
+	switch (maxv) {
+#define V(K) case K: return biased ? shading_frame_strategy<K, true>(p, show_lights, out_rgba) : shading_frame_strategy<K, false>(p, show_lights, out_rgba);
+	V(3) V(4) V(5) V(6) V(7)
+#undef V
+	default: return 1;
 	}
 }
 

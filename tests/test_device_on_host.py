@@ -211,6 +211,43 @@ def test_error_display_light_shader_reproduces_the_reference_shader_fixtures(nam
 	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
 
 
+def _base_fixture_names():
+	import os
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	return sorted({k.split("/")[0] for k in g.files if not any(t in k.split("/")[0] for t in ("_q", "_e", "_x", "_o"))})
+
+
+@pytest.mark.parametrize("name", _base_fixture_names())
+def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
+	"""csrc/vkr_shade_light.cuh -- shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE = false>, the per-(pixel, light) body of the benchmark kernel with the
+	shadow test compiled out -- executed on the CPU for whole frames of every base fixture configuration (all strategies, heuristics, vertex bounds 3..7, mixed
+	vertex counts, 1..32 lights, up to 256 spp). Against the oracle with rays off; the fixtures the reference shader rendered with rays off are compared
+	directly as well. Bit-identical. With test_host_logic's traversal tests this leaves only the warp-level ray ring of the GPU path unexercised on the CPU."""
+	import os
+	from tests.test_ref_shader import _config_from_name, oracle_cfg
+	from tests.ref_frames import WIDTH, HEIGHT, dataset_for
+	lib = _lib()
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	constants = bytes(g[name + "/constants"])
+	gb = np.ascontiguousarray(oi.gbuffer(WIDTH, HEIGHT, constants, g[name + "/visibility"]), dtype=np.float32)
+	out = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	noise = np.ascontiguousarray(oi.noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(oi.ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(oi.ltc1, dtype=np.uint16)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["strategy"]),
+		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), P(out))
+	assert rc == 0
+	no_rays = dict(cfg, trace=0)
+	ref, _ = oi.shade(oracle_cfg(no_rays), constants, gb)
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+	if cfg["trace"] == 0:
+		fixture = g[name + "/rgba"]
+		assert np.array_equal(out.view(np.uint32), fixture.view(np.uint32)), H.compare_radiance(out, fixture)
+
+
 def test_samples_point_at_the_light_and_densities_integrate():
 	"""Sanity of the oracle side itself (not only agreement): directions are unit vectors that hit the light's plane in front of the
 	shading point, and 1/density averages to the solid angle for the solid-angle techniques (2, 3, 4 agree with each other)."""

@@ -128,35 +128,36 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, pixel_sum& acc) {
 // finish (warp-uniform) = end of a light. Nothing waits here: the light's sum is closed when its last entry resolves.
 template <bool TRACE, bool OPTIMAL>
 VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir_world, float tmax, f3 c_visible, f3 c_occluded, pixel_sum& acc, bool finish) {
-	if (!TRACE) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
+	if constexpr (!TRACE) { // no shadow rays: visibility = (n.w > 0), nothing is ever pending, add in place
 		if (has) {
 			if (need_trace) acc.light = acc.light + c_visible;
 			else if (OPTIMAL) acc.light = acc.light + c_occluded;
 		}
 		if (finish) close_light(acc);
-		return;
 	}
-	const bool push = has && (need_trace || OPTIMAL);
-	const unsigned mask = __ballot_sync(kFullMask, push);
-	if (mask) {
-		const int k = __popc(mask);
-		while (q.fill + k - q.resolved > kRing) resolve_chunk<OPTIMAL>(q, lane, acc);
-		if (push) {
-			const uint32_t e = (uint32_t) (q.fill + __popc(mask & ((1u << lane) - 1u))) & (kRing - 1);
-			const uint32_t a = q.base + 4u * e;
-			sts_f(a + 4u * S_DX, dir_world.x); sts_f(a + 4u * S_DY, dir_world.y); sts_f(a + 4u * S_DZ, dir_world.z); sts_f(a + 4u * S_TMAX, tmax);
-			sts_f(a + 4u * S_CX, c_visible.x); sts_f(a + 4u * S_CY, c_visible.y); sts_f(a + 4u * S_CZ, c_visible.z);
-			if (OPTIMAL) { sts_f(a + 4u * S_OX, c_occluded.x); sts_f(a + 4u * S_OY, c_occluded.y); sts_f(a + 4u * S_OZ, c_occluded.z); }
-			const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
-			sts_u8(bytes + e, (unsigned) lane | acc.submit_parity | (need_trace ? 0u : 128u));
-			sts_u8(bytes + kRing + e, need_trace ? kPending : 1u);
-			acc.pushed = true;
+	else {
+		const bool push = has && (need_trace || OPTIMAL);
+		const unsigned mask = __ballot_sync(kFullMask, push);
+		if (mask) {
+			const int k = __popc(mask);
+			while (q.fill + k - q.resolved > kRing) resolve_chunk<OPTIMAL>(q, lane, acc);
+			if (push) {
+				const uint32_t e = (uint32_t) (q.fill + __popc(mask & ((1u << lane) - 1u))) & (kRing - 1);
+				const uint32_t a = q.base + 4u * e;
+				sts_f(a + 4u * S_DX, dir_world.x); sts_f(a + 4u * S_DY, dir_world.y); sts_f(a + 4u * S_DZ, dir_world.z); sts_f(a + 4u * S_TMAX, tmax);
+				sts_f(a + 4u * S_CX, c_visible.x); sts_f(a + 4u * S_CY, c_visible.y); sts_f(a + 4u * S_CZ, c_visible.z);
+				if (OPTIMAL) { sts_f(a + 4u * S_OX, c_occluded.x); sts_f(a + 4u * S_OY, c_occluded.y); sts_f(a + 4u * S_OZ, c_occluded.z); }
+				const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
+				sts_u8(bytes + e, (unsigned) lane | acc.submit_parity | (need_trace ? 0u : 128u));
+				sts_u8(bytes + kRing + e, need_trace ? kPending : 1u);
+				acc.pushed = true;
+			}
+			q.fill += k;
+			__syncwarp(kFullMask);
+			if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 4u, q.fill);
 		}
-		q.fill += k;
-		__syncwarp(kFullMask);
-		if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 4u, q.fill);
+		if (finish && acc.pushed) { acc.submit_parity ^= 32u; acc.pushed = false; }
 	}
-	if (finish && acc.pushed) { acc.submit_parity ^= 32u; acc.pushed = false; }
 }
 
 // End of the tile: resolves what is still pending, closes the last light and tells the trace warps that no ticket

@@ -315,4 +315,12 @@ VKR_DEV float ggx_reflected_direction_density(float o_dot_n, f3 o, f3 i, f3 n, f
 }
 
 
+// Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
+VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
+	const float num = dot4_point(light + L_PLANE, sp.position);
+	const float den = dot(dir_world, make3(ldf(light, L_PLANE), ldf(light, L_PLANE + 4), ldf(light, L_PLANE + 8)));
+	return -num / den;
+}
+VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8)); }
+
 } // namespace vkr

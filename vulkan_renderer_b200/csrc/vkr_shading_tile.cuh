@@ -22,14 +22,6 @@ constexpr int kTraceThreads = 32 * kTraceWarps;
 #define VKR_TRACE_REGS 56
 #endif
 
-// Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
-VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
-	const float num = dot4_point(light + L_PLANE, sp.position);
-	const float den = dot(dir_world, make3(ldf(light, L_PLANE), ldf(light, L_PLANE + 4), ldf(light, L_PLANE + 8)));
-	return -num / den;
-}
-VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8)); }
-
 // LightShader: void operator()(bool on, const shading_point&, const ltc_state&, const unsigned char* light, noise_stream&,
 //   const shading_kernel_params&, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer&, pixel_sum&, int lane) const
 // -- one polygonal light for the warp's 32 pixels; control flow must be warp-uniform (`on` masks lanes).
