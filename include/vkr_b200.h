@@ -198,6 +198,23 @@ int vkr_quick_load(vkr_scene_specification_t* spec, const char* quick_save_path)
 int vkr_quick_save(const vkr_scene_specification_t* spec, const char* quick_save_path);
 void vkr_destroy_scene_specification(vkr_scene_specification_t* spec);
 
+/* ---- light textures (replaces create_and_assign_light_textures / destroy_light_textures, src/main.c:364-418; sampled by
+        get_polygon_radiance(), src/shaders/shading_pass.frag.glsl:151-185). The unique texture_file_path entries of the lights, in the
+        order of their first use, each decoded to an RGBA32F mip chain (level 0 is what the shader reads); lights without a path or
+        with a path that cannot be opened share a white texture (the reference's data/white.vkt), with the reference's message.
+        Sets polygonal_lights[i].texture_index. light_textures = NULL: indices only (as the reference does at src/main.c:2167);
+        device = NULL: host copies only. */
+typedef struct vkr_light_textures_s {
+	uint32_t texture_count;
+	vkr_texture_t* textures;
+	void* d_texels;      /* float4 texels of all textures, chain after chain */
+	void* d_dims;        /* uint4 {width, height, mip_count, 0} per texture */
+	void* d_offsets;     /* uint64 index of the first texel of each texture in d_texels */
+	uint64_t texel_count;
+} vkr_light_textures_t;
+int vkr_create_and_assign_light_textures(vkr_light_textures_t* light_textures, const vkr_device_t* device, vkr_scene_specification_t* spec);
+void vkr_destroy_light_textures(vkr_light_textures_t* light_textures, const vkr_device_t* device);
+
 /* ---- render settings (the subset of render_settings_t, src/main.h:128-159, the shading pass consumes) */
 typedef struct vkr_render_settings_s {
 	float exposure_factor, roughness_factor;
@@ -277,6 +294,9 @@ typedef struct vkr_shading_pass_desc_s {
 	/* ERROR_DISPLAY_DIFFUSE / ERROR_DISPLAY_SPECULAR / ERROR_INDEX (src/main.c:735-750, 788-790); the scale comes from error_min_exponent
 	   in the render settings via g_error_factor in the constant block */
 	vkr_error_display_t error_display;
+	/* textures of the polygonal lights (g_light_textures); may be NULL as long as no light of a frame's constant block is textured.
+	   Frames with textured lights need projected solid angle sampling (technique 11 or 12) and no error display. */
+	const vkr_light_textures_t* light_textures;
 } vkr_shading_pass_desc_t;
 
 typedef struct vkr_shading_pass_s {

@@ -36,8 +36,9 @@ def _p(a):
 	return a.ctypes.data_as(C.c_void_p)
 
 
-def shade(cfg, constants, gbuffer, noise, ltc0, ltc1, tris):
-	"""cfg: dict of Config fields. Returns (rgba float32 [H,W,4], shadow ray count)."""
+def shade(cfg, constants, gbuffer, noise, ltc0, ltc1, tris, light_textures=None):
+	"""cfg: dict of Config fields. light_textures: None or (dims uint32 [T,3], offsets uint64 [T] in floats, data float32), the textures the lights'
+	texture_index refers to. Returns (rgba float32 [H,W,4], shadow ray count)."""
 	lib = load()
 	c = Config(**{"polygon_sampling_technique": 11, **cfg})
 	gbuffer = np.ascontiguousarray(gbuffer, dtype=np.float32)
@@ -46,8 +47,14 @@ def shade(cfg, constants, gbuffer, noise, ltc0, ltc1, tris):
 	out = np.zeros((c.height, c.width, 4), dtype=np.float32)
 	rays = C.c_uint64(0)
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
-	rc = lib.vkr_oracle_shade(C.byref(c), cb, _p(gbuffer), _p(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]),
-		_p(ltc0), _p(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), _p(tris), C.c_uint32(len(tris)), _p(out), C.byref(rays))
+	if light_textures is None:
+		count, dims, offsets, data = 0, None, None, None
+	else:
+		dims = np.ascontiguousarray(light_textures[0], dtype=np.uint32); offsets = np.ascontiguousarray(light_textures[1], dtype=np.uint64); data = np.ascontiguousarray(light_textures[2], dtype=np.float32)
+		count = len(dims)
+	rc = lib.vkr_oracle_shade_with_light_textures(C.byref(c), cb, _p(gbuffer), _p(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]),
+		_p(ltc0), _p(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), _p(tris), C.c_uint32(len(tris)),
+		C.c_uint32(count), _p(dims) if count else None, _p(offsets) if count else None, _p(data) if count else None, _p(out), C.byref(rays))
 	if rc != 0:
 		raise RuntimeError("vkr_oracle_shade failed")
 	return out, rays.value
@@ -179,3 +186,12 @@ def related_work_batch(technique, maxv, light_block, position, frame, random_num
 	if on < 0:
 		raise RuntimeError("unsupported technique / vertex bound")
 	return None if on == 0 else (dirs, dens, float(ggx.value))
+
+
+def light_texture_batch(texture, uv):
+	"""textureLod(..., 0) with the light-texture sampler (repeat in u, clamp in v) on one RGBA32F level [H, W, 4] for uv float32 [n, 2]."""
+	lib = load()
+	texture = np.ascontiguousarray(texture, dtype=np.float32); uv = np.ascontiguousarray(uv, dtype=np.float32)
+	out = np.zeros((len(uv), 4), dtype=np.float32)
+	lib.vkr_oracle_light_texture_batch(C.c_uint32(texture.shape[1]), C.c_uint32(texture.shape[0]), _p(texture), C.c_uint32(len(uv)), _p(uv), _p(out))
+	return out

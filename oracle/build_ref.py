@@ -45,6 +45,8 @@ def config_name(c):
 		name += "_e%d" % c["error_display"]
 	if c.get("textured", 0):                          # same -D defines, material textures that need filtering (data set mini_textured)
 		name += "_x1"
+	if c.get("light_textures", 0):                    # same -D defines, lights with area / portal / IES textures (data set mini_lit)
+		name += "_y1"
 	if c.get("srgb", 0) or c.get("frame_bits", 0):   # output stage: o<srgb><frame_bits>
 		name += "_o%d%d" % (c.get("srgb", 0), c.get("frame_bits", 0))
 	return name
@@ -54,7 +56,7 @@ def defines(c):
 	"""The -D list of create_shading_pass (src/main.c:752-792) for one configuration."""
 	d = {
 		"MATERIAL_COUNT": c["materials"], "POLYGONAL_LIGHT_COUNT": c["lights"], "POLYGONAL_LIGHT_ARRAY_SIZE": max(c["lights"], 1),
-		"POLYGONAL_LIGHT_COUNT_CLAMPED": min(c["lights"], 33), "LIGHT_TEXTURE_COUNT": 1,
+		"POLYGONAL_LIGHT_COUNT_CLAMPED": min(c["lights"], 33), "LIGHT_TEXTURE_COUNT": 4,
 		"MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING": c.get("min_vertices", c["max_vertices"]), "MAX_POLYGONAL_LIGHT_VERTEX_COUNT": c["max_vertices"],
 		"MAX_POLYGON_VERTEX_COUNT": c["max_vertices"] + (1 if c.get("technique", 11) in CLIPPING_TECHNIQUES else 0), "SAMPLE_COUNT": c["samples"], "SAMPLE_COUNT_CLAMPED": min(c["samples"], 33),
 		"TRACE_SHADOW_RAYS": c["trace"], "SHOW_POLYGONAL_LIGHTS": c["show_lights"],
@@ -156,6 +158,13 @@ def default_configs():
 		configs.append(dict(base, error_display=error_display, **extra))
 	configs.append(dict(base, textured=1))                                   # get_shading_data with filtered material textures
 	configs.append(dict(base, textured=1, strategy=1, heuristic=1, trace=0))
+	# lights with textures (get_polygon_radiance, shading_pass.frag.glsl:151-185): an area texture, a light probe behind a portal, an IES profile
+	configs.append(dict(base, light_textures=1))
+	configs.append(dict(base, light_textures=1, strategy=1, heuristic=0))
+	configs.append(dict(base, light_textures=1, strategy=0, heuristic=0))
+	configs.append(dict(base, light_textures=1, trace=0))
+	configs.append(dict(base, light_textures=1, trace=0, heuristic=4))
+	configs.append(dict(base, light_textures=1, strategy=0, heuristic=0, technique=4))
 	for srgb, frame_bits in [(1, 0), (0, 1), (0, 2), (1, 1), (1, 2)]:         # output stage: sRGB conversion, half-bit split for HDR screenshots (frame_bits is a uniform)
 		configs.append(dict(base, srgb=srgb, frame_bits=frame_bits))
 	return configs
@@ -177,8 +186,8 @@ def build(configs=None, verbose=False):
 	names = []
 	for c in configs:
 		name = config_name(c)
-		if c.get("textured", 0):   # textures are inputs, not defines: the entry point of the untextured configuration serves
-			names.append(dict(c, name=name, entry="ref_shade_" + config_name(dict(c, textured=0))))
+		if c.get("textured", 0) or c.get("light_textures", 0):   # textures are inputs, not defines: the entry point of the untextured configuration serves
+			names.append(dict(c, name=name, entry="ref_shade_" + config_name(dict(c, textured=0, light_textures=0))))
 			continue
 		names.append(dict(c, name=name, entry="ref_shade_" + name))
 		obj = os.path.join(OUT, name + ".o")
@@ -193,7 +202,7 @@ def build(configs=None, verbose=False):
 			sys.stderr.write("---- %s\n%s\n" % (name, out[-6000:]))
 	if failed:
 		raise SystemExit("build_ref: compiling the reference shader as C++ failed")
-	compiled = {n["entry"] for n in names if not n.get("textured", 0)}
+	compiled = {n["entry"] for n in names if not (n.get("textured", 0) or n.get("light_textures", 0))}
 	missing = [n["name"] for n in names if n["entry"] not in compiled]
 	if missing:
 		raise SystemExit("build_ref: textured configurations without an untextured twin: %s" % missing)

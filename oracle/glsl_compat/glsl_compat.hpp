@@ -321,7 +321,13 @@ inline vec4 textureGrad(const sampler2D& s, const vec2& uv, const vec2& ddx, con
 	vkr_texture_grad(out, s.texture, mk2(uv.x, uv.y), mk2(ddx.x, ddx.y), mk2(ddy.x, ddy.y));
 	return vec4(out[0], out[1], out[2], out[3]);
 }
-inline vec4 textureLod(const sampler2D& s, const vec2&, float) { return vec4(s.value[0], s.value[1], s.value[2], s.value[3]); }
+// only the light textures are read with textureLod() (shading_pass.frag.glsl:182, level 0; sampler src/main.c:613-623: repeat in u, clamp to edge in v)
+inline vec4 textureLod(const sampler2D& s, const vec2& c, float) {
+	if (!s.texture) return vec4(s.value[0], s.value[1], s.value[2], s.value[3]);
+	float t[4];
+	vkr_texture_bilinear_repeat_clamp(t, s.texture, c.x, c.y);
+	return vec4(t[0], t[1], t[2], t[3]);
+}
 
 inline void rayQueryInitializeEXT(rayQueryEXT& q, const accelerationStructureEXT&, uint, uint, const vec3& origin, float tmin, const vec3& dir, float tmax) {
 	q.hit = g_occluded_hook(g_occluded_user, origin.d, dir.d, tmin, tmax) != 0;

@@ -19,5 +19,7 @@ typedef struct ref_args_s {
 	/* material textures as mip chains (NULL: constant materials from material_params): 3 per material {base colour, specular, normal};
 	   texture_dims = {width, height, mip_count} per texture, texture_offsets = first float of level 0 in texture_data (oracle/texture_filter.h) */
 	const uint32_t* texture_dims; const uint64_t* texture_offsets; const float* texture_data;
+	/* light textures (g_light_textures; the lights' texture_index is in the constant block), same conventions; count <= LIGHT_TEXTURE_COUNT = 4 */
+	uint32_t light_texture_count; const uint32_t* light_texture_dims; const uint64_t* light_texture_offsets; const float* light_texture_data;
 } ref_args_t;
 #endif

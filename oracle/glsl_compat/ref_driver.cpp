@@ -85,7 +85,15 @@ static void set_uniforms(const ref_args_t* a) {
 		}
 	}
 	sampler2D white = {{1.0f, 1.0f, 1.0f, 1.0f}, nullptr};
-	for (int i = 0; i != LIGHT_TEXTURE_COUNT; ++i) g_light_textures[i] = white;
+	static thread_local vkr_texture_view_t light_views[LIGHT_TEXTURE_COUNT];
+	for (int i = 0; i != LIGHT_TEXTURE_COUNT; ++i) {
+		g_light_textures[i] = white;
+		if ((uint32_t) i < a->light_texture_count) {
+			light_views[i].width = a->light_texture_dims[3 * i]; light_views[i].height = a->light_texture_dims[3 * i + 1]; light_views[i].mip_count = a->light_texture_dims[3 * i + 2];
+			light_views[i].texels = a->light_texture_data + a->light_texture_offsets[i];
+			g_light_textures[i].texture = &light_views[i];
+		}
+	}
 	g_noise_table.data = a->noise; g_noise_table.w = (int) a->noise_w; g_noise_table.h = (int) a->noise_h; g_noise_table.layers = (int) a->noise_layers;
 	g_ltc_tables[0].data = a->ltc0; g_ltc_tables[0].res = (int) a->ltc_res; g_ltc_tables[0].layers = (int) a->ltc_layers; g_ltc_tables[0].channels = 4;
 	g_ltc_tables[1].data = a->ltc1; g_ltc_tables[1].res = (int) a->ltc_res; g_ltc_tables[1].layers = (int) a->ltc_layers; g_ltc_tables[1].channels = 2;
@@ -93,7 +101,7 @@ static void set_uniforms(const ref_args_t* a) {
 }
 
 extern "C" int REF_ENTRY(ref_args_t* a) {
-	if (a->light_count != POLYGONAL_LIGHT_COUNT || a->sample_count != SAMPLE_COUNT || a->max_light_vertex_count != MAX_POLYGONAL_LIGHT_VERTEX_COUNT || a->material_count > MATERIAL_COUNT) return 1;
+	if (a->light_count != POLYGONAL_LIGHT_COUNT || a->sample_count != SAMPLE_COUNT || a->max_light_vertex_count != MAX_POLYGONAL_LIGHT_VERTEX_COUNT || a->material_count > MATERIAL_COUNT || a->light_texture_count > LIGHT_TEXTURE_COUNT) return 1;
 	set_uniforms(a);
 	const uint32_t y0 = a->row_begin, y1 = a->row_end ? a->row_end : a->height;
 	const double begin = omp_get_wtime();

@@ -22,7 +22,8 @@ class RefArgs(C.Structure):
 		("ltc0", C.c_void_p), ("ltc1", C.c_void_p), ("ltc_res", C.c_uint32), ("ltc_layers", C.c_uint32),
 		("occluded_hook", C.c_void_p), ("occluded_user", C.c_void_p), ("out_rgba", C.c_void_p),
 		("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("band_height", C.c_uint32), ("band_stride", C.c_uint32), ("shade_seconds", C.c_double),
-		("texture_dims", C.c_void_p), ("texture_offsets", C.c_void_p), ("texture_data", C.c_void_p)]
+		("texture_dims", C.c_void_p), ("texture_offsets", C.c_void_p), ("texture_data", C.c_void_p),
+		("light_texture_count", C.c_uint32), ("light_texture_dims", C.c_void_p), ("light_texture_offsets", C.c_void_p), ("light_texture_data", C.c_void_p)]
 
 
 def available():
@@ -71,7 +72,7 @@ def find_config(**wanted):
 	return None
 
 
-def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris, row_begin=0, row_end=0, band_height=0, band_stride=0, textures=None):
+def shade(entry, width, height, cfg, constants, visibility, vks, material_params, noise, ltc0, ltc1, shadow_tris, row_begin=0, row_end=0, band_height=0, band_stride=0, textures=None, light_textures=None):
 	"""Runs the reference fragment shader (configuration `entry`) for every pixel (or the rows / bands asked for). Returns float32 [H, W, 4]."""
 	global _last_shade_seconds
 	lib = load()
@@ -91,6 +92,9 @@ def shade(entry, width, height, cfg, constants, visibility, vks, material_params
 		row_begin=row_begin, row_end=row_end, band_height=band_height, band_stride=band_stride)
 	if textures is not None:   # (dims uint32 [T,3], offsets uint64 [T], data float32): mip chains of 3 textures per material
 		a.texture_dims = arr(textures[0], np.uint32); a.texture_offsets = arr(textures[1], np.uint64); a.texture_data = arr(textures[2], np.float32)
+	if light_textures is not None:   # same triple for the textures of the lights
+		a.light_texture_count = len(light_textures[0])
+		a.light_texture_dims = arr(light_textures[0], np.uint32); a.light_texture_offsets = arr(light_textures[1], np.uint64); a.light_texture_data = arr(light_textures[2], np.float32)
 	fn = getattr(lib, entry)
 	rc = fn(C.byref(a))
 	lib.ref_bvh_destroy(bvh)

@@ -42,7 +42,8 @@ typedef struct {
 	v3 surface_radiance;
 	float plane[4];
 	uint32_t vertex_count;
-	uint32_t texturing_technique;
+	uint32_t texturing_technique, texture_index;
+	float inv_scaling_x, inv_scaling_y;
 	v3 vertices_world_space[PSA_MAXP];
 	/* only the related-work techniques read these (polygonal_light_utility.glsl:26-83) */
 	v3 translation, rotation_cols[3];
@@ -62,6 +63,7 @@ typedef struct {
 	const uint16_t* noise; uint32_t noise_w, noise_h;
 	const uint16_t* ltc0; const uint16_t* ltc1; uint32_t ltc_res, ltc_layers;
 	const obvh_t* bvh;
+	const vkr_texture_view_t* light_textures; uint32_t light_texture_count; /* g_light_textures (shading_pass.frag.glsl:60) */
 	uint32_t maxp;
 } ctx_t;
 
@@ -338,8 +340,38 @@ static void get_polygon_visibility(int* visibility, v3 sampled_dir, v3 shading_p
 	}
 }
 
-/* shading_pass.frag.glsl:151-185; only polygon_texturing_none is in scope (8a row a12) */
-static v3 get_polygon_radiance(const light_t* light) { return light->surface_radiance; }
+/* shading_pass.frag.glsl:151-185. polygon_texturing_technique_t (src/polygonal_light.h): 0 none, 1 area, 2 portal, 3 IES profile */
+static v3 get_polygon_radiance(v3 sampled_dir, v3 shading_position, const light_t* light, const ctx_t* c) {
+	v3 radiance = light->surface_radiance;
+	const uint32_t technique = light->texturing_technique;
+	if (technique != 0) {
+		v2 tex_coord;
+		if (technique == 1) {
+			/* intersect the ray with the plane of the light, go to plane space */
+			float num = fmaf(light->plane[3], 1.0f, fmaf(light->plane[2], shading_position.z, fmaf(light->plane[1], shading_position.y, light->plane[0] * shading_position.x)));
+			float intersection_t = -num / dot3(sampled_dir, mk3(light->plane[0], light->plane[1], light->plane[2]));
+			v3 intersection = add3(shading_position, scale3(sampled_dir, intersection_t));
+			intersection = sub3(intersection, light->translation);
+			tex_coord = mk2(dot3(light->rotation_cols[0], intersection), dot3(light->rotation_cols[1], intersection));
+			tex_coord = mk2(tex_coord.x * light->inv_scaling_x, tex_coord.y * light->inv_scaling_y);
+		}
+		else {
+			v3 lookup_dir;
+			if (technique == 3) {
+				lookup_dir = mk3(dot3(light->rotation_cols[0], sampled_dir), dot3(light->rotation_cols[1], sampled_dir), dot3(light->rotation_cols[2], sampled_dir));
+				radiance = scale3(radiance, 1.0f / fabsf(lookup_dir.z)); /* IES profiles include the cosine already */
+			}
+			else
+				lookup_dir = mk3(-sampled_dir.x, sampled_dir.y, sampled_dir.z);
+			tex_coord.x = vkr_atan2(lookup_dir.y, lookup_dir.x) * (0.5f * VKR_INV_PI);
+			tex_coord.y = vkr_acos(lookup_dir.z) * VKR_INV_PI;
+		}
+		float texel[4];
+		vkr_texture_bilinear_repeat_clamp(texel, &c->light_textures[light->texture_index], tex_coord.x, tex_coord.y);
+		radiance = mk3(radiance.x * texel[0], radiance.y * texel[1], radiance.z * texel[2]);
+	}
+	return radiance;
+}
 
 /* shading_pass.frag.glsl:203-231 */
 static v3 radiance_visibility_brdf_product(float* out_lambert, int* out_visibility, v3 sampled_dir, const shading_data_t* sd, const light_t* light, int diffuse, int specular, const ctx_t* c, uint64_t* ray_count) {
@@ -349,7 +381,7 @@ static v3 radiance_visibility_brdf_product(float* out_lambert, int* out_visibili
 	if (out_lambert) *out_lambert = lambert;
 	if (out_visibility) *out_visibility = visibility;
 	if (visibility) {
-		v3 radiance = get_polygon_radiance(light);
+		v3 radiance = get_polygon_radiance(sampled_dir, sd->position, light, c);
 		v3 brdf = evaluate_brdf(sd, sampled_dir, diffuse, specular);
 		return mk3(radiance.x * brdf.x, radiance.y * brdf.y, radiance.z * brdf.z);
 	}
@@ -747,7 +779,8 @@ static void parse_light(light_t* L, const uint8_t* p, uint32_t V) { /* polygonal
 	L->surface_radiance = mk3(rdf(p, L_SURFACE_RADIANCE), rdf(p, L_SURFACE_RADIANCE + 4), rdf(p, L_SURFACE_RADIANCE + 8));
 	for (int i = 0; i != 4; ++i) L->plane[i] = rdf(p, L_PLANE + 4 * i);
 	L->vertex_count = rdu(p, L_VERTEX_COUNT);
-	L->texturing_technique = rdu(p, L_TEXTURING);
+	L->texturing_technique = rdu(p, L_TEXTURING); L->texture_index = rdu(p, L_TEXTURING + 4);
+	L->inv_scaling_x = rdf(p, 44); L->inv_scaling_y = rdf(p, 60);
 	const uint8_t* vw = p + L_FIXED_SIZE + 16 * (size_t) V;
 	for (uint32_t i = 0; i != V; ++i) L->vertices_world_space[i] = mk3(rdf(vw, 16 * i), rdf(vw, 16 * i + 4), rdf(vw, 16 * i + 8));
 	L->translation = mk3(rdf(p, L_TRANSLATION), rdf(p, L_TRANSLATION + 4), rdf(p, L_TRANSLATION + 8));
@@ -789,13 +822,30 @@ static void parse_context(ctx_t* c, const vkr_oracle_config_t* cfg, const uint8_
 
 /* Wall-clock seconds of the pixel loop of the last vkr_oracle_shade call (BVH build excluded), for the CPU baseline */
 static double g_last_shade_seconds = 0.0;
+/* vkr_texture_bilinear_repeat_clamp for n (u, v) pairs on a one-level RGBA32F texture (tests) */
+void vkr_oracle_light_texture_batch(uint32_t width, uint32_t height, const float* texels, uint32_t n, const float* uv, float* out_rgba) {
+	vkr_texture_view_t t; t.width = width; t.height = height; t.mip_count = 1; t.texels = texels;
+	for (uint32_t i = 0; i != n; ++i) vkr_texture_bilinear_repeat_clamp(out_rgba + 4 * i, &t, uv[2 * i], uv[2 * i + 1]);
+}
+
 double vkr_oracle_last_shade_seconds(void) { return g_last_shade_seconds; }
 
-/* shading_pass.frag.glsl:824-866 with the G-buffer standing in for get_shading_data() */
 int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, const float* gbuffer,
 	const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
 	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
 	const float* tris, uint32_t tri_count, float* out_rgba, uint64_t* out_ray_count)
+{
+	return vkr_oracle_shade_with_light_textures(cfg, constants, gbuffer, noise, noise_w, noise_h, noise_layers, ltc0, ltc1, ltc_res, ltc_layers, tris, tri_count, 0, NULL, NULL, NULL, out_rgba, out_ray_count);
+}
+
+/* shading_pass.frag.glsl:824-866 with the G-buffer standing in for get_shading_data(). Light textures (g_light_textures, the indices are in the
+   light blocks): RGBA32F, light_texture_dims = {width, height, mip count} per texture, offsets in floats into light_texture_data; level 0 is used */
+int vkr_oracle_shade_with_light_textures(const vkr_oracle_config_t* cfg, const void* constants, const float* gbuffer,
+	const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
+	const float* tris, uint32_t tri_count,
+	uint32_t light_texture_count, const uint32_t* light_texture_dims, const uint64_t* light_texture_offsets, const float* light_texture_data,
+	float* out_rgba, uint64_t* out_ray_count)
 {
 	(void) noise_layers;
 	if (cfg->max_light_vertex_count < 3 || cfg->max_light_vertex_count > 7) return 1;
@@ -823,7 +873,15 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 	ctx_t c; memset(&c, 0, sizeof(c));
 	parse_context(&c, cfg, (const uint8_t*) constants);
 	for (uint32_t l = 0; l != cfg->light_count; ++l)
-		if (c.lights[l].texturing_technique != 0) { printf("oracle: textured lights are out of scope.\n"); free(c.lights); return 1; }
+		if (c.lights[l].texturing_technique > 3 || (c.lights[l].texturing_technique != 0 && c.lights[l].texture_index >= light_texture_count)) {
+			printf("oracle: light %u is textured (technique %u) with texture %u of %u.\n", l, c.lights[l].texturing_technique, c.lights[l].texture_index, light_texture_count); free(c.lights); return 1;
+		}
+	vkr_texture_view_t* light_views = (vkr_texture_view_t*) calloc(light_texture_count ? light_texture_count : 1, sizeof(vkr_texture_view_t));
+	for (uint32_t i = 0; i != light_texture_count; ++i) {
+		light_views[i].width = light_texture_dims[3 * i]; light_views[i].height = light_texture_dims[3 * i + 1]; light_views[i].mip_count = light_texture_dims[3 * i + 2];
+		light_views[i].texels = light_texture_data + light_texture_offsets[i];
+	}
+	c.light_textures = light_views; c.light_texture_count = light_texture_count;
 	c.noise = noise; c.noise_w = noise_w; c.noise_h = noise_h;
 	c.ltc0 = ltc0; c.ltc1 = ltc1; c.ltc_res = ltc_res; c.ltc_layers = ltc_layers;
 	obvh_t bvh; memset(&bvh, 0, sizeof(bvh));
@@ -862,9 +920,10 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 				ray_end = sd.position; ray_end_w = 1.0f;
 			}
 			if (cfg->show_polygonal_lights) {
+				const v3 view_dir_normalized = normalize3(view_dir); /* :844 */
 				for (uint32_t l = 0; l != cfg->light_count; ++l)
 					if (polygonal_light_ray_intersection(&c.lights[l], cfg->max_light_vertex_count, c.camera, ray_end, ray_end_w))
-						final_color = add3(final_color, get_polygon_radiance(&c.lights[l]));
+						final_color = add3(final_color, get_polygon_radiance(view_dir_normalized, c.camera, &c.lights[l], &c));
 			}
 			if (valid) {
 				float fresnel_luminance = dot3(sd.fresnel_0, mk3(0.2126f, 0.7152f, 0.0722f));
@@ -900,7 +959,7 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 #endif
 	if (out_ray_count) *out_ray_count = total_rays;
 	obvh_destroy(&bvh);
-	free(c.lights);
+	free(c.lights); free(light_views);
 	return 0;
 }
 

@@ -48,6 +48,29 @@ static inline void vkr_texture_bilinear(float out[4], const vkr_texture_view_t* 
 	}
 }
 
+/* textureLod(..., 0.0f) with the sampler of the light textures (src/main.c:613-623: linear filters, REPEAT in u, CLAMP_TO_EDGE in v
+ * -- "the way to go for theta-phi parametrizations"): one bilinear tap on level 0 with the conventions of vkr_texture_bilinear(). */
+static inline void vkr_texture_bilinear_repeat_clamp(float out[4], const vkr_texture_view_t* t, float u, float v) {
+	const uint32_t w = t->width, h = t->height;
+	const float* texels = t->texels;
+	float x = u * (float) w - 0.5f, y = v * (float) h - 0.5f;
+	if (!(fabsf(x) < 1.0e9f)) x = 0.0f;
+	if (!(fabsf(y) < 1.0e9f)) y = 0.0f;
+	const float x0f = floorf(x), y0f = floorf(y);
+	const float fx = x - x0f, fy = y - y0f;
+	const int x0 = vkr_texture_wrap((int) x0f, (int) w), x1 = vkr_texture_wrap((int) x0f + 1, (int) w);
+	int y0 = (int) y0f, y1 = (int) y0f + 1;
+	y0 = (y0 < 0) ? 0 : ((y0 > (int) h - 1) ? (int) h - 1 : y0);
+	y1 = (y1 < 0) ? 0 : ((y1 > (int) h - 1) ? (int) h - 1 : y1);
+	for (int c = 0; c != 4; ++c) {
+		const float t00 = texels[4 * ((size_t) y0 * w + x0) + c], t10 = texels[4 * ((size_t) y0 * w + x1) + c];
+		const float t01 = texels[4 * ((size_t) y1 * w + x0) + c], t11 = texels[4 * ((size_t) y1 * w + x1) + c];
+		const float a = fmaf(fx, t10 - t00, t00);
+		const float b = fmaf(fx, t11 - t01, t01);
+		out[c] = fmaf(fy, b - a, a);
+	}
+}
+
 static inline void vkr_texture_grad(float out[4], const vkr_texture_view_t* t, v2 uv, v2 ddx, v2 ddy) {
 	const v2 px = mk2(ddx.x * (float) t->width, ddx.y * (float) t->height), py = mk2(ddy.x * (float) t->width, ddy.y * (float) t->height);
 	const float lx2 = dot2(px, px), ly2 = dot2(py, py);

@@ -40,6 +40,12 @@ int vkr_oracle_shade(const vkr_oracle_config_t* cfg, const void* constants, cons
 	const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
 	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
 	const float* tris, uint32_t tri_count, float* out_rgba, uint64_t* out_ray_count);
+int vkr_oracle_shade_with_light_textures(const vkr_oracle_config_t* cfg, const void* constants, const float* gbuffer,
+	const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
+	const float* tris, uint32_t tri_count,
+	uint32_t light_texture_count, const uint32_t* light_texture_dims, const uint64_t* light_texture_offsets, const float* light_texture_data,
+	float* out_rgba, uint64_t* out_ray_count);
 void vkr_oracle_dequantize_for_bvh(const uint32_t* quantized_positions, uint64_t vertex_count, const float* factor, const float* summand, float* out_vertices);
 int vkr_oracle_visibility(uint32_t width, uint32_t height, const void* constants, const uint32_t* quantized_positions, uint64_t tri_count, uint32_t* out_visibility);
 int vkr_oracle_gbuffer(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
@@ -52,6 +58,7 @@ int vkr_oracle_error_display_batch(uint32_t technique, int biased, uint32_t maxv
 int vkr_oracle_gbuffer_textured(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility,
 	const uint32_t* quantized_positions, const uint16_t* normals_and_tex_coords, const uint8_t* material_indices,
 	uint32_t texture_count, const uint32_t* texture_dims, const uint64_t* texture_offsets, const float* texture_data, float* out_gbuffer);
+void vkr_oracle_light_texture_batch(uint32_t width, uint32_t height, const float* texels, uint32_t n, const float* uv, float* out_rgba);
 void vkr_oracle_texture_grad_batch(uint32_t width, uint32_t height, uint32_t mip_count, const float* texels, uint32_t n, const float* inputs, float* out_rgba);
 uint32_t vkr_oracle_clip(uint32_t vertex_count, float* vertices_xyz, uint32_t maxp);
 void vkr_oracle_psa_sample_batch(uint32_t vertex_count, const float* vertices_xyz, uint32_t maxp, int biased, int do_clip,

@@ -206,7 +206,7 @@ extern "C" void vkr_device_on_host_gbuffer(uint32_t width, uint32_t height, cons
 // display, LTC set-up, noise stream, NaN -> pink, exposure; restated here because that file is warp-level code) around the product's per-light function
 // error_display_of_light() (csrc/vkr_error_display.cuh). Linear output, g_frame_bits = 0.
 // light(sp, l, light_block, ns, x, y, acc): one light for one pixel; acc is the pixel's pixel_sum (vkr_ray_stream.cuh)
-template <int MAXV, class Light>
+template <int MAXV, bool LIGHT_TEXTURES = false, class Light>
 static void tile_frame(const shading_kernel_params& p, int show_lights, const Light& light_fn, float* out_rgba) {
 	const unsigned char* cb = p.constants;
 	const size_t plane = (size_t) p.width * p.height;
@@ -221,20 +221,18 @@ static void tile_frame(const shading_kernel_params& p, int show_lights, const Li
 		shading_point sp;
 		sp.position = make3(g0.x, g0.y, g0.z); sp.roughness = g0.w; sp.normal = make3(g1.x, g1.y, g1.z);
 		if (show_lights) {
-			f3 end; float end_w;
-			if (valid) { end = sp.position; end_w = 1.0f; }
-			else {
-				const float fx = (float) x, fy = (float) y;
-				end = make3(
-					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 8), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 4), fy, ldf(cb, OFF_PIXEL_TO_RAY) * fx)),
-					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 24), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 20), fy, ldf(cb, OFF_PIXEL_TO_RAY + 16) * fx)),
-					fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 40), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 36), fy, ldf(cb, OFF_PIXEL_TO_RAY + 32) * fx)));
-				end_w = 0.0f;
-			}
+			f3 end = sp.position; float end_w = 1.0f;
+			const float fx = (float) x, fy = (float) y;
+			f3 view_direction = make3(
+				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 8), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 4), fy, ldf(cb, OFF_PIXEL_TO_RAY) * fx)),
+				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 24), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 20), fy, ldf(cb, OFF_PIXEL_TO_RAY + 16) * fx)),
+				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 40), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 36), fy, ldf(cb, OFF_PIXEL_TO_RAY + 32) * fx)));
+			if (!valid) { end = view_direction; end_w = 0.0f; }
+			view_direction = normalize(view_direction);
 			for (int li = 0; li != p.light_count; ++li) {
 				const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
 				if (light_ray_intersection<MAXV>(light, camera, end, end_w))
-					color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
+					color = color + light_radiance<LIGHT_TEXTURES>(p, light, camera, view_direction);
 			}
 		}
 		pixel_sum acc;
@@ -269,43 +267,48 @@ static void error_display_frame(const shading_kernel_params& p, int show_lights,
 }
 
 // The shading pass without shadow rays (TRACE = false: every candidate sample is added in place) with the product's shade_light() (csrc/vkr_shade_light.cuh)
-template <int STRATEGY, int MAXV, bool BIASED, bool OPTIMAL>
+template <int STRATEGY, int MAXV, bool BIASED, bool OPTIMAL, bool LIGHT_TEXTURES>
 static void shading_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
-	tile_frame<MAXV>(p, show_lights, [&](const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns, uint32_t x, uint32_t y, pixel_sum& acc) {
+	tile_frame<MAXV, LIGHT_TEXTURES>(p, show_lights, [&](const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns, uint32_t x, uint32_t y, pixel_sum& acc) {
 		ray_producer q; q.base = 0; q.fill = 0; q.resolved = 0;
-		shade_light<STRATEGY, MAXV + 1, BIASED, OPTIMAL, false>(true, sp, l, light, ns, p, p.constants, x, y, q, acc, 0);
+		shade_light<STRATEGY, MAXV + 1, BIASED, OPTIMAL, false, LIGHT_TEXTURES>(true, sp, l, light, ns, p, p.constants, x, y, q, acc, 0);
 	}, out_rgba);
 }
 
-template <int MAXV, bool BIASED>
+template <int MAXV, bool BIASED, bool T>
 static int shading_frame_strategy(const shading_kernel_params& p, int show_lights, float* out_rgba) {
 	switch (p.sampling_strategies) {
-	case VKR_STRATEGY_DIFFUSE_ONLY: shading_frame<VKR_STRATEGY_DIFFUSE_ONLY, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
-	case VKR_STRATEGY_DIFFUSE_GGX_MIS: shading_frame<VKR_STRATEGY_DIFFUSE_GGX_MIS, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
-	case VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_ONLY: shading_frame<VKR_STRATEGY_DIFFUSE_ONLY, MAXV, BIASED, false, T>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_GGX_MIS: shading_frame<VKR_STRATEGY_DIFFUSE_GGX_MIS, MAXV, BIASED, false, T>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_SEPARATELY, MAXV, BIASED, false, T>(p, show_lights, out_rgba); return 0;
 	case VKR_STRATEGY_DIFFUSE_SPECULAR_MIS:
-		if (p.mis_heuristic == VKR_MIS_OPTIMAL) shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, true>(p, show_lights, out_rgba);
-		else shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, false>(p, show_lights, out_rgba);
+		if (p.mis_heuristic == VKR_MIS_OPTIMAL) shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, true, T>(p, show_lights, out_rgba);
+		else shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_MIS, MAXV, BIASED, false, T>(p, show_lights, out_rgba);
 		return 0;
-	case VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM, MAXV, BIASED, false>(p, show_lights, out_rgba); return 0;
+	case VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM: shading_frame<VKR_STRATEGY_DIFFUSE_SPECULAR_RANDOM, MAXV, BIASED, false, T>(p, show_lights, out_rgba); return 0;
 	default: return 1;
 	}
 }
 
-// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0.
+// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0. light_texture_count != 0:
+// the LIGHT_TEXTURES = true instantiation (csrc/vkr_textured_light_kernel.cu), dims = {width, height, mip count, 0} per texture, offsets in texels.
 extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t strategy, uint32_t heuristic, int biased, uint32_t sample_count, int show_lights,
 	const void* constants, const float* gbuffer, const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
-	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers, float* out_rgba)
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
+	uint32_t light_texture_count, const uint32_t* light_texture_dims4, const uint64_t* light_texture_offsets_texels, const float* light_texture_texels, float* out_rgba)
 {
 	shading_kernel_params p;
 	memset(&p, 0, sizeof(p));
 	p.width = (int) width; p.height = (int) height; p.gbuffer = reinterpret_cast<const float4*>(gbuffer); p.constants = (const unsigned char*) constants;
 	p.light_count = (int) light_count; p.max_light_vertex_count = (int) maxv; p.sample_count = (int) sample_count;
+	p.light_texture_count = light_texture_count; p.light_texture_dims = reinterpret_cast<const uint4*>(light_texture_dims4);
+	p.light_texture_offsets = reinterpret_cast<const unsigned long long*>(light_texture_offsets_texels); p.light_texture_texels = reinterpret_cast<const float4*>(light_texture_texels);
 	p.sampling_strategies = (int) strategy; p.mis_heuristic = (int) heuristic; p.biased_sampling = biased; p.polygon_sampling_technique = biased ? 12 : 11;
 	p.noise = noise; p.noise_w = (int) noise_w; p.noise_h = (int) noise_h; p.noise_layers = (int) noise_layers;
 	p.ltc0 = ltc0; p.ltc1 = ltc1; p.ltc_res = (int) ltc_res; p.ltc_layers = (int) ltc_layers;
 	switch (maxv) {
-#define V(K) case K: return biased ? shading_frame_strategy<K, true>(p, show_lights, out_rgba) : shading_frame_strategy<K, false>(p, show_lights, out_rgba);
+#define V(K) case K: if (light_texture_count) return biased ? shading_frame_strategy<K, true, true>(p, show_lights, out_rgba) : shading_frame_strategy<K, false, true>(p, show_lights, out_rgba); \
+	return biased ? shading_frame_strategy<K, true, false>(p, show_lights, out_rgba) : shading_frame_strategy<K, false, false>(p, show_lights, out_rgba);
 	V(3) V(4) V(5) V(6) V(7)
 #undef V
 	default: return 1;

@@ -115,6 +115,23 @@ def material_texture_set(info):
 	return np.array(dims, dtype=np.uint32), np.array(offsets, dtype=np.uint64), np.concatenate(chunks).astype(np.float32)
 
 
+def light_texture_set(lights, light_count=None):
+	"""The light textures as create_and_assign_light_textures() orders them (src/main.c:371-418): unique paths in the order of first use, lights
+	without a path share a white texture. Returns (texture index per light, (dims uint32 [T,3], offsets uint64 [T], data float32)), decoded in numpy."""
+	paths, indices = [], []
+	for light in lights[:light_count]:
+		path = light.get("texture_file_path", "")
+		if path not in paths: paths.append(path)
+		indices.append(paths.index(path))
+	if not paths: paths = [""]
+	dims, offsets, chunks, at = [], [], [], 0
+	for path in paths:
+		levels = read_vkt(path) if path else [np.ones((1, 1, 4), dtype=np.float32)]
+		dims.append((levels[0].shape[1], levels[0].shape[0], len(levels))); offsets.append(at)
+		for l in levels: chunks.append(l.reshape(-1)); at += l.size
+	return indices, (np.array(dims, dtype=np.uint32), np.array(offsets, dtype=np.uint64), np.concatenate(chunks).astype(np.float32))
+
+
 def wang_hash(seed):
 	"""src/math_utilities.h:50-57 on uint32 arrays"""
 	seed = np.asarray(seed, dtype=np.uint32)
@@ -168,6 +185,8 @@ class OracleInputs:
 		self.material_params = info["material_params"]
 		self.textures = material_texture_set(info) if info.get("textured") else None   # mip chains that need filtering, else constant materials
 		self._shadow_tris = None
+		# textures of the lights (area / portal / IES, shading_pass.frag.glsl:151-185), None when no light is textured
+		self.light_textures = light_texture_set(info["lights"])[1] if any(l.get("texturing_technique", 0) for l in info["lights"]) else None
 
 	@property
 	def shadow_tris(self):
@@ -186,7 +205,7 @@ class OracleInputs:
 	def shade(self, frame_cfg, constants, gbuffer, row_begin=0, row_end=0):
 		cfg = dict(frame_cfg); cfg["row_begin"] = row_begin; cfg["row_end"] = row_end
 		tris = self.shadow_tris if cfg["trace_shadow_rays"] else np.zeros((0, 9), dtype=np.float32)
-		return oracle.shade(cfg, constants, gbuffer, self.noise, self.ltc0, self.ltc1, tris)
+		return oracle.shade(cfg, constants, gbuffer, self.noise, self.ltc0, self.ltc1, tris, light_textures=self.light_textures)
 
 
 def oracle_config(frame, width, height):

@@ -9,6 +9,8 @@ WIDTH, HEIGHT = 64, 48
 def dataset_for(cfg):
 	if cfg.get("textured", 0):
 		return "mini_textured"
+	if cfg.get("light_textures", 0):
+		return "mini_lit"
 	if cfg["materials"] == 3:
 		return "cornell"
 	if cfg["lights"] > 3:
@@ -30,6 +32,7 @@ def host_constants(info, width, height, lights, sample_count=1, frame_bits=0):
 	assert lib.vkr_load_noise_table(C.byref(noise), None, 256, 256, 64, api.NOISE_WHITE) == 0
 	assert lib.vkr_quick_load(C.byref(spec), info["save"].encode()) == 0
 	assert lights <= spec.polygonal_light_count
+	assert lib.vkr_create_and_assign_light_textures(None, None, C.byref(spec)) == 0   # texture indices only (src/main.c:2167)
 	spec_count = spec.polygonal_light_count
 	spec.polygonal_light_count = lights
 	lib.vkr_specify_default_render_settings(C.byref(st)); st.animate_noise = 0; st.exposure_factor = 1.0; st.sample_count = sample_count

@@ -214,7 +214,7 @@ def test_error_display_light_shader_reproduces_the_reference_shader_fixtures(nam
 def _base_fixture_names():
 	import os
 	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
-	return sorted({k.split("/")[0] for k in g.files if not any(t in k.split("/")[0] for t in ("_q", "_e", "_x", "_o"))})
+	return sorted({k.split("/")[0] for k in g.files if not any(t in k.split("/")[0] for t in ("_q", "_e", "_x", "_y", "_o"))})
 
 
 @pytest.mark.parametrize("name", _base_fixture_names())
@@ -238,7 +238,8 @@ def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
 	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
-		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), P(out))
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		C.c_uint32(0), None, None, None, P(out))
 	assert rc == 0
 	no_rays = dict(cfg, trace=0)
 	ref, _ = oi.shade(oracle_cfg(no_rays), constants, gb)
@@ -246,6 +247,50 @@ def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
 	if cfg["trace"] == 0:
 		fixture = g[name + "/rgba"]
 		assert np.array_equal(out.view(np.uint32), fixture.view(np.uint32)), H.compare_radiance(out, fixture)
+
+
+def _textured_light_fixture_names():
+	import os
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	return sorted({k.split("/")[0] for k in g.files if "_y1" in k.split("/")[0] and "_q" not in k.split("/")[0]})
+
+
+@pytest.mark.parametrize("name", _textured_light_fixture_names())
+def test_textured_lights_without_rays_match_oracle_and_fixtures(name):
+	"""The LIGHT_TEXTURES = true instantiation of shade_light() and of the light display (what csrc/vkr_textured_light_kernel.cu runs per pixel: area texture,
+	portal onto a light probe, IES profile; get_polygon_radiance, shading_pass.frag.glsl:151-185) executed on the CPU for whole frames of the "_y1" fixture
+	configurations, rays off: bit-identical to the oracle, and to the reference shader's own frame where the fixture was rendered without rays."""
+	import os
+	from tests.test_ref_shader import _config_from_name, oracle_cfg
+	from tests.ref_frames import WIDTH, HEIGHT, dataset_for
+	lib = _lib()
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	assert oi.light_textures is not None
+	constants = bytes(g[name + "/constants"])
+	gb = np.ascontiguousarray(oi.gbuffer(WIDTH, HEIGHT, constants, g[name + "/visibility"]), dtype=np.float32)
+	out = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	noise = np.ascontiguousarray(oi.noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(oi.ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(oi.ltc1, dtype=np.uint16)
+	dims3, offsets, data = oi.light_textures
+	dims = np.zeros((len(dims3), 4), dtype=np.uint32); dims[:, :3] = dims3
+	offsets_texels = np.ascontiguousarray(offsets // 4, dtype=np.uint64); data = np.ascontiguousarray(data, dtype=np.float32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["strategy"]),
+		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		C.c_uint32(len(dims)), P(dims), P(offsets_texels), P(data), P(out))
+	assert rc == 0
+	ref, _ = oi.shade(oracle_cfg(dict(cfg, trace=0)), constants, gb)
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+	if cfg["trace"] == 0:
+		fixture = g[name + "/rgba"]
+		assert np.array_equal(out.view(np.uint32), fixture.view(np.uint32)), H.compare_radiance(out, fixture)
+	# the textures matter: the same frame with white textures differs
+	white, _ = H.oracle.shade(oracle_cfg(dict(cfg, trace=0)), constants, gb, oi.noise, oi.ltc0, oi.ltc1, np.zeros((0, 9), dtype=np.float32),
+		light_textures=(np.array([[1, 1, 1]] * len(dims), dtype=np.uint32), np.arange(len(dims), dtype=np.uint64) * 4, np.ones(4 * len(dims), dtype=np.float32)))
+	assert not np.array_equal(white, ref)
 
 
 def test_samples_point_at_the_light_and_densities_integrate():

@@ -83,7 +83,7 @@ def test_config3_like_many_samples():
 def _fixture_names():
 	import os
 	g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_shader.npz"))
-	return sorted({k.split("/")[0] for k in g.files if not any(tag in k.split("/")[0] for tag in ("_q", "_e", "_x"))})   # "_q<technique>": tests/test_gpu_related_work.py, "_e<error display>": tests/test_gpu_zz_error_display.py, "_x1" (textured): tests/test_gpu_zzy_textured_gbuffer.py
+	return sorted({k.split("/")[0] for k in g.files if not any(tag in k.split("/")[0] for tag in ("_q", "_e", "_x", "_y"))})   # "_q<technique>": tests/test_gpu_related_work.py, "_e<error display>": tests/test_gpu_zz_error_display.py, "_x1" (textured): tests/test_gpu_zzy_textured_gbuffer.py, "_y1" (textured lights): tests/test_gpu_zzx_textured_lights.py
 
 
 @pytest.mark.parametrize("name", _fixture_names())

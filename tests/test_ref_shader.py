@@ -25,10 +25,10 @@ def _golden():
 
 
 def _config_from_name(name):
-	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_q(\d+))?(?:_e(\d))?(?:_x(\d))?(?:_o(\d)(\d))?$", name)
-	s, h, b, L, V, Vmin, S, t, l, M, q, e, x, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
-	return dict(name=name, entry="ref_shade_" + name.replace("_x1", ""), strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
-		samples=S, trace=t, show_lights=l, materials=M, technique=11 if q is None else q, error_display=e or 0, textured=x or 0, srgb=srgb or 0, frame_bits=frame_bits or 0)
+	m = re.match(r"s(\d+)_h(\d+)_b(\d+)_L(\d+)_V(\d+)(?:m(\d+))?_S(\d+)_t(\d+)_l(\d+)_M(\d+)(?:_q(\d+))?(?:_e(\d))?(?:_x(\d))?(?:_y(\d))?(?:_o(\d)(\d))?$", name)
+	s, h, b, L, V, Vmin, S, t, l, M, q, e, x, y, srgb, frame_bits = (int(x) if x is not None else None for x in m.groups())
+	return dict(name=name, entry="ref_shade_" + name.replace("_x1", "").replace("_y1", ""), strategy=s, heuristic=h, biased=b, lights=L, max_vertices=V, min_vertices=V if Vmin is None else Vmin,
+		samples=S, trace=t, show_lights=l, materials=M, technique=11 if q is None else q, error_display=e or 0, textured=x or 0, light_textures=y or 0, srgb=srgb or 0, frame_bits=frame_bits or 0)
 
 
 def _names():
@@ -63,7 +63,7 @@ def test_live_reference_shader_matches_fixture():
 		cfg = live[name]
 		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
 		constants = bytes(g[name + "/constants"])
-		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, g[name + "/visibility"], oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures)
+		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, g[name + "/visibility"], oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures, light_textures=oi.light_textures)
 		assert np.array_equal(ref.view(np.uint32), g[name + "/rgba"].view(np.uint32)), name
 		checked += 1
 	assert checked > 0
@@ -84,7 +84,25 @@ def test_oracle_follows_the_live_reference_shader_at_other_resolutions(width, he
 		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
 		constants = host_constants(info, width, height, cfg["lights"])
 		vis = oi.visibility(width, height, constants)
-		ref = R.shade(cfg["entry"], width, height, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures)
+		ref = R.shade(cfg["entry"], width, height, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures, light_textures=oi.light_textures)
 		gb = oi.gbuffer(width, height, constants, vis)
 		out, _ = oi.shade(oracle_cfg(cfg, width, height), constants, gb)
 		assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), (name, H.compare_radiance(out, ref))
+
+
+def test_every_light_texturing_technique_shapes_the_textured_fixture():
+	"""The "_y1" fixtures exercise all three branches of get_polygon_radiance() (shading_pass.frag.glsl:155-181): replacing the texture of any one
+	light (area, portal, IES profile) by white changes the oracle's frame, and the frame with all three equals the reference shader's (test above)."""
+	g = _golden(); name = "s3_h3_b0_L3_V4_S3_t1_l1_M8_y1"; cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	assert [l["texturing_technique"] for l in info["lights"][:3]] == [1, 2, 3]
+	constants = bytes(g[name + "/constants"])
+	gb = oi.gbuffer(WIDTH, HEIGHT, constants, g[name + "/visibility"])
+	ref = g[name + "/rgba"]
+	dims, offsets, data = oi.light_textures
+	for i in range(3):
+		d = dims.copy(); o = offsets.copy(); white = np.concatenate([data, np.ones(4, dtype=np.float32)])
+		d[i] = (1, 1, 1); o[i] = len(data)
+		out, _ = H.oracle.shade(oracle_cfg(cfg), constants, gb, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, light_textures=(d, o, white))
+		changed = (out.view(np.uint32) != ref.view(np.uint32)).any(axis=-1).mean()
+		assert changed > 0.02, "light %d (technique %d) leaves the frame unchanged" % (i, i + 1)

@@ -131,3 +131,58 @@ def test_filter_definition_behaves_like_a_sampler():
 	# (6) degenerate inputs stay finite
 	weird = grad([[np.nan, 0.5, 0, 0, 0, 0], [0.5, 0.5, np.inf, 0, 0, 0], [1e30, -1e30, 1e-3, 0, 0, 1e-3], [0.5, 0.5, 0, 0, 0, 0]])
 	assert np.isfinite(weird).all()
+
+
+# ---- textures of the polygonal lights (create_and_assign_light_textures, src/main.c:371-418; sampler src/main.c:613-623)
+
+def test_light_textures_are_loaded_once_per_path_and_indexed_like_the_reference(tmp_path, capfd):
+	from tests import harness as H
+	lib = api.load_library()
+	info = H.dataset("mini_lit")
+	spec = api.SceneSpecification()
+	assert lib.vkr_quick_load(C.byref(spec), info["save"].encode()) == 0
+	assert [spec.polygonal_lights[i].texturing_technique for i in range(3)] == [1, 2, 3]
+	lt = api.LightTextures()
+	assert lib.vkr_create_and_assign_light_textures(C.byref(lt), None, C.byref(spec)) == 0
+	indices, (dims, offsets, data) = H.light_texture_set(info["lights"])
+	assert [spec.polygonal_lights[i].texture_index for i in range(3)] == indices == [0, 1, 2]
+	assert lt.texture_count == 3 and not lt.d_texels
+	for k in range(3):   # host copies == the numpy decoders, level by level
+		t = lt.textures[k]
+		assert (t.width, t.height, t.mip_count) == tuple(dims[k])
+		mine = np.ctypeslib.as_array(t.h_texels, (t.texel_float_count,))
+		assert np.array_equal(mine, data[offsets[k]:offsets[k] + t.texel_float_count])
+	lib.vkr_destroy_light_textures(C.byref(lt), None)
+	assert lt.texture_count == 0 and not lt.textures
+	# lights 0 and 2 share a path, light 1 points at a missing file -> white, with the reference's message; indices only when no struct is passed
+	shared = spec.polygonal_lights[0].texture_file_path
+	missing = str(tmp_path / "nowhere.vkt").encode()
+	saved = [spec.polygonal_lights[i].texture_file_path for i in range(3)]
+	keep = C.create_string_buffer(missing)
+	spec.polygonal_lights[2].texture_file_path = shared; spec.polygonal_lights[1].texture_file_path = C.cast(keep, C.c_void_p)
+	assert lib.vkr_create_and_assign_light_textures(None, None, C.byref(spec)) == 0
+	assert [spec.polygonal_lights[i].texture_index for i in range(3)] == [0, 1, 0]
+	assert lib.vkr_create_and_assign_light_textures(C.byref(lt), None, C.byref(spec)) == 0
+	assert "does not exist. Using a white texture instead." in capfd.readouterr().out
+	assert lt.texture_count == 2 and (lt.textures[1].width, lt.textures[1].height, lt.textures[1].mip_count) == (1, 1, 1)
+	assert list(np.ctypeslib.as_array(lt.textures[1].h_texels, (4,))) == [1.0, 1.0, 1.0, 1.0]
+	lib.vkr_destroy_light_textures(C.byref(lt), None)
+	for i in range(3): spec.polygonal_lights[i].texture_file_path = saved[i]
+	lib.vkr_destroy_scene_specification(C.byref(spec))
+
+
+def test_light_texture_sampler_repeats_in_u_and_clamps_in_v():
+	"""oracle/texture_filter.h: vkr_texture_bilinear_repeat_clamp (what the compiled reference shader, the oracle and the kernel use for textureLod on
+	light textures): texel centres are exact, u wraps around, v stops at the border rows."""
+	from tests import harness as H
+	rng = np.random.default_rng(11)
+	tex = rng.random((8, 16, 4)).astype(np.float32)
+	info = H.dataset("mini_lit"); oi = H.OracleInputs(info)
+	def sample(u, v):
+		uv = np.array([[u, v]], dtype=np.float32)
+		return O.light_texture_batch(tex, uv)[0]
+	assert np.array_equal(sample((3 + 0.5) / 16, (5 + 0.5) / 8), tex[5, 3])
+	assert np.array_equal(sample((3 + 0.5) / 16 + 2.0, (5 + 0.5) / 8), sample((3 + 0.5) / 16, (5 + 0.5) / 8))   # repeat in u
+	assert np.array_equal(sample((3 + 0.5) / 16, -0.7), tex[0, 3]) and np.array_equal(sample((3 + 0.5) / 16, 1.9), tex[7, 3])   # clamp in v
+	edge = sample(0.0, (2 + 0.5) / 8)   # between the last and the first column
+	assert np.allclose(edge, 0.5 * (tex[2, 15] + tex[2, 0]), atol=1e-6)

@@ -33,7 +33,7 @@ def main():
 		info = H.dataset(name); oi = H.OracleInputs(info)
 		constants = host_constants(info, WIDTH, HEIGHT, cfg["lights"], frame_bits=cfg.get("frame_bits", 0))
 		vis = oi.visibility(WIDTH, HEIGHT, constants)
-		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures)
+		ref = R.shade(cfg["entry"], WIDTH, HEIGHT, cfg, constants, vis, oi.vks, oi.material_params, oi.noise, oi.ltc0, oi.ltc1, oi.shadow_tris, textures=oi.textures, light_textures=oi.light_textures)
 		key = cfg["name"]
 		out[key + "/rgba"] = ref
 		out[key + "/visibility"] = vis

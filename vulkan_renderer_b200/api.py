@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_build_probe_with", "vkr_bvh_build_probe_device", "vkr_bvh4_build_probe", "vkr_bvh_free_probe",
 	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
 	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
-	"vkr_load_texture", "vkr_destroy_texture",
+	"vkr_load_texture", "vkr_destroy_texture", "vkr_create_and_assign_light_textures", "vkr_destroy_light_textures",
 	"vkr_create_render_targets", "vkr_destroy_render_targets", "vkr_download_frame", "vkr_download_gbuffer", "vkr_upload_gbuffer",
 ]
 
@@ -104,12 +104,17 @@ class RenderTargets(C.Structure):
 	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("d_visibility", C.c_void_p), ("d_gbuffer", C.c_void_p), ("d_frame", C.c_void_p)]
 
 
+class LightTextures(C.Structure):
+	_fields_ = [("texture_count", C.c_uint32), ("textures", C.POINTER(Texture)), ("d_texels", C.c_void_p), ("d_dims", C.c_void_p), ("d_offsets", C.c_void_p), ("texel_count", C.c_uint64)]
+
+
 class ShadingPassDesc(C.Structure):
 	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("polygonal_light_count", C.c_uint32),
 		("min_polygonal_light_vertex_count", C.c_uint32), ("max_polygonal_light_vertex_count", C.c_uint32), ("sample_count", C.c_uint32),
 		("sampling_strategies", C.c_int), ("mis_heuristic", C.c_int), ("polygon_sampling_technique", C.c_int),
 		("trace_shadow_rays", C.c_int), ("show_polygonal_lights", C.c_int), ("stripe_index", C.c_uint32), ("stripe_count", C.c_uint32),
-		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable)), ("output_srgb", C.c_int), ("error_display", C.c_int)]
+		("scene", C.POINTER(Scene)), ("ltc_table", C.POINTER(LtcTable)), ("noise_table", C.POINTER(NoiseTable)), ("output_srgb", C.c_int), ("error_display", C.c_int),
+		("light_textures", C.POINTER(LightTextures))]
 
 
 class ShadingPass(C.Structure):
@@ -172,6 +177,8 @@ def load_library():
 	lib.vkr_bvh4_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32), P(C.c_uint64), P(C.c_uint32)]
 	lib.vkr_bvh_free_probe.argtypes = [P(C.c_float), P(C.c_float), P(C.c_uint32)]; lib.vkr_bvh_free_probe.restype = None
 	lib.vkr_load_texture.argtypes = [P(Texture), C.c_char_p]
+	lib.vkr_create_and_assign_light_textures.argtypes = [P(LightTextures), P(Device), P(SceneSpecification)]
+	lib.vkr_destroy_light_textures.argtypes = [P(LightTextures), P(Device)]; lib.vkr_destroy_light_textures.restype = None
 	lib.vkr_destroy_texture.argtypes = [P(Texture)]; lib.vkr_destroy_texture.restype = None
 	lib.vkr_create_render_targets.argtypes = [P(RenderTargets), P(Device), C.c_uint32, C.c_uint32]
 	lib.vkr_destroy_render_targets.argtypes = [P(RenderTargets), P(Device)]; lib.vkr_destroy_render_targets.restype = None

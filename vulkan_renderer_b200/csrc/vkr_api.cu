@@ -157,6 +157,16 @@ cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaS
 		default: return cudaErrorInvalidValue;
 		}
 	}
+	if (p.light_texture_count != 0) { // at least one textured light in this frame (vkr_textured_light_kernel.cu)
+		switch (p.max_light_vertex_count) {
+		case 3: return vkr_launch_textured_light_kernel_maxp4(p, stream);
+		case 4: return vkr_launch_textured_light_kernel_maxp5(p, stream);
+		case 5: return vkr_launch_textured_light_kernel_maxp6(p, stream);
+		case 6: return vkr_launch_textured_light_kernel_maxp7(p, stream);
+		case 7: return vkr_launch_textured_light_kernel_maxp8(p, stream);
+		default: return cudaErrorInvalidValue;
+		}
+	}
 	switch (p.max_light_vertex_count) { // MAX_POLYGONAL_LIGHT_VERTEX_COUNT, a compile-time bound of the kernels
 	case 3: return vkr_launch_shading_kernel_maxp4(p, stream);
 	case 4: return vkr_launch_shading_kernel_maxp5(p, stream);
@@ -174,21 +184,31 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 			(unsigned long long) constants_size, (unsigned long long) pass->constants_size, d.polygonal_light_count, d.max_polygonal_light_vertex_count);
 		return 1;
 	}
+	bool any_textured_light = false;
 	{ // light blocks must match what the pass was created for (the reference recompiles the shader when they change)
 		const uint32_t v = d.max_polygonal_light_vertex_count;
 		const size_t stride = 160 + 16 * (size_t) v * 2 + 16 * (size_t) (v - 2);
 		for (uint32_t i = 0; i != d.polygonal_light_count; ++i) {
-			uint32_t vertex_count, texturing_technique;
+			uint32_t vertex_count, texturing_technique, texture_index;
 			memcpy(&vertex_count, (const char*) constants + 256 + stride * i + 80, 4);
 			memcpy(&texturing_technique, (const char*) constants + 256 + stride * i + 84, 4);
+			memcpy(&texture_index, (const char*) constants + 256 + stride * i + 88, 4);
 			if (vertex_count < d.min_polygonal_light_vertex_count || vertex_count > v) {
 				printf("Polygonal light %u has %u vertices but the shading pass was created for %u to %u.\n", i, vertex_count, d.min_polygonal_light_vertex_count, v);
 				return 1;
 			}
-			if (texturing_technique != 0) {
-				printf("Polygonal light %u is textured (technique %u); light textures are not supported by this shading pass.\n", i, texturing_technique);
-				return 1;
+			if (texturing_technique != 0) { // polygon_texturing_technique_t: 1 area, 2 portal, 3 IES profile
+				any_textured_light = true;
+				if (texturing_technique > 3 || !d.light_textures || !d.light_textures->d_texels || texture_index >= d.light_textures->texture_count) {
+					printf("Polygonal light %u is textured (technique %u, texture %u) but the shading pass has %u light textures on the device.\n", i, texturing_technique, texture_index,
+						(d.light_textures && d.light_textures->d_texels) ? d.light_textures->texture_count : 0u);
+					return 1;
+				}
 			}
+		}
+		if (any_textured_light && ((int) d.polygon_sampling_technique < 11 || d.error_display != 0)) {
+			printf("Textured polygonal lights need projected solid angle sampling without error display (technique %d, error display %d).\n", (int) d.polygon_sampling_technique, (int) d.error_display);
+			return 1;
 		}
 	}
 	cudaStream_t stream = (cudaStream_t) device->stream;
@@ -219,6 +239,10 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 		p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count;
 		p.stack_depth = (int) d.scene->shadow_max_depth + 2;
 		p.bvh_width = d.scene->shadow_bvh_width ? (int) d.scene->shadow_bvh_width : 2;
+	}
+	if (any_textured_light) {
+		p.light_texture_texels = (const float4*) d.light_textures->d_texels; p.light_texture_dims = (const uint4*) d.light_textures->d_dims;
+		p.light_texture_offsets = (const unsigned long long*) d.light_textures->d_offsets; p.light_texture_count = d.light_textures->texture_count;
 	}
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_begin, stream);
 	cudaError_t err = vkr_launch_shading_kernel(p, stream);

@@ -485,6 +485,72 @@ extern "C" void vkr_destroy_scene_specification(vkr_scene_specification_t* spec)
 	memset(spec, 0, sizeof(*spec));
 }
 
+// ------------------------------------------------------------------------------------------------
+// light textures (src/main.c:364-418)
+// ------------------------------------------------------------------------------------------------
+extern "C" void vkr_destroy_light_textures(vkr_light_textures_t* lt, const vkr_device_t* device) {
+	(void) device;
+	for (uint32_t i = 0; i != lt->texture_count && lt->textures; ++i) vkr_destroy_texture(&lt->textures[i]);
+	free(lt->textures);
+	void* dev_ptrs[] = { lt->d_texels, lt->d_dims, lt->d_offsets };
+	for (void* p : dev_ptrs) if (p) cudaFree(p);
+	memset(lt, 0, sizeof(*lt));
+}
+
+extern "C" int vkr_create_and_assign_light_textures(vkr_light_textures_t* lt, const vkr_device_t* device, vkr_scene_specification_t* spec) {
+	if (lt) memset(lt, 0, sizeof(*lt));
+	// unique paths in the order of first use; the empty string stands for the white default
+	std::vector<std::string> unique_paths;
+	for (uint32_t i = 0; i != spec->polygonal_light_count; ++i) {
+		std::string path = spec->polygonal_lights[i].texture_file_path ? spec->polygonal_lights[i].texture_file_path : "";
+		if (!path.empty()) {
+			FILE* file = fopen(path.c_str(), "rb");
+			if (file) fclose(file);
+			else {
+				printf("The light texture at path %s does not exist. Using a white texture instead.\n", path.c_str());
+				path.clear();
+			}
+		}
+		uint32_t index = (uint32_t) unique_paths.size();
+		for (uint32_t j = 0; j != unique_paths.size(); ++j) if (unique_paths[j] == path) index = j;
+		if (index == unique_paths.size()) unique_paths.push_back(path);
+		spec->polygonal_lights[i].texture_index = index;
+	}
+	if (!lt) return 0;
+	if (unique_paths.empty()) unique_paths.push_back(""); // the reference avoids empty descriptor arrays the same way
+	lt->texture_count = (uint32_t) unique_paths.size();
+	lt->textures = (vkr_texture_t*) calloc(lt->texture_count, sizeof(vkr_texture_t));
+	bool failed = false;
+	for (uint32_t i = 0; i != lt->texture_count && !failed; ++i) {
+		vkr_texture_t& t = lt->textures[i];
+		if (unique_paths[i].empty()) { // white, 1x1
+			t.width = t.height = t.mip_count = 1; t.vk_format = 109; t.texel_float_count = 4; t.is_constant = 1;
+			t.h_texels = (float*) malloc(4 * sizeof(float));
+			for (int c = 0; c != 4; ++c) t.h_texels[c] = 1.0f;
+		}
+		else failed = vkr_load_texture(&t, unique_paths[i].c_str()) != 0;
+	}
+	if (!failed) {
+		std::vector<uint32_t> dims(4 * (size_t) lt->texture_count); std::vector<uint64_t> offsets(lt->texture_count);
+		uint64_t texel_count = 0;
+		for (uint32_t k = 0; k != lt->texture_count; ++k) {
+			dims[4 * k] = lt->textures[k].width; dims[4 * k + 1] = lt->textures[k].height; dims[4 * k + 2] = lt->textures[k].mip_count; dims[4 * k + 3] = 0;
+			offsets[k] = texel_count; texel_count += lt->textures[k].texel_float_count / 4;
+		}
+		lt->texel_count = texel_count;
+		if (device) {
+			std::vector<float> data(4 * (size_t) texel_count);
+			for (uint32_t k = 0; k != lt->texture_count; ++k) memcpy(&data[4 * (size_t) offsets[k]], lt->textures[k].h_texels, sizeof(float) * (size_t) lt->textures[k].texel_float_count);
+			failed = upload(&lt->d_texels, data.data(), data.size() * 4, device) || upload(&lt->d_dims, dims.data(), dims.size() * 4, device) || upload(&lt->d_offsets, offsets.data(), offsets.size() * 8, device);
+		}
+	}
+	if (failed) {
+		printf("Failed to load the textures of the polygonal lights.\n");
+		vkr_destroy_light_textures(lt, device); return 1;
+	}
+	return 0;
+}
+
 extern "C" int vkr_quick_load(vkr_scene_specification_t* spec, const char* quick_save_path) {
 	FILE* file = fopen(quick_save_path, "rb");
 	if (!file) { printf("Failed to load a quick save. Please check path and permissions: %s\n", quick_save_path); return 1; }

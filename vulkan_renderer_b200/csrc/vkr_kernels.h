@@ -34,6 +34,8 @@ struct shading_kernel_params {
 	int polygon_sampling_technique;  // sample_polygon_technique_t (src/polygonal_light.h:30-66); 0..10 run vkr_related_work_kernel.cu
 	int bvh_width;                   // children per node of bvh_nodes: 2 (node pairs, default) or 4 (experimental, must equal the kernels' VKR_BVH_WIDTH)
 	int error_display;               // error_display_t (src/main.h:92-112); != 0 runs error_display_kernel (vkr_related_work_kernel.cu)
+	// light textures (vkr_light_textures_t); only the kernels of vkr_textured_light_kernel.cu read them. dims = {width, height, mip_count, -}, offsets in texels
+	const float4* light_texture_texels; const uint4* light_texture_dims; const unsigned long long* light_texture_offsets; uint32_t light_texture_count;
 };
 
 struct gbuffer_kernel_params {
@@ -58,6 +60,11 @@ cudaError_t vkr_launch_shading_kernel_maxp5(const vkr::shading_kernel_params& p,
 cudaError_t vkr_launch_shading_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_light_kernel_maxp4(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_textured_light_kernel.cu, frames with textured lights
+cudaError_t vkr_launch_textured_light_kernel_maxp5(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_light_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_light_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_light_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_related_work_kernel_maxv3(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_related_work_kernel.cu, one object per light vertex bound
 cudaError_t vkr_launch_related_work_kernel_maxv4(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_related_work_kernel_maxv5(const vkr::shading_kernel_params& p, cudaStream_t stream);

@@ -7,6 +7,7 @@
 #include "vkr_psa.cuh"
 #include "vkr_trace.cuh"
 #include "vkr_kernels.h"
+#include "vkr_texture.cuh"
 
 namespace vkr {
 
@@ -15,7 +16,7 @@ enum {
 	OFF_PIXEL_TO_RAY = 96, OFF_CAMERA = 144, OFF_MIS_VIS = 156, OFF_EXPOSURE = 176,
 	OFF_NOISE_RES_MASK = 184, OFF_NOISE_LAYER_MASK = 192, OFF_FRAME_BITS = 196, OFF_NOISE_RANDOM = 208, OFF_LTC = 224, CONSTANTS_FIXED = 256,
 	// inside one light block (polygonal_light_utility.glsl:26-83)
-	L_SURFACE_RADIANCE = 48, L_PLANE = 64, L_VERTEX_COUNT = 80, L_FIXED = 160
+	L_SURFACE_RADIANCE = 48, L_PLANE = 64, L_VERTEX_COUNT = 80, L_TRANSLATION = 16, L_INV_SCALING_X = 44, L_INV_SCALING_Y = 60, L_TEXTURING = 84, L_TEXTURE_INDEX = 88, L_ROTATION = 96, L_FIXED = 160
 };
 
 struct shading_point {
@@ -322,5 +323,48 @@ VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char*
 	return -num / den;
 }
 VKR_DEV f3 light_radiance(const unsigned char* light) { return make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8)); }
+
+// get_polygon_radiance() (shading_pass.frag.glsl:151-185): radiance received at position from direction dir (normalised, hits the light's plane).
+// LIGHT_TEXTURES = false is the untextured case every benchmark configuration runs; true adds the three texturing techniques
+// (polygon_texturing_technique_t, src/polygonal_light.h: 1 area, 2 portal onto a light probe, 3 IES profile).
+template <bool LIGHT_TEXTURES>
+VKR_DEV f3 light_radiance(const shading_kernel_params& p, const unsigned char* light, f3 position, f3 dir) {
+	f3 radiance = light_radiance(light);
+	if constexpr (LIGHT_TEXTURES) {
+		const uint32_t technique = ldu(light, L_TEXTURING);
+		if (technique != 0u) {
+			// plane space = transpose(rotation) * world; rotation is stored row major with a stride of four floats
+			const f3 c0 = make3(ldf(light, L_ROTATION), ldf(light, L_ROTATION + 16), ldf(light, L_ROTATION + 32));
+			const f3 c1 = make3(ldf(light, L_ROTATION + 4), ldf(light, L_ROTATION + 20), ldf(light, L_ROTATION + 36));
+			float u, v;
+			if (technique == 1u) {
+				const float num = dot4_point(light + L_PLANE, position);
+				const float t = -num / dot(dir, make3(ldf(light, L_PLANE), ldf(light, L_PLANE + 4), ldf(light, L_PLANE + 8)));
+				f3 intersection = position + dir * t;
+				intersection = intersection - make3(ldf(light, L_TRANSLATION), ldf(light, L_TRANSLATION + 4), ldf(light, L_TRANSLATION + 8));
+				u = dot(c0, intersection) * ldf(light, L_INV_SCALING_X);
+				v = dot(c1, intersection) * ldf(light, L_INV_SCALING_Y);
+			}
+			else {
+				f3 lookup;
+				if (technique == 3u) {
+					const f3 c2 = make3(ldf(light, L_ROTATION + 8), ldf(light, L_ROTATION + 24), ldf(light, L_ROTATION + 40));
+					lookup = make3(dot(c0, dir), dot(c1, dir), dot(c2, dir));
+					radiance = radiance * (1.0f / fabsf(lookup.z)); // IES profiles include the cosine already
+				}
+				else lookup = make3(-dir.x, dir.y, dir.z); // the layout of HDRI Haven light probes
+				u = atan2_poly(lookup.y, lookup.x) * (0.5f * kInvPi);
+				v = acos_full(lookup.z) * kInvPi;
+			}
+			const uint32_t index = ldu(light, L_TEXTURE_INDEX);
+			const uint4 dims = __ldg(p.light_texture_dims + index);
+			texture_view view;
+			view.width = dims.x; view.height = dims.y; view.mip_count = dims.z; view.texels = p.light_texture_texels + __ldg(p.light_texture_offsets + index);
+			const float4 texel = texture_bilinear_repeat_clamp(view, u, v);
+			radiance = make3(radiance.x * texel.x, radiance.y * texel.y, radiance.z * texel.z);
+		}
+	}
+	return radiance;
+}
 
 } // namespace vkr

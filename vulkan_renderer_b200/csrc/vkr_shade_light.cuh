@@ -11,7 +11,7 @@ namespace vkr {
 
 // One polygonal light for the warp's 32 pixels (shading_pass.frag.glsl:329-711, projected solid angle technique).
 // Control flow is warp-uniform; `on` masks lanes whose pixel is not shaded by this light.
-template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE, bool LIGHT_TEXTURES = false>
 VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
 	const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, pixel_sum& result, int lane)
 {
@@ -39,7 +39,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 				pre_vis = lambert > 0.0f;
 				if (pre_vis) {
 					tmax = light_plane_distance(sp, light, w);
-					const f3 rtb = light_radiance(light) * evaluate_brdf<true, true>(sp, w);
+					const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
 					if (STRATEGY == VKR_STRATEGY_DIFFUSE_ONLY) {
 						has = density > 0.0f;
 						c = rtb * (lambert / density);
@@ -72,7 +72,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 						if (lambert > 0.0f) {
 							has = true;
 							tmax = light_plane_distance(sp, light, w);
-							const f3 rtb = light_radiance(light) * evaluate_brdf<true, true>(sp, w);
+							const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
 							const float polygon_density = lambert * density_factor;
 							const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (ggx_density + polygon_density)) : (ggx_density / (ggx_density * ggx_density + polygon_density * polygon_density));
 							c = make3(rtb.x * lambert * wgt, rtb.y * lambert * wgt, rtb.z * lambert * wgt);
@@ -105,7 +105,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					if (dot(sp.normal, w) > 0.0f) {
 						has = true;
 						tmax = light_plane_distance(sp, light, w);
-						c = (light_radiance(light) * evaluate_brdf<true, false>(sp, w)) * pd.psa;
+						c = (light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, false>(sp, w)) * pd.psa;
 					}
 				}
 				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
@@ -118,7 +118,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					if (dot(sp.normal, w) > 0.0f && !(dsh.z <= 0.0f || dc.z <= 0.0f)) {
 						has = true;
 						tmax = light_plane_distance(sp, light, w);
-						const f3 rtb2 = light_radiance(light) * evaluate_brdf<false, true>(sp, w);
+						const f3 rtb2 = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<false, true>(sp, w);
 						c = make3(rtb2.x * dsh.z * ps.psa / ltc_density, rtb2.y * dsh.z * ps.psa / ltc_density, rtb2.z * dsh.z * ps.psa / ltc_density);
 					}
 				}
@@ -157,7 +157,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 							f3 integrand = zero;
 							if (pre_vis) {
 								tmax = light_plane_distance(sp, light, w);
-								integrand = (light_radiance(light) * evaluate_brdf<true, true>(sp, w)) * d.z;
+								integrand = (light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w)) * d.z;
 							}
 							if (j == 0 && !has_specular) { // one technique only: no MIS (:629-631)
 								c = integrand * (1.0f / diffuse_density);
@@ -197,7 +197,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					if (dot(sp.normal, w) > 0.0f && !(d.z <= 0.0f)) {
 						has = true;
 						tmax = light_plane_distance(sp, light, w);
-						const f3 rtb = light_radiance(light) * evaluate_brdf<true, true>(sp, w);
+						const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
 						c = make3(rtb.x * d.z / density, rtb.y * d.z / density, rtb.z * d.z / density);
 					}
 				}
@@ -209,12 +209,12 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 }
 
 // The light shader of this translation unit: projected solid angle sampling with the five sampling strategies
-template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
+template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE, bool LIGHT_TEXTURES = false>
 struct psa_light_shader {
 	VKR_DEV void operator()(bool on, const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns,
 		const shading_kernel_params& p, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer& q, pixel_sum& result, int lane) const
 	{
-		shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>(on, sp, l, light, ns, p, cb, px, py, q, result, lane);
+		shade_light<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE, LIGHT_TEXTURES>(on, sp, l, light, ns, p, cb, px, py, q, result, lane);
 	}
 };
 

@@ -25,7 +25,7 @@ constexpr int kTraceThreads = 32 * kTraceWarps;
 // LightShader: void operator()(bool on, const shading_point&, const ltc_state&, const unsigned char* light, noise_stream&,
 //   const shading_kernel_params&, const unsigned char* cb, uint32_t px, uint32_t py, ray_producer&, pixel_sum&, int lane) const
 // -- one polygonal light for the warp's 32 pixels; control flow must be warp-uniform (`on` masks lanes).
-template <int MAXP, bool OPTIMAL, bool TRACE, class LightShader>
+template <int MAXP, bool OPTIMAL, bool TRACE, bool LIGHT_TEXTURES = false, class LightShader>
 VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade) {
 	__builtin_assume(threadIdx.x < (unsigned) (TRACE ? kShadeThreads + kTraceThreads : kShadeThreads)); // the kernels' __launch_bounds__, for the inlined body
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -89,19 +89,21 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 	const int light_stride = L_FIXED + 16 * (MAXP - 1) * 2 + 16 * (MAXP - 3);
 	if (p.show_polygonal_lights && in_frame) { // shading_pass.frag.glsl:841-850
 		f3 end; float end_w;
+		f3 view_direction = make3(0.0f, 0.0f, 0.0f); // only textured lights look at it (:844, 847)
 		if (valid) { end = sp.position; end_w = 1.0f; }
-		else {
+		if (!valid || LIGHT_TEXTURES) {
 			const float fx = (float) x, fy = (float) y;
-			end = make3(
+			view_direction = make3(
 				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 8), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 4), fy, ldf(cb, OFF_PIXEL_TO_RAY) * fx)),
 				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 24), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 20), fy, ldf(cb, OFF_PIXEL_TO_RAY + 16) * fx)),
 				fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 40), 1.0f, fmaf(ldf(cb, OFF_PIXEL_TO_RAY + 36), fy, ldf(cb, OFF_PIXEL_TO_RAY + 32) * fx)));
-			end_w = 0.0f;
+			if (!valid) { end = view_direction; end_w = 0.0f; }
+			if (LIGHT_TEXTURES) view_direction = normalize(view_direction);
 		}
 		for (int li = 0; li != p.light_count; ++li) {
 			const unsigned char* light = cb + CONSTANTS_FIXED + li * light_stride;
 			if (light_ray_intersection<MAXP - 1>(light, camera, end, end_w))
-				color = color + make3(ldf(light, L_SURFACE_RADIANCE), ldf(light, L_SURFACE_RADIANCE + 4), ldf(light, L_SURFACE_RADIANCE + 8));
+				color = color + light_radiance<LIGHT_TEXTURES>(p, light, camera, view_direction);
 		}
 	}
 	// --- the warp's ray stream; trace lanes fetch ray origins from it by owner lane

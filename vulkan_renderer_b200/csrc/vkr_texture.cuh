@@ -40,6 +40,30 @@ VKR_DEV float4 texture_bilinear(const texture_view& t, uint32_t level, float u, 
 	return out;
 }
 
+// textureLod(..., 0.0f) with the sampler of the light textures (src/main.c:613-623: linear filters, repeat in u, clamp to edge in v):
+// one bilinear tap on level 0; oracle/texture_filter.h: vkr_texture_bilinear_repeat_clamp, word for word
+VKR_DEV float4 texture_bilinear_repeat_clamp(const texture_view& t, float u, float v) {
+	const float4* texels = t.texels;
+	const uint32_t w = t.width, h = t.height;
+	float x = u * (float) w - 0.5f, y = v * (float) h - 0.5f;
+	if (!(fabsf(x) < 1.0e9f)) x = 0.0f;
+	if (!(fabsf(y) < 1.0e9f)) y = 0.0f;
+	const float x0f = floorf(x), y0f = floorf(y);
+	const float fx = x - x0f, fy = y - y0f;
+	const int x0 = texture_wrap((int) x0f, (int) w), x1 = texture_wrap((int) x0f + 1, (int) w);
+	int y0 = (int) y0f, y1 = (int) y0f + 1;
+	y0 = (y0 < 0) ? 0 : ((y0 > (int) h - 1) ? (int) h - 1 : y0);
+	y1 = (y1 < 0) ? 0 : ((y1 > (int) h - 1) ? (int) h - 1 : y1);
+	const float4 t00 = __ldg(texels + (size_t) y0 * w + x0), t10 = __ldg(texels + (size_t) y0 * w + x1);
+	const float4 t01 = __ldg(texels + (size_t) y1 * w + x0), t11 = __ldg(texels + (size_t) y1 * w + x1);
+	float4 out;
+	{ const float a = fmaf(fx, t10.x - t00.x, t00.x), b = fmaf(fx, t11.x - t01.x, t01.x); out.x = fmaf(fy, b - a, a); }
+	{ const float a = fmaf(fx, t10.y - t00.y, t00.y), b = fmaf(fx, t11.y - t01.y, t01.y); out.y = fmaf(fy, b - a, a); }
+	{ const float a = fmaf(fx, t10.z - t00.z, t00.z), b = fmaf(fx, t11.z - t01.z, t01.z); out.z = fmaf(fy, b - a, a); }
+	{ const float a = fmaf(fx, t10.w - t00.w, t00.w), b = fmaf(fx, t11.w - t01.w, t01.w); out.w = fmaf(fy, b - a, a); }
+	return out;
+}
+
 VKR_DEV float4 texture_grad(const texture_view& t, f2 uv, f2 ddx, f2 ddy) {
 	const f2 px = make2(ddx.x * (float) t.width, ddx.y * (float) t.height), py = make2(ddy.x * (float) t.width, ddy.y * (float) t.height);
 	const float lx2 = dot(px, px), ly2 = dot(py, py);

@@ -22,6 +22,12 @@ class Frame:
 		self._check(self.lib.vkr_load_ltc_table(C.byref(self.ltc), C.byref(self.device), ltc_dir.encode(), fresnel_count), "vkr_load_ltc_table")
 		self._check(self.lib.vkr_load_noise_table(C.byref(self.noise), C.byref(self.device), noise[0], noise[1], noise[2], api.NOISE_WHITE), "vkr_load_noise_table")
 		self._check(self.lib.vkr_quick_load(C.byref(self.spec), save.encode()), "vkr_quick_load")
+		# create_and_assign_light_textures (src/main.c:371): texture indices for all lights; the textures go to the device only if a light is textured
+		self.light_textures = api.LightTextures()
+		if any(self.spec.polygonal_lights[i].texturing_technique != 0 for i in range(self.spec.polygonal_light_count)):
+			self._check(self.lib.vkr_create_and_assign_light_textures(C.byref(self.light_textures), C.byref(self.device), C.byref(self.spec)), "vkr_create_and_assign_light_textures")
+		else:
+			self._check(self.lib.vkr_create_and_assign_light_textures(None, None, C.byref(self.spec)), "vkr_create_and_assign_light_textures")
 		self.lib.vkr_specify_default_render_settings(C.byref(self.settings))
 		self.settings.animate_noise = 0
 		self.settings.exposure_factor = 1.0
@@ -86,6 +92,7 @@ class Frame:
 		d.scene = C.pointer(self.scene); d.ltc_table = C.pointer(self.ltc); d.noise_table = C.pointer(self.noise)
 		d.output_srgb = getattr(self, "output_srgb", 0)
 		d.error_display = getattr(self, "error_display", 0)
+		d.light_textures = C.pointer(self.light_textures) if self.light_textures.texture_count else None
 		return d
 
 	def create_pass(self, width, height, stripe_index=0, stripe_count=1, timing=False):
@@ -132,6 +139,7 @@ class Frame:
 		for p in list(self._passes):
 			self.destroy_pass(p)
 		dev = C.byref(self.device)
+		self.lib.vkr_destroy_light_textures(C.byref(self.light_textures), dev)
 		self.lib.vkr_destroy_scene_specification(C.byref(self.spec))
 		self.lib.vkr_destroy_noise_table(C.byref(self.noise), dev)
 		self.lib.vkr_destroy_ltc_table(C.byref(self.ltc), dev)

@@ -366,6 +366,24 @@ def write_vkt(path, level0, vk_format=97):
 		f.write(struct.pack("<I", 0x00E0FE0F))
 
 
+def write_light_textures(directory):
+	"""Three light textures: [0] an area texture (coloured checker with a soft spot, BC1), [1] a light probe in the theta-phi layout the
+	shader expects (u = azimuth / 2 pi, v = polar angle / pi; RGBA16F, values above 1), [2] an IES-like profile (rotationally
+	asymmetric lobe, RGBA16F). Returns the three paths."""
+	os.makedirs(directory, exist_ok=True)
+	paths = [os.path.join(directory, n) for n in ("area.vkt", "probe.vkt", "ies.vkt")]
+	v, u = np.meshgrid((np.arange(16) + 0.5) / 16.0, (np.arange(16) + 0.5) / 16.0, indexing="ij")
+	checker = ((np.floor(u * 4) + np.floor(v * 4)) % 2)[..., None]
+	area = np.clip(checker * np.array([0.9, 0.5, 0.1]) + (1.0 - checker) * np.array([0.1, 0.4, 0.9]) + 0.3 * np.exp(-8.0 * ((u - 0.5) ** 2 + (v - 0.5) ** 2))[..., None], 0.0, 1.0)
+	write_vkt(paths[0], area.astype(np.float32), vk_format=131)
+	v, u = np.meshgrid((np.arange(16) + 0.5) / 16.0, (np.arange(32) + 0.5) / 32.0, indexing="ij")
+	sky = np.stack([0.4 + 0.6 * v, 0.6 + 0.3 * np.cos(2.0 * np.pi * u), 1.2 - 0.8 * v], axis=-1) + 6.0 * np.exp(-40.0 * ((u - 0.3) ** 2 + (v - 0.35) ** 2))[..., None]
+	write_vkt(paths[1], sky.astype(np.float32), vk_format=97)
+	lobe = (np.cos(0.5 * np.pi * np.clip(v * 2.0, 0.0, 1.0)) ** 2 * (1.0 + 0.5 * np.cos(4.0 * np.pi * u)))[..., None] * np.array([1.0, 0.95, 0.8])
+	write_vkt(paths[2], lobe.astype(np.float32), vk_format=97)
+	return paths
+
+
 def write_material_textures(directory, materials):
 	os.makedirs(directory, exist_ok=True)
 	for m in materials:
@@ -446,8 +464,10 @@ def write_quicksave(path, camera, lights):
 			n = len(L["vertices"])
 			# the first 88 bytes of polygonal_light_t: 20 floats + vertex_count + texturing_technique
 			f.write(struct.pack("<3ff3ff3ff3ff4f", *L["rotation_angles"], L["scaling"][0], *L["translation"], L["scaling"][1], *L["flux"], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0))
-			f.write(struct.pack("<II", n, 0))
-			f.write(struct.pack("<Q", 0))        # no texture path
+			f.write(struct.pack("<II", n, int(L.get("texturing_technique", 0))))
+			path = L.get("texture_file_path", "").encode()
+			f.write(struct.pack("<Q", len(path) + 1 if path else 0))   # texture path with its terminator, 0 = none (src/main.c:94-100)
+			if path: f.write(path + b"\0")
 			f.write(struct.pack("<QQ", 0, 0))    # legacy NULL pointers
 			for (x, y) in L["vertices"]:
 				f.write(struct.pack("<4f", x, y, 0.0, 0.0))
@@ -483,7 +503,7 @@ def _ceiling_lights(rng, count, x_range, y_range, z_range, scale_range=(0.5, 2.0
 def build_dataset(directory, name, **overrides):
 	"""Writes <name>.vks, <name>_textures/, <name>.save and ggx_ltc_fit/ into directory; returns paths and metadata."""
 	os.makedirs(directory, exist_ok=True)
-	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_textured": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4, "mini_v5": 3, "mini_v6": 3, "mini_v7": 3, "mini_poly": 3}.get(name, 9))
+	rng = np.random.default_rng({"cornell": 0, "city": 1, "room": 2, "mini_city": 3, "mini_textured": 3, "mini_lit": 3, "mini_tri": 3, "mini_mixed": 3, "mini_room": 4, "mini_v5": 3, "mini_v6": 3, "mini_v7": 3, "mini_poly": 3}.get(name, 9))
 	if name == "cornell":
 		mesh, materials = scene_cornell()
 		camera = look_at_camera((0.5, -1.2, 0.5), (0.5, 0.5, 0.5))
@@ -509,6 +529,17 @@ def build_dataset(directory, name, **overrides):
 		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
 		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
 		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+	elif name == "mini_lit":
+		# the mini_city scene under textured lights (get_polygon_radiance, shading_pass.frag.glsl:151-185): an area texture (BC1), a light probe seen
+		# through a portal and an IES profile (both RGBA16F, theta-phi parametrisation); polygon_texturing_technique_t 1, 2, 3
+		mesh, materials = scene_city(seed=3, blocks=4, extent=32.0, detail=2, ground_cells=8, n_mat=8)
+		camera = look_at_camera((14.0, 1.0, 5.0), (16.0, 14.0, 1.5))
+		lights = _ceiling_lights(rng, overrides.get("lights", 3), (10.0, 22.0), (8.0, 20.0), (2.0, 4.0))
+		light_texture_directory = os.path.join(directory, name + "_light_textures")
+		paths = write_light_textures(light_texture_directory)
+		for i, light in enumerate(lights):
+			light["texturing_technique"] = 1 + i % 3
+			light["texture_file_path"] = paths[i % 3]
 	elif name in ("mini_tri", "mini_mixed"):
 		# the mini_city scene lit by triangles (MAX_POLYGONAL_LIGHT_VERTEX_COUNT = 3) or by a triangle, a quad and a
 		# triangle (MIN_POLYGON_VERTEX_COUNT_BEFORE_CLIPPING = 3 < MAX = 4, main.c:730-732)
