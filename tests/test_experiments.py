@@ -31,7 +31,7 @@ def test_timing_matrix_has_the_shape_and_names_of_the_reference_list():
 		assert s["polygon_sampling_technique"] == E.SAMPLE_POLYGON_NAME.index(m.group(4))
 	assert (E.SAMPLE_POLYGON_NAME.index("projected_solid_angle_ours"), E.SAMPLE_POLYGON_NAME.index("projected_solid_angle_biased_ours")) == (api.TECHNIQUE_PSA, api.TECHNIQUE_PSA_BIASED)
 	figures = E.experiment_list(all_timings=False)
-	assert figures[0]["name"] == "attic_solid_angle_and_ggx_mis_2spp" and len(figures) == 5 + 2 + 2 * 12 + 8 + 16 + 2 + 2
+	assert figures[0]["name"] == "attic_solid_angle_and_ggx_mis_2spp" and len(figures) == 5 + 2 + 2 * 12 + 8 + 16 + 2 + 1 + 3
 	assert len({e["name"] for e in figures}) == len(figures)
 	assert E.experiment_list(all_figs=False) == t and len(E.experiment_list()) == len(figures) + 260
 	by_name = {e["name"]: e for e in figures}
@@ -39,6 +39,9 @@ def test_timing_matrix_has_the_shape_and_names_of_the_reference_list():
 	assert "bistro_tiny_polygon_bilinear_cosine_warp_clipping_hart_1spp" not in by_name and by_name["bistro_small_polygon_reference_128spp"]["settings"]["sample_count"] == 128
 	assert by_name["mis_plane_optimal_ours_2spp"]["settings"]["mis_heuristic"] == api.MIS_OPTIMAL and by_name["shadowed_plane_biased_4096spp"]["settings"]["sample_count"] == 2048
 	assert by_name["cornell_box_projected_solid_angle_arvo_tilted_1spp"]["quick_save_path"] == "data/quicksaves/cornell_box_tilted_light.save"
+	names = [e["name"] for e in figures]   # the textured-light figures sit where the reference has them (src/experiment_list.c:294-362)
+	assert names.index("shadowed_plane_biased_4096spp") + 1 == names.index("ies_profile_attic_2spp") and names[-1] == "roughness_planes_screen_2spp"
+	assert by_name["ies_profile_attic_2spp"]["scene_parameters"] == dict(ies_profile=1) and by_name["roughness_planes_screen_2spp"]["settings"]["mis_heuristic"] == api.MIS_OPTIMAL_CLAMPED
 
 
 def test_every_experiment_is_a_legal_configuration(capfd):
@@ -54,11 +57,17 @@ def test_every_experiment_is_a_legal_configuration(capfd):
 		assert "missing LTC / noise tables" in capfd.readouterr().out, e["name"]
 
 
-@pytest.mark.parametrize("name", ["mis_plane_weighted_ours_2spp", "cornell_box_projected_solid_angle_arvo_tilted_1spp", "roughness_planes_lambertian_2spp"])
+@pytest.mark.parametrize("name", ["mis_plane_weighted_ours_2spp", "cornell_box_projected_solid_angle_arvo_tilted_1spp", "roughness_planes_lambertian_2spp",
+	"ies_profile_attic_2spp", "roughness_planes_screen_2spp"])
 def test_figure_scene_data_loads_and_is_lit(name):
 	e = [x for x in E.experiment_list(all_timings=False) if x["name"] == name][0]
-	info = H.dataset(e["scene"], **e["scene_parameters"])
+	parameters = dict(e["scene_parameters"])
+	if e["scene"] == "room": parameters.update(detail=6, clutter=60, n_mat=8)   # the same room with few triangles: the oracle's visibility pass is brute force
+	info = H.dataset(e["scene"], **parameters)
 	oi = H.OracleInputs(info)
+	textured = [l.get("texturing_technique", 0) for l in info["lights"]]
+	assert textured == {"ies_profile_attic_2spp": [3], "roughness_planes_screen_2spp": [1]}.get(name, [0] * len(info["lights"]))
+	assert (oi.light_textures is not None) == any(textured)
 	width, height = 64, 48
 	lights = len(info["lights"]); vertices = max(len(l["vertices"]) for l in info["lights"])
 	constants = host_constants(info, width, height, lights)

@@ -124,18 +124,25 @@ def shadowed_plane_experiments():
 		_figure("shadowed_plane_biased_4096spp", "shadowed_plane", 1024, 1024, polygon_sampling_technique=api.TECHNIQUE_PSA_BIASED, **base)]
 
 
+def ies_profile_experiments():
+	"""src/experiment_list.c:294-314: the attic under a rectangular light with an IES profile (polygon_texturing_ies_profile)."""
+	return [_figure("ies_profile_attic_2spp", "room", 1280, 1024, dict(ies_profile=1), "data/quicksaves/attic_ies_profile.save", exposure_factor=8.0,
+		sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_OPTIMAL_CLAMPED)]
+
+
 def roughness_planes_experiments():
-	"""src/experiment_list.c:316-339: three planes of different roughness under a Lambertian emitter (the textured emitter of :341-362 is out of scope)."""
-	base = dict(sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_WEIGHTED)
+	"""src/experiment_list.c:316-362: three planes of different roughness under a Lambertian emitter, then under a textured one (polygon_texturing_area)."""
+	base = dict(exposure_factor=8.0, sampling_strategies=api.STRATEGY_DIFFUSE_SPECULAR_MIS, mis_heuristic=api.MIS_WEIGHTED)
 	parameters = dict(vertices=4, central=1, lights=1)
 	return [_figure("roughness_planes_lambertian_2spp", "roughness_planes", 2048 + 256, 1024, parameters, **base),
-		_figure("roughness_planes_lambertian_diffuse_only_1spp", "roughness_planes", 2048 + 256, 1024, parameters, **dict(base, sampling_strategies=api.STRATEGY_DIFFUSE_ONLY))]
+		_figure("roughness_planes_lambertian_diffuse_only_1spp", "roughness_planes", 2048 + 256, 1024, parameters, **dict(base, sampling_strategies=api.STRATEGY_DIFFUSE_ONLY)),
+		_figure("roughness_planes_screen_2spp", "roughness_planes", 1280, 1024, dict(screen=1), "data/quicksaves/roughness_planes_screen.save", **dict(base, mis_heuristic=api.MIS_OPTIMAL_CLAMPED))]
 
 
 def experiment_list(all_figs=True, all_timings=True):
-	"""create_experiment_list (src/experiment_list.c:25-555) in its order, restricted to what runs on untextured polygonal lights: the IES-profile attic
-	(:294-314) and the textured screen (:341-362) are left out, as are the figures for the HTML viewer (html_figs = VK_FALSE in the reference)."""
-	figures = attic_experiments() + error_experiments() + small_light_experiments() + mis_plane_experiments() + cornell_box_experiments() + shadowed_plane_experiments() + roughness_planes_experiments()
+	"""create_experiment_list (src/experiment_list.c:25-555) in its order; the figures for the HTML viewer are left out (html_figs = VK_FALSE in the reference)."""
+	figures = (attic_experiments() + error_experiments() + small_light_experiments() + mis_plane_experiments() + cornell_box_experiments() + shadowed_plane_experiments()
+		+ ies_profile_experiments() + roughness_planes_experiments())
 	return (figures if all_figs else []) + (timing_experiments() if all_timings else [])
 
 

@@ -379,7 +379,7 @@ def write_light_textures(directory):
 	v, u = np.meshgrid((np.arange(16) + 0.5) / 16.0, (np.arange(32) + 0.5) / 32.0, indexing="ij")
 	sky = np.stack([0.4 + 0.6 * v, 0.6 + 0.3 * np.cos(2.0 * np.pi * u), 1.2 - 0.8 * v], axis=-1) + 6.0 * np.exp(-40.0 * ((u - 0.3) ** 2 + (v - 0.35) ** 2))[..., None]
 	write_vkt(paths[1], sky.astype(np.float32), vk_format=97)
-	lobe = (np.cos(0.5 * np.pi * np.clip(v * 2.0, 0.0, 1.0)) ** 2 * (1.0 + 0.5 * np.cos(4.0 * np.pi * u)))[..., None] * np.array([1.0, 0.95, 0.8])
+	lobe = (np.cos(np.pi * v) ** 2 * (1.0 + 0.5 * np.cos(4.0 * np.pi * u)))[..., None] * np.array([1.0, 0.95, 0.8])   # bright towards both poles of the light's normal, dark sideways
 	write_vkt(paths[2], lobe.astype(np.float32), vk_format=97)
 	return paths
 
@@ -574,10 +574,18 @@ def build_dataset(directory, name, **overrides):
 		mesh, materials = scene_roughness_planes()
 		camera = look_at_camera((0.0, -6.0, 7.5), (0.0, 0.0, 0.0))
 		lights = roughness_planes_lights(int(overrides.get("vertices", 4)), bool(overrides.get("central", 1)), int(overrides.get("lights", 1)))
+		if overrides.get("screen"):   # roughness_planes_screen.save (src/experiment_list.c:341-362): an upright rectangular emitter showing a picture
+			lights = [make_light((-4.0, 5.5, 0.3), (0.5 * np.pi, 0.0, 0.0), (8.0, 4.5), (60.0, 60.0, 60.0))]
+			lights[0]["texturing_technique"] = 1
+			lights[0]["texture_file_path"] = write_light_textures(os.path.join(directory, name + "_light_textures"))[0]
 	elif name == "room":
 		mesh, materials = scene_room(**{k: v for k, v in overrides.items() if k in ("seed", "detail", "clutter", "n_mat")})
 		camera = look_at_camera((0.7, 0.7, 1.65), (8.0, 5.0, 1.0))
 		lights = _ceiling_lights(rng, overrides.get("lights", 32), (1.0, 11.0), (1.0, 7.0), (2.4, 3.3), scale_range=(0.3, 1.0))
+		if overrides.get("ies_profile"):   # attic_ies_profile.save (src/experiment_list.c:294-314): one rectangular ceiling light with an IES profile
+			lights = [make_light((5.2, 3.4, 3.6), (np.pi, 0.0, 0.3), (1.6, 0.8), (120.0, 120.0, 120.0))]
+			lights[0]["texturing_technique"] = 3
+			lights[0]["texture_file_path"] = write_light_textures(os.path.join(directory, name + "_light_textures"))[2]
 	else:
 		raise ValueError(name)
 	vks = os.path.join(directory, name + ".vks")
