@@ -26,4 +26,6 @@ for i in range(3):
 	lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr())
 	lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device))
 	print("spp %d lights %d rays %d strategy %d: kernel %.3f ms -> %.1f Msamples/s" % (spp, lights, rays, strategy, p.last_kernel_ms, width * height * spp / p.last_kernel_ms / 1e3), flush=True)
-print("valid fraction", float((gb[1, :, :, 3] != 0).float().mean()), "mean radiance", float(out[..., :3].mean()))
+import hashlib
+print("valid fraction", float((gb[1, :, :, 3] != 0).float().mean()), "mean radiance", float(out[..., :3].mean()),
+	"frame sha256", hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()[:16])   # builders and traversal variants must leave the frame bit-identical
