@@ -295,7 +295,7 @@ typedef struct vkr_shading_pass_desc_s {
 	   in the render settings via g_error_factor in the constant block */
 	vkr_error_display_t error_display;
 	/* textures of the polygonal lights (g_light_textures); may be NULL as long as no light of a frame's constant block is textured.
-	   Frames with textured lights need projected solid angle sampling (technique 11 or 12) and no error display. */
+	   Every sampling technique works with textured lights; the error display does not (it shows no radiance). */
 	const vkr_light_textures_t* light_textures;
 } vkr_shading_pass_desc_t;
 

@@ -44,6 +44,7 @@ void __nanosleep(unsigned); unsigned __activemask(); int __shfl_sync(unsigned, i
 using std::min; using std::max;   // the integer min / max of the device headers
 #include "vkr_error_display.cuh"
 #include "vkr_shade_light.cuh"
+#include "vkr_related_work_light.cuh"
 #include "vkr_lbvh.cuh"
 #include <vector>
 
@@ -290,9 +291,18 @@ static int shading_frame_strategy(const shading_kernel_params& p, int show_light
 	}
 }
 
-// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0. light_texture_count != 0:
-// the LIGHT_TEXTURES = true instantiation (csrc/vkr_textured_light_kernel.cu), dims = {width, height, mip count, 0} per texture, offsets in texels.
-extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t strategy, uint32_t heuristic, int biased, uint32_t sample_count, int show_lights,
+// The same with the related-work techniques (csrc/vkr_related_work_light.cuh), technique = p.polygon_sampling_technique (0..10)
+template <int STRATEGY, int MAXV, bool LIGHT_TEXTURES>
+static void related_work_frame(const shading_kernel_params& p, int show_lights, float* out_rgba) {
+	tile_frame<MAXV, LIGHT_TEXTURES>(p, show_lights, [&](const shading_point& sp, const ltc_state& l, const unsigned char* light, noise_stream& ns, uint32_t x, uint32_t y, pixel_sum& acc) {
+		ray_producer q; q.base = 0; q.fill = 0; q.resolved = 0;
+		related_work_light_shader<STRATEGY, MAXV, false, LIGHT_TEXTURES>()(true, sp, l, light, ns, p, p.constants, x, y, q, acc, 0);
+	}, out_rgba);
+}
+
+// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0. technique: sample_polygon_technique_t, 11 = projected solid angle (biased: 12),
+// 0..10 = related work. light_texture_count != 0: the LIGHT_TEXTURES = true instantiation (csrc/vkr_textured_light_kernel.cu), dims = {width, height, mip count, 0} per texture, offsets in texels.
+extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t technique, uint32_t strategy, uint32_t heuristic, int biased, uint32_t sample_count, int show_lights,
 	const void* constants, const float* gbuffer, const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
 	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
 	uint32_t light_texture_count, const uint32_t* light_texture_dims4, const uint64_t* light_texture_offsets_texels, const float* light_texture_texels, float* out_rgba)
@@ -306,6 +316,17 @@ extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, u
 	p.sampling_strategies = (int) strategy; p.mis_heuristic = (int) heuristic; p.biased_sampling = biased; p.polygon_sampling_technique = biased ? 12 : 11;
 	p.noise = noise; p.noise_w = (int) noise_w; p.noise_h = (int) noise_h; p.noise_layers = (int) noise_layers;
 	p.ltc0 = ltc0; p.ltc1 = ltc1; p.ltc_res = (int) ltc_res; p.ltc_layers = (int) ltc_layers;
+	if (technique < 11) { // related work: diffuse only or GGX MIS
+		p.polygon_sampling_technique = (int) technique;
+		if (biased || strategy > 1) return 1;
+		switch (maxv) {
+#define V(K) case K: if (light_texture_count) { if (strategy) related_work_frame<1, K, true>(p, show_lights, out_rgba); else related_work_frame<0, K, true>(p, show_lights, out_rgba); } \
+	else { if (strategy) related_work_frame<1, K, false>(p, show_lights, out_rgba); else related_work_frame<0, K, false>(p, show_lights, out_rgba); } return 0;
+		V(3) V(4) V(5) V(6) V(7)
+#undef V
+		default: return 1;
+		}
+	}
 	switch (maxv) {
 #define V(K) case K: if (light_texture_count) return biased ? shading_frame_strategy<K, true, true>(p, show_lights, out_rgba) : shading_frame_strategy<K, false, true>(p, show_lights, out_rgba); \
 	return biased ? shading_frame_strategy<K, true, false>(p, show_lights, out_rgba) : shading_frame_strategy<K, false, false>(p, show_lights, out_rgba);

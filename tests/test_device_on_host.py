@@ -236,7 +236,7 @@ def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
 	P = lambda a: a.ctypes.data_as(C.c_void_p)
 	noise = np.ascontiguousarray(oi.noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(oi.ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(oi.ltc1, dtype=np.uint16)
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
-	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["strategy"]),
+	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
 		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
 		C.c_uint32(0), None, None, None, P(out))
@@ -249,10 +249,46 @@ def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
 		assert np.array_equal(out.view(np.uint32), fixture.view(np.uint32)), H.compare_radiance(out, fixture)
 
 
+def _related_work_fixture_names():
+	import os
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	return sorted({k.split("/")[0] for k in g.files if "_q" in k.split("/")[0] and not any(t in k.split("/")[0] for t in ("_e", "_y"))})
+
+
+@pytest.mark.parametrize("name", _related_work_fixture_names())
+def test_related_work_light_shader_without_rays_matches_oracle_and_fixtures(name):
+	"""csrc/vkr_related_work_light.cuh -- the per-(pixel, light) code of related_work_kernel: preparation, sample loop, the NaN rules, GGX MIS -- executed
+	on the CPU for whole frames of every "_q<technique>" fixture configuration with the shadow test compiled out, against the oracle with rays off (and the
+	fixture itself where the reference shader rendered it without rays). Bit-identical."""
+	import os
+	from tests.test_ref_shader import _config_from_name, oracle_cfg
+	from tests.ref_frames import WIDTH, HEIGHT, dataset_for
+	lib = _lib()
+	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
+	cfg = _config_from_name(name)
+	info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+	constants = bytes(g[name + "/constants"])
+	gb = np.ascontiguousarray(oi.gbuffer(WIDTH, HEIGHT, constants, g[name + "/visibility"]), dtype=np.float32)
+	out = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float32)
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	noise = np.ascontiguousarray(oi.noise, dtype=np.uint16); ltc0 = np.ascontiguousarray(oi.ltc0, dtype=np.uint16); ltc1 = np.ascontiguousarray(oi.ltc1, dtype=np.uint16)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
+		C.c_uint32(cfg["heuristic"]), C.c_int(0), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		C.c_uint32(0), None, None, None, P(out))
+	assert rc == 0
+	ref, _ = oi.shade(oracle_cfg(dict(cfg, trace=0)), constants, gb)
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+	if cfg["trace"] == 0:
+		fixture = g[name + "/rgba"]
+		assert np.array_equal(out.view(np.uint32), fixture.view(np.uint32)), H.compare_radiance(out, fixture)
+
+
 def _textured_light_fixture_names():
 	import os
 	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
-	return sorted({k.split("/")[0] for k in g.files if "_y1" in k.split("/")[0] and "_q" not in k.split("/")[0]})
+	return sorted({k.split("/")[0] for k in g.files if "_y1" in k.split("/")[0]})   # incl. "_q4_y1": a related-work technique under textured lights
 
 
 @pytest.mark.parametrize("name", _textured_light_fixture_names())
@@ -277,7 +313,7 @@ def test_textured_lights_without_rays_match_oracle_and_fixtures(name):
 	dims = np.zeros((len(dims3), 4), dtype=np.uint32); dims[:, :3] = dims3
 	offsets_texels = np.ascontiguousarray(offsets // 4, dtype=np.uint64); data = np.ascontiguousarray(data, dtype=np.float32)
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
-	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["strategy"]),
+	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
 		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
 		C.c_uint32(len(dims)), P(dims), P(offsets_texels), P(data), P(out))

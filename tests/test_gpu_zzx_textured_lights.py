@@ -17,7 +17,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref
 
 def _fixture_names():
 	g = np.load(GOLDEN)
-	return sorted({k.split("/")[0] for k in g.files if "_y1" in k.split("/")[0] and "_q" not in k.split("/")[0]})
+	return sorted({k.split("/")[0] for k in g.files if "_y1" in k.split("/")[0]})   # incl. "_q4_y1": a related-work technique (vkr_textured_related_work_kernel.cu)
 
 
 @pytest.mark.parametrize("name", _fixture_names())
@@ -30,7 +30,8 @@ def test_textured_lights_reproduce_reference_shader_fixture(name):
 	frame = H.open_frame(info)
 	try:
 		assert frame.light_textures.texture_count == 3
-		frame.configure(sample_count=cfg["samples"], strategy=cfg["strategy"], heuristic=cfg["heuristic"], technique=api.TECHNIQUE_PSA_BIASED if cfg["biased"] else api.TECHNIQUE_PSA,
+		technique = cfg["technique"] if cfg["technique"] != api.TECHNIQUE_PSA else (api.TECHNIQUE_PSA_BIASED if cfg["biased"] else api.TECHNIQUE_PSA)
+		frame.configure(sample_count=cfg["samples"], strategy=cfg["strategy"], heuristic=cfg["heuristic"], technique=technique,
 			trace_shadow_rays=cfg["trace"], show_lights=cfg["show_lights"], light_count=cfg["lights"])
 		constants = frame.constants(WIDTH, HEIGHT)
 		assert constants == bytes(g[name + "/constants"])
@@ -58,13 +59,30 @@ def test_textured_lights_match_the_oracle_on_a_larger_frame(technique):
 	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
 
 
-def test_textured_lights_are_refused_where_the_kernels_do_not_support_them():
-	"""Related-work techniques and the error display have no textured variant: the pass says so instead of rendering white lights."""
+@pytest.mark.parametrize("technique,strategy", [(api.TECHNIQUE_AREA_TURK, api.STRATEGY_DIFFUSE_ONLY), (api.TECHNIQUE_RECTANGLE_SOLID_ANGLE_URENA, api.STRATEGY_DIFFUSE_GGX_MIS),
+	(api.TECHNIQUE_PROJECTED_SOLID_ANGLE_ARVO, api.STRATEGY_DIFFUSE_GGX_MIS)])
+def test_related_work_techniques_under_textured_lights_match_the_oracle(technique, strategy):
+	info = H.dataset("mini_lit"); oi = H.OracleInputs(info)
+	width, height = 160, 90
+	frame = H.open_frame(info)
+	try:
+		frame.configure(sample_count=2, strategy=strategy, heuristic=api.MIS_BALANCE, technique=technique, trace_shadow_rays=1, show_lights=1)
+		constants = frame.constants(width, height)
+		vis = oi.visibility(width, height, constants); gb = oi.gbuffer(width, height, constants, vis)
+		out = frame.shade_host(width, height, gb)
+		ref, _ = oi.shade(H.oracle_config(frame, width, height), constants, gb)
+	finally:
+		frame.close()
+	assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), H.compare_radiance(out, ref)
+
+
+def test_the_error_display_refuses_textured_lights():
+	"""The error display shows no radiance and has no textured variant: the pass says so instead of ignoring the textures silently."""
 	info = H.dataset("mini_lit"); oi = H.OracleInputs(info)
 	width, height = 64, 48
 	frame = H.open_frame(info)
 	try:
-		frame.configure(sample_count=1, strategy=api.STRATEGY_DIFFUSE_ONLY, heuristic=api.MIS_BALANCE, technique=api.TECHNIQUE_SOLID_ANGLE, trace_shadow_rays=0)
+		frame.configure(sample_count=1, strategy=api.STRATEGY_DIFFUSE_ONLY, heuristic=api.MIS_BALANCE, technique=api.TECHNIQUE_PSA, trace_shadow_rays=0, error_display=api.ERROR_DISPLAY_DIFFUSE_BACKWARD)
 		constants = frame.constants(width, height)
 		vis = oi.visibility(width, height, constants); gb = oi.gbuffer(width, height, constants, vis)
 		with pytest.raises(RuntimeError):

@@ -147,6 +147,16 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 }
 
 cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream) {
+	if (p.light_texture_count != 0 && p.polygon_sampling_technique < 11 && p.error_display == 0) { // related-work techniques under textured lights
+		switch (p.max_light_vertex_count) {
+		case 3: return vkr_launch_textured_related_work_kernel_maxv3(p, stream);
+		case 4: return vkr_launch_textured_related_work_kernel_maxv4(p, stream);
+		case 5: return vkr_launch_textured_related_work_kernel_maxv5(p, stream);
+		case 6: return vkr_launch_textured_related_work_kernel_maxv6(p, stream);
+		case 7: return vkr_launch_textured_related_work_kernel_maxv7(p, stream);
+		default: return cudaErrorInvalidValue;
+		}
+	}
 	if (p.polygon_sampling_technique < 11 || p.error_display != 0) { // related-work techniques and error display
 		switch (p.max_light_vertex_count) {
 		case 3: return vkr_launch_related_work_kernel_maxv3(p, stream);
@@ -206,8 +216,8 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 				}
 			}
 		}
-		if (any_textured_light && ((int) d.polygon_sampling_technique < 11 || d.error_display != 0)) {
-			printf("Textured polygonal lights need projected solid angle sampling without error display (technique %d, error display %d).\n", (int) d.polygon_sampling_technique, (int) d.error_display);
+		if (any_textured_light && d.error_display != 0) { // the error display shows no radiance; it has no textured variant
+			printf("The error display (%d) is not available with textured polygonal lights.\n", (int) d.error_display);
 			return 1;
 		}
 	}

@@ -65,6 +65,11 @@ cudaError_t vkr_launch_textured_light_kernel_maxp5(const vkr::shading_kernel_par
 cudaError_t vkr_launch_textured_light_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_textured_light_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_textured_light_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_related_work_kernel_maxv3(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_textured_related_work_kernel.cu
+cudaError_t vkr_launch_textured_related_work_kernel_maxv4(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_related_work_kernel_maxv5(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_related_work_kernel_maxv6(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_textured_related_work_kernel_maxv7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_related_work_kernel_maxv3(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_related_work_kernel.cu, one object per light vertex bound
 cudaError_t vkr_launch_related_work_kernel_maxv4(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_related_work_kernel_maxv5(const vkr::shading_kernel_params& p, cudaStream_t stream);
