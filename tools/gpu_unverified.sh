@@ -12,7 +12,7 @@ for builder in sah lbvh_gpu; do
 	echo "== VKR_BVH_BUILDER=$builder"; VKR_BVH_BUILDER=$builder timeout 600 python tools/quick_time.py 64 8 1 3 2>&1 | tail -3 | tee gpurun_out/${tag}_builder_$builder.log
 done
 # the 4-wide traversal variant, if it was built here beforehand (tools/build_variant.sh bvh4 "-DVKR_BVH_WIDTH=4"): same frame first, then time
-if [ -f vulkan_renderer_b200/build/variants/libvkr_bvh4.so ]; then
-	echo "== bvh4 variant"; VKR_BVH_WIDTH=4 VKR_B200_LIB=$PWD/vulkan_renderer_b200/build/variants/libvkr_bvh4.so timeout 600 python tools/quick_time.py 64 8 1 3 2>&1 | tail -3 | tee gpurun_out/${tag}_bvh4.log
+if [ -f vulkan_renderer_b200/variants/libvkr_bvh4.so ]; then
+	echo "== bvh4 variant"; VKR_BVH_WIDTH=4 VKR_B200_LIB=$PWD/vulkan_renderer_b200/variants/libvkr_bvh4.so timeout 600 python tools/quick_time.py 64 8 1 3 2>&1 | tail -3 | tee gpurun_out/${tag}_bvh4.log
 fi
 ls -la gpurun_out | tail -12
