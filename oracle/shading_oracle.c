@@ -460,9 +460,10 @@ static inline float error_component(v3 e, uint32_t error_display) { uint32_t i =
 
 /* shading_pass.frag.glsl:676-709 for the related-work techniques: GGX sampling with MIS against the polygon density.
    polygon_density_is_constant: every technique except our projected solid angle sampling passes density_factor as is (:702) */
-static v3 ggx_mis_samples(float density_factor, int density_times_lambert, const shading_data_t* sd, const ltc_t* ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
+/* :676-709. `result` is the running sum of the light: the shader keeps adding to the variable that already holds the samples of the polygon
+   sampling loop (floating-point addition is not associative; tools/fuzz_parity.py found the frames where a separate partial sum shows) */
+static v3 ggx_mis_samples(v3 result, float density_factor, int density_times_lambert, const shading_data_t* sd, const ltc_t* ltc, const light_t* light, noise_accessor_t* accessor, const ctx_t* c, uint64_t* ray_count) {
 	const vkr_oracle_config_t* cfg = c->cfg;
-	v3 result = mk3(0.0f, 0.0f, 0.0f);
 	v3 outgoing_ss = mat43_mul_dir(ltc->world_to_shading, sd->outgoing);
 	outgoing_ss.y = 0.0f;
 	for (uint32_t s = 0; s != cfg->sample_count; ++s) {
@@ -604,7 +605,7 @@ static v3 evaluate_polygonal_light_shading_related_work(const shading_data_t* sd
 	}
 	if (cfg->sampling_strategies == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
 		memcpy(ltc.world_to_shading, sampler.world_to_shading, sizeof(ltc.world_to_shading));
-		result = add3(result, ggx_mis_samples(sampler.ggx_density_factor, 0, sd, &ltc, light, accessor, c, ray_count));
+		result = ggx_mis_samples(result, sampler.ggx_density_factor, 0, sd, &ltc, light, accessor, c, ray_count);
 	}
 	return scale3(result, 1.0f / (float) cfg->sample_count);
 }

@@ -79,11 +79,12 @@ VKR_DEV void shade_light_related_work(bool on, const shading_point& sp, const lt
 				w = shading_to_world(l, sp.normal, flip, d);
 				if (d.z > 0.0f && light_ray_intersection<MAXV>(light, sp.position, w, 0.0f)) {
 					const float lambert = dot(sp.normal, w);
-					if (lambert > 0.0f) {
+					const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (ggx_density + polygon_density)) : (ggx_density / (ggx_density * ggx_density + polygon_density * polygon_density));
+					if (!is_finite(lambert) || !is_finite(wgt)) { has = true; tmax = 0.0f; w = zero; c = make3(not_a_number, not_a_number, not_a_number); } // 0 * inf: NaN whether visible or not
+					else if (lambert > 0.0f) {
 						has = true;
 						tmax = light_plane_distance(sp, light, w);
 						const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
-						const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (ggx_density + polygon_density)) : (ggx_density / (ggx_density * ggx_density + polygon_density * polygon_density));
 						c = make3(rtb.x * lambert * wgt, rtb.y * lambert * wgt, rtb.z * lambert * wgt);
 					}
 				}

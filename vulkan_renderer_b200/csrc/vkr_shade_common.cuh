@@ -316,6 +316,10 @@ VKR_DEV float ggx_reflected_direction_density(float o_dot_n, f3 o, f3 i, f3 n, f
 }
 
 
+VKR_DEV bool is_finite(float x) { return fabsf(x) <= 3.402823466e+38f; } // false for NaN too
+VKR_DEV f3 not_a_number3() { const float n = __int_as_float(0x7fc00000); return make3(n, n, n); }
+VKR_DEV bool is_finite(f3 v) { return fabsf(v.x) <= 3.402823466e+38f && fabsf(v.y) <= 3.402823466e+38f && fabsf(v.z) <= 3.402823466e+38f; } // false for NaN too
+
 // Visibility pre-test and light-plane distance of a candidate direction (shading_pass.frag.glsl:120-124, 204-205)
 VKR_DEV float light_plane_distance(const shading_point& sp, const unsigned char* light, f3 dir_world) {
 	const float num = dot4_point(light + L_PLANE, sp.position);

@@ -37,22 +37,30 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 				w = shading_to_world(l, sp.normal, flip, d);
 				const float lambert = dot(sp.normal, w);
 				pre_vis = lambert > 0.0f;
-				if (pre_vis) {
+				// What the shader multiplies radiance * BRDF with -- which is ZERO, not absent, for a sample that is not visible (:203-231, 305-323).
+				// If that factor is not finite (degenerate polygon, NaN direction) the product is NaN either way and the pixel turns pink (:862-864):
+				// such a sample goes out as a certain miss (tmax = 0) that carries NaN.
+				float wgt = 0.0f; bool poisoned;
+				if (STRATEGY == VKR_STRATEGY_DIFFUSE_ONLY) {
+					has = density > 0.0f;
+					wgt = lambert / density;
+					poisoned = has && !is_finite(wgt);
+				}
+				else {
+					has = true;
+					const float ggx_density = ggx_reflected_direction_density(sp.lambert_outgoing, sp.outgoing, w, sp.normal, sp.roughness);
+					wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (density + ggx_density)) : (density / (density * density + ggx_density * ggx_density));
+					poisoned = !is_finite(lambert) || !is_finite(wgt);
+				}
+				if (poisoned) { pre_vis = true; tmax = 0.0f; w = zero; c = not_a_number3(); }
+				else if (pre_vis) {
 					tmax = light_plane_distance(sp, light, w);
 					const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
-					if (STRATEGY == VKR_STRATEGY_DIFFUSE_ONLY) {
-						has = density > 0.0f;
-						c = rtb * (lambert / density);
-					}
-					else {
-						has = true;
-						const float ggx_density = ggx_reflected_direction_density(sp.lambert_outgoing, sp.outgoing, w, sp.normal, sp.roughness);
-						const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (density + ggx_density)) : (density / (density * density + ggx_density * ggx_density));
-						c = make3(rtb.x * lambert * wgt, rtb.y * lambert * wgt, rtb.z * lambert * wgt);
-					}
+					if (STRATEGY == VKR_STRATEGY_DIFFUSE_ONLY) c = rtb * wgt;
+					else c = make3(rtb.x * lambert * wgt, rtb.y * lambert * wgt, rtb.z * lambert * wgt);
 				}
 			}
-			submit<TRACE, false>(q, lane, has, pre_vis, w, tmax, c, zero, result, false);
+			submit<TRACE, false>(q, lane, has && pre_vis, pre_vis, w, tmax, c, zero, result, false);
 		}
 		if (STRATEGY == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
 			const f3 o_ss = make3(
@@ -69,12 +77,13 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					w = shading_to_world(l, sp.normal, flip, d);
 					if (d.z > 0.0f && light_ray_intersection<MAXP - 1>(light, sp.position, w, 0.0f)) {
 						const float lambert = dot(sp.normal, w);
-						if (lambert > 0.0f) {
+						const float polygon_density = lambert * density_factor;
+						const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (ggx_density + polygon_density)) : (ggx_density / (ggx_density * ggx_density + polygon_density * polygon_density));
+						if (!is_finite(lambert) || !is_finite(wgt)) { has = true; tmax = 0.0f; w = zero; c = not_a_number3(); } // 0 * inf, see above
+						else if (lambert > 0.0f) {
 							has = true;
 							tmax = light_plane_distance(sp, light, w);
 							const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
-							const float polygon_density = lambert * density_factor;
-							const float wgt = (p.mis_heuristic == VKR_MIS_BALANCE) ? (1.0f / (ggx_density + polygon_density)) : (ggx_density / (ggx_density * ggx_density + polygon_density * polygon_density));
 							c = make3(rtb.x * lambert * wgt, rtb.y * lambert * wgt, rtb.z * lambert * wgt);
 						}
 					}
@@ -115,11 +124,15 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					const f3 dsh = normalize(c2s_mul(l, dc));
 					const float ltc_density = evaluate_ltc_density(l, dsh, 1.0f);
 					w = shading_to_world(l, sp.normal, flip, dsh);
-					if (dot(sp.normal, w) > 0.0f && !(dsh.z <= 0.0f || dc.z <= 0.0f)) {
-						has = true;
-						tmax = light_plane_distance(sp, light, w);
-						const f3 rtb2 = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<false, true>(sp, w);
-						c = make3(rtb2.x * dsh.z * ps.psa / ltc_density, rtb2.y * dsh.z * ps.psa / ltc_density, rtb2.z * dsh.z * ps.psa / ltc_density);
+					if (!(dsh.z <= 0.0f || dc.z <= 0.0f)) { // :587; true for NaN directions
+						const float hidden = 0.0f * dsh.z * ps.psa / ltc_density; // what one channel of the shader's expression is for a sample that is not visible
+						if (hidden != hidden) { has = true; tmax = 0.0f; w = zero; c = not_a_number3(); } // NaN either way, see above
+						else if (dot(sp.normal, w) > 0.0f) {
+							has = true;
+							tmax = light_plane_distance(sp, light, w);
+							const f3 rtb2 = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<false, true>(sp, w);
+							c = make3(rtb2.x * dsh.z * ps.psa / ltc_density, rtb2.y * dsh.z * ps.psa / ltc_density, rtb2.z * dsh.z * ps.psa / ltc_density);
+						}
 					}
 				}
 				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
@@ -148,7 +161,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					if (has) {
 						f3 d = sample_psa<MAXP, BIASED>(select_polygon(j != 0, pd, ps), next_noise_2(ns, p, cb, px, py));
 						if (j != 0) d = normalize(c2s_mul(l, d));
-						has = d.z > 0.0f;
+						has = !(d.z <= 0.0f); // as the shader writes it (:619): a NaN direction (degenerate, nearly edge-on polygon) is not skipped, it poisons the pixel
 						if (has) {
 							const float diffuse_density = d.z * rcp_d;
 							const float specular_density = evaluate_ltc_density(l, d, rcp_s);
@@ -166,8 +179,18 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 							else {
 								const f3 w_own = (j == 0) ? diffuse_weight : specular_weight_rgb, w_other = (j == 0) ? specular_weight_rgb : diffuse_weight;
 								const float p_own = (j == 0) ? diffuse_density : specular_density, p_other = (j == 0) ? specular_density : diffuse_density;
-								if (pre_vis) c = mis_estimate(p.mis_heuristic, integrand, w_own, p_own, w_other, p_other, v_est);
+								c = mis_estimate(p.mis_heuristic, integrand, w_own, p_own, w_other, p_other, v_est);
 								if (OPTIMAL) c_occ = mis_estimate(p.mis_heuristic, zero * d.z, w_own, p_own, w_other, p_other, v_est);
+								else if (!pre_vis || !is_finite(c)) {
+									// The shader multiplies a ZERO integrand by the MIS weights when the sample is not visible (:633-636); with degenerate
+									// densities the weights are not finite and 0 * inf = NaN turns the pixel pink whatever the shadow ray says. Such a sample
+									// is pushed as a certain miss (tmax = 0) carrying NaN. Found by tools/fuzz_parity.py; about one pixel in a million.
+									const f3 c_hidden = pre_vis ? mis_estimate(p.mis_heuristic, zero, w_own, p_own, w_other, p_other, v_est) : c;
+									if (c_hidden.x != c_hidden.x || c_hidden.y != c_hidden.y || c_hidden.z != c_hidden.z) {
+										pre_vis = true; tmax = 0.0f; w = zero;
+										c = make3(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+									}
+								}
 							}
 						}
 					}
@@ -194,11 +217,15 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 					const float specular_density = evaluate_ltc_density(l, d, specular_albedo);
 					const float density = (diffuse_density + specular_density) / (diffuse_weight + specular_weight);
 					w = shading_to_world(l, sp.normal, flip, d);
-					if (dot(sp.normal, w) > 0.0f && !(d.z <= 0.0f)) {
-						has = true;
-						tmax = light_plane_distance(sp, light, w);
-						const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
-						c = make3(rtb.x * d.z / density, rtb.y * d.z / density, rtb.z * d.z / density);
+					if (!(d.z <= 0.0f)) { // :669; true for a NaN direction
+						const float hidden = 0.0f * d.z / density; // what one channel of the shader's expression is for a sample that is not visible
+						if (hidden != hidden) { has = true; tmax = 0.0f; w = zero; c = not_a_number3(); } // NaN either way, see above
+						else if (dot(sp.normal, w) > 0.0f) {
+							has = true;
+							tmax = light_plane_distance(sp, light, w);
+							const f3 rtb = light_radiance<LIGHT_TEXTURES>(p, light, sp.position, w) * evaluate_brdf<true, true>(sp, w);
+							c = make3(rtb.x * d.z / density, rtb.y * d.z / density, rtb.z * d.z / density);
+						}
 					}
 				}
 				submit<TRACE, false>(q, lane, has, true, w, tmax, c, zero, result, false);
