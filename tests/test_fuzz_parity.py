@@ -16,11 +16,11 @@ from oracle import ref_binding as R  # noqa: E402
 def test_device_code_matches_the_oracle_on_random_frames():
 	mismatches, compared, lit = fuzz_parity.run(frames=24, seed=101, with_reference=False, verbose=False)
 	assert compared["device code vs oracle"] >= 18 and lit >= 20
-	assert mismatches["device code vs oracle"] == 0
+	assert mismatches["device code vs oracle"] == 0 and mismatches["device G-buffer code vs oracle"] == 0 and compared["device G-buffer code vs oracle"] == 24
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
 def test_oracle_matches_the_reference_shader_on_random_frames():
 	mismatches, compared, lit = fuzz_parity.run(frames=16, seed=202, with_reference=True, verbose=False)
 	assert compared["reference vs oracle"] == 16 and lit >= 12
-	assert mismatches == {"reference vs oracle": 0, "device code vs oracle": 0}
+	assert not any(mismatches.values())

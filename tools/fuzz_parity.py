@@ -25,16 +25,8 @@ from oracle import ref_binding as R  # noqa: E402
 from vulkan_renderer_b200 import api  # noqa: E402
 
 
-def random_constants(info, cfg, width, height, rng):
-	lib = api.load_library()
-	scene = api.Scene(); ltc = api.LtcTable(); noise = api.NoiseTable(); spec = api.SceneSpecification(); st = api.RenderSettings()
-	assert lib.vkr_load_scene(C.byref(scene), None, info["vks"].encode(), info["textures"].encode(), 0) == 0
-	assert lib.vkr_load_ltc_table(C.byref(ltc), None, info["ltc"].encode(), 51) == 0
-	assert lib.vkr_load_noise_table(C.byref(noise), None, 256, 256, 64, api.NOISE_WHITE) == 0
-	assert lib.vkr_quick_load(C.byref(spec), info["save"].encode()) == 0
-	assert lib.vkr_create_and_assign_light_textures(None, None, C.byref(spec)) == 0
-	count = spec.polygonal_light_count
-	spec.polygonal_light_count = cfg["lights"]
+def perturb(lib, spec, st, info, cfg, rng, wild=False):
+	"""Random camera, light transforms / fluxes and settings, written into the scene specification and render settings (shared with tests/test_gpu_zzw_fuzz.py)."""
 	cam = spec.camera
 	base = np.array(info["camera"]["position"], dtype=np.float64)
 	for a in range(3):
@@ -48,10 +40,30 @@ def random_constants(info, cfg, width, height, rng):
 			light.translation[a] = float(light.translation[a] + rng.uniform(-1.5, 1.5) * (0.5 if a == 2 else 1.0))
 			light.radiant_flux[a] = float(rng.uniform(1.0, 30.0))
 		light.scaling_x = float(rng.uniform(0.1, 3.0)); light.scaling_y = float(rng.uniform(0.1, 3.0))
+		if wild:   # needles, specks and walls of light; lights dropped into the ground plane or next to the camera
+			light.scaling_x = float(10.0 ** rng.uniform(-3.0, 1.5)); light.scaling_y = float(10.0 ** rng.uniform(-3.0, 1.5))
+			if rng.random() < 0.3: light.translation[2] = float(rng.uniform(-0.05, 0.05))
+			if rng.random() < 0.2:
+				for a in range(3): light.translation[a] = float(cam.position_world_space[a] + rng.uniform(-0.3, 0.3))
 		lib.vkr_update_polygonal_light(C.byref(light))
 	lib.vkr_specify_default_render_settings(C.byref(st)); st.animate_noise = 0
 	st.exposure_factor = float(rng.uniform(0.5, 4.0)); st.roughness_factor = float(rng.uniform(0.3, 1.5)); st.mis_visibility_estimate = float(rng.uniform(0.0, 1.0))
+	if wild:
+		st.roughness_factor = float(10.0 ** rng.uniform(-2.0, 0.7)); st.mis_visibility_estimate = float(rng.choice([0.0, 1.0, rng.uniform(0.0, 1.0)])); st.exposure_factor = float(10.0 ** rng.uniform(-3.0, 3.0))
 	st.error_min_exponent = float(rng.uniform(-7.0, -3.0)); st.sample_count = cfg["samples"]
+
+
+def random_constants(info, cfg, width, height, rng, wild=False):
+	lib = api.load_library()
+	scene = api.Scene(); ltc = api.LtcTable(); noise = api.NoiseTable(); spec = api.SceneSpecification(); st = api.RenderSettings()
+	assert lib.vkr_load_scene(C.byref(scene), None, info["vks"].encode(), info["textures"].encode(), 0) == 0
+	assert lib.vkr_load_ltc_table(C.byref(ltc), None, info["ltc"].encode(), 51) == 0
+	assert lib.vkr_load_noise_table(C.byref(noise), None, 256, 256, 64, api.NOISE_WHITE) == 0
+	assert lib.vkr_quick_load(C.byref(spec), info["save"].encode()) == 0
+	assert lib.vkr_create_and_assign_light_textures(None, None, C.byref(spec)) == 0
+	count = spec.polygonal_light_count
+	spec.polygonal_light_count = cfg["lights"]
+	perturb(lib, spec, st, info, cfg, rng, wild)
 	size = lib.vkr_get_constants_size(C.byref(spec)); buf = (C.c_uint8 * size)()
 	lib.vkr_write_constants(buf, C.byref(spec), C.byref(st), C.byref(scene), C.byref(ltc), C.byref(noise), width, height)
 	if cfg.get("frame_bits", 0):
@@ -59,6 +71,25 @@ def random_constants(info, cfg, width, height, rng):
 	spec.polygonal_light_count = count
 	lib.vkr_destroy_scene_specification(C.byref(spec)); lib.vkr_destroy_noise_table(C.byref(noise), None); lib.vkr_destroy_ltc_table(C.byref(ltc), None); lib.vkr_destroy_scene(C.byref(scene), None)
 	return bytes(buf)
+
+
+def device_on_host_gbuffer(dev, oi, constants, vis, width, height):
+	"""The per-pixel body of the G-buffer kernel (csrc/vkr_gbuffer.cuh) on the CPU."""
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	out = np.zeros((4, height, width, 4), dtype=np.float32)
+	q = np.ascontiguousarray(oi.vks["positions"], dtype=np.uint32); nt = np.ascontiguousarray(oi.vks["normals_uv"], dtype=np.uint16)
+	mi = np.ascontiguousarray(oi.vks["material_indices"], dtype=np.uint8); mp = np.ascontiguousarray(oi.material_params, dtype=np.float32)
+	vis = np.ascontiguousarray(vis, dtype=np.uint32)
+	if oi.textures is not None:
+		dims3, offsets, data = oi.textures
+		dims = np.zeros((len(dims3), 4), dtype=np.uint32); dims[:, :3] = dims3
+		offsets_texels = (offsets // 4).astype(np.uint64); data = np.ascontiguousarray(data, dtype=np.float32)
+		tex = (P(dims), P(offsets_texels), P(data))
+	else:
+		tex = (None, None, None)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	dev.vkr_device_on_host_gbuffer(C.c_uint32(width), C.c_uint32(height), cb, P(vis), P(q), P(nt), P(mi), P(mp), tex[0], tex[1], tex[2], P(out))
+	return out
 
 
 def device_on_host_frame(dev, cfg, oi, constants, gb, width, height):
@@ -96,14 +127,15 @@ def fixture_configs():
 	return [_config_from_name(n) for n in sorted({k.split("/")[0] for k in g.files})]
 
 
-def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, verbose=True, only=None):
+def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, verbose=True, only=None, wild=False):
 	"""Returns (mismatches, compared): dicts with the keys "reference vs oracle" and "device code vs oracle"."""
 	import __graft_entry__
 	dev = C.CDLL(__graft_entry__.build_device_on_host())
 	rng = np.random.default_rng(seed)
 	source = fixture_configs()   # the same frames with and without the reference arm
 	configs = [dict(technique=11, error_display=0, srgb=0, frame_bits=0, textured=0, light_textures=0, **{"min_vertices": c["max_vertices"]}) | c for c in source if c["samples"] <= max_samples and (only is None or re.search(only, c["name"]))]
-	mismatches = {"reference vs oracle": 0, "device code vs oracle": 0}; compared = {"reference vs oracle": 0, "device code vs oracle": 0}; lit = 0; pink = 0
+	keys = ("reference vs oracle", "device code vs oracle", "device G-buffer code vs oracle")
+	mismatches = {k: 0 for k in keys}; compared = {k: 0 for k in keys}; lit = 0; pink = 0
 	inputs = {}
 	for f in range(frames):
 		cfg = configs[int(rng.integers(len(configs)))]
@@ -113,9 +145,14 @@ def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, v
 		info, oi = inputs[name]
 		w0, h0 = width, height
 		width, height = w0 + int(rng.integers(0, 17)), h0 + int(rng.integers(0, 9))
-		constants = random_constants(info, cfg, width, height, rng)
+		constants = random_constants(info, cfg, width, height, rng, wild)
 		vis = oi.visibility(width, height, constants)
 		gb = oi.gbuffer(width, height, constants, vis)
+		host_gb = device_on_host_gbuffer(dev, oi, constants, vis, width, height)
+		compared["device G-buffer code vs oracle"] += 1
+		if not np.array_equal(host_gb.view(np.uint32), np.ascontiguousarray(gb, dtype=np.float32).view(np.uint32)):
+			mismatches["device G-buffer code vs oracle"] += 1
+			print("MISMATCH device G-buffer code vs oracle: frame %d seed %d %s %dx%d" % (f, seed, cfg["name"], width, height), flush=True)
 		out, _ = oi.shade(oracle_cfg(cfg, width, height), constants, gb)
 		lit += int((out[..., :3].sum(-1) > 0).any()); pink += int(((out[..., 1] == 0) & (out[..., 0] > 0) & (out[..., 2] > 0)).any())
 		if with_reference:
@@ -146,11 +183,12 @@ def main():
 	ap.add_argument("--height", type=int, default=32)
 	ap.add_argument("--max-samples", type=int, default=8, help="skip configurations with more samples per pixel (time)")
 	ap.add_argument("--only", default=None, help="regular expression on the configuration name, e.g. '^s[0124]_' for the strategies other than MIS")
+	ap.add_argument("--wild", action="store_true", help="extreme light sizes and positions, roughness factors, exposures")
 	ap.add_argument("--no-reference", action="store_true", help="device code vs oracle only (where oracle/_ref is not built)")
 	args = ap.parse_args()
 	if not args.no_reference and not R.available():
 		raise SystemExit("oracle/_ref/libref_shader.so is not built (needs /root/reference); --no-reference compares the device code with the oracle only")
-	mismatches, _, _ = run(args.frames, args.seed, args.width, args.height, args.max_samples, with_reference=not args.no_reference, only=args.only)
+	mismatches, _, _ = run(args.frames, args.seed, args.width, args.height, args.max_samples, with_reference=not args.no_reference, only=args.only, wild=args.wild)
 	return 1 if any(mismatches.values()) else 0
 
 

@@ -3,7 +3,7 @@
 # (a failure in one file must not hide the others).  usage (under gpurun): bash tools/gpu_unverified.sh [tag]
 tag=${1:-r02}
 mkdir -p gpurun_out
-for t in test_gpu_zzx_textured_lights test_gpu_zz_error_display test_gpu_zzy_textured_gbuffer test_gpu_zzz_lbvh_gpu; do
+for t in test_gpu_zzw_fuzz test_gpu_zzx_textured_lights test_gpu_zz_error_display test_gpu_zzy_textured_gbuffer test_gpu_zzz_lbvh_gpu; do
 	timeout 600 python -m pytest tests/$t.py -m gpu -q > gpurun_out/${tag}_$t.log 2>&1; echo "exit $?" >> gpurun_out/${tag}_$t.log
 	echo "== $t: $(tail -2 gpurun_out/${tag}_$t.log | tr '\n' ' ')"
 done
