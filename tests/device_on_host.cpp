@@ -32,6 +32,12 @@ static inline void __threadfence() {}
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long) x) : 64; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 
+// binary16 conversion of the output stage: the CPU's own round-to-nearest-even conversion (F16C) stands in for the GPU's cvt.rn.f16.f32
+#include <immintrin.h>
+struct __half { uint16_t bits; };
+static inline __half __float2half_rn(float x) { __half h; h.bits = (uint16_t) _cvtss_sh(x, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC); return h; }
+static inline uint16_t __half_as_ushort(__half h) { return h.bits; }
+
 // warp-level intrinsics: declared so that the ray-stream header parses; the TRACE = false instantiations used here never call them
 unsigned __ballot_sync(unsigned, int); int __any_sync(unsigned, int); int __all_sync(unsigned, int); void __syncwarp(unsigned); int __popc(unsigned); int __ffs(unsigned);
 void __nanosleep(unsigned); unsigned __activemask(); int __shfl_sync(unsigned, int, int); size_t __cvta_generic_to_shared(const void*);
@@ -255,7 +261,8 @@ static void tile_frame(const shading_kernel_params& p, int show_lights, const Li
 		if (std::isnan(color.x) || std::isnan(color.y) || std::isnan(color.z) || std::isinf(color.x) || std::isinf(color.y) || std::isinf(color.z))
 			final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
 		float* o = out_rgba + 4 * pixel;
-		o[0] = final_color.x * exposure; o[1] = final_color.y * exposure; o[2] = final_color.z * exposure; o[3] = 1.0f;
+		const f3 out_color = output_stage(make3(final_color.x * exposure, final_color.y * exposure, final_color.z * exposure), ldu(cb, OFF_FRAME_BITS), p.output_srgb != 0);
+		o[0] = out_color.x; o[1] = out_color.y; o[2] = out_color.z; o[3] = 1.0f;
 	}
 }
 
@@ -300,11 +307,11 @@ static void related_work_frame(const shading_kernel_params& p, int show_lights, 
 	}, out_rgba);
 }
 
-// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Linear output, g_frame_bits = 0. technique: sample_polygon_technique_t, 11 = projected solid angle (biased: 12),
+// One frame of the shading pass WITHOUT shadow rays on the CPU (light vertex bounds 3 to 7). Output stage as the constant block (g_frame_bits) and output_srgb say. technique: sample_polygon_technique_t, 11 = projected solid angle (biased: 12),
 // 0..10 = related work. light_texture_count != 0: the LIGHT_TEXTURES = true instantiation (csrc/vkr_textured_light_kernel.cu), dims = {width, height, mip count, 0} per texture, offsets in texels.
 extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, uint32_t maxv, uint32_t light_count, uint32_t technique, uint32_t strategy, uint32_t heuristic, int biased, uint32_t sample_count, int show_lights,
 	const void* constants, const float* gbuffer, const uint16_t* noise, uint32_t noise_w, uint32_t noise_h, uint32_t noise_layers,
-	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers,
+	const uint16_t* ltc0, const uint16_t* ltc1, uint32_t ltc_res, uint32_t ltc_layers, int output_srgb,
 	uint32_t light_texture_count, const uint32_t* light_texture_dims4, const uint64_t* light_texture_offsets_texels, const float* light_texture_texels, float* out_rgba)
 {
 	shading_kernel_params p;
@@ -313,7 +320,7 @@ extern "C" int vkr_device_on_host_shade_frame(uint32_t width, uint32_t height, u
 	p.light_count = (int) light_count; p.max_light_vertex_count = (int) maxv; p.sample_count = (int) sample_count;
 	p.light_texture_count = light_texture_count; p.light_texture_dims = reinterpret_cast<const uint4*>(light_texture_dims4);
 	p.light_texture_offsets = reinterpret_cast<const unsigned long long*>(light_texture_offsets_texels); p.light_texture_texels = reinterpret_cast<const float4*>(light_texture_texels);
-	p.sampling_strategies = (int) strategy; p.mis_heuristic = (int) heuristic; p.biased_sampling = biased; p.polygon_sampling_technique = biased ? 12 : 11;
+	p.sampling_strategies = (int) strategy; p.mis_heuristic = (int) heuristic; p.biased_sampling = biased; p.polygon_sampling_technique = biased ? 12 : 11; p.output_srgb = output_srgb;
 	p.noise = noise; p.noise_w = (int) noise_w; p.noise_h = (int) noise_h; p.noise_layers = (int) noise_layers;
 	p.ltc0 = ltc0; p.ltc1 = ltc1; p.ltc_res = (int) ltc_res; p.ltc_layers = (int) ltc_layers;
 	if (technique < 11) { // related work: diffuse only or GGX MIS

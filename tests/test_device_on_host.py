@@ -214,7 +214,7 @@ def test_error_display_light_shader_reproduces_the_reference_shader_fixtures(nam
 def _base_fixture_names():
 	import os
 	g = np.load(os.path.join(ROOT, "tests", "golden", "ref_shader.npz"))
-	return sorted({k.split("/")[0] for k in g.files if not any(t in k.split("/")[0] for t in ("_q", "_e", "_x", "_y", "_o"))})
+	return sorted({k.split("/")[0] for k in g.files if not any(t in k.split("/")[0] for t in ("_q", "_e", "_x", "_y"))})   # incl. "_o<srgb><frame bits>": the output stage
 
 
 @pytest.mark.parametrize("name", _base_fixture_names())
@@ -238,7 +238,7 @@ def test_shade_light_without_rays_matches_oracle_and_fixtures(name):
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
 	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
-		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), C.c_int(cfg["srgb"]),
 		C.c_uint32(0), None, None, None, P(out))
 	assert rc == 0
 	no_rays = dict(cfg, trace=0)
@@ -275,7 +275,7 @@ def test_related_work_light_shader_without_rays_matches_oracle_and_fixtures(name
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
 	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(0), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
-		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), C.c_int(0),
 		C.c_uint32(0), None, None, None, P(out))
 	assert rc == 0
 	ref, _ = oi.shade(oracle_cfg(dict(cfg, trace=0)), constants, gb)
@@ -315,7 +315,7 @@ def test_textured_lights_without_rays_match_oracle_and_fixtures(name):
 	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
 	rc = lib.vkr_device_on_host_shade_frame(C.c_uint32(WIDTH), C.c_uint32(HEIGHT), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
 		C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb),
-		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]),
+		P(noise), C.c_uint32(noise.shape[2]), C.c_uint32(noise.shape[1]), C.c_uint32(noise.shape[0]), P(ltc0), P(ltc1), C.c_uint32(ltc0.shape[1]), C.c_uint32(ltc0.shape[0]), C.c_int(0),
 		C.c_uint32(len(dims)), P(dims), P(offsets_texels), P(data), P(out))
 	assert rc == 0
 	ref, _ = oi.shade(oracle_cfg(dict(cfg, trace=0)), constants, gb)

@@ -93,8 +93,8 @@ def device_on_host_gbuffer(dev, oi, constants, vis, width, height):
 
 
 def device_on_host_frame(dev, cfg, oi, constants, gb, width, height):
-	"""Rays off. Returns None where tests/device_on_host.cpp has no entry for the configuration (sRGB / half-bit output stage)."""
-	if cfg.get("srgb", 0) or cfg.get("frame_bits", 0):
+	"""Rays off. Returns None where tests/device_on_host.cpp has no entry for the configuration (error display with an sRGB / half-bit output stage)."""
+	if cfg.get("error_display", 0) and (cfg.get("srgb", 0) or cfg.get("frame_bits", 0)):
 		return None
 	P = lambda a: a.ctypes.data_as(C.c_void_p)
 	out = np.zeros((height, width, 4), dtype=np.float32)
@@ -115,7 +115,7 @@ def device_on_host_frame(dev, cfg, oi, constants, gb, width, height):
 		else:
 			tex = (C.c_uint32(0), None, None, None)
 		rc = dev.vkr_device_on_host_shade_frame(C.c_uint32(width), C.c_uint32(height), C.c_uint32(cfg["max_vertices"]), C.c_uint32(cfg["lights"]), C.c_uint32(cfg["technique"]), C.c_uint32(cfg["strategy"]),
-			C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb), *table, *tex, P(out))
+			C.c_uint32(cfg["heuristic"]), C.c_int(cfg["biased"]), C.c_uint32(cfg["samples"]), C.c_int(cfg["show_lights"]), cb, P(gb), *table, C.c_int(cfg.get("srgb", 0)), *tex, P(out))
 	assert rc == 0, cfg["name"]
 	return out
 

@@ -8,6 +8,9 @@
 #include "vkr_trace.cuh"
 #include "vkr_kernels.h"
 #include "vkr_texture.cuh"
+#ifndef VKR_DEVICE_CODE_ON_HOST
+#include <cuda_fp16.h>
+#endif
 
 namespace vkr {
 
@@ -369,6 +372,20 @@ VKR_DEV f3 light_radiance(const shading_kernel_params& p, const unsigned char* l
 		}
 	}
 	return radiance;
+}
+
+// Output stage of the shader (shading_pass.frag.glsl:871-892) on the colour that is already multiplied by the exposure: the half-bit split for HDR
+// screenshots (g_frame_bits 1 / 2: the low / high bytes of the three binary16 values, as 8-bit UNORM) and the sRGB conversion of !OUTPUT_LINEAR_RGB
+VKR_DEV f3 output_stage(f3 out_color, uint32_t frame_bits, bool output_srgb) {
+	if (frame_bits > 0u) {
+		const uint32_t mask = (frame_bits == 1u) ? 0xFFu : 0xFF00u, shift = (frame_bits == 1u) ? 0u : 8u;
+		const uint32_t h0 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.x)) | ((uint32_t) __half_as_ushort(__float2half_rn(out_color.y)) << 16);
+		const uint32_t h1 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.z));
+		out_color = make3((float) ((h0 & mask) >> shift) * (1.0f / 255.0f), (float) ((((h0 & 0xFFFF0000u) >> 16) & mask) >> shift) * (1.0f / 255.0f), (float) ((h1 & mask) >> shift) * (1.0f / 255.0f));
+		if (!output_srgb) out_color = make3(srgb_to_linear(out_color.x), srgb_to_linear(out_color.y), srgb_to_linear(out_color.z));
+	}
+	else if (output_srgb) out_color = make3(linear_to_srgb(out_color.x), linear_to_srgb(out_color.y), linear_to_srgb(out_color.z));
+	return out_color;
 }
 
 } // namespace vkr

@@ -144,16 +144,7 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 	if (isnan(color.x) || isnan(color.y) || isnan(color.z) || isinf(color.x) || isinf(color.y) || isinf(color.z))
 		final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
 	f3 out_color = make3(final_color.x * exposure, final_color.y * exposure, final_color.z * exposure);
-	// --- output stage (shading_pass.frag.glsl:871-892): half-bit split for HDR screenshots, sRGB conversion
-	const uint32_t frame_bits = ldu(cb, OFF_FRAME_BITS);
-	if (frame_bits > 0u) {
-		const uint32_t mask = (frame_bits == 1u) ? 0xFFu : 0xFF00u, shift = (frame_bits == 1u) ? 0u : 8u;
-		const uint32_t h0 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.x)) | ((uint32_t) __half_as_ushort(__float2half_rn(out_color.y)) << 16);
-		const uint32_t h1 = (uint32_t) __half_as_ushort(__float2half_rn(out_color.z));
-		out_color = make3((float) ((h0 & mask) >> shift) * (1.0f / 255.0f), (float) ((((h0 & 0xFFFF0000u) >> 16) & mask) >> shift) * (1.0f / 255.0f), (float) ((h1 & mask) >> shift) * (1.0f / 255.0f));
-		if (!p.output_srgb) out_color = make3(srgb_to_linear(out_color.x), srgb_to_linear(out_color.y), srgb_to_linear(out_color.z));
-	}
-	else if (p.output_srgb) out_color = make3(linear_to_srgb(out_color.x), linear_to_srgb(out_color.y), linear_to_srgb(out_color.z));
+	out_color = output_stage(out_color, ldu(cb, OFF_FRAME_BITS), p.output_srgb != 0);
 	p.out[pixel] = make_float4(out_color.x, out_color.y, out_color.z, 1.0f);
 }
 
