@@ -70,7 +70,8 @@ def _compare(technique, maxv, dataset, seed, points=24, samples=16):
 				culled += 1
 				continue
 			for a, b, what in zip(ref[:2], dev[:2], ("direction", "density")):
-				assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "%s differs: technique %d (%s), %s" % (what, technique, TECHNIQUES[technique], dataset)
+				same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))   # sign and payload of a NaN are the host compiler's business (x86: 0 / 0 is -NaN)
+				assert same.all(), "%s differs: technique %d (%s), %s" % (what, technique, TECHNIQUES[technique], dataset)
 			assert np.float32(ref[2]).view(np.uint32) == np.float32(dev[2]).view(np.uint32)
 			checked += 1
 	return checked, culled
