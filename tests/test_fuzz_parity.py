@@ -19,6 +19,14 @@ def test_device_code_matches_the_oracle_on_random_frames():
 	assert mismatches["device code vs oracle"] == 0 and mismatches["device G-buffer code vs oracle"] == 0 and compared["device G-buffer code vs oracle"] == 24
 
 
+def test_device_code_matches_the_oracle_on_any_legal_configuration():
+	"""Settings the reference was not compiled for here (other strategy / heuristic / biased / vertex count / output stage combinations): run-time parameters for
+	both the oracle and the kernels."""
+	mismatches, compared, lit = fuzz_parity.run(frames=30, seed=303, with_reference=False, verbose=False, any_config=True, wild=True)
+	assert compared["device code vs oracle"] == 30 and lit >= 24
+	assert not any(mismatches.values())
+
+
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
 def test_oracle_matches_the_reference_shader_on_random_frames():
 	mismatches, compared, lit = fuzz_parity.run(frames=16, seed=202, with_reference=True, verbose=False)

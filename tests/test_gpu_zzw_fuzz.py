@@ -18,14 +18,15 @@ import fuzz_parity  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed,wild", [(1, False), (2, True), (3, True)])
-def test_kernels_match_the_oracle_on_random_frames(seed, wild):
+@pytest.mark.parametrize("seed,wild,any_config", [(1, False, False), (2, True, False), (3, True, False), (4, False, True), (5, True, True)])
+def test_kernels_match_the_oracle_on_random_frames(seed, wild, any_config):
+	"""any_config: any legal combination of the run-time settings instead of the configurations a reference shader was compiled for."""
 	rng = np.random.default_rng(1000 + seed)
 	configs = [c for c in fuzz_parity.fixture_configs() if c["samples"] <= 8]
 	pink_frames = 0
 	for k in range(14):
-		cfg = configs[int(rng.integers(len(configs)))]
-		info = H.dataset(dataset_for(cfg)); oi = H.OracleInputs(info)
+		cfg = fuzz_parity.random_config(rng) if any_config else configs[int(rng.integers(len(configs)))]
+		info = H.dataset(cfg.get("dataset") or dataset_for(cfg)); oi = H.OracleInputs(info)
 		width, height = 48 + int(rng.integers(0, 40)), 32 + int(rng.integers(0, 24))
 		frame = H.open_frame(info)
 		try:

@@ -127,7 +127,37 @@ def fixture_configs():
 	return [_config_from_name(n) for n in sorted({k.split("/")[0] for k in g.files})]
 
 
-def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, verbose=True, only=None, wild=False):
+def random_config(rng):
+	"""Any legal combination of the run-time settings (src/user_interface.cpp:90-180), not only the ones a reference shader was compiled for: for the device code
+	against the oracle. Vertex counts come with the data set."""
+	dataset, vmax, vmin = [("mini_tri", 3, 3), ("mini_city", 4, 4), ("mini_mixed", 4, 3), ("mini_v5", 5, 5), ("mini_v6", 6, 6), ("mini_v7", 7, 7), ("mini_poly", 7, 5), ("mini_lit", 4, 4)][int(rng.integers(8))]
+	cfg = dict(strategy=int(rng.integers(5)), heuristic=0, biased=0, lights=int(rng.integers(1, 4)), max_vertices=vmax, min_vertices=vmin, samples=int(rng.integers(1, 6)), trace=1,
+		show_lights=int(rng.integers(2)), materials=8, technique=11, error_display=0, textured=0, light_textures=int(dataset == "mini_lit"), srgb=int(rng.random() < 0.2), frame_bits=int(rng.choice([0, 0, 0, 1, 2])))
+	if dataset == "mini_poly" and cfg["lights"] < 3: cfg["min_vertices"] = [5, 5][cfg["lights"] - 1]   # lights are pentagon, heptagon, hexagon
+	if dataset == "mini_mixed" and cfg["lights"] == 1: cfg["min_vertices"] = 3; 
+	if dataset == "mini_mixed" and cfg["lights"] == 1: cfg["max_vertices"] = 4
+	roll = rng.random()
+	if roll < 0.35 and dataset != "mini_lit":   # related work: diffuse only, or GGX MIS where the density stands alone
+		cfg["technique"] = int(rng.integers(0, 11))
+		ggx_ok = cfg["technique"] in (2, 3, 4, 5, 10)
+		cfg["strategy"] = int(rng.integers(2)) if ggx_ok else 0
+	elif roll < 0.5:
+		cfg["biased"] = 1
+	if cfg["strategy"] == 1: cfg["heuristic"] = int(rng.integers(2))
+	if cfg["strategy"] == 3: cfg["heuristic"] = int(rng.integers(5))
+	if cfg["technique"] in (10, 11) and rng.random() < 0.15 and not cfg["light_textures"]:
+		cfg["error_display"] = int(rng.integers(1, 7)); cfg["srgb"] = 0; cfg["frame_bits"] = 0
+		if cfg["error_display"] >= 4 and cfg["strategy"] < 2: cfg["strategy"] = 2 + int(rng.integers(3)); cfg["heuristic"] = 0
+		if cfg["technique"] == 10:
+			cfg["strategy"] = 0; cfg["heuristic"] = 0
+			if cfg["error_display"] >= 3: cfg["error_display"] = 1 + int(rng.integers(2))
+		if cfg["strategy"] == 3: cfg["heuristic"] = int(rng.integers(5))
+	cfg["name"] = "any:%s s%d h%d b%d L%d S%d q%d e%d o%d%d" % (dataset, cfg["strategy"], cfg["heuristic"], cfg["biased"], cfg["lights"], cfg["samples"], cfg["technique"], cfg["error_display"], cfg["srgb"], cfg["frame_bits"])
+	cfg["dataset"] = dataset
+	return cfg
+
+
+def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, verbose=True, only=None, wild=False, any_config=False):
 	"""Returns (mismatches, compared): dicts with the keys "reference vs oracle" and "device code vs oracle"."""
 	import __graft_entry__
 	dev = C.CDLL(__graft_entry__.build_device_on_host())
@@ -138,8 +168,8 @@ def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, v
 	mismatches = {k: 0 for k in keys}; compared = {k: 0 for k in keys}; lit = 0; pink = 0
 	inputs = {}
 	for f in range(frames):
-		cfg = configs[int(rng.integers(len(configs)))]
-		name = dataset_for(cfg)
+		cfg = random_config(rng) if any_config else configs[int(rng.integers(len(configs)))]
+		name = cfg.get("dataset") or dataset_for(cfg)
 		if name not in inputs:
 			info = H.dataset(name); inputs[name] = (info, H.OracleInputs(info))
 		info, oi = inputs[name]
@@ -184,11 +214,12 @@ def main():
 	ap.add_argument("--max-samples", type=int, default=8, help="skip configurations with more samples per pixel (time)")
 	ap.add_argument("--only", default=None, help="regular expression on the configuration name, e.g. '^s[0124]_' for the strategies other than MIS")
 	ap.add_argument("--wild", action="store_true", help="extreme light sizes and positions, roughness factors, exposures")
+	ap.add_argument("--any-config", action="store_true", help="any legal combination of settings instead of the compiled shader configurations (implies --no-reference)")
 	ap.add_argument("--no-reference", action="store_true", help="device code vs oracle only (where oracle/_ref is not built)")
 	args = ap.parse_args()
-	if not args.no_reference and not R.available():
+	if not (args.no_reference or args.any_config) and not R.available():
 		raise SystemExit("oracle/_ref/libref_shader.so is not built (needs /root/reference); --no-reference compares the device code with the oracle only")
-	mismatches, _, _ = run(args.frames, args.seed, args.width, args.height, args.max_samples, with_reference=not args.no_reference, only=args.only, wild=args.wild)
+	mismatches, _, _ = run(args.frames, args.seed, args.width, args.height, args.max_samples, with_reference=not (args.no_reference or args.any_config), only=args.only, wild=args.wild, any_config=args.any_config)
 	return 1 if any(mismatches.values()) else 0
 
 
