@@ -137,7 +137,7 @@ def random_config(rng):
 	if dataset == "mini_mixed" and cfg["lights"] == 1: cfg["min_vertices"] = 3; 
 	if dataset == "mini_mixed" and cfg["lights"] == 1: cfg["max_vertices"] = 4
 	roll = rng.random()
-	if roll < 0.35 and dataset != "mini_lit":   # related work: diffuse only, or GGX MIS where the density stands alone
+	if roll < 0.35:   # related work (also under textured lights): diffuse only, or GGX MIS where the density stands alone
 		cfg["technique"] = int(rng.integers(0, 11))
 		ggx_ok = cfg["technique"] in (2, 3, 4, 5, 10)
 		cfg["strategy"] = int(rng.integers(2)) if ggx_ok else 0
