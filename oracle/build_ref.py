@@ -170,7 +170,7 @@ def default_configs():
 	return configs
 
 
-def build(configs=None, verbose=False):
+def build(configs=None, verbose=False, set_name=""):
 	if not os.path.isdir(REF_SHADERS):
 		print("build_ref: /root/reference is not present; keeping the prebuilt oracle/_ref as it is")
 		return None
@@ -206,15 +206,46 @@ def build(configs=None, verbose=False):
 	missing = [n["name"] for n in names if n["entry"] not in compiled]
 	if missing:
 		raise SystemExit("build_ref: textured configurations without an untextured twin: %s" % missing)
-	lib = os.path.join(OUT, "libref_shader.so")
+	lib = os.path.join(OUT, "libref_shader%s.so" % (("_" + set_name) if set_name else ""))
 	subprocess.check_call([CXX, "-shared", "-fopenmp", "-o", lib] + objects)
-	with open(os.path.join(OUT, "configs.json"), "w") as f:
+	with open(os.path.join(OUT, "configs%s.json" % (("_" + set_name) if set_name else "")), "w") as f:
 		json.dump(names, f, indent=1)
 	for o in objects:
 		os.remove(o)
 	print("build_ref: %d configurations -> %s" % (len(configs), lib))
-	build_host()
+	if not set_name:
+		build_host()
 	return lib
+
+
+def random_configs(count, seed):
+	"""Legal combinations of the settings (src/user_interface.cpp:90-180) beyond default_configs(), for tools/fuzz_parity.py --ref-set: the oracle takes all of
+	them as run-time parameters, the reference needs one compiled shader each."""
+	import random
+	rng = random.Random(seed)
+	out, seen = [], {config_name(c) for c in default_configs()}
+	while len(out) < count:
+		vmax, vmin = rng.choice([(3, 3), (4, 4), (4, 3), (5, 5), (6, 6), (7, 7), (7, 5)])
+		c = dict(strategy=rng.randrange(5), heuristic=0, biased=0, lights=3, max_vertices=vmax, min_vertices=vmin, samples=rng.randrange(1, 5), trace=rng.randrange(2), show_lights=rng.randrange(2), materials=8)
+		roll = rng.random()
+		if roll < 0.35:
+			c["technique"] = rng.randrange(11)
+			c["strategy"] = rng.randrange(2) if c["technique"] in (2, 3, 4, 5, 10) else 0
+		elif roll < 0.55:
+			c["biased"] = 1
+		if c["strategy"] == 1: c["heuristic"] = rng.randrange(2)
+		if c["strategy"] == 3: c["heuristic"] = rng.randrange(5)
+		if c.get("technique", 11) in (10, 11) and rng.random() < 0.2:
+			c["error_display"] = rng.randrange(1, 7)
+			if c.get("technique", 11) == 10: c["strategy"] = 0; c["heuristic"] = 0; c["error_display"] = rng.randrange(1, 3)
+			elif c["error_display"] >= 4 and c["strategy"] < 2: c["strategy"] = rng.randrange(2, 5); c["heuristic"] = rng.randrange(5) if c["strategy"] == 3 else 0
+		elif rng.random() < 0.25:
+			c["srgb"] = rng.randrange(2); c["frame_bits"] = rng.randrange(3)
+		if vmin == vmax: c.pop("min_vertices")
+		name = config_name(c)
+		if name not in seen:
+			seen.add(name); out.append(c)
+	return out
 
 
 def build_host():
@@ -236,4 +267,8 @@ def build_host():
 
 
 if __name__ == "__main__":
-	build(verbose="-v" in sys.argv)
+	if "--random" in sys.argv:   # python oracle/build_ref.py --random <count> <seed> <set name>
+		i = sys.argv.index("--random")
+		build(random_configs(int(sys.argv[i + 1]), int(sys.argv[i + 2])), set_name=sys.argv[i + 3])
+	else:
+		build(verbose="-v" in sys.argv)

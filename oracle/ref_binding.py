@@ -8,8 +8,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libref_shader.so")
-CONFIGS_PATH = os.path.join(_HERE, "_ref", "configs.json")
+# VKR_REF_SET=<name>: a second set of configurations compiled by `python oracle/build_ref.py --random <count> <seed> <name>` (tools/fuzz_parity.py --ref-set)
+_SET = os.environ.get("VKR_REF_SET", "")
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_shader%s.so" % (("_" + _SET) if _SET else ""))
+CONFIGS_PATH = os.path.join(_HERE, "_ref", "configs%s.json" % (("_" + _SET) if _SET else ""))
 
 HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_float)
 

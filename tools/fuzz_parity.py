@@ -162,7 +162,9 @@ def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, v
 	import __graft_entry__
 	dev = C.CDLL(__graft_entry__.build_device_on_host())
 	rng = np.random.default_rng(seed)
-	source = fixture_configs()   # the same frames with and without the reference arm
+	# the fixture configurations (the same frames with and without the reference arm), or a second set compiled with
+	# `python oracle/build_ref.py --random <count> <seed> <name>` and selected with VKR_REF_SET=<name>
+	source = R.configs() if os.environ.get("VKR_REF_SET") else fixture_configs()
 	configs = [dict(technique=11, error_display=0, srgb=0, frame_bits=0, textured=0, light_textures=0, **{"min_vertices": c["max_vertices"]}) | c for c in source if c["samples"] <= max_samples and (only is None or re.search(only, c["name"]))]
 	keys = ("reference vs oracle", "device code vs oracle", "device G-buffer code vs oracle")
 	mismatches = {k: 0 for k in keys}; compared = {k: 0 for k in keys}; lit = 0; pink = 0
