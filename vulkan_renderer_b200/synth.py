@@ -12,7 +12,18 @@ This is authoring tooling (like the reference's Blender exporter), not part of t
 import os
 import struct
 
+import contextlib
+
 import numpy as np
+
+
+@contextlib.contextmanager
+def _atomic_write(path):
+	"""Writes to a temporary file and renames it: another process reading (or writing) the same data set never sees a truncated file."""
+	tmp = "%s.%d.tmp" % (path, os.getpid())
+	with open(tmp, "wb") as f:
+		yield f
+	os.replace(tmp, path)
 
 # ---------------------------------------------------------------------------------------------
 # geometry helpers: everything is a list of (triangles[n,3,3], normals[n,3,3], material_id)
@@ -265,7 +276,7 @@ def write_vks(path, mesh, materials, sort_triangles=True):
 	# planar uv: unit square per triangle
 	uv = np.tile(np.array([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0]]), (n, 1))
 	nuv[:, 2:4] = np.clip(uv * ((2.0 ** 16 - 1.0) / 8.0) + 0.5, 0.0, 65535.0).astype(np.uint16)
-	with open(path, "wb") as f:
+	with _atomic_write(path) as f:
 		f.write(struct.pack("<II", 0x00ABCABC, 1))
 		f.write(struct.pack("<QQ", len(materials), n))
 		f.write(struct.pack("<fff", *dequantization_factor))
@@ -293,7 +304,7 @@ def write_vkt_constant(path, rgba):
 		data = np.tile(texel, w * h).astype("<f2").tobytes()
 		headers += struct.pack("<IIQQ", w, h, len(data), len(payload))
 		payload += data
-	with open(path, "wb") as f:
+	with _atomic_write(path) as f:
 		f.write(struct.pack("<IIIIIIQ", 0x00BC1BC1, 1, len(mips), 4, 4, 97, len(payload)))
 		f.write(headers); f.write(payload)
 		f.write(struct.pack("<I", 0x00E0FE0F))
@@ -360,7 +371,7 @@ def write_vkt(path, level0, vk_format=97):
 					data += _encode_bc1_block(blk[..., :3]) if vk_format == 131 else (_encode_bc4_block(blk[..., 0]) + _encode_bc4_block(blk[..., 1]))
 		headers += struct.pack("<IIQQ", w, h, len(data), len(payload))
 		payload += data
-	with open(path, "wb") as f:
+	with _atomic_write(path) as f:
 		f.write(struct.pack("<IIIIIIQ", 0x00BC1BC1, 1, len(levels), level0.shape[1], level0.shape[0], vk_format, len(payload)))
 		f.write(headers); f.write(payload)
 		f.write(struct.pack("<I", 0x00E0FE0F))
@@ -438,7 +449,7 @@ def write_ltc_fits(directory, resolution=64, fresnel_count=51):
 		m20 = 0.15 * np.sin(I) * (1.0 - a) * a
 		albedo = np.clip((0.04 + 0.96 * f0) * (1.0 - 0.5 * a) + 0.3 * (1.0 - f0) * (1.0 - np.cos(I)) ** 3, 0.0, 1.0)
 		data = np.stack([m00, m02, m11, m20, albedo], axis=-1).astype("<f4")
-		with open(os.path.join(directory, "fit%d.dat" % i), "wb") as f:
+		with _atomic_write(os.path.join(directory, "fit%d.dat" % i)) as f:
 			f.write(struct.pack("<Q", resolution))
 			f.write(data.tobytes())
 
@@ -456,7 +467,7 @@ def make_light(translation, rotation_angles, scaling, flux, vertices_plane_space
 
 def write_quicksave(path, camera, lights):
 	"""camera: dict(position, rotation_z, rotation_x, vertical_fov, near, far, speed)"""
-	with open(path, "wb") as f:
+	with _atomic_write(path) as f:
 		f.write(struct.pack("<3f3f2ffi2f", *camera["position"], camera["rotation_z"], camera["rotation_x"], camera["vertical_fov"],
 			camera["near"], camera["far"], camera.get("speed", 2.0), 0, 0.0, 0.0))
 		f.write(struct.pack("<II", 0, len(lights)))
