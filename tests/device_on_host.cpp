@@ -189,6 +189,29 @@ extern "C" void vkr_device_on_host_trace_any_wide(const float* nodes2, const flo
 	(void) out_steps2;
 }
 
+// Shader-side vertex decode (vkr_gbuffer.cuh: decode_position, mesh_quantization.glsl:38-45) for all vertices: the input of the primary-ray BVH
+extern "C" void vkr_device_on_host_decode_positions(const void* constants, const uint32_t* quantized_positions, uint64_t vertex_count, float* out_xyz) {
+	const uint2* q = reinterpret_cast<const uint2*>(quantized_positions);
+	for (uint64_t i = 0; i != vertex_count; ++i) {
+		const f3 v = decode_position(q[i], (const unsigned char*) constants);
+		out_xyz[3 * i] = v.x; out_xyz[3 * i + 1] = v.y; out_xyz[3 * i + 2] = v.z;
+	}
+}
+
+// The body of visibility_kernel (csrc/vkr_gbuffer_kernel.cu): primary ray through the pixel, closest hit (vkr_trace.cuh), ties -> lowest triangle index
+extern "C" void vkr_device_on_host_visibility(uint32_t width, uint32_t height, const void* constants, const float* nodes, const float* tris, const uint32_t* tri_ids, uint32_t tri_count, uint32_t* out_visibility) {
+	bvh_view bvh; bvh.nodes = reinterpret_cast<const float4*>(nodes); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = tri_ids; bvh.tri_count = tri_count;
+	const unsigned char* cb = (const unsigned char*) constants;
+	const f3 camera = make3(gldf(cb, G_OFF_CAMERA), gldf(cb, G_OFF_CAMERA + 4), gldf(cb, G_OFF_CAMERA + 8));
+	std::vector<int> stack(kMaxStackDepth);
+	for (uint32_t y = 0; y != height; ++y) for (uint32_t x = 0; x != width; ++x) {
+		const f3 d = pixel_ray(cb, (int) x, (int) y);
+		int hit = -1;
+		if (tri_count) hit = closest_hit(bvh, camera, d, 0.0f, __int_as_float(0x7f800000), stack.data(), 1);
+		out_visibility[(size_t) y * width + x] = (hit < 0) ? 0xFFFFFFFFu : (uint32_t) hit;
+	}
+}
+
 // The body of the G-buffer kernel (vkr_gbuffer.cuh: shade_gbuffer_pixel) for every pixel, on host arrays laid out like the device buffers.
 // texture_dims = uint32[4] per texture, texture_offsets in texels, texture_data = RGBA32F texels; all three null for constant materials.
 extern "C" void vkr_device_on_host_gbuffer(uint32_t width, uint32_t height, const void* constants, const uint32_t* visibility, const uint32_t* quantized_positions,

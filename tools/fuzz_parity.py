@@ -73,6 +73,32 @@ def random_constants(info, cfg, width, height, rng, wild=False):
 	return bytes(buf)
 
 
+_primary_bvh = {}
+
+
+def device_on_host_visibility(dev, oi, constants, width, height):
+	"""The body of visibility_kernel on the CPU: shader-side vertex decode (device function), the product's host BVH builder, closest_hit per pixel."""
+	P = lambda a: a.ctypes.data_as(C.c_void_p)
+	q = np.ascontiguousarray(oi.vks["positions"], dtype=np.uint32)
+	key = (id(oi), constants[:32])   # the dequantisation constants decide the vertices
+	if key not in _primary_bvh:
+		cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+		verts = np.zeros((len(q), 3), dtype=np.float32)
+		dev.vkr_device_on_host_decode_positions(cb, P(q), C.c_uint64(len(q)), P(verts))
+		lib = api.load_library(); PT = C.POINTER
+		nodes = PT(C.c_float)(); tri = PT(C.c_float)(); ids = PT(C.c_uint32)(); nc = C.c_uint64(); md = C.c_uint32()
+		tris = np.ascontiguousarray(verts.reshape(-1, 9))
+		assert lib.vkr_bvh_build_probe(tris.ctypes.data, len(tris), C.byref(nodes), C.byref(nc), C.byref(tri), C.byref(ids), C.byref(md)) == 0
+		n = len(tris)
+		_primary_bvh[key] = (np.ctypeslib.as_array(nodes, (nc.value, 16)).copy(), np.ctypeslib.as_array(tri, (n, 12)).copy(), np.ctypeslib.as_array(ids, (n,)).copy())
+		lib.vkr_bvh_free_probe(nodes, tri, ids)
+	nodes, tri, ids = _primary_bvh[key]
+	out = np.zeros((height, width), dtype=np.uint32)
+	cb = (C.c_uint8 * len(constants)).from_buffer_copy(constants)
+	dev.vkr_device_on_host_visibility(C.c_uint32(width), C.c_uint32(height), cb, P(nodes), P(tri), P(ids), C.c_uint32(len(ids)), P(out))
+	return out
+
+
 def device_on_host_gbuffer(dev, oi, constants, vis, width, height):
 	"""The per-pixel body of the G-buffer kernel (csrc/vkr_gbuffer.cuh) on the CPU."""
 	P = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -166,7 +192,7 @@ def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, v
 	# `python oracle/build_ref.py --random <count> <seed> <name>` and selected with VKR_REF_SET=<name>
 	source = R.configs() if os.environ.get("VKR_REF_SET") else fixture_configs()
 	configs = [dict(technique=11, error_display=0, srgb=0, frame_bits=0, textured=0, light_textures=0, **{"min_vertices": c["max_vertices"]}) | c for c in source if c["samples"] <= max_samples and (only is None or re.search(only, c["name"]))]
-	keys = ("reference vs oracle", "device code vs oracle", "device G-buffer code vs oracle")
+	keys = ("reference vs oracle", "device code vs oracle", "device G-buffer code vs oracle", "device visibility code vs oracle")
 	mismatches = {k: 0 for k in keys}; compared = {k: 0 for k in keys}; lit = 0; pink = 0
 	inputs = {}
 	for f in range(frames):
@@ -180,6 +206,11 @@ def run(frames, seed, width=48, height=32, max_samples=8, with_reference=True, v
 		constants = random_constants(info, cfg, width, height, rng, wild)
 		vis = oi.visibility(width, height, constants)
 		gb = oi.gbuffer(width, height, constants, vis)
+		host_vis = device_on_host_visibility(dev, oi, constants, width, height)
+		compared["device visibility code vs oracle"] += 1
+		if not np.array_equal(host_vis, vis):
+			mismatches["device visibility code vs oracle"] += 1
+			print("MISMATCH device visibility code vs oracle: frame %d seed %d %s %dx%d, %d pixels" % (f, seed, cfg["name"], width, height, int((host_vis != vis).sum())), flush=True)
 		host_gb = device_on_host_gbuffer(dev, oi, constants, vis, width, height)
 		compared["device G-buffer code vs oracle"] += 1
 		if not np.array_equal(host_gb.view(np.uint32), np.ascontiguousarray(gb, dtype=np.float32).view(np.uint32)):
