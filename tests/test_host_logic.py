@@ -381,3 +381,53 @@ def test_white_noise_and_synthetic_formats_are_what_the_reference_loaders_expect
 	assert (marker, version, mips, w, h, fmt) == (0xBC1BC1, 1, 3, 4, 4, 97) and struct.unpack_from("<I", tex, len(tex) - 4)[0] == 0xE0FE0F
 	fit = open(os.path.join(info["ltc"], "fit0.dat"), "rb").read()
 	assert struct.unpack_from("<Q", fit, 0)[0] == 64 and len(fit) == 8 + 64 * 64 * 20
+
+
+def test_loaders_survive_corrupted_files(tmp_path, capfd):
+	"""Truncated, bit-flipped and padded *.vks / *.vkt / *.save / fit*.dat files: every loader either rejects the file with a diagnostic (non-zero return, object
+	zeroed, like the reference: src/scene.c:68-72, src/textures.c:117-121) or loads it; none may crash or leave a half-built object behind."""
+	import shutil
+	lib = api.load_library()
+	info = H.dataset("mini_lit")
+	rng = np.random.default_rng(17)
+	light_textures = [l["texture_file_path"] for l in info["lights"]]
+	def mutate(src, dst):
+		data = bytearray(open(src, "rb").read())
+		mode = int(rng.integers(4))
+		if mode == 0: data = data[:int(rng.integers(0, len(data)))]
+		elif mode == 1:
+			for _ in range(int(rng.integers(1, 8))): data[int(rng.integers(0, min(len(data), 96)))] = int(rng.integers(0, 256))
+		elif mode == 2:
+			for _ in range(int(rng.integers(1, 30))): data[int(rng.integers(0, len(data)))] = int(rng.integers(0, 256))
+		else: data = data + bytes(rng.integers(0, 256, int(rng.integers(1, 64)), dtype=np.uint8))
+		open(dst, "wb").write(data)
+	rejected = 0
+	for i in range(160):
+		kind = i % 4
+		if kind == 0:
+			dst = str(tmp_path / "s.vks"); mutate(info["vks"], dst)
+			scene = api.Scene(); rc = lib.vkr_load_scene(C.byref(scene), None, dst.encode(), info["textures"].encode(), 1)
+			if rc == 0: lib.vkr_destroy_scene(C.byref(scene), None)
+			assert rc == 0 or (scene.triangle_count == 0 and not scene.material_params)
+		elif kind == 1:
+			dst = str(tmp_path / "t.vkt"); mutate(light_textures[i % 3], dst)
+			t = api.Texture(); rc = lib.vkr_load_texture(C.byref(t), dst.encode())
+			if rc == 0: lib.vkr_destroy_texture(C.byref(t))
+			assert rc == 0 or not t.h_texels
+		elif kind == 2:
+			dst = str(tmp_path / "q.save"); mutate(info["save"], dst)
+			spec = api.SceneSpecification(); rc = lib.vkr_quick_load(C.byref(spec), dst.encode())
+			if rc == 0:
+				lt = api.LightTextures()
+				if lib.vkr_create_and_assign_light_textures(C.byref(lt), None, C.byref(spec)) == 0: lib.vkr_destroy_light_textures(C.byref(lt), None)
+				lib.vkr_destroy_scene_specification(C.byref(spec))
+			assert rc == 0 or spec.polygonal_light_count == 0
+		else:
+			d = str(tmp_path / "ltc"); shutil.rmtree(d, ignore_errors=True); shutil.copytree(info["ltc"], d)
+			f = os.path.join(d, "fit%d.dat" % int(rng.integers(51))); mutate(f, f)
+			ltc = api.LtcTable(); rc = lib.vkr_load_ltc_table(C.byref(ltc), None, d.encode(), 51)
+			if rc == 0: lib.vkr_destroy_ltc_table(C.byref(ltc), None)
+			assert rc == 0 or not ltc.h_table0
+		rejected += rc != 0
+	assert 30 < rejected < 130
+	capfd.readouterr()
