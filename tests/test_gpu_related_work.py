@@ -21,7 +21,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref
 
 def _fixture_names():
 	g = np.load(GOLDEN)
-	return sorted({k.split("/")[0] for k in g.files if "_q" in k.split("/")[0] and "_e" not in k.split("/")[0]})   # "_e<error display>": tests/test_gpu_zz_error_display.py
+	return sorted({k.split("/")[0] for k in g.files if "_q" in k.split("/")[0] and "_e" not in k.split("/")[0] and "_y" not in k.split("/")[0]})   # "_e<error display>": tests/test_gpu_zz_error_display.py, "_y1" (textured lights): tests/test_gpu_zzx_textured_lights.py
 
 
 @pytest.mark.parametrize("name", _fixture_names())
