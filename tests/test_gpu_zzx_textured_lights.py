@@ -89,3 +89,15 @@ def test_the_error_display_refuses_textured_lights():
 			frame.shade_host(width, height, gb)
 	finally:
 		frame.close()
+
+
+def test_textured_light_figures_of_the_experiment_list_run(tmp_path):
+	"""The IES-profile attic and the textured screen over the roughness planes (src/experiment_list.c:294-314, 341-362) through the experiment runner, small."""
+	from vulkan_renderer_b200 import experiments as E
+	todo = [dict(e) for e in E.experiment_list(all_timings=False) if e["name"] in ("ies_profile_attic_2spp", "roughness_planes_screen_2spp")]
+	assert len(todo) == 2
+	for e in todo:
+		if e["scene"] == "room": e["scene_parameters"] = dict(e["scene_parameters"], detail=6, clutter=60, n_mat=8)   # the same room with few triangles
+	records = E.run(todo, str(tmp_path / "data"), str(tmp_path / "out"), frames=3, warmup=1, width=160, height=128)
+	for r in records:
+		assert r["frame_time_ms"] > 0.0 and os.path.exists(r["screenshot"]) and os.path.getsize(r["screenshot"]) > 1000
