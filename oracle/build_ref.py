@@ -245,6 +245,11 @@ def random_configs(count, seed):
 		name = config_name(c)
 		if name not in seen:
 			seen.add(name); out.append(c)
+			# textures are inputs, not defines: a twin of the same shader under textured lights (data set mini_lit: three quads) or with filtered material textures
+			if vmax == 4 and vmin == 4 and not c.get("error_display", 0) and rng.random() < 0.3:
+				out.append(dict(c, light_textures=1))
+			elif vmax == 4 and vmin == 4 and rng.random() < 0.15:
+				out.append(dict(c, textured=1))
 	return out
 
 
