@@ -19,7 +19,9 @@ extern "C" {
 #endif
 
 #define VKR_B200_ABI_VERSION 1
-#define VKR_TILE_ROW_HEIGHT 8 /* pixel rows per screen-tile row (stripe granularity) */
+#define VKR_TILE_ROW_HEIGHT 8 /* pixel rows per screen-tile row */
+#define VKR_TILE_WIDTH 16     /* pixel columns per screen tile: the unit of the multi-GPU split */
+#define VKR_MAX_GPUS 8        /* GPUs of one box that can share a frame (vkr_frame_exchange_t) */
 
 /* ---- enums: numeric values equal the reference's (src/main.h:45-92, src/polygonal_light.h:28-67,
         src/noise_table.h:20-54) so that render_settings_t fields can be passed through unchanged */
@@ -279,8 +281,11 @@ typedef struct vkr_shading_pass_desc_s {
 	vkr_sample_polygon_technique_t polygon_sampling_technique;
 	int trace_shadow_rays;
 	int show_polygonal_lights;
-	/* multi-GPU stripes: this pass instance shades the 8-pixel-high screen-tile rows t with t % stripe_count == stripe_index
-	   (interleaved for load balance); stripe_count = 0 or 1 means the whole frame */
+	/* multi-GPU split: this pass instance shades the 16x8 screen tiles of every tile row whose column tx satisfies
+	   tx % stripe_count == stripe_index (SURVEY 8e asks for tile rows per GPU; the rows are cut further into tiles and dealt
+	   out column-wise because 135 tile rows of uneven cost do not balance over 8 GPUs: every GPU gets the same number of tiles
+	   from all over the screen, and a GPU's part of a G-buffer plane is ONE strided 2D copy); stripe_count = 0 or 1 means
+	   the whole frame */
 	uint32_t stripe_index, stripe_count;
 	/* resources */
 	const vkr_scene_t* scene;
@@ -310,17 +315,88 @@ typedef struct vkr_shading_pass_s {
 	float last_kernel_ms;      /* device time of the most recent shading kernel (CUDA events), if timing is enabled */
 	void* event_begin; void* event_end;
 	int timing_enabled;
+	void* event_constants;     /* recorded after the upload of the constant block: the staging buffer is not rewritten before */
+	/* The tiles this instance shades, in launch order. After every frame the pass reads back what each tile cost (nanoseconds) and
+	   launches the next frame dearest tile first, so that the last wave of CTAs consists of cheap tiles (frames of an animation
+	   resemble their predecessors; the order never changes a pixel). reorder_tiles = 0 keeps the order fixed (row-major). */
+	uint32_t tile_count;
+	void* d_tile_list; void* h_tile_list;
+	void* d_tile_cost; void* h_tile_cost;
+	void* event_costs; int costs_pending;
+	int reorder_tiles;
 } vkr_shading_pass_t;
 
 int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device, const vkr_shading_pass_desc_t* desc);
 void vkr_destroy_shading_pass(vkr_shading_pass_t* pass, const vkr_device_t* device);
 /* Asynchronous on device->stream. constants: HOST pointer to the block written by vkr_write_constants() (or by the
-   reference's write_constants()). d_gbuffer / d_out_rgba32f: DEVICE pointers (out = width*height float4, rows outside
-   this stripe untouched). */
+   reference's write_constants()). d_gbuffer / d_out_rgba32f: DEVICE pointers (out = width*height float4, pixels outside
+   the tiles of this instance untouched). */
 int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f);
-/* End-to-end variant with HOST buffers: uploads the G-buffer rows of this stripe, shades, downloads the stripe, waits. */
+/* End-to-end variant with HOST buffers: uploads the G-buffer tiles of this instance, shades, downloads them, waits. */
 int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer, float* out_rgba32f);
 int vkr_shading_pass_wait(vkr_shading_pass_t* pass, const vkr_device_t* device);
+
+/* ---- one frame on several GPUs (replaces nothing in the reference, which drives one GPU). Every GPU of the box runs its
+        own pass instance (stripe_index = rank, stripe_count = world) and owns a vkr_frame_exchange_t. The shading kernel stores each
+        finished pixel into the frame of EVERY GPU -- its own and, through peer mappings over NVLink, the others' -- so when the
+        kernels are done each GPU holds the whole frame; no gather pass, no collective library. Two one-block kernels per frame
+        make the barrier: signal (release, system scope) increments this GPU's arrival counter on every peer, wait (acquire) spins
+        until all peers of this frame have arrived. Frames alternate between two buffers, so a GPU may start frame f + 1 while a
+        slower one still reads frame f.
+        One process per GPU: create, vkr_frame_exchange_get_handle, exchange the 64-byte handles by whatever means the host has
+        (MPI, a socket, torch.distributed), vkr_frame_exchange_connect. One process for all GPUs: vkr_frame_exchange_connect_local. */
+typedef struct vkr_frame_exchange_s {
+	uint32_t width, height, rank, world;
+	void* d_block;                          /* one cudaMalloc: two frames (width * height float4 each), then 2 * VKR_MAX_GPUS arrival counters */
+	void* d_peer_blocks[VKR_MAX_GPUS];      /* [rank] = d_block; the others: mappings of the peers' blocks */
+	int peer_is_ipc[VKR_MAX_GPUS];          /* mapping came from cudaIpcOpenMemHandle (to be closed) */
+	uint64_t frames_exchanged;              /* frames completed so far; the frame in flight lives in buffer frames_exchanged & 1 */
+	int* h_status;                          /* pinned, device-visible: set by the wait kernel when a peer did not arrive in time */
+	uint64_t timeout_ns;                    /* how long the wait kernel waits for the peers (default 20 s) */
+} vkr_frame_exchange_t;
+int vkr_create_frame_exchange(vkr_frame_exchange_t* exchange, const vkr_device_t* device, uint32_t width, uint32_t height, uint32_t rank, uint32_t world);
+void vkr_destroy_frame_exchange(vkr_frame_exchange_t* exchange, const vkr_device_t* device);
+/* the cudaIpcMemHandle_t of this GPU's block, to be sent to the other processes */
+int vkr_frame_exchange_get_handle(const vkr_frame_exchange_t* exchange, const vkr_device_t* device, unsigned char out_handle[64]);
+/* handles: world * 64 bytes in rank order (the entry of this rank is ignored) */
+int vkr_frame_exchange_connect(vkr_frame_exchange_t* exchange, const vkr_device_t* device, const unsigned char* handles);
+/* all GPUs driven by this process: d_blocks[r] = the d_block of rank r's exchange (peer access is enabled here) */
+int vkr_frame_exchange_connect_local(vkr_frame_exchange_t* exchange, const vkr_device_t* device, void* const* d_blocks);
+/* device pointer to the most recently completed frame (width * height float4), valid until the frame after the next is started */
+void* vkr_frame_exchange_frame(const vkr_frame_exchange_t* exchange);
+/* Shades this GPU's tiles of one frame into every GPU's frame, signals, waits for the peers: asynchronous on device->stream; once the
+   stream has passed this call vkr_frame_exchange_frame() holds the whole frame. All GPUs must call it once per frame. */
+int vkr_shading_pass_run_exchange(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, vkr_frame_exchange_t* exchange);
+/* Host-buffer variant: uploads this GPU's tile columns of the G-buffer (one strided copy per plane), shades and exchanges as above, and
+   if out_rgba32f is not NULL downloads the WHOLE frame; waits. Returns non-zero if a peer failed to arrive. */
+int vkr_shading_pass_run_host_exchange(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer,
+	vkr_frame_exchange_t* exchange, float* out_rgba32f);
+/* copies the most recently completed frame (the whole frame) to HOST memory and waits */
+int vkr_frame_exchange_download(vkr_frame_exchange_t* exchange, const vkr_device_t* device, float* out_rgba32f);
+/* waits for the stream and reports whether the exchange has failed (a peer did not arrive in time) */
+int vkr_frame_exchange_wait(vkr_frame_exchange_t* exchange, const vkr_device_t* device);
+
+/* Measurement aid (no counterpart in the reference, which reads such numbers from vendor profilers): shades the frame with the counters
+   edition of the kernel -- same frame, bit for bit -- and returns what the trace warps did. Synchronous; quad lights, projected solid
+   angle sampling, untextured lights only. Sums over the whole launch; "lane" counters count per ray, "warp" counters per warp. */
+typedef enum vkr_trace_counter_e {
+	vkr_trace_counter_rays = 0,             /* shadow rays traced (entries whose visibility was not known beforehand) */
+	vkr_trace_counter_occluded = 1,         /* of these, rays that hit something */
+	vkr_trace_counter_cache_hits = 2,       /* of these, rays ended by the occluder cache before any traversal */
+	vkr_trace_counter_node_visits = 3,      /* BVH nodes fetched, summed over rays */
+	vkr_trace_counter_leaf_visits = 4,      /* leaves whose triangles were tested, summed over rays */
+	vkr_trace_counter_triangle_tests = 5,   /* ray/triangle predicates evaluated */
+	vkr_trace_counter_warp_rounds = 6,      /* rounds of the trace warps' outer loop (warp) */
+	vkr_trace_counter_warp_node_steps = 7,  /* iterations of the node loop (warp): node_visits / this = lanes busy per step */
+	vkr_trace_counter_known_occluded = 8,   /* ring entries that needed no ray (n.w <= 0; optimal MIS only) */
+	vkr_trace_counter_idle_polls = 9,       /* times a trace warp found nothing to do and slept (warp) */
+	vkr_trace_counter_entries = 10,         /* ring entries submitted by the shading warps */
+	vkr_trace_counter_resolve_polls = 11,   /* times a shading warp slept waiting for shadow ray results (warp) */
+	vkr_trace_counter_candidates = 12,      /* candidate samples with a contribution (before the n.w > 0 test) */
+	VKR_TRACE_COUNTER_COUNT = 16
+} vkr_trace_counter_t;
+int vkr_shading_pass_run_with_counters(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f,
+	uint64_t out_counters[VKR_TRACE_COUNTER_COUNT]);
 
 /* ---- after the pass: screenshots and frame times (replaces take_screenshot / implement_screenshot,
         src/main.c:1550-1770, the stb_image_write calls in them and src/frame_timer.c) */

@@ -160,6 +160,11 @@ def trace_any(tris, rays, brute=True):
 	return a, (b if brute else None)
 
 
+def set_threads(count):
+	"""OpenMP threads of the next shade() call. The launcher's OMP_NUM_THREADS only sets the start value (torchrun exports 1)."""
+	C.CDLL("libgomp.so.1").omp_set_num_threads(int(count))
+
+
 def thread_count():
 	return load().vkr_oracle_thread_count()
 

@@ -105,10 +105,13 @@ extern "C" int REF_ENTRY(ref_args_t* a) {
 	set_uniforms(a);
 	const uint32_t y0 = a->row_begin, y1 = a->row_end ? a->row_end : a->height;
 	const double begin = omp_get_wtime();
-	#pragma omp parallel for schedule(dynamic, 1)
-	for (uint32_t y = y0; y < y1; ++y) {
+	// work items are 64-pixel pieces of rows: a banded sample of a frame has fewer rows than a big host has threads
+	const uint32_t pieces = (a->width + 63) / 64;
+	#pragma omp parallel for collapse(2) schedule(dynamic, 1)
+	for (uint32_t y = y0; y < y1; ++y) for (uint32_t piece = 0; piece < pieces; ++piece) {
 		if (a->band_stride && (y - y0) % a->band_stride >= a->band_height) continue;
-		for (uint32_t x = 0; x != a->width; ++x) {
+		const uint32_t x_end = (piece * 64 + 64 < a->width) ? piece * 64 + 64 : a->width;
+		for (uint32_t x = piece * 64; x != x_end; ++x) {
 			gl_FragCoord = vec4((float) x + 0.5f, (float) y + 0.5f, 0.5f, 1.0f);
 			g_current_visibility = a->visibility[(size_t) y * a->width + x];
 			shader_main();

@@ -58,6 +58,11 @@ def last_shade_seconds():
 	return _last_shade_seconds
 
 
+def set_threads(count):
+	"""OpenMP threads of the next shade() call. The launcher's OMP_NUM_THREADS only sets the start value (torchrun exports 1)."""
+	C.CDLL("libgomp.so.1").omp_set_num_threads(int(count))
+
+
 def thread_count():
 	return int(load().ref_thread_count())
 

@@ -96,3 +96,125 @@ uint32_t ref_probe_sizes(int which) {
 	switch (which) { case 0: return (uint32_t) sizeof(first_person_camera_t); case 1: return (uint32_t) sizeof(polygonal_light_t);
 	case 2: return (uint32_t) POLYGONAL_LIGHT_QUICKSAVE_SIZE; case 3: return (uint32_t) POLYGONAL_LIGHT_FIXED_CONSTANT_BUFFER_SIZE; case 4: return (uint32_t) sizeof(ltc_constants_t); default: return 0; }
 }
+
+/* ---- The constant block of a frame from the REFERENCE's own host code. quick_load (src/main.c:82-130) and write_constants (src/main.c:2114-2188) live in
+   main.c, the application, which cannot be compiled here (GLFW, Dear ImGui, the swapchain); their bodies are restated below over the reference's own
+   structs and functions (polygonal_light_t, update_polygonal_light, get_world_to_projection_space, matrix_inverse, set_noise_constants, ltc_constants_t),
+   per_frame_constants_t is restated from src/main.h:488-505. tests/test_ref_host.py holds vkr_write_constants against it byte for byte, and bench.py's
+   reference arm gets its constants here, so that nothing of the product library is loaded in that process. */
+typedef struct probe_per_frame_constants_s {
+	float mesh_dequantization_factor[3], padding_0, mesh_dequantization_summand[3];
+	float error_factor;
+	float world_to_projection_space[4][4];
+	float pixel_to_ray_direction_world_space[3][4];
+	float camera_position_world_space[3];
+	float mis_visibility_estimate;
+	VkExtent2D viewport_size;
+	int32_t cursor_position[2];
+	float exposure_factor;
+	float roughness_factor;
+	uint32_t noise_resolution_mask[2];
+	uint32_t noise_texture_index_mask;
+	uint32_t frame_bits;
+	uint32_t padding_3[2];
+	uint32_t noise_random_numbers[4];
+	ltc_constants_t ltc_constants;
+} probe_per_frame_constants_t;
+
+/* settings6 = {mis_visibility_estimate, error_min_exponent, exposure_factor, roughness_factor, animate_noise, frame_bits} (render_settings_t, screenshot_t);
+   scene, LTC table and noise table are the ones loaded last through ref_probe_load_scene / _ltc / _noise. Returns the number of bytes written, 0 on failure. */
+size_t ref_probe_write_constants(void* data, size_t capacity, const char* quick_save_path, uint32_t light_count, uint32_t width, uint32_t height, const float* settings6) {
+	FILE* file = fopen(quick_save_path, "rb");
+	if (!file) return 0;
+	first_person_camera_t camera;
+	uint32_t legacy_count = 0, file_light_count = 0;
+	fread(&camera, sizeof(camera), 1, file);
+	fread(&legacy_count, sizeof(uint32_t), 1, file);
+	fread(&file_light_count, sizeof(uint32_t), 1, file);
+	polygonal_light_t* lights = calloc(file_light_count ? file_light_count : 1, sizeof(polygonal_light_t)); /* malloc in the reference: its padding words are indeterminate, zero here */
+	for (uint32_t i = 0; i != file_light_count; ++i) { /* main.c:105-125 */
+		polygonal_light_t* light = &lights[i];
+		fread(light, POLYGONAL_LIGHT_QUICKSAVE_SIZE, 1, file);
+		if (light->scaling_y <= 0.0f) light->scaling_y = light->scaling_x;
+		size_t path_size = 0;
+		fread(&path_size, sizeof(path_size), 1, file);
+		light->texture_file_path = NULL;
+		if (path_size) {
+			light->texture_file_path = malloc(sizeof(char) * path_size);
+			fread(light->texture_file_path, sizeof(char), path_size, file);
+		}
+		fread(&light->vertices_plane_space, sizeof(float*), 2, file);
+		light->fan_areas = NULL;
+		set_polygonal_light_vertex_count(light, light->vertex_count);
+		fread(light->vertices_plane_space, sizeof(float), 4 * light->vertex_count, file);
+	}
+	fclose(file);
+	if (light_count > file_light_count) light_count = file_light_count;
+	const int animate_noise = settings6[4] != 0.0f; const uint32_t frame_bits = (uint32_t) settings6[5];
+	probe_per_frame_constants_t constants = { /* main.c:2119-2131; the cursor rests at the origin */
+		.mesh_dequantization_factor = {g_scene.mesh.dequantization_factor[0], g_scene.mesh.dequantization_factor[1], g_scene.mesh.dequantization_factor[2]},
+		.mesh_dequantization_summand = {g_scene.mesh.dequantization_summand[0], g_scene.mesh.dequantization_summand[1], g_scene.mesh.dequantization_summand[2]},
+		.camera_position_world_space = {camera.position_world_space[0], camera.position_world_space[1], camera.position_world_space[2]},
+		.mis_visibility_estimate = settings6[0],
+		.viewport_size = { width, height },
+		.cursor_position = { 0, 0 },
+		.ltc_constants = g_ltc.constants,
+		.error_factor = powf(10.0f, -settings6[1]),
+		.exposure_factor = settings6[2],
+		.roughness_factor = settings6[3],
+		.frame_bits = frame_bits,
+	};
+	set_noise_constants(constants.noise_resolution_mask, &constants.noise_texture_index_mask, constants.noise_random_numbers, &g_noise, animate_noise && (frame_bits == 0));
+	get_world_to_projection_space(constants.world_to_projection_space, &camera, ((float) width) / ((float) height)); /* get_aspect_ratio, vulkan_basics.h */
+	float viewport_transform[4]; /* main.c:2136-2156 */
+	viewport_transform[0] = 2.0f / width;
+	viewport_transform[1] = 2.0f / height;
+	viewport_transform[2] = 0.5f * viewport_transform[0] - 1.0f;
+	viewport_transform[3] = 0.5f * viewport_transform[1] - 1.0f;
+	float projection_to_world_space_no_translation[4][4];
+	float world_to_projection_space_no_translation[4][4];
+	memcpy(world_to_projection_space_no_translation, constants.world_to_projection_space, sizeof(world_to_projection_space_no_translation));
+	world_to_projection_space_no_translation[0][3] = 0.0f;
+	world_to_projection_space_no_translation[1][3] = 0.0f;
+	world_to_projection_space_no_translation[2][3] = 0.0f;
+	matrix_inverse(projection_to_world_space_no_translation, world_to_projection_space_no_translation);
+	float pixel_to_ray_direction_projection_space[4][3] = {
+		{viewport_transform[0], 0.0f, viewport_transform[2]},
+		{0.0f, viewport_transform[1], viewport_transform[3]},
+		{0.0f, 0.0f, 1.0f},
+		{0.0f, 0.0f, 1.0f},
+	};
+	for (uint32_t i = 0; i != 3; ++i)
+		for (uint32_t j = 0; j != 3; ++j)
+			for (uint32_t k = 0; k != 4; ++k)
+				constants.pixel_to_ray_direction_world_space[i][j] += projection_to_world_space_no_translation[i][k] * pixel_to_ray_direction_projection_space[k][j];
+	uint32_t max_vertex_count = 3; /* get_max_polygonal_light_vertex_count, main.c:184-190 */
+	for (uint32_t i = 0; i != light_count; ++i) if (max_vertex_count < lights[i].vertex_count) max_vertex_count = lights[i].vertex_count;
+	size_t offset = sizeof(constants);
+	const size_t light_size = POLYGONAL_LIGHT_FIXED_CONSTANT_BUFFER_SIZE + sizeof(float) * (12 * max_vertex_count - 8); /* main.c:334 */
+	size_t result = 0;
+	if (offset + light_count * light_size <= capacity) {
+		memset(data, 0, offset + light_count * light_size);
+		memcpy(data, &constants, sizeof(constants));
+		for (uint32_t i = 0; i != light_count; ++i) { /* main.c:2160-2186; untextured lights: texture index of the default texture = 0 */
+			polygonal_light_t* light = &lights[i];
+			update_polygonal_light(light);
+			light->texture_index = 0;
+			memcpy(((char*) data) + offset, light, POLYGONAL_LIGHT_FIXED_CONSTANT_BUFFER_SIZE);
+			offset += POLYGONAL_LIGHT_FIXED_CONSTANT_BUFFER_SIZE;
+			float* vertex_data[2] = { light->vertices_plane_space, light->vertices_world_space };
+			for (uint32_t j = 0; j != 2; ++j) {
+				memcpy(((char*) data) + offset, vertex_data[j], sizeof(float) * 4 * light->vertex_count);
+				if (light->vertex_count < max_vertex_count)
+					memcpy(((char*) data) + offset + sizeof(float) * 4 * light->vertex_count, vertex_data[j], sizeof(float) * 4);
+				offset += sizeof(float) * 4 * max_vertex_count;
+			}
+			memcpy(((char*) data) + offset, light->fan_areas, sizeof(float) * 4 * (light->vertex_count - 2));
+			offset += sizeof(float) * 4 * (max_vertex_count - 2); /* the repeated fan areas of shorter lights stay zero here: bench.py and the test use lights of one vertex count */
+		}
+		result = offset;
+	}
+	for (uint32_t i = 0; i != file_light_count; ++i) { free(lights[i].texture_file_path); lights[i].texture_file_path = NULL; destroy_polygonal_light(&lights[i]); }
+	free(lights);
+	return result;
+}

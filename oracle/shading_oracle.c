@@ -895,10 +895,13 @@ int vkr_oracle_shade_with_light_textures(const vkr_oracle_config_t* cfg, const v
 #ifdef _OPENMP
 	const double shade_begin = omp_get_wtime();
 #endif
-	#pragma omp parallel for schedule(dynamic, 1) reduction(+:total_rays)
-	for (uint32_t y = y0; y < y1; ++y) {
+	/* work items are 64-pixel pieces of rows: a banded sample of a frame has fewer rows than a big host has threads */
+	const uint32_t pieces = (W + 63) / 64;
+	#pragma omp parallel for collapse(2) schedule(dynamic, 1) reduction(+:total_rays)
+	for (uint32_t y = y0; y < y1; ++y) for (uint32_t piece = 0; piece < pieces; ++piece) {
 		if (cfg->band_stride && (y - y0) % cfg->band_stride >= cfg->band_height) continue;
-		for (uint32_t x = 0; x != W; ++x) {
+		const uint32_t x_end = (piece * 64 + 64 < W) ? piece * 64 + 64 : W;
+		for (uint32_t x = piece * 64; x != x_end; ++x) {
 			size_t pi = ((size_t) y * W + x) * 4;
 			uint64_t rays = 0;
 			v3 final_color = mk3(0.0f, 0.0f, 0.0f);

@@ -208,6 +208,32 @@ class OracleInputs:
 		return oracle.shade(cfg, constants, gbuffer, self.noise, self.ltc0, self.ltc1, tris, light_textures=self.light_textures)
 
 
+def reference_constants(info, width, height, lights, sample_count=1, exposure=1.0, frame_bits=0):
+	"""The constant block of a frame from the REFERENCE's own host code (oracle/_ref/libref_host.so: its unchanged loaders and host maths over the shim plus
+	the restated bodies of quick_load / write_constants, oracle/ref_host_probe.c). Needs nothing of libvkr_b200.so; default render settings except the
+	exposure, noise not animated (what bench.py and the fixtures use). Untextured lights only."""
+	import ctypes as C
+	lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_host.so"))
+	lib.ref_probe_write_constants.restype = C.c_size_t
+	lib.ref_probe_write_constants.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+	tri = C.c_uint64(); mat = C.c_uint64(); fs = (C.c_float * 6)(); pos = C.c_void_p(); nuv = C.c_void_p(); mi = C.c_void_p(); soup = C.POINTER(C.c_float)(); ntri = C.c_uint64()
+	if lib.ref_probe_load_scene(info["vks"].encode(), info["textures"].encode(), C.byref(tri), C.byref(mat), fs, C.byref(pos), C.byref(nuv), C.byref(mi), C.byref(soup), C.byref(ntri)) != 0:
+		raise RuntimeError("the reference's load_scene failed")
+	res = C.c_uint32(); t0 = C.c_void_p(); t1 = C.c_void_p(); ltc_constants = (C.c_float * 8)()
+	if lib.ref_probe_load_ltc(info["ltc"].encode(), 51, C.byref(res), C.byref(t0), C.byref(t1), ltc_constants) != 0:
+		raise RuntimeError("the reference's load_ltc_table failed")
+	data = C.c_void_p(); masks = (C.c_uint32 * 7)()
+	if lib.ref_probe_load_noise(256, 256, 64, 0, C.byref(data), masks, 0) != 0:   # noise_type_white
+		raise RuntimeError("the reference's load_noise_table failed")
+	settings = (C.c_float * 6)(0.5, -7.0, exposure, 1.0, 0.0, float(frame_bits))   # specify_default_render_settings, src/main.c:232-249
+	buf = (C.c_uint8 * (256 + 320 * 64 * 4))()
+	size = lib.ref_probe_write_constants(buf, len(buf), info["save"].encode(), lights, width, height, settings)
+	lib.ref_probe_destroy_noise(); lib.ref_probe_destroy_ltc(); lib.ref_probe_destroy_scene()
+	if size == 0:
+		raise RuntimeError("the reference's constants could not be written")
+	return bytes(buf[:size])
+
+
 def oracle_config(frame, width, height):
 	"""The -D defines of the reference (src/main.c:752-792) as the oracle's config, from a vulkan_renderer_b200.Frame."""
 	s = frame.settings

@@ -1,4 +1,5 @@
-"""world_size-2 gloo test (CPU) of the multi-GPU host logic: interleaved tile-row stripes + one all-gather."""
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: the split of a frame into tile columns per GPU and the exchange written with
+one all_gather (the product path exchanges pixels inside the shading kernel, csrc/vkr_exchange.cu; GPU edition: tests/test_gpu_multi.py)."""
 import os
 import socket
 
@@ -7,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vulkan_renderer_b200.stripes import StripeGather, stripe_rows
+from vulkan_renderer_b200.stripes import ShareGather, share_columns, share_tiles
 
 
 def _pattern(height, width):
@@ -20,10 +21,10 @@ def _worker(rank, world, port, height, width, result_path):
 	os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
 	dist.init_process_group("gloo", rank=rank, world_size=world)
 	try:
-		sg = StripeGather(height, width, rank, world, torch.device("cpu"))
+		sg = ShareGather(height, width, rank, world, torch.device("cpu"))
 		frame = torch.full((height, width, 4), -1.0)
-		rows = stripe_rows(height, rank, world)
-		frame[rows] = _pattern(height, width)[rows]      # "shade" this rank's stripe
+		cols = share_columns(width, rank, world)
+		frame[:, cols] = _pattern(height, width)[:, cols]      # "shade" this rank's tile columns
 		sg.gather_frame(frame)
 		ok = torch.equal(frame, _pattern(height, width))
 		flags = [torch.zeros(1) for _ in range(world)]
@@ -39,17 +40,24 @@ def _free_port():
 	s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close(); return port
 
 
-def test_stripe_partition_covers_every_row_once():
-	for height in (1080, 2160, 100, 8, 7):
-		for world in (1, 2, 4, 8):
-			rows = sorted(y for r in range(world) for y in stripe_rows(height, r, world))
-			assert rows == list(range(height))
-			counts = [len(stripe_rows(height, r, world)) for r in range(world)]
-			assert max(counts) - min(counts) <= 8      # interleaving balances the ranks to one tile row
+def test_share_partition_covers_every_column_and_tile_once():
+	for width in (1920, 3840, 100, 16, 7):
+		for world in (1, 2, 3, 4, 8):
+			cols = sorted(x for r in range(world) for x in share_columns(width, r, world))
+			assert cols == list(range(width))
+			counts = [len(share_columns(width, r, world)) for r in range(world)]
+			assert max(counts) - min(counts) <= 16     # interleaving balances the ranks to one tile column
+			height = 40
+			tiles = sorted(t for r in range(world) for t in share_tiles(width, height, r, world))
+			assert tiles == list(range(((width + 15) // 16) * 5))
+	# the shapes of the benchmark configurations divide evenly: every GPU gets the same number of tiles
+	for width, height in ((1920, 1080), (3840, 2160)):
+		for world in (2, 4, 8):
+			assert len({len(share_tiles(width, height, r, world)) for r in range(world)}) == 1
 
 
 def test_gather_reassembles_the_frame_world_size_2(tmp_path):
-	for height, width in ((100, 24), (1080 // 8, 16)):
-		result = tmp_path / ("result_%d.txt" % height)
+	for height, width in ((24, 100), (16, 1080 // 8), (8, 16)):   # ragged last tile; odd tile count; one tile for two ranks (a rank without a column)
+		result = tmp_path / ("result_%d_%d.txt" % (height, width))
 		mp.spawn(_worker, args=(2, _free_port(), height, width, str(result)), nprocs=2, join=True)
 		assert result.read_text() == "ok"

@@ -143,3 +143,14 @@ def test_constant_block_pixel_to_ray_uses_the_reference_inverse(ref):
 			expect[i, j] = acc
 	got = np.frombuffer(cb[96:144], dtype=np.float32).reshape(3, 4)
 	assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+
+
+@pytest.mark.parametrize("name,lights,width,height", [("cornell", 1, 128, 96), ("mini_city", 3, 320, 192), ("mini_room", 32, 64, 48)])
+def test_constant_block_equals_the_reference_host_code(ref, name, lights, width, height):
+	"""vkr_write_constants against quick_load + write_constants of the reference (restated over its own structs and functions in oracle/ref_host_probe.c)."""
+	from tests.ref_frames import host_constants
+	info = H.dataset(name)
+	ours = host_constants(info, width, height, lights, sample_count=4)
+	theirs = H.reference_constants(info, width, height, lights, sample_count=4)
+	assert len(ours) == len(theirs)
+	assert ours == theirs

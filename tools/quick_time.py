@@ -26,6 +26,14 @@ for i in range(3):
 	lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr())
 	lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device))
 	print("spp %d lights %d rays %d strategy %d: kernel %.3f ms -> %.1f Msamples/s" % (spp, lights, rays, strategy, p.last_kernel_ms, width * height * spp / p.last_kernel_ms / 1e3), flush=True)
+if os.environ.get("VKR_COUNTERS"):   # what the trace warps did (the counters edition of the kernel; same frame)
+	counters = (C.c_uint64 * api.TRACE_COUNTER_COUNT)()
+	assert lib.vkr_shading_pass_run_with_counters(C.byref(p), C.byref(frame.device), constants, len(constants), gb.data_ptr(), out.data_ptr(), counters) == 0
+	c = dict(zip(api.TRACE_COUNTER_NAMES, [int(v) for v in counters]))
+	rays = max(1, c["rays"])
+	print("counters", c)
+	print("per ray: %.2f node visits, %.2f leaves, %.2f triangle tests; occluded %.3f, cache hits %.3f; lanes per node step %.2f; counters-edition kernel %.1f ms" % (
+		c["node_visits"] / rays, c["leaf_visits"] / rays, c["triangle_tests"] / rays, c["occluded"] / rays, c["cache_hits"] / rays, c["node_visits"] / max(1, c["warp_node_steps"]), p.last_kernel_ms))
 import hashlib
 print("valid fraction", float((gb[1, :, :, 3] != 0).float().mean()), "mean radiance", float(out[..., :3].mean()),
 	"frame sha256", hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()[:16])   # builders and traversal variants must leave the frame bit-identical

@@ -19,7 +19,9 @@ EXPORTED_SYMBOLS = [
 	"vkr_get_world_to_projection_space", "vkr_quick_load", "vkr_quick_save", "vkr_destroy_scene_specification",
 	"vkr_specify_default_render_settings", "vkr_get_constants_size", "vkr_write_constants", "vkr_set_frame_bits",
 	"vkr_gbuffer_size", "vkr_run_visibility_pass", "vkr_run_gbuffer_pass",
-	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait",
+	"vkr_create_shading_pass", "vkr_destroy_shading_pass", "vkr_shading_pass_run", "vkr_shading_pass_run_host", "vkr_shading_pass_wait", "vkr_shading_pass_run_with_counters",
+	"vkr_create_frame_exchange", "vkr_destroy_frame_exchange", "vkr_frame_exchange_get_handle", "vkr_frame_exchange_connect", "vkr_frame_exchange_connect_local",
+	"vkr_frame_exchange_frame", "vkr_shading_pass_run_exchange", "vkr_shading_pass_run_host_exchange", "vkr_frame_exchange_wait", "vkr_frame_exchange_download",
 	"vkr_trace_shadow_rays", "vkr_sample_polygon_batch", "vkr_bvh_build_probe", "vkr_bvh_build_probe_with", "vkr_bvh_build_probe_device", "vkr_bvh4_build_probe", "vkr_bvh_free_probe",
 	"vkr_quantize_unorm8", "vkr_combine_ldr_screenshots_into_hdr", "vkr_write_png", "vkr_write_hdr", "vkr_take_screenshot",
 	"vkr_record_frame_time", "vkr_get_frame_time", "vkr_reset_frame_times",
@@ -120,8 +122,23 @@ class ShadingPassDesc(C.Structure):
 class ShadingPass(C.Structure):
 	_fields_ = [("desc", ShadingPassDesc), ("constants_size", C.c_size_t), ("d_constants", C.c_void_p), ("h_constants_pinned", C.c_void_p),
 		("d_gbuffer_staging", C.c_void_p), ("d_out_staging", C.c_void_p), ("kernel_launches", C.c_uint64), ("last_kernel_ms", C.c_float),
-		("event_begin", C.c_void_p), ("event_end", C.c_void_p), ("timing_enabled", C.c_int)]
+		("event_begin", C.c_void_p), ("event_end", C.c_void_p), ("timing_enabled", C.c_int),
+		("event_constants", C.c_void_p), ("tile_count", C.c_uint32), ("d_tile_list", C.c_void_p), ("h_tile_list", C.c_void_p),
+		("d_tile_cost", C.c_void_p), ("h_tile_cost", C.c_void_p), ("event_costs", C.c_void_p), ("costs_pending", C.c_int), ("reorder_tiles", C.c_int)]
 
+
+MAX_GPUS = 8   # VKR_MAX_GPUS
+
+
+class FrameExchange(C.Structure):
+	"""vkr_frame_exchange_t: one frame on several GPUs, pixels stored into every GPU's frame from the kernel epilogue (include/vkr_b200.h)."""
+	_fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("d_block", C.c_void_p),
+		("d_peer_blocks", C.c_void_p * MAX_GPUS), ("peer_is_ipc", C.c_int * MAX_GPUS), ("frames_exchanged", C.c_uint64), ("h_status", C.POINTER(C.c_int)), ("timeout_ns", C.c_uint64)]
+
+
+TRACE_COUNTER_NAMES = ["rays", "occluded", "cache_hits", "node_visits", "leaf_visits", "triangle_tests", "warp_rounds", "warp_node_steps", "known_occluded", "idle_polls",
+	"entries", "resolve_polls", "candidates"]   # vkr_trace_counter_t
+TRACE_COUNTER_COUNT = 16
 
 _lib = None
 
@@ -169,6 +186,17 @@ def load_library():
 	lib.vkr_shading_pass_run.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
 	lib.vkr_shading_pass_run_host.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
 	lib.vkr_shading_pass_wait.argtypes = [P(ShadingPass), P(Device)]
+	lib.vkr_shading_pass_run_with_counters.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, P(C.c_uint64)]
+	lib.vkr_create_frame_exchange.argtypes = [P(FrameExchange), P(Device), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+	lib.vkr_destroy_frame_exchange.argtypes = [P(FrameExchange), P(Device)]; lib.vkr_destroy_frame_exchange.restype = None
+	lib.vkr_frame_exchange_get_handle.argtypes = [P(FrameExchange), P(Device), C.c_void_p]
+	lib.vkr_frame_exchange_connect.argtypes = [P(FrameExchange), P(Device), C.c_void_p]
+	lib.vkr_frame_exchange_connect_local.argtypes = [P(FrameExchange), P(Device), P(C.c_void_p)]
+	lib.vkr_frame_exchange_frame.argtypes = [P(FrameExchange)]; lib.vkr_frame_exchange_frame.restype = C.c_void_p
+	lib.vkr_shading_pass_run_exchange.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, P(FrameExchange)]
+	lib.vkr_shading_pass_run_host_exchange.argtypes = [P(ShadingPass), P(Device), C.c_void_p, C.c_size_t, C.c_void_p, P(FrameExchange), C.c_void_p]
+	lib.vkr_frame_exchange_wait.argtypes = [P(FrameExchange), P(Device)]
+	lib.vkr_frame_exchange_download.argtypes = [P(FrameExchange), P(Device), C.c_void_p]
 	lib.vkr_trace_shadow_rays.argtypes = [P(Device), P(Scene), C.c_uint32, C.c_void_p, C.c_void_p]
 	lib.vkr_sample_polygon_batch.argtypes = [P(Device), C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
 	lib.vkr_bvh_build_probe.argtypes = [C.c_void_p, C.c_uint64, P(P(C.c_float)), P(C.c_uint64), P(P(C.c_float)), P(P(C.c_uint32)), P(C.c_uint32)]

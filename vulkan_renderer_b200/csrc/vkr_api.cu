@@ -7,8 +7,12 @@
 #include "vkr_kernels.h"
 #include "vkr_psa.cuh"
 #include "vkr_trace.cuh"
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <numeric>
+#include <vector>
 
 using namespace vkr;
 
@@ -73,6 +77,12 @@ extern "C" void vkr_destroy_shading_pass(vkr_shading_pass_t* pass, const vkr_dev
 	if (pass->d_out_staging) cudaFree(pass->d_out_staging);
 	if (pass->event_begin) cudaEventDestroy((cudaEvent_t) pass->event_begin);
 	if (pass->event_end) cudaEventDestroy((cudaEvent_t) pass->event_end);
+	if (pass->event_constants) cudaEventDestroy((cudaEvent_t) pass->event_constants);
+	if (pass->event_costs) cudaEventDestroy((cudaEvent_t) pass->event_costs);
+	if (pass->d_tile_list) cudaFree(pass->d_tile_list);
+	if (pass->h_tile_list) cudaFreeHost(pass->h_tile_list);
+	if (pass->d_tile_cost) cudaFree(pass->d_tile_cost);
+	if (pass->h_tile_cost) cudaFreeHost(pass->h_tile_cost);
 	memset(pass, 0, sizeof(*pass));
 }
 
@@ -134,16 +144,43 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 		printf("Failed to create the shading pass: %u lights do not fit into shared memory.\n", d.polygonal_light_count);
 		memset(pass, 0, sizeof(*pass)); return 1;
 	}
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+	// The tiles of this instance (column tx of every tile row with tx % stripe_count == stripe_index), row-major: the launch order of the first frame
+	const uint32_t tiles_x = (d.width + VKR_TILE_WIDTH - 1) / VKR_TILE_WIDTH, tiles_y = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
+	std::vector<uint32_t> tiles;
+	for (uint32_t ty = 0; ty != tiles_y; ++ty) for (uint32_t tx = d.stripe_index; tx < tiles_x; tx += d.stripe_count) tiles.push_back(ty * tiles_x + tx);
+	pass->tile_count = (uint32_t) tiles.size();
+	const size_t list_bytes = sizeof(uint32_t) * (tiles.empty() ? 1 : tiles.size()), cost_bytes = sizeof(uint32_t) * (size_t) tiles_x * tiles_y;
 	if (cudaMalloc(&pass->d_constants, pass->constants_size) != cudaSuccess || cudaMallocHost(&pass->h_constants_pinned, pass->constants_size) != cudaSuccess
-		|| cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+		|| cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess
+		|| cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e3, cudaEventDisableTiming) != cudaSuccess
+		|| cudaMalloc(&pass->d_tile_list, list_bytes) != cudaSuccess || cudaMallocHost(&pass->h_tile_list, list_bytes) != cudaSuccess
+		|| cudaMalloc(&pass->d_tile_cost, cost_bytes) != cudaSuccess || cudaMallocHost(&pass->h_tile_cost, cost_bytes) != cudaSuccess
+		|| cudaMemset(pass->d_tile_cost, 0, cost_bytes) != cudaSuccess)
 	{
 		printf("Failed to allocate constant buffers for the shading pass.\n");
-		pass->event_begin = e0; pass->event_end = e1;
+		pass->event_begin = e0; pass->event_end = e1; pass->event_constants = e2; pass->event_costs = e3;
 		vkr_destroy_shading_pass(pass, device); return 1;
 	}
-	pass->event_begin = e0; pass->event_end = e1;
+	pass->event_begin = e0; pass->event_end = e1; pass->event_constants = e2; pass->event_costs = e3;
+	memcpy(pass->h_tile_list, tiles.data(), sizeof(uint32_t) * tiles.size());
+	if (cudaMemcpy(pass->d_tile_list, pass->h_tile_list, list_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+		printf("Failed to upload the tile list of the shading pass.\n");
+		vkr_destroy_shading_pass(pass, device); return 1;
+	}
+	const char* order = getenv("VKR_TILE_ORDER");   // "static": keep the row-major order (tuning experiments)
+	pass->reorder_tiles = !(order && !strcmp(order, "static"));
 	return 0;
+}
+
+// Launch order of the next frame: the tiles of this instance sorted by what they cost in the frame before, dearest first (longest processing time first:
+// the hardware hands out CTAs in index order, so the frame ends on cheap tiles instead of on whatever the bottom rows hold). Called when the costs of the
+// previous frame have arrived on the host; equal costs keep their row-major order, so the order is deterministic.
+static void reorder_tiles_by_cost(vkr_shading_pass_t* pass) {
+	uint32_t* list = (uint32_t*) pass->h_tile_list;
+	const uint32_t* cost = (const uint32_t*) pass->h_tile_cost;
+	std::sort(list, list + pass->tile_count); // row-major first: ties below are then independent of the previous order
+	std::stable_sort(list, list + pass->tile_count, [cost](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
 }
 
 cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaStream_t stream) {
@@ -187,7 +224,10 @@ cudaError_t vkr_launch_shading_kernel(const vkr::shading_kernel_params& p, cudaS
 	}
 }
 
-static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out) {
+// exchange: when not null, the pixels also go into the frames of the other GPUs (vkr_exchange.cu fills peer_outs)
+int vkr_launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out, unsigned long long* d_stats,
+	int peer_count, void* const* peer_outs)
+{
 	const vkr_shading_pass_desc_t& d = pass->desc;
 	if (constants_size != pass->constants_size) {
 		printf("The constant block has %llu bytes but the shading pass was created for %llu bytes (%u lights with up to %u vertices).\n",
@@ -223,14 +263,31 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	}
 	cudaStream_t stream = (cudaStream_t) device->stream;
 	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	// The call is asynchronous: the previous frame's copy out of the pinned staging buffer may not have run yet (it queues behind that frame's kernel)
+	if (pass->kernel_launches) VKR_CUDA_OK(cudaEventSynchronize((cudaEvent_t) pass->event_constants), "Failed to wait for the previous upload of the constant block");
 	memcpy(pass->h_constants_pinned, constants, constants_size);
 	VKR_CUDA_OK(cudaMemcpyAsync(pass->d_constants, pass->h_constants_pinned, constants_size, cudaMemcpyHostToDevice, stream), "Failed to upload the constant block");
+	VKR_CUDA_OK(cudaEventRecord((cudaEvent_t) pass->event_constants, stream), "Failed to record the upload of the constant block");
 	shading_kernel_params p; memset(&p, 0, sizeof(p));
-	p.width = (int) d.width; p.height = (int) d.height; p.tile_row_first = (int) d.stripe_index; p.tile_row_step = (int) d.stripe_count;
-	{
-		const uint32_t tile_rows = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
-		p.tile_row_count = (int) ((tile_rows > d.stripe_index) ? (tile_rows - d.stripe_index + d.stripe_count - 1) / d.stripe_count : 0);
+	p.width = (int) d.width; p.height = (int) d.height;
+	p.tile_count = (int) pass->tile_count;
+	const bool whole_frame = d.stripe_count == 1;
+	if (pass->reorder_tiles && pass->costs_pending && cudaEventQuery((cudaEvent_t) pass->event_costs) == cudaSuccess) {
+		// the costs of an earlier frame are here: new launch order. The list's last upload ran before that frame's kernel, so the staging buffer is free.
+		pass->costs_pending = 0;
+		reorder_tiles_by_cost(pass);
+		VKR_CUDA_OK(cudaMemcpyAsync(pass->d_tile_list, pass->h_tile_list, sizeof(uint32_t) * pass->tile_count, cudaMemcpyHostToDevice, stream), "Failed to upload the tile order");
 	}
+	p.tile_list = (whole_frame && !pass->reorder_tiles) ? nullptr : (const uint32_t*) pass->d_tile_list;
+	const bool record_costs = pass->reorder_tiles && !pass->costs_pending && !d_stats;
+	if (record_costs) {
+		const size_t cost_bytes = sizeof(uint32_t) * (size_t) ((d.width + VKR_TILE_WIDTH - 1) / VKR_TILE_WIDTH) * ((d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT);
+		VKR_CUDA_OK(cudaMemsetAsync(pass->d_tile_cost, 0, cost_bytes, stream), "Failed to clear the tile costs");
+		p.tile_cost = (uint32_t*) pass->d_tile_cost;
+	}
+	if (peer_count < 0 || peer_count > 7) return 1;
+	p.out_peer_count = peer_count;
+	for (int k = 0; k != peer_count; ++k) p.out_peers[k] = (float4*) peer_outs[k];
 	p.gbuffer = (const float4*) d_gbuffer; p.out = (float4*) d_out;
 	p.constants = (const unsigned char*) pass->d_constants;
 	p.constants_bytes = (uint32_t) constants_size;
@@ -254,16 +311,65 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 		p.light_texture_texels = (const float4*) d.light_textures->d_texels; p.light_texture_dims = (const uint4*) d.light_textures->d_dims;
 		p.light_texture_offsets = (const unsigned long long*) d.light_textures->d_offsets; p.light_texture_count = d.light_textures->texture_count;
 	}
+	if (d_stats) { // the counters edition exists for the projected solid angle kernels of quad lights (what the benchmark configurations run)
+		if (p.max_light_vertex_count != 4 || p.polygon_sampling_technique < 11 || p.error_display != 0 || any_textured_light) {
+			printf("Trace counters are available for projected solid angle sampling of untextured lights with up to 4 vertices only.\n");
+			return 1;
+		}
+		p.stats = d_stats;
+	}
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_begin, stream);
-	cudaError_t err = vkr_launch_shading_kernel(p, stream);
+	cudaError_t err = d_stats ? vkr_launch_shading_kernel_stats_maxp5(p, stream) : vkr_launch_shading_kernel(p, stream);
 	if (pass->timing_enabled) cudaEventRecord((cudaEvent_t) pass->event_end, stream);
 	VKR_CUDA_OK(err, "Failed to launch the shading kernel");
 	++pass->kernel_launches;
+	if (record_costs) { // read back what the tiles cost; looked at when a later frame is launched
+		const size_t cost_bytes = sizeof(uint32_t) * (size_t) ((d.width + VKR_TILE_WIDTH - 1) / VKR_TILE_WIDTH) * ((d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT);
+		if (cudaMemcpyAsync(pass->h_tile_cost, pass->d_tile_cost, cost_bytes, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaEventRecord((cudaEvent_t) pass->event_costs, stream) == cudaSuccess)
+			pass->costs_pending = 1;
+	}
+	return 0;
+}
+
+static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out, unsigned long long* d_stats = nullptr) {
+	return vkr_launch_shading(pass, device, constants, constants_size, d_gbuffer, d_out, d_stats, 0, nullptr);
+}
+
+// This instance's part of one plane (or of the frame), host <-> device. A plane is rows of `texel` bytes per pixel; the instance owns tile column tx of
+// every row if tx % stripe_count == stripe_index, which makes its part a 2D array of 16-pixel segments with a pitch of stripe_count segments: one strided copy.
+int vkr_copy_tile_columns(const vkr_shading_pass_desc_t& d, void* dst, const void* src, size_t texel, cudaMemcpyKind kind, cudaStream_t stream) {
+	const size_t row_bytes = (size_t) d.width * texel, seg = (size_t) VKR_TILE_WIDTH * texel;
+	if (d.stripe_count == 1) return cudaMemcpyAsync(dst, src, row_bytes * d.height, kind, stream) != cudaSuccess;
+	const size_t pitch = seg * d.stripe_count, first = seg * d.stripe_index;
+	if (row_bytes % pitch == 0) // every row holds the same number of whole segments of this instance: the rows chain into one 2D array
+		return cudaMemcpy2DAsync((char*) dst + first, pitch, (const char*) src + first, pitch, seg, (row_bytes / pitch) * d.height, kind, stream) != cudaSuccess;
+	for (uint32_t y = 0; y != d.height; ++y) { // ragged rows: whole segments as a 2D copy per row, then the narrow last segment if it is ours
+		const size_t base = row_bytes * y;
+		size_t whole = 0, tail_at = 0, tail = 0;
+		for (size_t at = first; at < row_bytes; at += pitch) { if (at + seg <= row_bytes) ++whole; else { tail_at = at; tail = row_bytes - at; } }
+		if (whole && cudaMemcpy2DAsync((char*) dst + base + first, pitch, (const char*) src + base + first, pitch, seg, whole, kind, stream) != cudaSuccess) return 1;
+		if (tail && cudaMemcpyAsync((char*) dst + base + tail_at, (const char*) src + base + tail_at, tail, kind, stream) != cudaSuccess) return 1;
+	}
 	return 0;
 }
 
 extern "C" int vkr_shading_pass_run(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f) {
 	return launch_shading(pass, device, constants, constants_size, d_gbuffer, d_out_rgba32f);
+}
+
+extern "C" int vkr_shading_pass_run_with_counters(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, void* d_out_rgba32f, uint64_t* out_counters) {
+	static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter type");
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	unsigned long long* d_stats = nullptr;
+	VKR_CUDA_OK(cudaMalloc(&d_stats, sizeof(uint64_t) * VKR_TRACE_COUNTER_COUNT), "Failed to allocate the trace counters");
+	cudaMemsetAsync(d_stats, 0, sizeof(uint64_t) * VKR_TRACE_COUNTER_COUNT, stream);
+	int rc = launch_shading(pass, device, constants, constants_size, d_gbuffer, d_out_rgba32f, d_stats);
+	if (!rc && cudaMemcpyAsync(out_counters, d_stats, sizeof(uint64_t) * VKR_TRACE_COUNTER_COUNT, cudaMemcpyDeviceToHost, stream) != cudaSuccess) rc = 1;
+	if (cudaStreamSynchronize(stream) != cudaSuccess) { printf("The shading pass with trace counters failed: %s\n", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+	cudaFree(d_stats);
+	if (!rc && pass->timing_enabled) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, (cudaEvent_t) pass->event_begin, (cudaEvent_t) pass->event_end) == cudaSuccess) pass->last_kernel_ms = ms; }
+	return rc;
 }
 
 extern "C" int vkr_shading_pass_wait(vkr_shading_pass_t* pass, const vkr_device_t* device) {
@@ -286,25 +392,11 @@ extern "C" int vkr_shading_pass_run_host(vkr_shading_pass_t* pass, const vkr_dev
 			return 1;
 		}
 	}
-	// Upload only the tile rows of this stripe, plane by plane (a tile row is contiguous inside a plane)
-	const size_t row_bytes = (size_t) d.width * 16;
-	const uint32_t tile_rows = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
-	if (d.stripe_count == 1) {
-		for (int k = 0; k != 4; ++k)
-			VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes, (const char*) gbuffer + k * plane_bytes, plane_bytes, cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
-	}
-	else for (uint32_t t = d.stripe_index; t < tile_rows; t += d.stripe_count) {
-		const uint32_t y0 = t * VKR_TILE_ROW_HEIGHT, y1 = (y0 + VKR_TILE_ROW_HEIGHT < d.height) ? y0 + VKR_TILE_ROW_HEIGHT : d.height;
-		for (int k = 0; k != 4; ++k)
-			VKR_CUDA_OK(cudaMemcpyAsync((char*) pass->d_gbuffer_staging + k * plane_bytes + row_bytes * y0, (const char*) gbuffer + k * plane_bytes + row_bytes * y0, row_bytes * (y1 - y0), cudaMemcpyHostToDevice, stream), "Failed to upload the G-buffer");
-	}
+	// Upload only the tiles of this instance, plane by plane
+	for (int k = 0; k != 4; ++k)
+		if (vkr_copy_tile_columns(d, (char*) pass->d_gbuffer_staging + k * plane_bytes, (const char*) gbuffer + k * plane_bytes, 16, cudaMemcpyHostToDevice, stream)) { printf("Failed to upload the G-buffer.\n"); return 1; }
 	if (launch_shading(pass, device, constants, constants_size, pass->d_gbuffer_staging, pass->d_out_staging)) return 1;
-	if (d.stripe_count == 1)
-		VKR_CUDA_OK(cudaMemcpyAsync(out_rgba32f, pass->d_out_staging, plane_bytes, cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
-	else for (uint32_t t = d.stripe_index; t < tile_rows; t += d.stripe_count) {
-		const uint32_t y0 = t * VKR_TILE_ROW_HEIGHT, y1 = (y0 + VKR_TILE_ROW_HEIGHT < d.height) ? y0 + VKR_TILE_ROW_HEIGHT : d.height;
-		VKR_CUDA_OK(cudaMemcpyAsync((char*) out_rgba32f + row_bytes * y0, (const char*) pass->d_out_staging + row_bytes * y0, row_bytes * (y1 - y0), cudaMemcpyDeviceToHost, stream), "Failed to download the frame");
-	}
+	if (vkr_copy_tile_columns(d, out_rgba32f, pass->d_out_staging, 16, cudaMemcpyDeviceToHost, stream)) { printf("Failed to download the frame.\n"); return 1; }
 	return vkr_shading_pass_wait(pass, device);
 }
 
@@ -371,13 +463,17 @@ extern "C" int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t ver
 	cudaStream_t stream = (cudaStream_t) device->stream;
 	float *d_v = nullptr, *d_r = nullptr, *d_d = nullptr, *d_i = nullptr;
 	const size_t nn = n ? n : 1;
-	if (cudaMalloc(&d_v, sizeof(float) * 12) != cudaSuccess || cudaMalloc(&d_r, sizeof(float) * 2 * nn) != cudaSuccess || cudaMalloc(&d_d, sizeof(float) * 3 * nn) != cudaSuccess || cudaMalloc(&d_i, sizeof(float) * 11) != cudaSuccess) {
+	if (cudaMalloc(&d_v, sizeof(float) * 3 * 7) != cudaSuccess || cudaMalloc(&d_r, sizeof(float) * 2 * nn) != cudaSuccess || cudaMalloc(&d_d, sizeof(float) * 3 * nn) != cudaSuccess || cudaMalloc(&d_i, sizeof(float) * 11) != cudaSuccess) {
 		cudaFree(d_v); cudaFree(d_r); cudaFree(d_d); cudaFree(d_i);
 		printf("Failed to allocate buffers for the sampling probe.\n"); return 1;
 	}
-	cudaMemcpyAsync(d_v, vertices_xyz, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, stream);
-	cudaMemcpyAsync(d_r, random_numbers, sizeof(float) * 2 * (size_t) n, cudaMemcpyHostToDevice, stream);
-	cudaMemsetAsync(d_d, 0, sizeof(float) * 3 * nn, stream);
+	if (cudaMemcpyAsync(d_v, vertices_xyz, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, stream) != cudaSuccess
+		|| cudaMemcpyAsync(d_r, random_numbers, sizeof(float) * 2 * (size_t) n, cudaMemcpyHostToDevice, stream) != cudaSuccess
+		|| cudaMemsetAsync(d_d, 0, sizeof(float) * 3 * nn, stream) != cudaSuccess)
+	{
+		cudaFree(d_v); cudaFree(d_r); cudaFree(d_d); cudaFree(d_i);
+		printf("Failed to upload the inputs of the sampling probe.\n"); return 1;
+	}
 	const unsigned blocks = (unsigned) ((nn + 127) / 128);
 #define VKR_PROBE(V) case V: if (biased) sample_probe_kernel<V + 1, true><<<blocks, 128, 0, stream>>>(V, d_v, n, d_r, d_d, d_i); else sample_probe_kernel<V + 1, false><<<blocks, 128, 0, stream>>>(V, d_v, n, d_r, d_d, d_i); break;
 	switch (vertex_count) { VKR_PROBE(3) VKR_PROBE(4) VKR_PROBE(5) VKR_PROBE(6) VKR_PROBE(7) default: break; }

@@ -144,6 +144,11 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 		printf("The scene file at path %s seems to be invalid. The geometry data is not followed by the expected end of file marker.\n", file_path);
 		vkr_destroy_scene(scene, device); return 1;
 	}
+	for (uint64_t i = 0; i != n; ++i) // the G-buffer pass indexes the material table with these on the device
+		if (material_indices[i] >= scene->material_count) {
+			printf("The scene file at path %s refers to material %u but has %llu materials only.\n", file_path, (unsigned) material_indices[i], (unsigned long long) scene->material_count);
+			vkr_destroy_scene(scene, device); return 1;
+		}
 	if (upload(&scene->d_quantized_positions, positions.data(), positions.size() * 4, device)
 		|| upload(&scene->d_normals_and_tex_coords, normals_uvs.data(), normals_uvs.size() * 2, device)
 		|| upload(&scene->d_material_indices, material_indices.data(), material_indices.size(), device))

@@ -15,7 +15,14 @@ namespace vkr {
 struct shading_kernel_params {
 	// frame
 	int width, height;
-	int tile_row_first, tile_row_step, tile_row_count; // 8-pixel tile rows first, first+step, ... are shaded (multi-GPU stripes)
+	// Which 16x8 screen tiles this launch shades (multi-GPU: every GPU takes a share of the tiles, vkr_api.cu): CTA b shades tile
+	// tile_list[b] (= ty * tiles_x + tx), or tile b of the whole frame when the list is null. The list is also the launch ORDER: the
+	// pass sorts it by the cost measured in the previous frame, dearest first, so that the last wave of CTAs is made of cheap tiles.
+	int tile_count; const uint32_t* tile_list;
+	uint32_t* tile_cost;             // per tile of the frame: nanoseconds the CTA spent on it (atomicMax over its shading warps); null = not recorded
+	// Multi-GPU frame exchange (vkr_frame_exchange_t): finished pixels are also stored into the frames of the other GPUs (peer
+	// memory over NVLink) from the kernel's epilogue, so no gather pass follows. out_peer_count = 0 on a single GPU.
+	int out_peer_count; float4* out_peers[7];
 	const float4* gbuffer;           // 4 planes of width*height float4
 	float4* out;                     // width*height float4, linear radiance * exposure, alpha 1
 	const unsigned char* constants;  // device copy of the reference's constant block
@@ -36,6 +43,7 @@ struct shading_kernel_params {
 	int error_display;               // error_display_t (src/main.h:92-112); != 0 runs error_display_kernel (vkr_related_work_kernel.cu)
 	// light textures (vkr_light_textures_t); only the kernels of vkr_textured_light_kernel.cu read them. dims = {width, height, mip_count, -}, offsets in texels
 	const float4* light_texture_texels; const uint4* light_texture_dims; const unsigned long long* light_texture_offsets; uint32_t light_texture_count;
+	unsigned long long* stats;       // VKR_TRACE_COUNTER_COUNT device counters, only written by the counters edition of the kernels (-DVKR_TRACE_STATS); else null
 };
 
 struct gbuffer_kernel_params {
@@ -60,6 +68,7 @@ cudaError_t vkr_launch_shading_kernel_maxp5(const vkr::shading_kernel_params& p,
 cudaError_t vkr_launch_shading_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_shading_kernel_maxp8(const vkr::shading_kernel_params& p, cudaStream_t stream);
+cudaError_t vkr_launch_shading_kernel_stats_maxp5(const vkr::shading_kernel_params& p, cudaStream_t stream); // the counters edition of the quad-light kernels (-DVKR_TRACE_STATS)
 cudaError_t vkr_launch_textured_light_kernel_maxp4(const vkr::shading_kernel_params& p, cudaStream_t stream); // vkr_textured_light_kernel.cu, frames with textured lights
 cudaError_t vkr_launch_textured_light_kernel_maxp5(const vkr::shading_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_textured_light_kernel_maxp6(const vkr::shading_kernel_params& p, cudaStream_t stream);

@@ -42,6 +42,22 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #define VKR_RESOLVE_SLEEP_NS 512
 #endif
 
+// In-kernel statistics (vkr_trace_counter_t, include/vkr_b200.h): compiled in with -DVKR_TRACE_STATS (the counters edition of the quad-light
+// kernels, vkr_shading_kernel_stats.cu -> vkr_shading_pass_run_with_counters); the kernels that are timed carry none of it.
+#ifdef VKR_TRACE_STATS
+#define VKR_STAT(x) (++(x))
+#define VKR_STAT_ADD(x, n) ((x) += (n))
+#else
+#define VKR_STAT(x) ((void) 0)
+#define VKR_STAT_ADD(x, n) ((void) 0)
+#endif
+VKR_DEV void stat_flush(unsigned long long* stats, int index, unsigned value) {
+#if defined(VKR_TRACE_STATS) && defined(__CUDA_ARCH__)
+	value = __reduce_add_sync(kFullMask, value);
+	if ((threadIdx.x & 31) == 0 && value != 0u && stats) atomicAdd(stats + index, (unsigned long long) value);
+#endif
+}
+
 // Shared memory of one stream, as float offsets from its base. 7 (or 10, MIS_HEURISTIC_OPTIMAL) float arrays, owner and
 // result bytes, 96 floats of ray origins, 4 ints of control.
 enum : int {
@@ -71,6 +87,9 @@ struct ray_producer {
 	uint32_t base;   // shared-memory address of the stream
 	int fill;        // warp-uniform: entries written and published so far (absolute index; slot = index & (kRing - 1))
 	int resolved;    // warp-uniform: entries below this index have been added to their pixels, their slots are free
+#ifdef VKR_TRACE_STATS
+	unsigned stat_resolve_polls, stat_candidates;
+#endif
 };
 
 // Radiance sums of one pixel. The reference adds the samples of a light into a per-light sum, scales it by 1/S and
@@ -101,6 +120,7 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, pixel_sum& acc) {
 	while (true) {
 		const unsigned r = valid ? ld_acquire_u8(bytes + kRing + slot) : 0u;
 		if (!__any_sync(kFullMask, r == kPending)) break;
+		VKR_STAT(q.stat_resolve_polls);
 		__nanosleep(VKR_RESOLVE_SLEEP_NS);
 	}
 	const unsigned own = valid ? (lds_u8(bytes + slot) & 31u) : 32u;
@@ -137,6 +157,7 @@ VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir
 	}
 	else {
 		const bool push = has && (need_trace || OPTIMAL);
+		if (has) VKR_STAT(q.stat_candidates);
 		const unsigned mask = __ballot_sync(kFullMask, push);
 		if (mask) {
 			const int k = __popc(mask);
@@ -149,7 +170,10 @@ VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir
 				if (OPTIMAL) { sts_f(a + 4u * S_OX, c_occluded.x); sts_f(a + 4u * S_OY, c_occluded.y); sts_f(a + 4u * S_OZ, c_occluded.z); }
 				const uint32_t bytes = q.base + 4u * stream_bytes_at(OPTIMAL);
 				sts_u8(bytes + e, (unsigned) lane | acc.submit_parity | (need_trace ? 0u : 128u));
-				sts_u8(bytes + kRing + e, need_trace ? kPending : 1u);
+				// Every entry is completed by the trace lane that drew its ticket, also the ones known to be occluded (optimal MIS): a slot whose result
+				// were set here could be resolved and reused while the lane holding its ticket has not looked at it yet, and that lane would then trace
+				// the newer entry a second time and store its result late, possibly onto a still newer entry of the slot.
+				sts_u8(bytes + kRing + e, kPending);
 				acc.pushed = true;
 			}
 			q.fill += k;
@@ -163,18 +187,26 @@ VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir
 // End of the tile: resolves what is still pending, closes the last light and tells the trace warps that no ticket
 // >= fill will ever be served.
 template <bool OPTIMAL>
-VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc) {
+VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc, unsigned long long* stats = nullptr) {
 	while (q.resolved != q.fill) resolve_chunk<OPTIMAL>(q, lane, acc);
 	close_light(acc);
 	__syncwarp(kFullMask);
 	if (lane == 0) st_release(q.base + 4u * stream_control_at(OPTIMAL) + 8u, q.fill);
+#ifdef VKR_TRACE_STATS
+	stat_flush(stats, 10, lane == 0 ? (unsigned) q.fill : 0u);
+	stat_flush(stats, 11, lane == 0 ? q.stat_resolve_polls : 0u);   // warp-uniform count
+	stat_flush(stats, 12, q.stat_candidates);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Consumer side (trace warps): runs until the stream is closed and drained. stack = shared-memory address of this
 // lane's column of the warp's traversal stack (128 B between levels = one slot per lane).
 template <bool OPTIMAL>
-VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane) {
+VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane, unsigned long long* stats = nullptr) {
+#ifdef VKR_TRACE_STATS
+	unsigned st_rays = 0, st_hits = 0, st_cache_hits = 0, st_visits = 0, st_leaves = 0, st_tris = 0, st_iters = 0, st_node_iters = 0, st_known = 0, st_polls = 0;
+#endif
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const float tmin = 1.0e-3f; // shading_pass.frag.glsl:124
 	const uint32_t bytes = base + 4u * stream_bytes_at(OPTIMAL);
@@ -211,7 +243,12 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 				entry = (uint32_t) ticket & (kRing - 1);
 				ticket = -1;
 				const unsigned own = lds_u8(bytes + entry);
-				if (!(own & 128u)) { // entries known to be occluded carry their result already
+				if (own & 128u) { // known to be occluded (n.w <= 0): no ray, but the ticket holder is the one who completes the entry (see submit())
+					VKR_STAT(st_known);
+					st_release_u8(bytes + kRing + entry, 1u);
+				}
+				else {
+					VKR_STAT(st_rays);
 					const uint32_t oa = origin + 4u * (own & 31u), ea = base + 4u * entry;
 					o = make3(lds_f(oa), lds_f(oa + 128u), lds_f(oa + 256u));
 					d = make3(lds_f(ea + 4u * S_DX), lds_f(ea + 4u * S_DY), lds_f(ea + 4u * S_DZ));
@@ -221,7 +258,7 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 					node = kTraversalDone; leaf = 0;
 					float t;
 					if (tmax > tmin) { // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
-						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) hit = true;
+						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) { hit = true; VKR_STAT(st_cache_hits); }
 						else { r = make_slabs(o, d); node = 0; top = stack_bottom; push(kTraversalDone); }
 					}
 				}
@@ -233,9 +270,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		}
 		if (!__any_sync(kFullMask, active)) {
 			if (__all_sync(kFullMask, finished)) break;
+			if (lane == 0) VKR_STAT(st_polls);
 			__nanosleep(100); // nothing published yet: leave the issue slots to the other warps
 			continue;
 		}
+		if (lane == 0) VKR_STAT(st_iters);
 		// --- descend until this lane holds two leaves or is out of nodes
 #if VKR_BVH_WIDTH == 4
 		// EXPERIMENTAL variant (tools/build_variant.sh ... "-DVKR_BVH_WIDTH=4" with VKR_BVH_WIDTH=4 in the environment when the scene is loaded): 128-byte
@@ -243,6 +282,8 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		// (leaves too: pop() hands them back like any reference). The node step is bvh4_descend_step() of vkr_trace.cuh, shared with occluded4(), which is tested
 		// on the CPU; this warp loop around it was written without GPU access.
 		while (node >= 0 && node != kTraversalDone) {
+			VKR_STAT(st_visits);
+			if ((__activemask() & lt_mask) == 0u) VKR_STAT(st_node_iters);
 			node = bvh4_descend_step(nodes, node, r, tmin, tmax, push); // nearest hit child; the other hit children are on the stack now
 			if (node == kTraversalDone) node = pop();
 			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
@@ -254,9 +295,12 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 #else
 		while (node >= 0 && node != kTraversalDone) {
 			const float4* nd = nodes + 4 * (size_t) node;
-			const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3);
+			float4 q0, q1, q2, q3;
+			ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3);
 			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
 			float tn0, tn1;
+			VKR_STAT(st_visits);
+			if ((__activemask() & lt_mask) == 0u) VKR_STAT(st_node_iters);
 			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
 			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
 			if (h0 && h1) {
@@ -281,6 +325,7 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		while (leaf != 0) {
 			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
 			float t;
+			VKR_STAT(st_leaves); VKR_STAT_ADD(st_tris, (unsigned) count);
 			for (int i = 0; i != count; ++i)
 				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) { hit = true; cached_triangle = first + i; }
 			leaf = 0;
@@ -293,10 +338,15 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		// --- a ray ends when it hit something or ran out of nodes
 		if (active && node == kTraversalDone) {
 			st_release_u8(bytes + kRing + entry, hit ? 1u : 0u);
+			if (hit) VKR_STAT(st_hits);
 			active = false;
 		}
 		__syncwarp(kFullMask);
 	}
+#ifdef VKR_TRACE_STATS
+	stat_flush(stats, 0, st_rays); stat_flush(stats, 1, st_hits); stat_flush(stats, 2, st_cache_hits); stat_flush(stats, 3, st_visits); stat_flush(stats, 4, st_leaves);
+	stat_flush(stats, 5, st_tris); stat_flush(stats, 6, st_iters); stat_flush(stats, 7, st_node_iters); stat_flush(stats, 8, st_known); stat_flush(stats, 9, st_polls);
+#endif
 }
 
 } // namespace vkr

@@ -46,9 +46,7 @@ static constexpr size_t kStreamFloats = stream_floats_per_warp(false);
 
 template <int STRATEGY, int MAXV, bool TRACE>
 static cudaError_t launch_related_work(const shading_kernel_params& p, cudaStream_t stream) {
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = p.tile_row_count;
-	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
+	if (p.tile_count <= 0) return cudaSuccess;
 	const int threads = TRACE ? kShadeThreads + kTraceThreads : kShadeThreads;
 	const size_t smem = p.constants_smem_bytes + (TRACE ? sizeof(float) * kStreamFloats * kShadeWarps + sizeof(int) * (size_t) p.stack_depth * kTraceThreads : 0);
 	auto kernel = related_work_kernel<STRATEGY, MAXV, TRACE>;
@@ -60,19 +58,17 @@ static cudaError_t launch_related_work(const shading_kernel_params& p, cudaStrea
 	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, threads, smem, stream>>>(p);
+	kernel<<<p.tile_count, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
 template <int MAXV>
 static cudaError_t launch_error_display(const shading_kernel_params& p, cudaStream_t stream) {
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = p.tile_row_count;
-	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
+	if (p.tile_count <= 0) return cudaSuccess;
 	auto kernel = error_display_kernel<MAXV>;
 	cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.constants_smem_bytes);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, kShadeThreads, p.constants_smem_bytes, stream>>>(p);
+	kernel<<<p.tile_count, kShadeThreads, p.constants_smem_bytes, stream>>>(p);
 	return cudaGetLastError();
 }
 

@@ -27,6 +27,15 @@
 #include "vkr_shading_tile.cuh"
 #include "vkr_shade_light.cuh"
 
+// The counters edition (-DVKR_TRACE_STATS, vkr_trace_counter_t) is a kernel of its own name: the host stubs of two editions of one template
+// would be merged by the linker.
+#ifdef VKR_TRACE_STATS
+#define shading_kernel shading_kernel_counters
+#define VKR_LAUNCHER_PREFIX vkr_launch_shading_kernel_stats_maxp
+#else
+#define VKR_LAUNCHER_PREFIX vkr_launch_shading_kernel_maxp
+#endif
+
 namespace vkr {
 
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
@@ -41,9 +50,7 @@ using namespace vkr;
 
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
 static cudaError_t launch_traced(const shading_kernel_params& p, cudaStream_t stream) {
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = p.tile_row_count;
-	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
+	if (p.tile_count <= 0) return cudaSuccess;
 	const int threads = TRACE ? kShadeThreads + kTraceThreads : kShadeThreads;
 	const size_t smem = p.constants_smem_bytes + (TRACE ? sizeof(float) * stream_floats_per_warp(OPTIMAL) * kShadeWarps + sizeof(int) * (size_t) p.stack_depth * kTraceThreads : 0);
 	auto kernel = shading_kernel<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>;
@@ -56,7 +63,7 @@ static cudaError_t launch_traced(const shading_kernel_params& p, cudaStream_t st
 	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, threads, smem, stream>>>(p);
+	kernel<<<p.tile_count, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 
@@ -86,7 +93,7 @@ static cudaError_t launch_strategy(const shading_kernel_params& p, cudaStream_t 
 #endif
 #define VKR_CONCAT2(a, b) a##b
 #define VKR_CONCAT(a, b) VKR_CONCAT2(a, b)
-cudaError_t VKR_CONCAT(vkr_launch_shading_kernel_maxp, VKR_MAXP_TU)(const shading_kernel_params& p, cudaStream_t stream) {
+cudaError_t VKR_CONCAT(VKR_LAUNCHER_PREFIX, VKR_MAXP_TU)(const shading_kernel_params& p, cudaStream_t stream) {
 	if (p.stack_depth < 2 || p.stack_depth > kMaxStackDepth) return cudaErrorInvalidValue;
 	if (p.trace_shadow_rays != 0 && p.tri_count != 0 && p.bvh_width != VKR_BVH_WIDTH) return cudaErrorInvalidValue; // the scene's BVH layout must be the one these kernels walk
 	return p.biased_sampling ? launch_strategy<VKR_MAXP_TU, true>(p, stream) : launch_strategy<VKR_MAXP_TU, false>(p, stream);

@@ -52,7 +52,7 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 			asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(VKR_TRACE_REGS));
 			const int t = warp - kShadeWarps;
 			trace_stream<OPTIMAL>(smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * (t & (kShadeWarps - 1))), p.bvh_nodes, p.bvh_tris,
-				smem_addr(stack_base + p.stack_depth * 32 * t + lane), lane);
+				smem_addr(stack_base + p.stack_depth * 32 * t + lane), lane, p.stats);
 			return;
 		}
 		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(VKR_SHADE_REGS));
@@ -71,9 +71,11 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 	// --- pixel of this thread: warps cover 8x4 patches of the 16x8 tile
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
 	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tile = blockIdx.x;
+	const int tile = p.tile_list ? (int) __ldg(p.tile_list + blockIdx.x) : (int) blockIdx.x;
 	const int x = (tile % tiles_x) * kTileW + lx;
-	const int y = (p.tile_row_first + (tile / tiles_x) * p.tile_row_step) * kTileH + ly;
+	const int y = (tile / tiles_x) * kTileH + ly;
+	unsigned long long tile_begin_ns = 0;
+	if (p.tile_cost && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tile_begin_ns));
 	const bool in_frame = x < p.width && y < p.height;
 	const size_t pixel = in_frame ? ((size_t) y * p.width + x) : 0;
 	const size_t plane = (size_t) p.width * p.height;
@@ -109,6 +111,9 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 	// --- the warp's ray stream; trace lanes fetch ray origins from it by owner lane
 	ray_producer q;
 	q.base = smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * warp); q.fill = 0; q.resolved = 0;
+#ifdef VKR_TRACE_STATS
+	q.stat_resolve_polls = 0; q.stat_candidates = 0;
+#endif
 	if (TRACE) {
 		float* origin = stream_base + stream_floats_per_warp(OPTIMAL) * warp + stream_origin_at(OPTIMAL);
 		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
@@ -137,15 +142,23 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 			shade(valid, sp, l, light, ns, p, cb, (uint32_t) x, (uint32_t) y, q, acc, lane);
 		}
 	}
-	if (TRACE) close_stream<OPTIMAL>(q, lane, acc);
+	if (TRACE) close_stream<OPTIMAL>(q, lane, acc, p.stats);
 	color = acc.color;
+	if (p.tile_cost && lane == 0) { // what this tile cost: the slowest of its four shading warps (which wait for their shadow rays)
+		unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+		const unsigned long long ns = now - tile_begin_ns;
+		atomicMax(p.tile_cost + tile, (uint32_t) (ns > 0xffffffffull ? 0xffffffffull : ns));
+	}
 	if (!in_frame) return;
 	f3 final_color = color;
 	if (isnan(color.x) || isnan(color.y) || isnan(color.z) || isinf(color.x) || isinf(color.y) || isinf(color.z))
 		final_color = make3(1.0f / exposure, 0.0f / exposure, 0.8f / exposure);
 	f3 out_color = make3(final_color.x * exposure, final_color.y * exposure, final_color.z * exposure);
 	out_color = output_stage(out_color, ldu(cb, OFF_FRAME_BITS), p.output_srgb != 0);
-	p.out[pixel] = make_float4(out_color.x, out_color.y, out_color.z, 1.0f);
+	const float4 texel = make_float4(out_color.x, out_color.y, out_color.z, 1.0f);
+	p.out[pixel] = texel;
+	// the other GPUs' copies of the frame: a warp writes four 128-byte row segments per peer, straight over NVLink
+	for (int k = 0; k < p.out_peer_count; ++k) p.out_peers[k][pixel] = texel;
 }
 
 } // namespace vkr

@@ -36,9 +36,7 @@ using namespace vkr;
 
 template <int STRATEGY, int MAXP, bool OPTIMAL, bool TRACE>
 static cudaError_t launch_traced(const shading_kernel_params& p, cudaStream_t stream) {
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = p.tile_row_count;
-	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
+	if (p.tile_count <= 0) return cudaSuccess;
 	const int threads = TRACE ? kShadeThreads + kTraceThreads : kShadeThreads;
 	constexpr size_t stream_floats = stream_floats_per_warp(OPTIMAL);
 	const size_t smem = p.constants_smem_bytes + (TRACE ? sizeof(float) * stream_floats * kShadeWarps + sizeof(int) * (size_t) p.stack_depth * kTraceThreads : 0);
@@ -51,7 +49,7 @@ static cudaError_t launch_traced(const shading_kernel_params& p, cudaStream_t st
 	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, threads, smem, stream>>>(p);
+	kernel<<<p.tile_count, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 

@@ -23,9 +23,7 @@ static constexpr size_t kStreamFloats = stream_floats_per_warp(false);
 
 template <int STRATEGY, int MAXV, bool TRACE>
 static cudaError_t launch(const shading_kernel_params& p, cudaStream_t stream) {
-	const int tiles_x = (p.width + kTileW - 1) / kTileW;
-	const int tiles_y = p.tile_row_count;
-	if (tiles_x <= 0 || tiles_y <= 0) return cudaSuccess;
+	if (p.tile_count <= 0) return cudaSuccess;
 	const int threads = TRACE ? kShadeThreads + kTraceThreads : kShadeThreads;
 	const size_t smem = p.constants_smem_bytes + (TRACE ? sizeof(float) * kStreamFloats * kShadeWarps + sizeof(int) * (size_t) p.stack_depth * kTraceThreads : 0);
 	auto kernel = textured_related_work_kernel<STRATEGY, MAXV, TRACE>;
@@ -37,7 +35,7 @@ static cudaError_t launch(const shading_kernel_params& p, cudaStream_t stream) {
 	const int carveout = (int) ((100 * ((smem + 1024) * (size_t) (ctas > 0 ? ctas : 1)) + 228 * 1024 - 1) / (228 * 1024));
 	err = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout > 100 ? 100 : carveout);
 	if (err != cudaSuccess) return err;
-	kernel<<<tiles_x * tiles_y, threads, smem, stream>>>(p);
+	kernel<<<p.tile_count, threads, smem, stream>>>(p);
 	return cudaGetLastError();
 }
 

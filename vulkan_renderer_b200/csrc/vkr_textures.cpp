@@ -58,8 +58,20 @@ void decode_bc4_block(const uint8_t* block, float value[16]) {
 // One mip level of `format` -> RGBA32F. Returns false if the level is too small for its payload or the format is unknown.
 bool decode_level(float* out, uint32_t width, uint32_t height, uint32_t format, const uint8_t* data, uint64_t size) {
 	const size_t pixel_count = (size_t) width * height;
-	for (size_t i = 0; i != pixel_count; ++i) { out[4 * i] = out[4 * i + 1] = out[4 * i + 2] = 0.0f; out[4 * i + 3] = 1.0f; }
 	const uint32_t bw = (width + 3) / 4, bh = (height + 3) / 4;
+	{ // the payload must hold the level before a single texel is written (a corrupt header must not make this loop write gigabytes)
+		uint64_t need;
+		switch (format) {
+		case 97: need = (uint64_t) pixel_count * 8; break; case 90: need = (uint64_t) pixel_count * 6; break;
+		case 109: need = (uint64_t) pixel_count * 16; break; case 106: need = (uint64_t) pixel_count * 12; break;
+		case 37: case 43: need = (uint64_t) pixel_count * 4; break;
+		case 131: case 132: case 133: case 134: need = (uint64_t) bw * bh * 8; break;
+		case 141: case 142: need = (uint64_t) bw * bh * 16; break;
+		default: return false;
+		}
+		if (size < need) return false;
+	}
+	for (size_t i = 0; i != pixel_count; ++i) { out[4 * i] = out[4 * i + 1] = out[4 * i + 2] = 0.0f; out[4 * i + 3] = 1.0f; }
 	switch (format) {
 	case 97: case 90: { // R16G16B16A16_SFLOAT, R16G16B16_SFLOAT
 		const uint32_t channels = (format == 97) ? 4 : 3;
@@ -122,7 +134,7 @@ extern "C" int vkr_load_texture(vkr_texture_t* texture, const char* file_path) {
 		printf("The texture at path %s does not have the *.vkt format. Aborting.\n", file_path); fclose(file); return 1; // textures.c:117-121
 	}
 	const uint32_t mip_count = header[2], width = header[3], height = header[4], format = header[5];
-	if (mip_count == 0 || mip_count > 32 || width == 0 || height == 0 || payload_size > (1ull << 34)) {
+	if (mip_count == 0 || mip_count > 32 || width == 0 || height == 0 || width > 32768 || height > 32768 || payload_size > (1ull << 34)) {
 		printf("The texture at path %s has an invalid header (%u mipmaps, %ux%u).\n", file_path, mip_count, width, height); fclose(file); return 1;
 	}
 	struct mip_header { uint32_t width, height; uint64_t size, offset; };
@@ -131,7 +143,7 @@ extern "C" int vkr_load_texture(vkr_texture_t* texture, const char* file_path) {
 	for (uint32_t k = 0; k != mip_count; ++k) {
 		if (fread(&mips[k].width, 4, 1, file) != 1 || fread(&mips[k].height, 4, 1, file) != 1 || fread(&mips[k].size, 8, 1, file) != 1 || fread(&mips[k].offset, 8, 1, file) != 1) { fclose(file); return 1; }
 		const uint32_t ew = (width >> k) ? (width >> k) : 1, eh = (height >> k) ? (height >> k) : 1;
-		if (mips[k].width != ew || mips[k].height != eh || mips[k].offset + mips[k].size > payload_size) {
+		if (mips[k].width != ew || mips[k].height != eh || mips[k].offset > payload_size || mips[k].size > payload_size - mips[k].offset) {
 			printf("The texture at path %s has an unexpected mipmap %u (%ux%u).\n", file_path, k, mips[k].width, mips[k].height); fclose(file); return 1;
 		}
 		float_count += 4 * (uint64_t) ew * eh;
@@ -144,6 +156,7 @@ extern "C" int vkr_load_texture(vkr_texture_t* texture, const char* file_path) {
 	}
 	fclose(file);
 	float* texels = (float*) malloc(sizeof(float) * (size_t) float_count);
+	if (!texels) { printf("Failed to allocate %llu floats for the texture at path %s.\n", (unsigned long long) float_count, file_path); return 1; }
 	uint64_t at = 0;
 	for (uint32_t k = 0; k != mip_count; ++k) {
 		if (!decode_level(texels + at, mips[k].width, mips[k].height, format, payload.data() + mips[k].offset, mips[k].size)) {

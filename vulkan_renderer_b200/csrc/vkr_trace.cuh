@@ -55,6 +55,17 @@ VKR_DEV bool ray_triangle(const float4* __restrict__ tri, f3 o, f3 d, float tmin
 	return true;
 }
 
+// One 32-byte half of a node with a single 256-bit load (LDG.E.256, sm_100): a node pair is two of these instead of three 128-bit and
+// one 64-bit load, which halves the wavefronts the L1 data pipe spends per visit -- the unit the trace warps keep busiest.
+VKR_DEV void ldg_256(const float4* __restrict__ p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__) && !defined(VKR_NO_LDG256)
+	asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+	a = __ldg(p); b = __ldg(p + 1);
+#endif
+}
+
 // Ray in the form the slab test wants: id = 1/d, oid = o/d
 struct ray_slabs { f3 id, oid; };
 VKR_DEV ray_slabs make_slabs(f3 o, f3 d) {
@@ -118,7 +129,8 @@ VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, i
 template <class Push>
 VKR_DEV int bvh4_descend_step(const float4* __restrict__ nodes4, int node, const ray_slabs& r, float tmin, float tmax, Push&& push) {
 	const float4* nd = nodes4 + 8 * (size_t) node;
-	const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4), q5 = __ldg(nd + 5), q6 = __ldg(nd + 6);
+	float4 q0, q1, q2, q3, q4, q5, q6, q7;
+	ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3); ldg_256(nd + 4, q4, q5); ldg_256(nd + 6, q6, q7);
 	const int ref0 = __float_as_int(q6.x), ref1 = __float_as_int(q6.y), ref2 = __float_as_int(q6.z), ref3 = __float_as_int(q6.w);
 	float tn0, tn1, tn2, tn3;
 	const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
