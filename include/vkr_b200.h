@@ -128,6 +128,26 @@ typedef struct vkr_texture_s {
 } vkr_texture_t;
 int vkr_load_texture(vkr_texture_t* texture, const char* file_path);
 void vkr_destroy_texture(vkr_texture_t* texture);
+/* Boundary B1: the mip levels of an image as the reference's load_2d_textures() holds them (raw bytes of vk_format per level, src/textures.c:111-169) */
+int vkr_texture_from_levels(vkr_texture_t* texture, uint32_t width, uint32_t height, uint32_t mip_count, uint32_t vk_format, const void* const* level_data, const uint64_t* level_sizes);
+
+/* ---- boundary B1: the reference's UNCHANGED loaders -- load_scene (src/scene.c:409-581), load_ltc_table (src/ltc_table.c:23-200),
+        load_noise_table (src/noise_table.c:46-168) -- compiled against shim/ leave their staging buffers, images and the triangle soup of the
+        acceleration structure build (the vkCmdBuildAccelerationStructuresKHR hook, src/scene.c:354-378) in host memory; these entry points take
+        them over: device copies byte for byte, the software BVH built from the very vertices the reference hands to the driver.
+        INTEGRATION.md (Route B) and tests/c_host/route_b.c show the calls. */
+typedef struct vkr_scene_buffers_s {
+	uint64_t triangle_count, material_count;
+	float dequantization_factor[3], dequantization_summand[3];   /* mesh_t, src/scene.h:85-95 */
+	const char* const* material_names;               /* materials_t::material_names; may be NULL if material_textures is given */
+	const uint32_t* quantized_positions;             /* mesh.positions: uint32[2] per vertex (src/scene.h:56-62) */
+	const uint16_t* normals_and_tex_coords;          /* mesh.normals_and_tex_coords: uint16[4] per vertex */
+	const uint8_t* material_indices;                 /* mesh.material_indices: one per triangle */
+	const float* acceleration_structure_vertices;    /* 9 floats per triangle as passed to the bottom-level build (src/scene.c:175-209); NULL: dequantised the same way here */
+	const vkr_texture_t* material_textures;          /* 3 per material {base colour, specular, normal} (vkr_texture_from_levels), or NULL: read from texture_path */
+	const char* texture_path;
+} vkr_scene_buffers_t;
+int vkr_scene_from_buffers(vkr_scene_t* scene, const vkr_device_t* device, const vkr_scene_buffers_t* buffers, int request_acceleration_structure);
 
 /* ---- LTC table (replaces load_ltc_table / destroy_ltc_table, src/ltc_table.h:69-72, ltc_table.c:23-200) */
 typedef struct vkr_ltc_constants_s { /* = ltc_constants_t, src/ltc_table.h:23-35 */
@@ -146,6 +166,9 @@ typedef struct vkr_ltc_table_s {
 } vkr_ltc_table_t;
 
 int vkr_load_ltc_table(vkr_ltc_table_t* table, const vkr_device_t* device, const char* directory, uint32_t fresnel_count);
+/* Boundary B1: the two texture arrays as load_ltc_table() uploads them (RGBA16_UNORM, RG16_UNORM; src/ltc_table.c:86-141) and its constants */
+int vkr_ltc_table_from_images(vkr_ltc_table_t* table, const vkr_device_t* device, uint32_t roughness_count, uint32_t inclination_count, uint32_t fresnel_count,
+	const uint16_t* table0_rgba16, const uint16_t* table1_rg16, const vkr_ltc_constants_t* constants);
 void vkr_destroy_ltc_table(vkr_ltc_table_t* table, const vkr_device_t* device);
 
 /* ---- noise table (replaces load_noise_table / set_noise_constants, src/noise_table.h:81-89, noise_table.c:46-168) */
@@ -157,6 +180,8 @@ typedef struct vkr_noise_table_s {
 } vkr_noise_table_t;
 
 int vkr_load_noise_table(vkr_noise_table_t* noise, const vkr_device_t* device, uint32_t width, uint32_t height, uint32_t layers, vkr_noise_type_t noise_type);
+/* Boundary B1: the texture array as load_noise_table() uploads it (RGBA16_UNORM, layer-major; src/noise_table.c:105-160) and noise_table_t::random_seed */
+int vkr_noise_table_from_image(vkr_noise_table_t* noise, const vkr_device_t* device, uint32_t width, uint32_t height, uint32_t layers, const uint16_t* texels_rgba16, uint32_t random_seed);
 void vkr_destroy_noise_table(vkr_noise_table_t* noise, const vkr_device_t* device);
 void vkr_set_noise_constants(uint32_t resolution_mask[2], uint32_t* texture_index_mask, uint32_t random_numbers[4], vkr_noise_table_t* noise, int animate_noise);
 

@@ -271,9 +271,30 @@ def build_host():
 	return lib
 
 
+def build_c_host():
+	"""tests/c_host/route_b.c: a plain C host that loads a data set with the reference's UNCHANGED loaders (over shim/), hands their buffers to
+	libvkr_b200.so and renders a frame through the C-ABI (Routes B and A) -> tests/build/route_b. Needs /root/reference and the built library."""
+	ref_src = "/root/reference/src"
+	root = os.path.dirname(HERE)
+	package = os.path.join(root, "vulkan_renderer_b200")
+	if not os.path.isdir(ref_src) or not os.path.exists(os.path.join(package, "libvkr_b200.so")):
+		return None
+	shim = os.path.join(root, "shim")
+	out_dir = os.path.join(root, "tests", "build")
+	os.makedirs(out_dir, exist_ok=True)
+	binary = os.path.join(out_dir, "route_b")
+	sources = [os.path.join(ref_src, n) for n in ("scene.c", "textures.c", "ltc_table.c", "noise_table.c")]
+	cmd = ["/usr/bin/gcc", "-O2", "-std=gnu11", "-w", "-ffp-contract=off", "-I", shim, "-I", ref_src, "-I", os.path.join(root, "include"),
+		os.path.join(root, "tests", "c_host", "route_b.c"), os.path.join(shim, "vkr_shim.c")] + sources + ["-L", package, "-l:libvkr_b200.so", "-Wl,-rpath,$ORIGIN/../../vulkan_renderer_b200", "-lm", "-o", binary]
+	subprocess.check_call(cmd)
+	print("build_ref: C host over the reference's loaders and the C-ABI -> %s" % binary)
+	return binary
+
+
 if __name__ == "__main__":
 	if "--random" in sys.argv:   # python oracle/build_ref.py --random <count> <seed> <set name>
 		i = sys.argv.index("--random")
 		build(random_configs(int(sys.argv[i + 1]), int(sys.argv[i + 2])), set_name=sys.argv[i + 3])
 	else:
 		build(verbose="-v" in sys.argv)
+		build_c_host()

@@ -98,60 +98,17 @@ static void unpack_position(const uint32_t q[2], float p[3]) { // bit layout: sr
 	p[2] = (float) ((q[1] & 0x7FFFFC00u) >> 10);
 }
 
-extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, const char* file_path, const char* texture_path, int request_acceleration_structure) {
-	memset(scene, 0, sizeof(*scene));
-	FILE* file = fopen(file_path, "rb");
-	if (!file) { printf("Failed to open the scene file at %s.\n", file_path); return 1; }
-	uint32_t file_marker = 0, version = 0;
-	fread(&file_marker, 4, 1, file); fread(&version, 4, 1, file);
-	if (file_marker != 0xabcabc || version != 1) {
-		printf("The scene file at path %s is invalid or unsupported. The format marker is 0x%x, the version is %d.\n", file_path, file_marker, version);
-		fclose(file); return 1;
-	}
-	fread(&scene->material_count, 8, 1, file);
-	fread(&scene->triangle_count, 8, 1, file);
-	fread(scene->dequantization_factor, 4, 3, file);
-	fread(scene->dequantization_summand, 4, 3, file);
-	printf("Triangle count: %llu\n", (unsigned long long) scene->triangle_count);
-	if (scene->triangle_count == 0) {
-		printf("The scene file at path %s is completely empty, i.e. it holds 0 triangles.\n", file_path);
-		fclose(file); memset(scene, 0, sizeof(*scene)); return 1;
-	}
-	if (scene->triangle_count >= (1ull << 27) || scene->material_count > 256) {
-		printf("The scene file at path %s is too large for this library (%llu triangles, %llu materials).\n", file_path, (unsigned long long) scene->triangle_count, (unsigned long long) scene->material_count);
-		fclose(file); memset(scene, 0, sizeof(*scene)); return 1;
-	}
-	scene->material_names = (char**) calloc(scene->material_count ? scene->material_count : 1, sizeof(char*));
-	for (uint64_t i = 0; i != scene->material_count; ++i) {
-		uint64_t name_length = 0;
-		fread(&name_length, 8, 1, file);
-		if (name_length > 4096) { printf("The scene file at path %s has a corrupt material table.\n", file_path); fclose(file); vkr_destroy_scene(scene, device); return 1; }
-		scene->material_names[i] = (char*) malloc(name_length + 1);
-		fread(scene->material_names[i], 1, name_length + 1, file);
-		scene->material_names[i][name_length] = 0;
-	}
+// Everything of load_scene() that follows the file: device copies of the three mesh buffers, acceleration structures, materials. Shared by vkr_load_scene
+// (the library's own *.vks reader) and vkr_scene_from_buffers (boundary B1: the reference's unchanged load_scene() ran against shim/ and hands its buffers over).
+// as_vertices: the triangle soup of the acceleration structure build (scene.c:175-209) or NULL (dequantised here the same way); given_textures: 3 per
+// material, decoded (vkr_texture_t), or NULL to read <texture_path>/<material>_{BaseColor,Specular,Normal}.vkt.
+static int scene_from_arrays(vkr_scene_t* scene, const vkr_device_t* device, const uint32_t* positions, const uint16_t* normals_uvs, const uint8_t* material_indices,
+	const float* as_vertices, const vkr_texture_t* given_textures, const char* file_path, const char* texture_path, int request_acceleration_structure)
+{
 	const uint64_t n = scene->triangle_count;
-	std::vector<uint32_t> positions(2 * 3 * n);
-	std::vector<uint16_t> normals_uvs(4 * 3 * n);
-	std::vector<uint8_t> material_indices(n);
-	fread(positions.data(), 4, positions.size(), file);
-	fread(normals_uvs.data(), 2, normals_uvs.size(), file);
-	fread(material_indices.data(), 1, material_indices.size(), file);
-	uint32_t eof_marker = 0;
-	fread(&eof_marker, 4, 1, file);
-	fclose(file);
-	if (eof_marker != 0xE0FE0F) {
-		printf("The scene file at path %s seems to be invalid. The geometry data is not followed by the expected end of file marker.\n", file_path);
-		vkr_destroy_scene(scene, device); return 1;
-	}
-	for (uint64_t i = 0; i != n; ++i) // the G-buffer pass indexes the material table with these on the device
-		if (material_indices[i] >= scene->material_count) {
-			printf("The scene file at path %s refers to material %u but has %llu materials only.\n", file_path, (unsigned) material_indices[i], (unsigned long long) scene->material_count);
-			vkr_destroy_scene(scene, device); return 1;
-		}
-	if (upload(&scene->d_quantized_positions, positions.data(), positions.size() * 4, device)
-		|| upload(&scene->d_normals_and_tex_coords, normals_uvs.data(), normals_uvs.size() * 2, device)
-		|| upload(&scene->d_material_indices, material_indices.data(), material_indices.size(), device))
+	if (upload(&scene->d_quantized_positions, positions, (size_t) n * 3 * 2 * 4, device)
+		|| upload(&scene->d_normals_and_tex_coords, normals_uvs, (size_t) n * 3 * 4 * 2, device)
+		|| upload(&scene->d_material_indices, material_indices, (size_t) n, device))
 	{
 		printf("Failed to create device buffers and allocate memory for meshes of the scene file at path %s. It has %llu triangles.\n", file_path, (unsigned long long) n);
 		vkr_destroy_scene(scene, device); return 1;
@@ -162,7 +119,8 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 		std::vector<float> soup(9 * n);
 		host_bvh bvh;
 		// (a) shadow rays: the float soup of scene.c:175-187 (multiply, then add)
-		for (uint64_t i = 0; i != 3 * n; ++i) {
+		if (as_vertices) memcpy(soup.data(), as_vertices, sizeof(float) * 9 * n); // what the reference hands to vkCmdBuildAccelerationStructuresKHR
+		else for (uint64_t i = 0; i != 3 * n; ++i) {
 			float p[3]; unpack_position(&positions[2 * i], p);
 			for (int j = 0; j != 3; ++j) soup[3 * i + j] = p[j] * scene->dequantization_factor[j] + scene->dequantization_summand[j];
 		}
@@ -219,12 +177,16 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 	static const char* suffixes[3] = { "BaseColor", "Specular", "Normal" };
 	std::vector<vkr_texture_t> textures(3 * (size_t) scene->material_count);
 	bool failed = false, any_pattern = false;
+	const bool own_textures = given_textures == nullptr;
 	for (uint64_t i = 0; i != scene->material_count && !failed; ++i) {
 		float tex[3][4];
 		for (int j = 0; j != 3 && !failed; ++j) {
-			const std::string path = std::string(texture_path) + "/" + scene->material_names[i] + "_" + suffixes[j] + ".vkt";
 			vkr_texture_t& t = textures[3 * i + j];
-			failed = vkr_load_texture(&t, path.c_str()) != 0;
+			if (own_textures) {
+				const std::string path = std::string(texture_path) + "/" + scene->material_names[i] + "_" + suffixes[j] + ".vkt";
+				failed = vkr_load_texture(&t, path.c_str()) != 0;
+			}
+			else { t = given_textures[3 * i + j]; failed = !t.h_texels || !t.mip_count; }
 			if (failed) break;
 			any_pattern = any_pattern || !t.is_constant;
 			const uint32_t last = t.mip_count - 1;
@@ -251,12 +213,92 @@ extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, co
 			|| upload(&scene->d_texture_offsets, offsets.data(), offsets.size() * 8, device);
 		scene->textured = 1; scene->texture_texel_count = texel_count;
 	}
-	for (vkr_texture_t& t : textures) vkr_destroy_texture(&t);
+	if (own_textures) for (vkr_texture_t& t : textures) vkr_destroy_texture(&t);
 	if (failed) {
-		printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path);
+		printf("Failed to load material textures for the scene file at path %s using texture path %s.\n", file_path, texture_path ? texture_path : "(textures handed over)");
 		vkr_destroy_scene(scene, device); return 1;
 	}
 	return 0;
+}
+
+
+extern "C" int vkr_scene_from_buffers(vkr_scene_t* scene, const vkr_device_t* device, const vkr_scene_buffers_t* b, int request_acceleration_structure) {
+	memset(scene, 0, sizeof(*scene));
+	if (!b->triangle_count || b->triangle_count >= (1ull << 27) || b->material_count > 256 || !b->quantized_positions || !b->normals_and_tex_coords || !b->material_indices
+		|| (!b->material_textures && !b->texture_path) || (!b->material_names && !b->material_textures))
+	{
+		printf("Failed to take over a scene: %llu triangles, %llu materials, or buffers are missing.\n", (unsigned long long) b->triangle_count, (unsigned long long) b->material_count);
+		return 1;
+	}
+	scene->triangle_count = b->triangle_count; scene->material_count = b->material_count;
+	memcpy(scene->dequantization_factor, b->dequantization_factor, 12); memcpy(scene->dequantization_summand, b->dequantization_summand, 12);
+	scene->material_names = (char**) calloc(scene->material_count ? scene->material_count : 1, sizeof(char*));
+	for (uint64_t i = 0; i != scene->material_count; ++i) {
+		const char* name = (b->material_names && b->material_names[i]) ? b->material_names[i] : "";
+		scene->material_names[i] = (char*) malloc(strlen(name) + 1);
+		strcpy(scene->material_names[i], name);
+	}
+	for (uint64_t i = 0; i != b->triangle_count; ++i)
+		if (b->material_indices[i] >= scene->material_count) {
+			printf("The scene refers to material %u but has %llu materials only.\n", (unsigned) b->material_indices[i], (unsigned long long) scene->material_count);
+			vkr_destroy_scene(scene, device); return 1;
+		}
+	return scene_from_arrays(scene, device, b->quantized_positions, b->normals_and_tex_coords, b->material_indices, b->acceleration_structure_vertices, b->material_textures,
+		"(buffers handed over)", b->texture_path, request_acceleration_structure);
+}
+
+extern "C" int vkr_load_scene(vkr_scene_t* scene, const vkr_device_t* device, const char* file_path, const char* texture_path, int request_acceleration_structure) {
+	memset(scene, 0, sizeof(*scene));
+	FILE* file = fopen(file_path, "rb");
+	if (!file) { printf("Failed to open the scene file at %s.\n", file_path); return 1; }
+	uint32_t file_marker = 0, version = 0;
+	fread(&file_marker, 4, 1, file); fread(&version, 4, 1, file);
+	if (file_marker != 0xabcabc || version != 1) {
+		printf("The scene file at path %s is invalid or unsupported. The format marker is 0x%x, the version is %d.\n", file_path, file_marker, version);
+		fclose(file); return 1;
+	}
+	fread(&scene->material_count, 8, 1, file);
+	fread(&scene->triangle_count, 8, 1, file);
+	fread(scene->dequantization_factor, 4, 3, file);
+	fread(scene->dequantization_summand, 4, 3, file);
+	printf("Triangle count: %llu\n", (unsigned long long) scene->triangle_count);
+	if (scene->triangle_count == 0) {
+		printf("The scene file at path %s is completely empty, i.e. it holds 0 triangles.\n", file_path);
+		fclose(file); memset(scene, 0, sizeof(*scene)); return 1;
+	}
+	if (scene->triangle_count >= (1ull << 27) || scene->material_count > 256) {
+		printf("The scene file at path %s is too large for this library (%llu triangles, %llu materials).\n", file_path, (unsigned long long) scene->triangle_count, (unsigned long long) scene->material_count);
+		fclose(file); memset(scene, 0, sizeof(*scene)); return 1;
+	}
+	scene->material_names = (char**) calloc(scene->material_count ? scene->material_count : 1, sizeof(char*));
+	for (uint64_t i = 0; i != scene->material_count; ++i) {
+		uint64_t name_length = 0;
+		fread(&name_length, 8, 1, file);
+		if (name_length > 4096) { printf("The scene file at path %s has a corrupt material table.\n", file_path); fclose(file); vkr_destroy_scene(scene, device); return 1; }
+		scene->material_names[i] = (char*) malloc(name_length + 1);
+		fread(scene->material_names[i], 1, name_length + 1, file);
+		scene->material_names[i][name_length] = 0;
+	}
+	const uint64_t n = scene->triangle_count;
+	std::vector<uint32_t> positions(2 * 3 * n);
+	std::vector<uint16_t> normals_uvs(4 * 3 * n);
+	std::vector<uint8_t> material_indices(n);
+	fread(positions.data(), 4, positions.size(), file);
+	fread(normals_uvs.data(), 2, normals_uvs.size(), file);
+	fread(material_indices.data(), 1, material_indices.size(), file);
+	uint32_t eof_marker = 0;
+	fread(&eof_marker, 4, 1, file);
+	fclose(file);
+	if (eof_marker != 0xE0FE0F) {
+		printf("The scene file at path %s seems to be invalid. The geometry data is not followed by the expected end of file marker.\n", file_path);
+		vkr_destroy_scene(scene, device); return 1;
+	}
+	for (uint64_t i = 0; i != n; ++i) // the G-buffer pass indexes the material table with these on the device
+		if (material_indices[i] >= scene->material_count) {
+			printf("The scene file at path %s refers to material %u but has %llu materials only.\n", file_path, (unsigned) material_indices[i], (unsigned long long) scene->material_count);
+			vkr_destroy_scene(scene, device); return 1;
+		}
+	return scene_from_arrays(scene, device, positions.data(), normals_uvs.data(), material_indices.data(), nullptr, nullptr, file_path, texture_path, request_acceleration_structure);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -325,6 +367,27 @@ extern "C" int vkr_load_ltc_table(vkr_ltc_table_t* table, const vkr_device_t* de
 	return 0;
 }
 
+// Boundary B1: the two texture arrays as the reference's load_ltc_table() uploads them (ltc_table.c:86-141: RGBA16_UNORM and RG16_UNORM, fresnel-major)
+extern "C" int vkr_ltc_table_from_images(vkr_ltc_table_t* table, const vkr_device_t* device, uint32_t roughness_count, uint32_t inclination_count, uint32_t fresnel_count,
+	const uint16_t* table0_rgba16, const uint16_t* table1_rg16, const vkr_ltc_constants_t* constants)
+{
+	memset(table, 0, sizeof(*table));
+	if (!roughness_count || roughness_count != inclination_count || !fresnel_count || !table0_rgba16 || !table1_rg16 || !constants) {
+		printf("Failed to take over a linearly transformed cosine table of resolution %ux%u with %u slices.\n", roughness_count, inclination_count, fresnel_count);
+		return 1;
+	}
+	table->roughness_count = roughness_count; table->inclination_count = inclination_count; table->fresnel_count = fresnel_count;
+	const size_t n0 = (size_t) roughness_count * inclination_count * 4 * fresnel_count, n1 = n0 / 2;
+	table->h_table0 = (uint16_t*) malloc(2 * n0); table->h_table1 = (uint16_t*) malloc(2 * n1);
+	memcpy(table->h_table0, table0_rgba16, 2 * n0); memcpy(table->h_table1, table1_rg16, 2 * n1);
+	table->constants = *constants;
+	if (upload(&table->d_table0, table->h_table0, 2 * n0, device) || upload(&table->d_table1, table->h_table1, 2 * n1, device)) {
+		printf("Failed to create device local textures for LTC tables.");
+		vkr_destroy_ltc_table(table, device); return 1;
+	}
+	return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // noise table (src/noise_table.c:46-168)
 // ------------------------------------------------------------------------------------------------
@@ -367,6 +430,24 @@ extern "C" int vkr_load_noise_table(vkr_noise_table_t* noise, const vkr_device_t
 		fclose(file);
 	}
 	noise->width = width; noise->height = height; noise->layers = layers;
+	if (upload(&noise->d_noise, noise->h_noise, sizeof(uint16_t) * cell_count, device)) {
+		printf("Failed to create a noise texture of resolution %ux%u with %u layers.\n", width, height, layers);
+		vkr_destroy_noise_table(noise, device); return 1;
+	}
+	return 0;
+}
+
+// Boundary B1: the texture array as the reference's load_noise_table() uploads it (noise_table.c:105-160: RGBA16_UNORM, layer-major)
+extern "C" int vkr_noise_table_from_image(vkr_noise_table_t* noise, const vkr_device_t* device, uint32_t width, uint32_t height, uint32_t layers, const uint16_t* texels_rgba16, uint32_t random_seed) {
+	memset(noise, 0, sizeof(*noise));
+	if (!width || !height || !layers || (width & (width - 1)) || (height & (height - 1)) || (layers & (layers - 1)) || !texels_rgba16) {
+		printf("Invalid noise resolution or slice count.\n");
+		return 1;
+	}
+	const size_t cell_count = (size_t) width * height * layers * 4;
+	noise->h_noise = (uint16_t*) malloc(sizeof(uint16_t) * cell_count);
+	memcpy(noise->h_noise, texels_rgba16, sizeof(uint16_t) * cell_count);
+	noise->width = width; noise->height = height; noise->layers = layers; noise->random_seed = random_seed;
 	if (upload(&noise->d_noise, noise->h_noise, sizeof(uint16_t) * cell_count, device)) {
 		printf("Failed to create a noise texture of resolution %ux%u with %u layers.\n", width, height, layers);
 		vkr_destroy_noise_table(noise, device); return 1;

@@ -125,6 +125,30 @@ extern "C" void vkr_destroy_texture(vkr_texture_t* texture) {
 	memset(texture, 0, sizeof(*texture));
 }
 
+// Boundary B1: the mip levels of an image as the reference's load_2d_textures() holds them after reading a *.vkt file (textures.c:111-169): raw bytes of `vk_format`
+extern "C" int vkr_texture_from_levels(vkr_texture_t* texture, uint32_t width, uint32_t height, uint32_t mip_count, uint32_t vk_format, const void* const* level_data, const uint64_t* level_sizes) {
+	memset(texture, 0, sizeof(*texture));
+	if (!mip_count || mip_count > 32 || !width || !height || width > 32768 || height > 32768) { printf("Cannot take over a texture of %ux%u texels with %u mipmaps.\n", width, height, mip_count); return 1; }
+	uint64_t float_count = 0;
+	for (uint32_t k = 0; k != mip_count; ++k) float_count += 4 * (uint64_t) ((width >> k) ? (width >> k) : 1) * ((height >> k) ? (height >> k) : 1);
+	float* texels = (float*) malloc(sizeof(float) * (size_t) float_count);
+	if (!texels) return 1;
+	uint64_t at = 0;
+	for (uint32_t k = 0; k != mip_count; ++k) {
+		const uint32_t w = (width >> k) ? (width >> k) : 1, h = (height >> k) ? (height >> k) : 1;
+		if (!level_data[k] || !decode_level(texels + at, w, h, vk_format, (const uint8_t*) level_data[k], level_sizes[k])) {
+			printf("A texture handed over has VkFormat %u or a mipmap size that this library cannot read.\n", vk_format);
+			free(texels); return 1;
+		}
+		at += 4 * (uint64_t) w * h;
+	}
+	int constant = 1;
+	for (uint64_t i = 4; i < float_count && constant; ++i) constant = texels[i] == texels[i & 3];
+	texture->width = width; texture->height = height; texture->mip_count = mip_count; texture->vk_format = vk_format;
+	texture->h_texels = texels; texture->texel_float_count = float_count; texture->is_constant = constant;
+	return 0;
+}
+
 extern "C" int vkr_load_texture(vkr_texture_t* texture, const char* file_path) {
 	memset(texture, 0, sizeof(*texture));
 	FILE* file = fopen(file_path, "rb");
