@@ -44,6 +44,7 @@ void __nanosleep(unsigned); unsigned __activemask(); int __shfl_sync(unsigned, i
 
 #include "vkr_related_work.cuh"
 #include "vkr_trace.cuh"
+#include "vkr_anchor.cuh"
 #include "vkr_texture.cuh"
 #include "vkr_gbuffer.cuh"
 #include <algorithm>
@@ -190,6 +191,34 @@ extern "C" void vkr_device_on_host_trace_any_wide(const float* nodes2, const flo
 }
 
 // Shader-side vertex decode (vkr_gbuffer.cuh: decode_position, mesh_quantization.glsl:38-45) for all vertices: the input of the primary-ray BVH
+// Anchored shadow rays (vkr_anchor.cuh): rays from `origins` towards points of a polygonal light through (a) the plain traversal, (b) the anchored one with
+// all siblings of the origin path, (c) with the siblings the light's cone touches; rays = {origin index, dx, dy, dz, tmax}. out[3 * i + {0, 1, 2}] = answers,
+// visits[3]: node pairs fetched in total, info = {rays outside their cone, siblings kept, siblings along the paths}
+extern "C" void vkr_device_on_host_trace_anchored(const float* nodes, const float* tris, uint32_t origin_count, const float* origins, uint32_t vertex_count, const float* light_vertices_xyzw,
+	uint32_t ray_count, const float* rays, uint8_t* out, uint64_t* visits, uint64_t* info)
+{
+	bvh_view bvh; bvh.nodes = reinterpret_cast<const float4*>(nodes); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = nullptr; bvh.tri_count = 0;
+	visits[0] = visits[1] = visits[2] = 0; info[0] = info[1] = info[2] = 0;
+	int stack[kMaxStackDepth + 2];
+	for (uint32_t i = 0; i != ray_count; ++i) {
+		const float* r = rays + 5 * (size_t) i;
+		const uint32_t pi = (uint32_t) r[0];
+		const f3 o = make3(origins[3 * pi], origins[3 * pi + 1], origins[3 * pi + 2]), d = make3(r[1], r[2], r[3]);
+		uint32_t path[kPathLevels]; int tail = 0;
+		const int count = find_origin_path(bvh.nodes, o, &tail, [&](int k, uint32_t e) { path[k] = e; });
+		const light_cone cone = make_light_cone(o, reinterpret_cast<const unsigned char*>(light_vertices_xyzw), (int) vertex_count);
+		uint32_t mask = cull_siblings(bvh.nodes, o, cone, count, [&](int k) { return path[k]; });
+		if (!ray_in_cone(cone, d, r[4])) { mask = kAllSiblings; ++info[0]; }
+		info[1] += (uint64_t) __builtin_popcount(mask & ((1u << count) - 1u)); info[2] += (uint64_t) count;
+		int v0 = 0, v1 = 0, v2 = 0;
+		out[3 * i] = occluded_anchored(bvh, o, d, 1.0e-3f, r[4], path, 0, 0, 0u, stack, 1, &v0) ? 1 : 0;   // no path, tail = root: the plain traversal
+		out[3 * i + 1] = occluded_anchored(bvh, o, d, 1.0e-3f, r[4], path, count, tail, kAllSiblings, stack, 1, &v1) ? 1 : 0;
+		out[3 * i + 2] = occluded_anchored(bvh, o, d, 1.0e-3f, r[4], path, count, tail, mask, stack, 1, &v2) ? 1 : 0;
+		if (out[3 * i] != (occluded(bvh, o, d, 1.0e-3f, r[4], stack, 1) ? 1 : 0)) out[3 * i] = 2;   // the counting edition must agree with the probe kernel's traversal
+		visits[0] += v0; visits[1] += v1; visits[2] += v2;
+	}
+}
+
 extern "C" void vkr_device_on_host_decode_positions(const void* constants, const uint32_t* quantized_positions, uint64_t vertex_count, float* out_xyz) {
 	const uint2* q = reinterpret_cast<const uint2*>(quantized_positions);
 	for (uint64_t i = 0; i != vertex_count; ++i) {

@@ -240,6 +240,46 @@ def test_four_wide_collapse_keeps_the_tree_and_the_answers(name):
 	assert np.array_equal(out2, out4) and 0.02 < out2.mean() < 0.99
 
 
+@pytest.mark.parametrize("name,light", [("mini_city", 0), ("mini_city", 2), ("mini_room", 5), ("cornell", 0)])
+def test_anchored_shadow_rays_answer_like_the_plain_traversal(name, light):
+	"""vkr_anchor.cuh (compiled for the CPU): shadow rays that start at the siblings of their pixel's origin path -- all of them, or those the light's cone
+	touches -- give the answers of the plain traversal from the root, with fewer node visits. Origins are surface points as the G-buffer holds them, the
+	rays go to points of a light of the data set and a little beyond its rim (rays outside the cone must keep all siblings)."""
+	from tests.test_device_on_host import _lib
+	from tests.ref_frames import host_constants
+	dev = _lib(); lib = api.load_library()
+	info = H.dataset(name); oi = H.OracleInputs(info)
+	w, h = 96, 64
+	lights = len(info["lights"])
+	constants = host_constants(info, w, h, lights)
+	gb = oi.gbuffer(w, h, constants, oi.visibility(w, h, constants))
+	nodes, slots, ids, depth = _probe_bvh(lib, oi.shadow_tris, BUILDERS["sah"])
+	valid = np.argwhere(gb[1, :, :, 3] != 0)
+	rng = np.random.default_rng(11)
+	pick = valid[rng.choice(len(valid), min(400, len(valid)), replace=False)]
+	origins = np.ascontiguousarray(gb[0, pick[:, 0], pick[:, 1], :3], dtype=np.float32)
+	stride = 256 + (160 + 16 * 4 * 2 + 16 * 2) * light
+	lv = np.frombuffer(constants[stride + 160 + 64:stride + 160 + 128], dtype=np.float32).reshape(4, 4).copy()
+	rays = []
+	for pi in range(len(origins)):
+		uv = rng.uniform(-0.15, 1.15, (6, 2))   # some targets lie beyond the rim of the light
+		pts = lv[0, :3] + uv[:, :1] * (lv[1, :3] - lv[0, :3]) + uv[:, 1:] * (lv[3, :3] - lv[0, :3])
+		e = pts - origins[pi]; dist = np.linalg.norm(e, axis=1)
+		for i in range(len(pts)):
+			rays.append((pi, e[i, 0] / dist[i], e[i, 1] / dist[i], e[i, 2] / dist[i], dist[i] * (1.0 if i else 1.3)))   # the first of each pixel overshoots the light
+	rays = np.ascontiguousarray(np.array(rays, dtype=np.float32))
+	out = np.zeros((len(rays), 3), dtype=np.uint8); visits = (C.c_uint64 * 3)(); stats = (C.c_uint64 * 3)()
+	n2 = np.ascontiguousarray(nodes, dtype=np.float32); sl = np.ascontiguousarray(slots, dtype=np.float32)
+	dev.vkr_device_on_host_trace_anchored(n2.ctypes.data_as(C.c_void_p), sl.ctypes.data_as(C.c_void_p), C.c_uint32(len(origins)), origins.ctypes.data_as(C.c_void_p), C.c_uint32(4), lv.ctypes.data_as(C.c_void_p),
+		C.c_uint32(len(rays)), rays.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), visits, stats)
+	assert out.max() <= 1                                                      # (2 = the two plain traversals disagree)
+	assert np.array_equal(out[:, 0], out[:, 1]) and np.array_equal(out[:, 0], out[:, 2])
+	assert stats[0] > 0 and stats[0] < len(rays)                              # rays outside the cone were among them, and rays inside
+	assert visits[2] <= visits[1]                                             # (visiting all siblings deepest first is not always cheaper than the plain order)
+	if name != "cornell":
+		assert stats[1] < stats[2] and visits[2] < visits[0]                   # the cone removes siblings, and visits with them
+
+
 @pytest.mark.parametrize("source", ["cornell", "mini_city", "roughness_planes", "soup_5", "soup_4097", "soup_60000"])
 def test_gpu_builder_steps_reproduce_the_reference_on_the_cpu(source):
 	"""csrc/vkr_lbvh.cuh -- the per-element functions the GPU builder's kernels call -- run on the CPU with every launch replaced by a loop (tests/device_on_host.cpp)

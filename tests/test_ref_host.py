@@ -154,3 +154,27 @@ def test_constant_block_equals_the_reference_host_code(ref, name, lights, width,
 	theirs = H.reference_constants(info, width, height, lights, sample_count=4)
 	assert len(ours) == len(theirs)
 	assert ours == theirs
+
+
+def test_noise_blob_files_are_read_as_the_reference_lays_them_out(tmp_path, monkeypatch):
+	"""The *.blob branch of load_noise_table (src/noise_table.c:76-107; the reference's timing runs use noise_type_ahmed, src/experiment_list.c:371): raw uint16 RGBA
+	cells, layer-major, under data/noise/<type>_<w>x<h>_<layers>.blob. The reference's own loader cannot be the judge here: it formats the path with
+	sprintf(file_path, file_path, ...) onto itself (noise_table.c:96, undefined behaviour; with this C library the path comes out empty and the load fails),
+	so a synthetic blob is compared with what vkr_load_noise_table hands to the device; a missing file fails."""
+	lib = api.load_library()
+	monkeypatch.chdir(tmp_path)
+	os.makedirs("data/noise")
+	w, h, layers = 16, 8, 4
+	rng = np.random.default_rng(3)
+	cells = rng.integers(0, 65536, w * h * layers * 4, dtype=np.uint16)
+	for noise_type, pattern in ((api.NOISE_AHMED, "data/noise/ahmed_2d_rgba_%02dx%02d_%02d.blob"), (api.NOISE_BLUE, "data/noise/blue_noise_rgba_%02dx%02d_%02d.blob")):
+		noise = api.NoiseTable()
+		assert lib.vkr_load_noise_table(C.byref(noise), None, w, h, layers, noise_type) != 0    # no file yet
+		cells.tofile(pattern % (w, h, layers))
+		assert lib.vkr_load_noise_table(C.byref(noise), None, w, h, layers, noise_type) == 0
+		assert (noise.width, noise.height, noise.layers) == (w, h, layers)
+		assert np.array_equal(np.ctypeslib.as_array(noise.h_noise, (len(cells),)), cells)
+		masks = (C.c_uint32 * 2)(); layer = C.c_uint32(); rnd = (C.c_uint32 * 4)()
+		lib.vkr_set_noise_constants(masks, C.byref(layer), rnd, C.byref(noise), 0)
+		assert list(masks) == [w - 1, h - 1] and layer.value == layers - 1
+		lib.vkr_destroy_noise_table(C.byref(noise), None)

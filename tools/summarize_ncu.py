@@ -140,7 +140,15 @@ def main():
 			return num(name) * scale.get(m[name][1], 1.0) if name in m else 0.0
 		path = os.path.join(ROOT, "profiles", "kernel_counters.json")
 		data = json.load(open(path)) if os.path.exists(path) else {}
+		def frac(name): return round(num(name) / 100.0, 4) if num(name) is not None else None
+		git = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], stdout=subprocess.PIPE, text=True).stdout.strip()
 		data[sys.argv[4]] = {"source": os.path.basename(out) + "_summary.md (ncu --set full --clock-control none, one launch)",
+			"git": os.environ.get("VKR_CAPTURE_GIT", git),   # the commit whose kernel was captured (the commit of the tree the capture ran on)
+			"warp_instructions": int(num("smsp__inst_executed.sum")) if num("smsp__inst_executed.sum") is not None else None,
+			"lanes_per_instruction": num("smsp__thread_inst_executed_per_inst_executed.ratio"),
+			"pipe_fma_frac": frac("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"), "pipe_alu_frac": frac("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+			"pipe_xu_frac": frac("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"), "pipe_lsu_frac": frac("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+			"l1_hit_frac": frac("l1tex__t_sector_hit_rate.pct"), "l2_hit_frac": frac("lts__t_sector_hit_rate.pct"), "warps_active_frac": frac("sm__warps_active.avg.pct_of_peak_sustained_active"),
 			"dram_bytes_per_launch": int(in_bytes("dram__bytes_read.sum") + in_bytes("dram__bytes_write.sum")),
 			"issue_active_frac": round(num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0, 4),
 			"l1_data_pipe_frac": round(num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0, 4) if num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") is not None else None,

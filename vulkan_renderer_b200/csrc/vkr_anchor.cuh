@@ -19,7 +19,7 @@
 
 namespace vkr {
 
-constexpr int kPathLevels = 28;              // chain pairs remembered per pixel (one bit each in the sibling masks); deeper trees continue in the tail
+constexpr int kPathLevels = 20;              // chain pairs remembered per pixel (one bit each in the sibling masks); deeper trees continue in the tail
 constexpr uint32_t kAllSiblings = 0xffffffffu;
 
 VKR_DEV bool box_contains(float cx, float cy, float cz, float hx, float hy, float hz, f3 o) {

@@ -18,8 +18,15 @@
 // (setmaxnreg), which is what lets 24 warps per SM live where the monolithic kernel had 12.
 #pragma once
 #include "vkr_trace.cuh"
+#include "vkr_anchor.cuh"
 
 namespace vkr {
+
+// Anchored shadow rays (vkr_anchor.cuh): rays start at the siblings of their pixel's origin path that the light's cone touches instead of at the root.
+// A compile-time edition of the kernels (-DVKR_ANCHORED=1); frames are bit-identical either way.
+#ifndef VKR_ANCHORED
+#define VKR_ANCHORED 0
+#endif
 
 #ifndef VKR_RING
 #define VKR_RING 256
@@ -38,6 +45,9 @@ constexpr unsigned kPending = 0xffu;
 #define VKR_NODE_LOOP_MIN_LANES 16
 #endif
 constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
+#if VKR_ANCHORED && VKR_BVH_WIDTH != 2
+#error "anchored rays walk node pairs"
+#endif
 #ifndef VKR_RESOLVE_SLEEP_NS
 #define VKR_RESOLVE_SLEEP_NS 512
 #endif
@@ -68,9 +78,15 @@ enum : int {
 VKR_DEV constexpr int stream_bytes_at(bool optimal) { return (optimal ? 10 : 7) * kRing; }           // owner[kRing] bytes: lane of the owning pixel; bit 7: known to be occluded (n.w <= 0)
 VKR_DEV constexpr int stream_origin_at(bool optimal) { return stream_bytes_at(optimal) + 2 * kRing / 4; }  // after result[kRing] bytes: kPending / 0 visible / 1 occluded
 VKR_DEV constexpr int stream_control_at(bool optimal) { return stream_origin_at(optimal) + 96; }     // {head: next ticket, tail: entries published, closed: -1 or the final tail, -}
-VKR_DEV constexpr size_t stream_floats_per_warp(bool optimal) { return (size_t) stream_control_at(optimal) + 4; }
+// anchored rays: per entry the sibling mask of its ray; per pixel (lane) the origin path, its tail and length, and the cone + mask of the light being sampled
+VKR_DEV constexpr int stream_mask_at(bool optimal) { return stream_control_at(optimal) + 4; }
+VKR_DEV constexpr int stream_path_at(bool optimal) { return stream_mask_at(optimal) + kRing; }      // [kPathLevels + 2][32]: entries, then tail, then count
+VKR_DEV constexpr int stream_cone_at(bool optimal) { return stream_path_at(optimal) + 32 * (kPathLevels + 2); }   // [6][32]: axis xyz, cos2_valid, len2_valid, mask
+VKR_DEV constexpr size_t stream_floats_per_warp(bool optimal) { return VKR_ANCHORED ? (size_t) stream_cone_at(optimal) + 6 * 32 : (size_t) stream_control_at(optimal) + 4; }
 
 VKR_DEV uint32_t smem_addr(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+VKR_DEV uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+VKR_DEV void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 VKR_DEV float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
 VKR_DEV void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
 VKR_DEV unsigned lds_u8(uint32_t a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
@@ -90,6 +106,7 @@ struct ray_producer {
 #ifdef VKR_TRACE_STATS
 	unsigned stat_resolve_polls, stat_candidates;
 #endif
+	bool cone_set;   // this lane has stored a cone and a sibling mask for the light it is sampling (set_light_cone); else its rays keep all siblings
 };
 
 // Radiance sums of one pixel. The reference adds the samples of a light into a per-light sum, scales it by 1/S and
@@ -143,6 +160,29 @@ VKR_DEV void resolve_chunk(ray_producer& q, int lane, pixel_sum& acc) {
 	__syncwarp(kFullMask);
 }
 
+#define OPTIMAL_STREAM_HAS_CONE(q) ((q).cone_set)
+// Called by a light shader at the start of a light (warp-convergent; `on` = this lane samples the light): the cone around the light as seen from the
+// pixel and the siblings of the pixel's origin path that the cone touches, for submit() to hand to the rays. vertices: world-space vertices of the light,
+// 16 bytes apart. Light shaders that do not call it leave all siblings to their rays.
+template <bool TRACE, bool OPTIMAL>
+VKR_DEV void set_light_cone(ray_producer& q, int lane, bool on, f3 origin, const unsigned char* vertices, int vertex_count, const float4* __restrict__ nodes) {
+#if VKR_ANCHORED
+	if constexpr (TRACE) {
+		q.cone_set = false;
+		if (on) {
+			const light_cone c = make_light_cone(origin, vertices, vertex_count);
+			if (c.enabled) {
+				const uint32_t path = q.base + 4u * (uint32_t) stream_path_at(OPTIMAL) + 4u * (uint32_t) lane;
+				const int count = (int) lds_u32(path + 128u * (uint32_t) (kPathLevels + 1));
+				const uint32_t siblings = cull_siblings(nodes, origin, c, count, [&](int k) { return lds_u32(path + 128u * (uint32_t) k); });
+				const uint32_t ca = q.base + 4u * (uint32_t) stream_cone_at(OPTIMAL) + 4u * (uint32_t) lane;
+				sts_f(ca, c.axis.x); sts_f(ca + 128u, c.axis.y); sts_f(ca + 256u, c.axis.z); sts_f(ca + 384u, c.cos2_valid); sts_f(ca + 512u, c.len2_valid); sts_u32(ca + 640u, siblings);
+				q.cone_set = true;
+			}
+		}
+	}
+#endif
+}
 // Warp-convergent: every lane calls it once per candidate sample. has = this lane contributes something.
 // need_trace = visibility is not known yet (n.w > 0); otherwise the sample is known to be occluded.
 // finish (warp-uniform) = end of a light. Nothing waits here: the light's sum is closed when its last entry resolves.
@@ -174,6 +214,18 @@ VKR_DEV void submit(ray_producer& q, int lane, bool has, bool need_trace, f3 dir
 				// were set here could be resolved and reused while the lane holding its ticket has not looked at it yet, and that lane would then trace
 				// the newer entry a second time and store its result late, possibly onto a still newer entry of the slot.
 				sts_u8(bytes + kRing + e, kPending);
+#if VKR_ANCHORED
+				{ // the siblings this ray has to look at: the light's mask if the ray is inside the cone the mask was made for (vkr_anchor.cuh), else all
+					uint32_t siblings = kAllSiblings;
+					if (OPTIMAL_STREAM_HAS_CONE(q)) {
+						const uint32_t ca = q.base + 4u * (uint32_t) stream_cone_at(OPTIMAL) + 4u * (uint32_t) lane;
+						const f3 axis = make3(lds_f(ca), lds_f(ca + 128u), lds_f(ca + 256u));
+						const float aw = dot(axis, dir_world), ww = dot(dir_world, dir_world);
+						if (aw > 0.0f && aw * aw >= lds_f(ca + 384u) * ww && tmax * tmax * ww <= lds_f(ca + 512u)) siblings = lds_u32(ca + 640u);
+					}
+					sts_u32(q.base + 4u * (uint32_t) stream_mask_at(OPTIMAL) + 4u * e, siblings);
+				}
+#endif
 				acc.pushed = true;
 			}
 			q.fill += k;
@@ -205,7 +257,7 @@ VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc, unsigned lo
 template <bool OPTIMAL>
 VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane, unsigned long long* stats = nullptr) {
 #ifdef VKR_TRACE_STATS
-	unsigned st_rays = 0, st_hits = 0, st_cache_hits = 0, st_visits = 0, st_leaves = 0, st_tris = 0, st_iters = 0, st_node_iters = 0, st_known = 0, st_polls = 0;
+	unsigned st_rays = 0, st_hits = 0, st_cache_hits = 0, st_visits = 0, st_leaves = 0, st_tris = 0, st_iters = 0, st_node_iters = 0, st_known = 0, st_polls = 0, st_siblings = 0;
 #endif
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const float tmin = 1.0e-3f; // shading_pass.frag.glsl:124
@@ -223,6 +275,10 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 	bool hit = false;
 	bool finished = false;       // the stream is closed and this lane's ticket lies beyond its end
 	int node = kTraversalDone, leaf = 0;
+#if VKR_ANCHORED
+	uint32_t pending = 0u;       // levels of the origin path whose siblings this ray still has to visit (deepest first)
+	uint32_t path = 0u;          // shared-memory address of the origin path of the ray's pixel
+#endif
 	int cached_triangle = -1;    // slot of the last triangle that occluded a ray of this lane
 	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
 	float tmax = 0.0f;
@@ -256,10 +312,25 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 					active = true;
 					hit = false;
 					node = kTraversalDone; leaf = 0;
+#if VKR_ANCHORED
+					pending = 0u;
+#endif
 					float t;
 					if (tmax > tmin) { // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
 						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) { hit = true; VKR_STAT(st_cache_hits); }
-						else { r = make_slabs(o, d); node = 0; top = stack_bottom; push(kTraversalDone); }
+						else {
+							r = make_slabs(o, d); top = stack_bottom; push(kTraversalDone);
+#if VKR_ANCHORED
+							// start at the end of the pixel's origin path; the siblings along it follow when the stack runs empty
+							path = base + 4u * (uint32_t) stream_path_at(OPTIMAL) + 4u * (own & 31u);
+							const uint32_t count = lds_u32(path + 128u * (uint32_t) (kPathLevels + 1));
+							pending = lds_u32(base + 4u * (uint32_t) stream_mask_at(OPTIMAL) + 4u * entry) & ((1u << count) - 1u);   // count <= kPathLevels < 32
+							node = (int) lds_u32(path + 128u * (uint32_t) kPathLevels);
+							if (node < 0) { leaf = node; node = pop(); }
+#else
+							node = 0;
+#endif
+						}
 					}
 				}
 			}
@@ -293,7 +364,21 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			if (kNodeLoopMinLanes > 0 && __popc(__activemask()) < kNodeLoopMinLanes) break;
 		}
 #else
+#if VKR_ANCHORED
+		while (node >= 0 && (node != kTraversalDone || (pending != 0u && active && !hit))) {
+			int skip = 2;   // the child of this pair that is not looked at: none
+			if (node == kTraversalDone) { // the stack is empty: on to the deepest sibling of the origin path that is left, i.e. a visit of its parent pair without the path's child
+				const int k = 31 - __clz((int) pending);
+				pending &= ~(1u << k);
+				const uint32_t e = lds_u32(path + 128u * (uint32_t) k);
+				node = (int) (e >> 1); skip = (int) (e & 1u);
+				top = stack_bottom; push(kTraversalDone);
+				VKR_STAT(st_siblings);
+			}
+#else
 		while (node >= 0 && node != kTraversalDone) {
+			const int skip = 2;
+#endif
 			const float4* nd = nodes + 4 * (size_t) node;
 			float4 q0, q1, q2, q3;
 			ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3);
@@ -301,8 +386,8 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			float tn0, tn1;
 			VKR_STAT(st_visits);
 			if ((__activemask() & lt_mask) == 0u) VKR_STAT(st_node_iters);
-			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0);
-			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1);
+			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0) && skip != 0;
+			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1) && skip != 1;
 			if (h0 && h1) {
 				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
 				node = swap ? ref1 : ref0;
@@ -336,7 +421,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			}
 		}
 		// --- a ray ends when it hit something or ran out of nodes
+#if VKR_ANCHORED
+		if (active && node == kTraversalDone && (hit || pending == 0u)) {
+#else
 		if (active && node == kTraversalDone) {
+#endif
 			st_release_u8(bytes + kRing + entry, hit ? 1u : 0u);
 			if (hit) VKR_STAT(st_hits);
 			active = false;
@@ -345,7 +434,7 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 	}
 #ifdef VKR_TRACE_STATS
 	stat_flush(stats, 0, st_rays); stat_flush(stats, 1, st_hits); stat_flush(stats, 2, st_cache_hits); stat_flush(stats, 3, st_visits); stat_flush(stats, 4, st_leaves);
-	stat_flush(stats, 5, st_tris); stat_flush(stats, 6, st_iters); stat_flush(stats, 7, st_node_iters); stat_flush(stats, 8, st_known); stat_flush(stats, 9, st_polls);
+	stat_flush(stats, 5, st_tris); stat_flush(stats, 6, st_iters); stat_flush(stats, 7, st_node_iters); stat_flush(stats, 8, st_known); stat_flush(stats, 9, st_polls); stat_flush(stats, 13, st_siblings);
 #endif
 }
 

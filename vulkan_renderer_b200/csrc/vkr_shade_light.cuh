@@ -26,6 +26,7 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 		if (vc == 0) on = false;
 		else prepare_psa<MAXP, BIASED>(pd, vc, v);
 	}
+	set_light_cone<TRACE, OPTIMAL>(q, lane, on, sp.position, light + L_FIXED + 16 * (MAXP - 1), (int) ldu(light, L_VERTEX_COUNT), p.bvh_nodes);
 	if (STRATEGY == VKR_STRATEGY_DIFFUSE_ONLY || STRATEGY == VKR_STRATEGY_DIFFUSE_GGX_MIS) {
 		if (on && pd.psa <= 0.0f) on = false;
 #pragma unroll 1

@@ -114,6 +114,16 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 #ifdef VKR_TRACE_STATS
 	q.stat_resolve_polls = 0; q.stat_candidates = 0;
 #endif
+	q.cone_set = false;
+#if VKR_ANCHORED
+	if (TRACE) { // the origin path of this pixel (vkr_anchor.cuh): all of its shadow rays start from it
+		const uint32_t path = q.base + 4u * (uint32_t) stream_path_at(OPTIMAL) + 4u * (uint32_t) lane;
+		int tail = kTraversalDone, count = 0;
+		if (valid) count = find_origin_path(p.bvh_nodes, sp.position, &tail, [&](int k, uint32_t e) { sts_u32(path + 128u * (uint32_t) k, e); });
+		sts_u32(path + 128u * (uint32_t) kPathLevels, (uint32_t) tail);
+		sts_u32(path + 128u * (uint32_t) (kPathLevels + 1), (uint32_t) count);
+	}
+#endif
 	if (TRACE) {
 		float* origin = stream_base + stream_floats_per_warp(OPTIMAL) * warp + stream_origin_at(OPTIMAL);
 		origin[lane] = sp.position.x; origin[32 + lane] = sp.position.y; origin[64 + lane] = sp.position.z;
