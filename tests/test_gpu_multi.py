@@ -43,6 +43,7 @@ def _run_exchanged(cuda_devices, width, height, frames=3, spp=2, dataset="mini_c
 			passes.append(frame.create_pass(width, height, stripe_index=r, stripe_count=world))
 			ex = api.FrameExchange()
 			assert lib.vkr_create_frame_exchange(C.byref(ex), C.byref(frame.device), width, height, r, world) == 0
+			ex.timeout_ns = 5 * 10 ** 9   # a barrier that never completes must fail this test quickly, not stall it
 			exchanges.append(ex)
 		blocks = (C.c_void_p * world)(*[ex.d_block for ex in exchanges])
 		for r, frame in enumerate(rigs):
