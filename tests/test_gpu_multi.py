@@ -126,7 +126,7 @@ def test_tile_order_follows_the_measured_costs_and_never_changes_a_pixel():
 		assert p.reorder_tiles == 1 and p.tile_count == (w // 16) * (h // 8)
 		frames = []
 		for f in range(4):
-			out.zero_()
+			out.zero_(); torch.cuda.synchronize()   # torch's stream is not the library's
 			assert lib.vkr_shading_pass_run(C.byref(p), C.byref(frame.device), constants, len(constants), gbd.data_ptr(), out.data_ptr()) == 0
 			assert lib.vkr_shading_pass_wait(C.byref(p), C.byref(frame.device)) == 0
 			frames.append(out.cpu().numpy().copy())
