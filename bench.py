@@ -447,6 +447,7 @@ def run_reference(args):
 	if rank != 0:
 		return
 	os.environ["OMP_NUM_THREADS"] = str(host_threads())   # torchrun exports OMP_NUM_THREADS=1
+	os.environ["VKR_B200_NO_AUTOLOAD"] = "1"              # the package's data-set generator is used here, its CUDA library is not
 	from tests import harness as H
 	info, w = build_frame(args.workload)
 	width, height, lights, spp = w["width"], w["height"], w["lights"], w["spp"]
@@ -458,11 +459,13 @@ def run_reference(args):
 	# a step = the same bounded sample of the frame every time; the sample is sized so that warm-up + steps stay within a few minutes
 	values = []
 	budget_s = float(os.environ.get("VKR_REFERENCE_BUDGET_S", "240"))
+	# one thin probe (an 8-row band every 32 tile rows) gives seconds per row; the sample of a step is the densest set of bands that fits the budget
+	probe = cpu_baseline(args, info, w, constants, band_stride_tiles=32, visibility=vis)
+	probe_rows = sum(1 for y in range(height) if y % (8 * 32) < 8)
+	rows_allowed = budget_s / (args.steps + args.warmup) / (probe["seconds"] / probe_rows)
 	stride = args.cpu_band_stride
-	probe = cpu_baseline(args, info, w, constants, band_stride_tiles=stride, visibility=vis)
-	while probe["seconds"] * (args.steps + args.warmup) > budget_s and stride < 64:   # thin the sample out (never the steps) until the run fits
+	while stride < 64 and sum(1 for y in range(height) if y % (8 * stride) < 8) > rows_allowed:
 		stride *= 2
-		probe = cpu_baseline(args, info, w, constants, band_stride_tiles=stride, visibility=vis)
 	for i in range(args.warmup + args.steps):
 		r = cpu_baseline(args, info, w, constants, band_stride_tiles=stride, visibility=vis)
 		if i >= args.warmup:
