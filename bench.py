@@ -146,6 +146,12 @@ def run_b200(args):
 	if world > 1:
 		os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+		# torchrun exports OMP_NUM_THREADS=1; every rank builds the scene's BVH on the host (OpenMP tasks), so give each its share of the cores
+		os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // world))
+		try:
+			C.CDLL("libgomp.so.1").omp_set_num_threads(max(1, host_threads() // world))
+		except OSError:
+			pass
 	torch.cuda.set_device(local_rank)
 	dev = torch.device("cuda", local_rank)
 	# A dedicated stream shared by torch and the library: the default stream's handle is 0, which the C-ABI

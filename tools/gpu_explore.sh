@@ -10,7 +10,7 @@ for lib in vulkan_renderer_b200/variants/libvkr_*.so; do
 	[ -f "$lib" ] || continue
 	name=$(basename $lib .so); name=${name#libvkr_}
 	width=2; case $name in bvh4*) width=4;; esac
-	echo "== $name"; VKR_BVH_WIDTH=$width VKR_B200_LIB=$PWD/$lib timeout 600 python tools/quick_time.py $args 2>&1 | tail -3 | tee gpurun_out/${tag}_$name.log
+	echo "== $name"; VKR_COUNTERS=1 VKR_BVH_WIDTH=$width VKR_B200_LIB=$PWD/$lib timeout 600 python tools/quick_time.py $args 2>&1 | tail -6 | tee gpurun_out/${tag}_$name.log
 done
 if [ -n "$2" ]; then
 	timeout 900 ncu --set full --clock-control none --import-source on -k regex:shading_kernel -c 1 -o gpurun_out/${tag}_full -f python tools/quick_time.py $args > gpurun_out/${tag}_full.log 2>&1

@@ -45,6 +45,15 @@ constexpr unsigned kPending = 0xffu;
 #define VKR_NODE_LOOP_MIN_LANES 16
 #endif
 constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
+// Tuning knobs of the trace warps' round (lane utilisation only, never results): a new batch of rays is set up once at least VKR_REFILL_MIN_LANES lanes are
+// free (or none is busy): ray set-up is a long divergent stretch that should run with many lanes; VKR_LEAF_ONCE: a round tests one leaf per lane, a second
+// leaf waits for the next round, when more lanes have one.
+#ifndef VKR_REFILL_MIN_LANES
+#define VKR_REFILL_MIN_LANES 1
+#endif
+#ifndef VKR_LEAF_ONCE
+#define VKR_LEAF_ONCE 0
+#endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
 #endif
@@ -287,14 +296,20 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		// --- lanes whose ray has terminated draw a ticket and start on it as soon as it is published
 		const bool wants = !active && ticket < 0 && !finished;
 		const unsigned want = __ballot_sync(kFullMask, wants);
-		if (want) {
+#if VKR_REFILL_MIN_LANES > 1
+		const unsigned busy = __ballot_sync(kFullMask, active);
+		const bool refill = busy == 0u || __popc(~busy) >= VKR_REFILL_MIN_LANES;   // warp-uniform
+#else
+		const bool refill = true;
+#endif
+		if (want && refill) {
 			const int leader = __ffs(want) - 1;
 			int first = 0;
 			if (lane == leader) first = atom_add_shared(control, __popc(want));
 			first = __shfl_sync(kFullMask, first, leader);
 			if (wants) ticket = first + __popc(want & lt_mask);
 		}
-		if (ticket >= 0) {
+		if (ticket >= 0 && refill) {
 			if (ticket < ld_acquire(control + 4u)) {
 				entry = (uint32_t) ticket & (kRing - 1);
 				ticket = -1;
@@ -407,7 +422,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 #endif
 		__syncwarp(kFullMask);
 		// --- leaves: `leaf` and possibly `node` (a second leaf)
+#if VKR_LEAF_ONCE
+		if (leaf != 0) {
+#else
 		while (leaf != 0) {
+#endif
 			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
 			float t;
 			VKR_STAT(st_leaves); VKR_STAT_ADD(st_tris, (unsigned) count);
@@ -422,9 +441,9 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		}
 		// --- a ray ends when it hit something or ran out of nodes
 #if VKR_ANCHORED
-		if (active && node == kTraversalDone && (hit || pending == 0u)) {
+		if (active && node == kTraversalDone && leaf == 0 && (hit || pending == 0u)) {
 #else
-		if (active && node == kTraversalDone) {
+		if (active && node == kTraversalDone && leaf == 0) {
 #endif
 			st_release_u8(bytes + kRing + entry, hit ? 1u : 0u);
 			if (hit) VKR_STAT(st_hits);
