@@ -14,6 +14,14 @@
 #include <limits>
 #include <memory>
 
+// builder parameters (tuning experiments may override them on the compiler's command line)
+#ifndef VKR_BVH_BINS
+#define VKR_BVH_BINS 16
+#endif
+#ifndef VKR_BVH_LEAF_SIZE
+#define VKR_BVH_LEAF_SIZE 4
+#endif
+
 namespace vkr {
 namespace {
 
@@ -40,8 +48,8 @@ struct builder {
 	std::vector<box3> tri_box;
 	std::vector<float> centroid; // 3 per triangle
 	std::vector<uint32_t> order;
-	static constexpr int kBins = 16;
-	static constexpr uint32_t kLeafSize = 4;
+	static constexpr int kBins = VKR_BVH_BINS;
+	static constexpr uint32_t kLeafSize = VKR_BVH_LEAF_SIZE;
 	static constexpr uint32_t kMedianDepth = 32;
 
 	void build(build_node* node, uint32_t first, uint32_t count, uint32_t depth) {
