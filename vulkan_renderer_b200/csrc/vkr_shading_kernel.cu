@@ -36,10 +36,14 @@
 #define VKR_LAUNCHER_PREFIX vkr_launch_shading_kernel_maxp
 #endif
 
+#ifndef VKR_TRACED_CTAS_PER_SM
+#define VKR_TRACED_CTAS_PER_SM 2   // CTAs per SM the register allocation of the kernels with shadow rays is made for (tuning knob, with VKR_SHADE_REGS / VKR_TRACE_REGS)
+#endif
+
 namespace vkr {
 
 template <int STRATEGY, int MAXP, bool BIASED, bool OPTIMAL, bool TRACE>
-__global__ void __launch_bounds__(TRACE ? kShadeThreads + kTraceThreads : kShadeThreads, TRACE ? 2 : 3)
+__global__ void __launch_bounds__(TRACE ? kShadeThreads + kTraceThreads : kShadeThreads, TRACE ? VKR_TRACED_CTAS_PER_SM : 3)
 shading_kernel(const shading_kernel_params p) {
 	shade_tile<MAXP, OPTIMAL, TRACE>(p, psa_light_shader<STRATEGY, MAXP, BIASED, OPTIMAL, TRACE>());
 }
