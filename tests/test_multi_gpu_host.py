@@ -1,5 +1,5 @@
 """world_size-2 gloo test (CPU) of the multi-GPU host logic: the split of a frame into tile columns per GPU and the exchange written with
-one all_gather (the product path exchanges pixels inside the shading kernel, csrc/vkr_exchange.cu; GPU edition: tests/test_gpu_multi.py)."""
+one all_gather (the product path exchanges pixels inside the shading kernel, csrc/vkr_exchange.cu; GPU edition: tests/test_gpu_zzzy_multi.py)."""
 import os
 import socket
 
