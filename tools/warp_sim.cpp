@@ -16,7 +16,7 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned) x) : 32; }
 #include "vkr_anchor.cuh"
 using namespace vkr;
 
-struct params { int min_lanes, refill_min, leaf_once, anchored; };
+struct params { int min_lanes, refill_min, leaf_once, anchored, pooled_tris; };
 struct ray { uint32_t pixel; f3 d; float tmax; uint32_t mask; };
 struct lane_state {
 	bool active = false, hit = false; int node = kTraversalDone, leaf = 0, cached = -1; uint32_t pending = 0; int ray_index = -1;
@@ -28,7 +28,7 @@ static const int C_ROUND = 14, C_TICKET = 22, C_SETUP_FETCH = 28, C_CACHE_TEST =
 extern "C" void simulate(const float* nodes, const float* tris, const float* origins, uint32_t pixel_count, const uint32_t* paths /*[pixel][kPathLevels+2]*/, uint32_t ray_count, const float* rays /*pixel, dx,dy,dz,tmax, mask(bits as float)*/,
 	const int* prm, double* out)
 {
-	const params P = { prm[0], prm[1], prm[2], prm[3] };
+	const params P = { prm[0], prm[1], prm[2], prm[3], prm[4] };
 	const float4* N = (const float4*) nodes; const float4* T = (const float4*) tris;
 	const float tmin = 1e-3f;
 	double warp_instr = 0, node_iters = 0, node_lane_visits = 0, leaf_iters = 0, leaf_lane_tests = 0, setup_rounds = 0, setup_lanes = 0, rounds = 0, hits = 0, lane_instr = 0;
@@ -100,8 +100,15 @@ extern "C" void simulate(const float* nodes, const float* tris, const float* ori
 			int with_leaf = 0, max_count = 0;
 			for (int l = 0; l != 32; ++l) if (L[l].active && L[l].leaf != 0) { ++with_leaf; const int c = L[l].leaf & 15; if (c > max_count) max_count = c; }
 			if (!with_leaf) break;
-			for (int i = 0; i != max_count; ++i) { int testers = 0; for (int l = 0; l != 32; ++l) if (L[l].active && L[l].leaf != 0 && (L[l].leaf & 15) > i) ++testers; warp_instr += C_TRI; ++leaf_iters; leaf_lane_tests += testers; lane_instr += testers * C_TRI; }
-			warp_instr += C_LEAF_OVERHEAD;
+			if (P.pooled_tris) { // all (ray, triangle) pairs of the round go into one list that the warp works off 32 at a time
+				int total = 0; for (int l = 0; l != 32; ++l) if (L[l].active && L[l].leaf != 0) total += L[l].leaf & 15;
+				const int chunks = (total + 31) / 32;
+				warp_instr += 24 + chunks * (C_TRI + 10); leaf_iters += chunks; leaf_lane_tests += total; lane_instr += total * C_TRI;
+			}
+			else {
+				for (int i = 0; i != max_count; ++i) { int testers = 0; for (int l = 0; l != 32; ++l) if (L[l].active && L[l].leaf != 0 && (L[l].leaf & 15) > i) ++testers; warp_instr += C_TRI; ++leaf_iters; leaf_lane_tests += testers; lane_instr += testers * C_TRI; }
+				warp_instr += C_LEAF_OVERHEAD;
+			}
 			for (int l = 0; l != 32; ++l) {
 				lane_state& s = L[l]; if (!(s.active && s.leaf != 0)) continue;
 				const int first = (s.leaf & 0x7fffffff) >> 4, c = s.leaf & 15; float t;

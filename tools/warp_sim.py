@@ -57,10 +57,12 @@ subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-con
 sim = C.CDLL(so)
 paths = np.zeros((len(origins), 22), dtype=np.uint32)
 sim.prepare(nodes, origins.ctypes.data_as(C.c_void_p), C.c_uint32(len(origins)), lv.ctypes.data_as(C.c_void_p), C.c_uint32(len(rays)), rays.ctypes.data_as(C.c_void_p), paths.ctypes.data_as(C.c_void_p))
-for name, prm in (("baseline (16, 1, 0, plain)", (16, 1, 0, 0)), ("min lanes 8", (8, 1, 0, 0)), ("min lanes 24", (24, 1, 0, 0)), ("refill 8", (16, 8, 0, 0)), ("refill 16", (16, 16, 0, 0)), ("leaf once", (16, 1, 1, 0)),
-	("refill 8 + leaf once", (16, 8, 1, 0)), ("anchored", (16, 1, 0, 1)), ("anchored + refill 8", (16, 8, 0, 1)), ("anchored + refill 8 + leaf once", (16, 8, 1, 1)), ("anchored + refill 12 + min lanes 12", (12, 12, 0, 1)),
-	("min lanes 1", (1, 1, 0, 0)), ("refill 32 (batches)", (16, 32, 0, 0))):
-	out = (C.c_double * 16)(); p = (C.c_int * 4)(*prm)
+for name, prm in (("baseline (node loop left below 16 lanes, refill at once, all leaves per round, plain)", (16, 1, 0, 0, 0)), ("node loop left below 8 lanes", (8, 1, 0, 0, 0)), ("node loop left below 24 lanes", (24, 1, 0, 0, 0)),
+	("refill once 8 lanes are free", (16, 8, 0, 0, 0)), ("one leaf per round", (16, 1, 1, 0, 0)), ("pooled triangle tests", (16, 1, 0, 0, 1)), ("pooled triangle tests, one leaf per round", (16, 1, 1, 0, 1)),
+	("anchored", (16, 1, 0, 1, 0)), ("anchored, one leaf per round", (16, 1, 1, 1, 0)), ("anchored, refill 8, one leaf per round", (16, 8, 1, 1, 0)), ("anchored, pooled triangle tests, one leaf per round", (16, 1, 1, 1, 1)),
+	("anchored, one leaf per round, loop left below 20", (20, 1, 1, 1, 0)), ("anchored, one leaf per round, loop left below 24", (24, 1, 1, 1, 0)), ("one leaf per round, loop left below 20", (20, 1, 1, 0, 0)),
+	("anchored, pooled triangle tests, one leaf per round, loop left below 12", (12, 1, 1, 1, 1)), ("anchored, pooled triangle tests, one leaf per round, loop left below 20", (20, 1, 1, 1, 1))):
+	out = (C.c_double * 16)(); p = (C.c_int * 5)(*prm)
 	sim.simulate(nodes, tri, origins.ctypes.data_as(C.c_void_p), C.c_uint32(len(origins)), paths.ctypes.data_as(C.c_void_p), C.c_uint32(len(rays)), rays.ctypes.data_as(C.c_void_p), p, out)
 	o = list(out)
-	print('%-40s warp-instr per 32 rays %7.0f | lanes/node step %.1f lanes/tri test %.1f lanes/setup %.1f | visits/ray %.1f tri tests/ray %.1f occluded %.2f | lane-instr/ray %.0f rounds/32 rays %.1f' % (name, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8]))
+	print('%-78s warp-instr per 32 rays %7.0f | lanes/node step %.1f lanes/tri test %.1f lanes/setup %.1f | visits/ray %.1f tri tests/ray %.1f occluded %.2f | lane-instr/ray %.0f rounds/32 rays %.1f' % (name, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8]))
