@@ -17,6 +17,7 @@ dev = torch.device("cuda", 0); stream = torch.cuda.Stream(dev); torch.cuda.set_s
 frame = Frame(info["vks"], info["textures"], info["save"], info["ltc"], cuda_device=0, stream=stream.cuda_stream)
 frame.configure(sample_count=spp, strategy=strategy, heuristic=api.MIS_OPTIMAL_CLAMPED, trace_shadow_rays=rays, show_lights=1, light_count=lights)
 lib = frame.lib
+print("BVH: %d node pairs, depth %d, built in %.3f s (%s)" % (frame.scene.shadow_node_count, frame.scene.shadow_max_depth, frame.scene.build_seconds, os.environ.get("VKR_BVH_BUILDER", "sah on the host")), flush=True)
 constants = frame.constants(width, height)
 vis = torch.empty((height, width), dtype=torch.int32, device=dev); gb = torch.empty((4, height, width, 4), dtype=torch.float32, device=dev); out = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
 lib.vkr_run_visibility_pass(C.byref(frame.device), C.byref(frame.scene), constants, width, height, vis.data_ptr())

@@ -54,6 +54,9 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_LEAF_ONCE
 #define VKR_LEAF_ONCE 0
 #endif
+#ifndef VKR_STACK_TOP_IN_REGISTER
+#define VKR_STACK_TOP_IN_REGISTER 0
+#endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
 #endif
@@ -276,8 +279,16 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 	// The stack is addressed through ONE loop-carried register with a kTraversalDone sentinel at the bottom, so a pop
 	// never needs an "empty" test.
 	uint32_t top = stack_bottom;
+#if VKR_STACK_TOP_IN_REGISTER
+	// The top element lives in a register: a pop hands it out at once and refills the register with a load whose result is not needed before the next
+	// pop or push, so the latency of the shared-memory load (the address of the next node hangs on it) is off the critical path of the step.
+	int stack_top = kTraversalDone;
+	auto push = [&](int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"(stack_top) : "memory"); top += 128u; stack_top = v; };
+	auto pop = [&]() { const int v = stack_top; top -= 128u; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(stack_top) : "r"(top) : "memory"); return v; };
+#else
 	auto push = [&](int v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"(v) : "memory"); top += 128u; };
 	auto pop = [&]() { int v; top -= 128u; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top) : "memory"); return v; };
+#endif
 	int ticket = -1;             // >= 0: index of the entry this lane will trace next, not published yet
 	uint32_t entry = 0;          // slot of the ray in flight
 	bool active = false;         // a ray is in flight
@@ -332,7 +343,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 #endif
 					float t;
 					if (tmax > tmin) { // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
+#ifndef VKR_NO_OCCLUDER_CACHE
 						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) { hit = true; VKR_STAT(st_cache_hits); }
+#else
+						if (false) {}
+#endif
 						else {
 							r = make_slabs(o, d); top = stack_bottom; push(kTraversalDone);
 #if VKR_ANCHORED
