@@ -57,6 +57,9 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_STACK_TOP_IN_REGISTER
 #define VKR_STACK_TOP_IN_REGISTER 0
 #endif
+#ifndef VKR_TRACE_RELOAD_RAY
+#define VKR_TRACE_RELOAD_RAY 0
+#endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
 #endif
@@ -300,9 +303,15 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 	uint32_t path = 0u;          // shared-memory address of the origin path of the ray's pixel
 #endif
 	int cached_triangle = -1;    // slot of the last triangle that occluded a ray of this lane
+#if VKR_TRACE_RELOAD_RAY
+	// origin and direction are not kept across the node loop (which only needs the slab form of the ray): the leaf tests read them again from the
+	// ring, six registers less per trace lane
+	unsigned own_lane = 0;
+#else
 	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
+#endif
 	float tmax = 0.0f;
-	ray_slabs r = make_slabs(o, d);
+	ray_slabs r = make_slabs(make3(0.0f, 0.0f, 0.0f), make3(0.0f, 0.0f, 1.0f));
 	while (true) {
 		// --- lanes whose ray has terminated draw a ticket and start on it as soon as it is published
 		const bool wants = !active && ticket < 0 && !finished;
@@ -332,8 +341,14 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 				else {
 					VKR_STAT(st_rays);
 					const uint32_t oa = origin + 4u * (own & 31u), ea = base + 4u * entry;
+#if VKR_TRACE_RELOAD_RAY
+					own_lane = own & 31u;
+					const f3 o = make3(lds_f(oa), lds_f(oa + 128u), lds_f(oa + 256u));
+					const f3 d = make3(lds_f(ea + 4u * S_DX), lds_f(ea + 4u * S_DY), lds_f(ea + 4u * S_DZ));
+#else
 					o = make3(lds_f(oa), lds_f(oa + 128u), lds_f(oa + 256u));
 					d = make3(lds_f(ea + 4u * S_DX), lds_f(ea + 4u * S_DY), lds_f(ea + 4u * S_DZ));
+#endif
 					tmax = lds_f(ea + 4u * S_TMAX);
 					active = true;
 					hit = false;
@@ -342,7 +357,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 					pending = 0u;
 #endif
 					float t;
+#ifdef VKR_NULL_TRACE   // diagnostic edition: every ray is a miss at once -- what is left is the time of the shading warps and the ring (the frame is wrong, of course)
+					if (false) {
+#else
 					if (tmax > tmin) { // tmax <= tmin / NaN: undefined in Vulkan, defined as "miss" 
+#endif
 #ifndef VKR_NO_OCCLUDER_CACHE
 						if (cached_triangle >= 0 && ray_triangle(tris + 3 * (size_t) cached_triangle, o, d, tmin, tmax, &t)) { hit = true; VKR_STAT(st_cache_hits); }
 #else
@@ -444,6 +463,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 #endif
 			const int first = (leaf & 0x7fffffff) >> 4, count = leaf & 15;
 			float t;
+#if VKR_TRACE_RELOAD_RAY
+			const uint32_t oa = origin + 4u * own_lane, ea = base + 4u * entry;
+			const f3 o = make3(lds_f(oa), lds_f(oa + 128u), lds_f(oa + 256u));
+			const f3 d = make3(lds_f(ea + 4u * S_DX), lds_f(ea + 4u * S_DY), lds_f(ea + 4u * S_DZ));
+#endif
 			VKR_STAT(st_leaves); VKR_STAT_ADD(st_tris, (unsigned) count);
 			for (int i = 0; i != count; ++i)
 				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) { hit = true; cached_triangle = first + i; }
