@@ -108,6 +108,10 @@ typedef struct vkr_scene_s {
 	void* d_texture_offsets;   /* uint64 per texture: first texel of level 0 in d_texture_data */
 	uint64_t texture_texel_count;
 	uint32_t shadow_bvh_width;  /* children per node of d_shadow_nodes: 2 (64-byte node pairs); 4 only with VKR_BVH_WIDTH=4 in the environment, for the experimental kernel variant */
+	/* the node pairs of d_shadow_nodes once more, 32 bytes each: child boxes as 16-bit coordinates on a grid over the scene, rounded outwards (what the trace
+	   warps of the shading kernels fetch; the float pairs serve the probes and the tests). shadow_grid = minimum xyz, cells per world unit xyz */
+	void* d_shadow_nodes_quantised;
+	float shadow_grid[6];
 } vkr_scene_t;
 
 /* device may be NULL for vkr_load_scene / vkr_load_ltc_table / vkr_load_noise_table: the files are parsed and the host

@@ -191,6 +191,23 @@ extern "C" void vkr_device_on_host_trace_any_wide(const float* nodes2, const flo
 }
 
 // Shader-side vertex decode (vkr_gbuffer.cuh: decode_position, mesh_quantization.glsl:38-45) for all vertices: the input of the primary-ray BVH
+// Quantised node pairs (vkr_trace.cuh): the float pairs of a tree quantised with quantise_node_pair() on the grid shadow_grid_from_root() chooses, then the same
+// rays through occluded() on the float pairs and occluded_grid() on the quantised ones; grid = minimum xyz, cells per unit xyz. visits[2]: pairs fetched
+extern "C" void vkr_device_on_host_trace_quantised(const float* nodes, uint64_t pair_count, const float* tris, const float* grid, uint32_t ray_count, const float* rays, uint8_t* out_float, uint8_t* out_grid, uint32_t* out_pairs8, uint64_t* visits) {
+	bvh_view bvh; bvh.nodes = reinterpret_cast<const float4*>(nodes); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = nullptr; bvh.tri_count = 0;
+	for (uint64_t i = 0; i != pair_count; ++i) quantise_node_pair(bvh.nodes + 4 * i, grid, grid + 3, out_pairs8 + 8 * i);
+	int stack[kMaxStackDepth + 2];
+	visits[0] = visits[1] = 0;
+	for (uint32_t i = 0; i != ray_count; ++i) {
+		const float* r = rays + 8 * (size_t) i;
+		const f3 o = make3(r[0], r[1], r[2]), d = make3(r[3], r[4], r[5]);
+		int v = 0;
+		out_float[i] = occluded(bvh, o, d, r[6], r[7], stack, 1) ? 1 : 0;
+		out_grid[i] = occluded_grid(out_pairs8, bvh.tris, grid, grid + 3, o, d, r[6], r[7], stack, 1, &v) ? 1 : 0;
+		visits[1] += (uint64_t) v;
+	}
+}
+
 // Anchored shadow rays (vkr_anchor.cuh): rays from `origins` towards points of a polygonal light through (a) the plain traversal, (b) the anchored one with
 // all siblings of the origin path, (c) with the siblings the light's cone touches; rays = {origin index, dx, dy, dz, tmax}. out[3 * i + {0, 1, 2}] = answers,
 // visits[3]: node pairs fetched in total, info = {rays outside their cone, siblings kept, siblings along the paths}

@@ -240,6 +240,47 @@ def test_four_wide_collapse_keeps_the_tree_and_the_answers(name):
 	assert np.array_equal(out2, out4) and 0.02 < out2.mean() < 0.99
 
 
+@pytest.mark.parametrize("name", ["cornell", "mini_city", "mini_room", "roughness_planes"])
+def test_quantised_node_pairs_answer_like_the_float_pairs(name):
+	"""The trace warps walk 32-byte node pairs whose child boxes are 16-bit grid coordinates (vkr_trace.cuh). Quantisation must be conservative: every box
+	contains its float box (checked by decoding), and rays -- axis-parallel ones, rays along box faces, rays from surface points -- get the answers of the
+	float pairs, bit for bit, because hit / miss is the OR over the triangles the predicate accepts."""
+	from tests.test_device_on_host import _lib
+	dev = _lib(); lib = api.load_library()
+	info = H.dataset(name); vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes, slots, ids, depth = _probe_bvh(lib, tris, BUILDERS["sah"])
+	n2 = np.ascontiguousarray(nodes, dtype=np.float32); sl = np.ascontiguousarray(slots, dtype=np.float32)
+	# the grid as shadow_grid_from_root() makes it (vkr_bvh.cpp), restated: the root's boxes with two cells to spare, 65531 cells across
+	c = n2[0, [0, 1, 2, 6, 7, 8]].reshape(2, 3); hx = n2[0, [3, 4, 5, 9, 10, 11]].reshape(2, 3)
+	lo = (c - hx).min(0); hi = (c + hx).max(0); extent = hi - lo
+	extent = np.where(extent > 1e-6 * extent.max(), extent, max(1e-6 * extent.max(), 1e-30)).astype(np.float32)
+	scale = (np.float32(65531.0) / extent).astype(np.float32); gmin = (lo - np.float32(2.0) / scale).astype(np.float32)
+	grid = np.concatenate([gmin, scale]).astype(np.float32)
+	rng = np.random.default_rng(21)
+	T = tris.reshape(-1, 3, 3); blo = T.reshape(-1, 3).min(0); bhi = T.reshape(-1, 3).max(0)
+	n_rays = 6000
+	origins = rng.uniform(blo, bhi, (n_rays, 3)); targets = T[rng.integers(0, len(T), n_rays)].mean(1) + rng.normal(scale=0.02, size=(n_rays, 3))
+	origins[:2000] = T[rng.integers(0, len(T), 2000)].mean(1)                       # rays that start on a surface, like shadow rays do
+	d = targets - origins; length = np.linalg.norm(d, axis=1, keepdims=True); length[length == 0] = 1.0; d /= length
+	rays = np.concatenate([origins, d, np.full((n_rays, 1), 1e-3), length * rng.uniform(0.3, 1.5, (n_rays, 1))], axis=1).astype(np.float32)
+	rays[:60, 3:6] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 60)] * rng.choice([-1.0, 1.0], (60, 1)).astype(np.float32)   # axis-parallel: infinite slab distances
+	out_f = np.zeros(n_rays, dtype=np.uint8); out_q = np.zeros(n_rays, dtype=np.uint8); pairs8 = np.zeros((len(n2), 8), dtype=np.uint32); visits = (C.c_uint64 * 2)()
+	dev.vkr_device_on_host_trace_quantised(n2.ctypes.data_as(C.c_void_p), C.c_uint64(len(n2)), sl.ctypes.data_as(C.c_void_p), grid.ctypes.data_as(C.c_void_p), C.c_uint32(n_rays), rays.ctypes.data_as(C.c_void_p),
+		out_f.ctypes.data_as(C.c_void_p), out_q.ctypes.data_as(C.c_void_p), pairs8.ctypes.data_as(C.c_void_p), visits)
+	assert np.array_equal(out_f, out_q) and 0.01 < out_f.mean() < 0.995
+	# every quantised box contains its float box, with at least one and at most three cells to spare
+	for k in range(2):
+		cc = n2[:, 6 * k:6 * k + 3].astype(np.float64); hh = n2[:, 6 * k + 3:6 * k + 6].astype(np.float64)
+		real = hh[:, 0] >= 0
+		qlo = (pairs8[:, 3 * k:3 * k + 3] & 0xffff).astype(np.float64); qhi = (pairs8[:, 3 * k:3 * k + 3] >> 16).astype(np.float64)
+		glo = ((cc - hh) - gmin) * scale; ghi = ((cc + hh) - gmin) * scale
+		assert (qlo[real] <= glo[real] - 0.99).all() and (qhi[real] >= ghi[real] + 0.99).all()
+		assert (qlo[real] >= glo[real] - 2.01).all() and (qhi[real] <= ghi[real] + 2.01).all()
+		assert (qlo[real] >= 0).all() and (qhi[real] <= 65535).all()
+	assert np.array_equal(pairs8[:, 6:8], n2[:, 12:14].copy().view(np.uint32))
+
+
 @pytest.mark.parametrize("name,light", [("mini_city", 0), ("mini_city", 2), ("mini_room", 5), ("cornell", 0)])
 def test_anchored_shadow_rays_answer_like_the_plain_traversal(name, light):
 	"""vkr_anchor.cuh (compiled for the CPU): shadow rays that start at the siblings of their pixel's origin path -- all of them, or those the light's cone

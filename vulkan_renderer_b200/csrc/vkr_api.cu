@@ -306,6 +306,8 @@ int vkr_launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, con
 		p.bvh_nodes = (const float4*) d.scene->d_shadow_nodes; p.bvh_tris = (const float4*) d.scene->d_shadow_tris; p.tri_count = (uint32_t) d.scene->triangle_count;
 		p.stack_depth = (int) d.scene->shadow_max_depth + 2;
 		p.bvh_width = d.scene->shadow_bvh_width ? (int) d.scene->shadow_bvh_width : 2;
+		p.bvh_nodes_q = (const uint4*) d.scene->d_shadow_nodes_quantised;
+		for (int k = 0; k != 6; ++k) p.bvh_grid[k] = d.scene->shadow_grid[k];
 	}
 	if (any_textured_light) {
 		p.light_texture_texels = (const float4*) d.light_textures->d_texels; p.light_texture_dims = (const uint4*) d.light_textures->d_dims;

@@ -128,6 +128,24 @@ inline float as_float(int32_t bits) { float f; std::memcpy(&f, &bits, 4); return
 
 } // namespace
 
+void shadow_grid_from_root(const float* p, float grid[6]) {
+	// root pair: child 0 = centre p[0..2], half extent p[3..5]; child 1 = p[6..8], p[9..11]
+	float extent_max = 0.0f, lo[3], hi[3];
+	for (int a = 0; a != 3; ++a) {
+		const bool has1 = p[9 + a] >= 0.0f;   // an empty second child (single-leaf trees) has a negative half extent
+		lo[a] = std::min(p[a] - p[3 + a], has1 ? p[6 + a] - p[9 + a] : p[a] - p[3 + a]);
+		hi[a] = std::max(p[a] + p[3 + a], has1 ? p[6 + a] + p[9 + a] : p[a] + p[3 + a]);
+		extent_max = std::max(extent_max, hi[a] - lo[a]);
+	}
+	for (int a = 0; a != 3; ++a) {
+		float extent = hi[a] - lo[a];
+		if (!(extent > 1.0e-6f * extent_max) || !(extent > 0.0f)) extent = (extent_max > 0.0f) ? 1.0e-6f * extent_max : 1.0f;   // flat scenes: any finite cell size does
+		const float cells_per_unit = 65531.0f / extent;   // coordinates land in [2, 65533]: the rounding outwards plus one cell never leaves the 16 bits
+		grid[3 + a] = cells_per_unit;
+		grid[a] = lo[a] - 2.0f / cells_per_unit;
+	}
+}
+
 void build_bvh(host_bvh& out, const float* vertices, uint64_t triangle_count) {
 	out = host_bvh();
 	const uint32_t n = (uint32_t) triangle_count;

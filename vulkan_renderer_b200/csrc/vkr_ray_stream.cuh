@@ -60,6 +60,10 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_TRACE_RELOAD_RAY
 #define VKR_TRACE_RELOAD_RAY 0
 #endif
+// The trace warps walk the quantised node pairs (32 bytes, vkr_trace.cuh) unless this is 0; anchored rays and the 4-wide variant keep the float pairs.
+#ifndef VKR_QUANTISED_NODES
+#define VKR_QUANTISED_NODES ((VKR_BVH_WIDTH == 2) && !VKR_ANCHORED)
+#endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
 #endif
@@ -270,7 +274,9 @@ VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc, unsigned lo
 // Consumer side (trace warps): runs until the stream is closed and drained. stack = shared-memory address of this
 // lane's column of the warp's traversal stack (128 B between levels = one slot per lane).
 template <bool OPTIMAL>
-VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane, unsigned long long* stats = nullptr) {
+VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane, unsigned long long* stats = nullptr,
+	const uint4* __restrict__ nodes_q = nullptr, f3 grid_min = f3(), f3 grid_scale = f3())
+{
 #ifdef VKR_TRACE_STATS
 	unsigned st_rays = 0, st_hits = 0, st_cache_hits = 0, st_visits = 0, st_leaves = 0, st_tris = 0, st_iters = 0, st_node_iters = 0, st_known = 0, st_polls = 0, st_siblings = 0;
 #endif
@@ -311,7 +317,11 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 	f3 o = make3(0.0f, 0.0f, 0.0f), d = make3(0.0f, 0.0f, 1.0f);
 #endif
 	float tmax = 0.0f;
+#if VKR_QUANTISED_NODES
+	ray_grid r = make_ray_grid(make3(0.0f, 0.0f, 0.0f), make3(0.0f, 0.0f, 1.0f), grid_min, grid_scale);
+#else
 	ray_slabs r = make_slabs(make3(0.0f, 0.0f, 0.0f), make3(0.0f, 0.0f, 1.0f));
+#endif
 	while (true) {
 		// --- lanes whose ray has terminated draw a ticket and start on it as soon as it is published
 		const bool wants = !active && ticket < 0 && !finished;
@@ -368,7 +378,12 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 						if (false) {}
 #endif
 						else {
-							r = make_slabs(o, d); top = stack_bottom; push(kTraversalDone);
+#if VKR_QUANTISED_NODES
+							r = make_ray_grid(o, d, grid_min, grid_scale);
+#else
+							r = make_slabs(o, d);
+#endif
+							top = stack_bottom; push(kTraversalDone);
 #if VKR_ANCHORED
 							// start at the end of the pixel's origin path; the siblings along it follow when the stack runs empty
 							path = base + 4u * (uint32_t) stream_path_at(OPTIMAL) + 4u * (own & 31u);
@@ -428,15 +443,23 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		while (node >= 0 && node != kTraversalDone) {
 			const int skip = 2;
 #endif
+			float tn0, tn1;
+			VKR_STAT(st_visits);
+			if ((__activemask() & lt_mask) == 0u) VKR_STAT(st_node_iters);
+#if VKR_QUANTISED_NODES
+			float4 q0, q1;   // one 32-byte pair: six words of 16-bit box coordinates, two references
+			ldg_256(reinterpret_cast<const float4*>(nodes_q) + 2 * (size_t) node, q0, q1);
+			const int ref0 = __float_as_int(q1.z), ref1 = __float_as_int(q1.w);
+			const bool h0 = ray_box_grid(__float_as_uint(q0.x), __float_as_uint(q0.y), __float_as_uint(q0.z), r, tmin, tmax, &tn0);
+			const bool h1 = ray_box_grid(__float_as_uint(q0.w), __float_as_uint(q1.x), __float_as_uint(q1.y), r, tmin, tmax, &tn1);
+#else
 			const float4* nd = nodes + 4 * (size_t) node;
 			float4 q0, q1, q2, q3;
 			ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3);
 			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
-			float tn0, tn1;
-			VKR_STAT(st_visits);
-			if ((__activemask() & lt_mask) == 0u) VKR_STAT(st_node_iters);
 			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0) && skip != 0;
 			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1) && skip != 1;
+#endif
 			if (h0 && h1) {
 				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
 				node = swap ? ref1 : ref0;

@@ -97,6 +97,82 @@ VKR_DEV bool ray_box(float cx, float cy, float cz, float hx, float hy, float hz,
 	return tn <= tf;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// Quantised node pairs: the form the trace warps of the shading kernels walk. ncu puts those warps at the limit of the L1 data pipe (74 % of its
+// wavefronts, 87 % of them node fetches of lanes that diverge): the lever is bytes per visit, not instructions. A pair shrinks from 64 to 32 bytes
+// -- one 256-bit load, one sector per lane -- by storing the two child boxes as 16-bit coordinates on a grid over the scene's bounding box:
+//   word 0..2  child 0: x, y, z as (low | high << 16)      word 3..5  child 1      word 6, 7  the two child references (as in the float pairs)
+// Boxes are rounded outwards to the grid and one more cell (below), so the test stays conservative; the triangle predicate is untouched and hit / miss
+// remains the OR over the triangles it accepts. The ray is taken to grid coordinates once (t is invariant under per-axis scaling), a plane's
+// coordinate q becomes the float 2^23 + q with one byte permutation (no integer-to-float conversion), and the slab distance one FFMA:
+// (2^23 + q) * id - (2^23 * id + o_grid * id). The rounding of that constant is worth at most 0.504 grid cells -- the extra cell of padding.
+struct ray_grid { f3 id, c; unsigned near_x, near_y, near_z; };   // c = -(2^23 * id + o_grid * id); near_*: byte selectors of the plane the ray enters through
+constexpr unsigned kGridMagic = 0x4B000000u;   // float 2^23
+VKR_DEV ray_grid make_ray_grid(f3 o, f3 d, f3 grid_min, f3 grid_scale) {
+	ray_grid g;
+	const f3 og = make3((o.x - grid_min.x) * grid_scale.x, (o.y - grid_min.y) * grid_scale.y, (o.z - grid_min.z) * grid_scale.z);
+	const f3 dg = make3(d.x * grid_scale.x, d.y * grid_scale.y, d.z * grid_scale.z);
+	g.id = make3(slab_reciprocal(dg.x), slab_reciprocal(dg.y), slab_reciprocal(dg.z));
+	g.c = make3(-fmaf(8388608.0f, g.id.x, og.x * g.id.x), -fmaf(8388608.0f, g.id.y, og.y * g.id.y), -fmaf(8388608.0f, g.id.z, og.z * g.id.z));
+	g.near_x = (dg.x < 0.0f) ? 0x7632u : 0x7610u; g.near_y = (dg.y < 0.0f) ? 0x7632u : 0x7610u; g.near_z = (dg.z < 0.0f) ? 0x7632u : 0x7610u;
+	return g;
+}
+VKR_DEV float grid_plane(unsigned word, unsigned selector) { // float(2^23 + the 16-bit half of `word` that `selector` names)
+#if defined(__CUDA_ARCH__)
+	return __uint_as_float(__byte_perm(word, kGridMagic, selector));
+#else
+	return __uint_as_float(kGridMagic | ((selector == 0x7632u) ? (word >> 16) : (word & 0xffffu)));
+#endif
+}
+// Slab test of one quantised child box (its three words). NaNs (a direction component of zero) drop out of fminf / fmaxf as in ray_box().
+VKR_DEV bool ray_box_grid(unsigned wx, unsigned wy, unsigned wz, const ray_grid& g, float tmin, float tmax, float* t_near) {
+	const float nx = fmaf(grid_plane(wx, g.near_x), g.id.x, g.c.x), ny = fmaf(grid_plane(wy, g.near_y), g.id.y, g.c.y), nz = fmaf(grid_plane(wz, g.near_z), g.id.z, g.c.z);
+	const float fx = fmaf(grid_plane(wx, g.near_x ^ 0x0022u), g.id.x, g.c.x), fy = fmaf(grid_plane(wy, g.near_y ^ 0x0022u), g.id.y, g.c.y), fz = fmaf(grid_plane(wz, g.near_z ^ 0x0022u), g.id.z, g.c.z);
+	const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+	const float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
+	*t_near = tn;
+	return tn <= tf;
+}
+// One float node pair -> its quantised form (8 words). Used by the quantisation kernel (vkr_lbvh_gpu.cu) and by the CPU tests.
+VKR_DEV void quantise_node_pair(const float4* __restrict__ pair, const float* grid_min, const float* grid_scale, unsigned* out8) {
+	const float4 q0 = pair[0], q1 = pair[1], q2 = pair[2], q3 = pair[3];
+	const float c[2][3] = { { q0.x, q0.y, q0.z }, { q1.z, q1.w, q2.x } }, h[2][3] = { { q0.w, q1.x, q1.y }, { q2.y, q2.z, q2.w } };
+	for (int k = 0; k != 2; ++k)
+		for (int a = 0; a != 3; ++a) {
+			// outwards to the grid, then one cell more; an empty child (negative half extent) stays empty: low > high
+			float lo = floorf(((c[k][a] - h[k][a]) - grid_min[a]) * grid_scale[a]) - 1.0f, hi = ceilf(((c[k][a] + h[k][a]) - grid_min[a]) * grid_scale[a]) + 1.0f;
+			if (h[k][a] < 0.0f) { lo = 65535.0f; hi = 0.0f; }
+			lo = fminf(fmaxf(lo, 0.0f), 65535.0f); hi = fminf(fmaxf(hi, 0.0f), 65535.0f);
+			out8[3 * k + a] = (unsigned) lo | ((unsigned) hi << 16);
+		}
+	out8[6] = __float_as_uint(q3.x); out8[7] = __float_as_uint(q3.y);
+}
+// Per-thread any-hit query over quantised pairs: the reference form of the trace warps' loop (vkr_ray_stream.cuh), run on the CPU against occluded().
+VKR_DEV bool occluded_grid(const unsigned* __restrict__ pairs8, const float4* __restrict__ tris, const float* grid_min, const float* grid_scale, f3 o, f3 d, float tmin, float tmax, int* stack, int stride, int* visits) {
+	if (!(tmax > tmin)) return false;
+	const ray_grid g = make_ray_grid(o, d, make3(grid_min[0], grid_min[1], grid_min[2]), make3(grid_scale[0], grid_scale[1], grid_scale[2]));
+	int sp = 0, node = 0;
+	float t, tn0, tn1;
+	while (true) {
+		if (node < 0) {
+			const int first = (node & 0x7fffffff) >> 4, count = node & 15;
+			for (int i = 0; i != count; ++i)
+				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) return true;
+			if (sp == 0) return false;
+			--sp; node = stack[sp * stride];
+			continue;
+		}
+		if (visits) ++*visits;
+		const unsigned* w = pairs8 + 8 * (size_t) node;
+		const bool h0 = ray_box_grid(w[0], w[1], w[2], g, tmin, tmax, &tn0), h1 = ray_box_grid(w[3], w[4], w[5], g, tmin, tmax, &tn1);
+		const int ref0 = (int) w[6], ref1 = (int) w[7];
+		if (h0 && h1) { const bool swap = tn1 < tn0; stack[sp * stride] = swap ? ref0 : ref1; ++sp; node = swap ? ref1 : ref0; }
+		else if (h0) node = ref0;
+		else if (h1) node = ref1;
+		else { if (sp == 0) return false; --sp; node = stack[sp * stride]; }
+	}
+}
+
 // Per-thread any-hit query (probe kernel vkr_trace_shadow_rays); the shading kernel's own traversal loop lives in
 // vkr_ray_stream.cuh (trace warps), built from the same ray_box / ray_triangle.
 VKR_DEV bool occluded(const bvh_view& bvh, f3 o, f3 d, float tmin, float tmax, int* stack, int stride) {
