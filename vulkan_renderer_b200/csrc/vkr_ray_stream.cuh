@@ -60,9 +60,11 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_TRACE_RELOAD_RAY
 #define VKR_TRACE_RELOAD_RAY 0
 #endif
-// The trace warps walk the quantised node pairs (32 bytes, vkr_trace.cuh) unless this is 0; anchored rays and the 4-wide variant keep the float pairs.
+// 1: the trace warps walk the quantised node pairs (32 bytes, vkr_trace.cuh) instead of the float pairs. Measured on the B200 (profiles/r02_variants.md): half
+// the bytes per visit, bit-identical frames, 2.7 % SLOWER (4 more instructions per visit, 6 % more triangle tests behind the fatter boxes) -- the kernel is not
+// bound by the L1 data pipe after all. Kept as a compile-time edition; not with anchored rays or the 4-wide variant.
 #ifndef VKR_QUANTISED_NODES
-#define VKR_QUANTISED_NODES ((VKR_BVH_WIDTH == 2) && !VKR_ANCHORED)
+#define VKR_QUANTISED_NODES 0
 #endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
