@@ -60,6 +60,17 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_TRACE_RELOAD_RAY
 #define VKR_TRACE_RELOAD_RAY 0
 #endif
+// The four shading warps of a CTA can walk their sample loop in loose lock step (a named barrier per iteration: 1 = per sample pair, 2 = per technique),
+// so that they fetch the loop's 32 KB of instructions together instead of four times: the SM's instruction cache is 32 KB and ncu shows the next level
+// (the GPC's) at 90 % of its request rate. Only tiles in which all four warps have pixels to shade use it (the barrier needs all of them).
+#ifndef VKR_SHADING_LOCKSTEP
+#define VKR_SHADING_LOCKSTEP 0
+#endif
+VKR_DEV void shading_lockstep_barrier() {
+#if defined(__CUDA_ARCH__)
+	asm volatile("bar.sync 1, 128;" ::: "memory");
+#endif
+}
 // 1: the trace warps walk the quantised node pairs (32 bytes, vkr_trace.cuh) instead of the float pairs. Measured on the B200 (profiles/r02_variants.md): half
 // the bytes per visit, bit-identical frames, 2.7 % SLOWER (4 more instructions per visit, 6 % more triangle tests behind the fatter boxes) -- the kernel is not
 // bound by the L1 data pipe after all. Kept as a compile-time edition; not with anchored rays or the 4-wide variant.
@@ -128,6 +139,7 @@ struct ray_producer {
 	unsigned stat_resolve_polls, stat_candidates;
 #endif
 	bool cone_set;   // this lane has stored a cone and a sibling mask for the light it is sampling (set_light_cone); else its rays keep all siblings
+	bool lockstep;   // warp-uniform: this tile's shading warps keep in step (VKR_SHADING_LOCKSTEP)
 };
 
 // Radiance sums of one pixel. The reference adds the samples of a light into a per-light sum, scales it by 1/S and

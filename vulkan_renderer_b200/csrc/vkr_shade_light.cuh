@@ -155,8 +155,14 @@ VKR_DEV void shade_light(bool on, const shading_point& sp, const ltc_state& l, c
 			// each sample right before its evaluation consumes the noise stream in the same order. One loop body serves
 			// both techniques and the end-of-light flush (s == S), so the kernel holds one copy of sample_psa and drain.
 			for (int s = 0; s <= S; ++s) {
+#if VKR_SHADING_LOCKSTEP == 1
+				if (TRACE && q.lockstep) shading_lockstep_barrier();
+#endif
 #pragma unroll 1
 				for (int j = 0; j != 2; ++j) {
+#if VKR_SHADING_LOCKSTEP == 2
+					if (TRACE && q.lockstep) shading_lockstep_barrier();
+#endif
 					bool has = on && s != S && (j == 0 || has_specular);
 					bool pre_vis = false; f3 w = zero, c = zero, c_occ = zero; float tmax = 0.0f;
 					if (has) {

@@ -116,6 +116,18 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 	q.stat_resolve_polls = 0; q.stat_candidates = 0;
 #endif
 	q.cone_set = false;
+	q.lockstep = false;
+#if VKR_SHADING_LOCKSTEP
+	if (TRACE) { // do all four shading warps of the tile have something to shade? (control word 3 of every stream is free for this)
+		const bool any_valid = __any_sync(kFullMask, valid) != 0;
+		if (lane == 0) sts_u32(q.base + 4u * (uint32_t) stream_control_at(OPTIMAL) + 12u, any_valid ? 1u : 0u);
+		shading_lockstep_barrier();
+		const uint32_t first_stream = smem_addr(stream_base);
+		bool all = true;
+		for (int w = 0; w != kShadeWarps; ++w) all = all && lds_u32(first_stream + 4u * (uint32_t) (stream_floats_per_warp(OPTIMAL) * w + stream_control_at(OPTIMAL)) + 12u) != 0u;
+		q.lockstep = all;
+	}
+#endif
 #if VKR_ANCHORED
 	if (TRACE) { // the origin path of this pixel (vkr_anchor.cuh): all of its shadow rays start from it
 		const uint32_t path = q.base + 4u * (uint32_t) stream_path_at(OPTIMAL) + 4u * (uint32_t) lane;
