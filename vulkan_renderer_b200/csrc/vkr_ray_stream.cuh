@@ -66,6 +66,9 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_SHADING_LOCKSTEP
 #define VKR_SHADING_LOCKSTEP 0
 #endif
+#ifndef VKR_NODE_LOOP_CHECK_EVERY
+#define VKR_NODE_LOOP_CHECK_EVERY 1   // power of two: the node loop counts its descending lanes every this many steps
+#endif
 VKR_DEV void shading_lockstep_barrier() {
 #if defined(__CUDA_ARCH__)
 	asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -424,6 +427,9 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			continue;
 		}
 		if (lane == 0) VKR_STAT(st_iters);
+#if VKR_NODE_LOOP_CHECK_EVERY > 1
+		unsigned node_steps = 0u;
+#endif
 		// --- descend until this lane holds two leaves or is out of nodes
 #if VKR_BVH_WIDTH == 4
 		// EXPERIMENTAL variant (tools/build_variant.sh ... "-DVKR_BVH_WIDTH=4" with VKR_BVH_WIDTH=4 in the environment when the scene is loaded): 128-byte
@@ -488,6 +494,9 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			}
 			// lanes that are done or hold two leaves wait at the loop exit: once too few are left descending, let
 			// everybody test triangles and fetch new rays (affects lane utilisation only, not results)
+#if VKR_NODE_LOOP_CHECK_EVERY > 1
+			if ((++node_steps & (VKR_NODE_LOOP_CHECK_EVERY - 1)) != 0) continue;   // the head count costs four instructions of a step: look every other step only
+#endif
 			if (kNodeLoopMinLanes > 0 && __popc(__activemask()) < kNodeLoopMinLanes) break;
 		}
 #endif
