@@ -21,6 +21,7 @@ extern "C" {
 #define VKR_B200_ABI_VERSION 1
 #define VKR_TILE_ROW_HEIGHT 8 /* pixel rows per screen-tile row */
 #define VKR_TILE_WIDTH 16     /* pixel columns per screen tile: the unit of the multi-GPU split */
+#define VKR_TILE_BAND_ROWS 8  /* tile rows per band of the multi-GPU split: the tile columns of a share move on by one from band to band */
 #define VKR_MAX_GPUS 8        /* GPUs of one box that can share a frame (vkr_frame_exchange_t) */
 
 /* ---- enums: numeric values equal the reference's (src/main.h:45-92, src/polygonal_light.h:28-67,
@@ -310,11 +311,12 @@ typedef struct vkr_shading_pass_desc_s {
 	vkr_sample_polygon_technique_t polygon_sampling_technique;
 	int trace_shadow_rays;
 	int show_polygonal_lights;
-	/* multi-GPU split: this pass instance shades the 16x8 screen tiles of every tile row whose column tx satisfies
-	   tx % stripe_count == stripe_index (SURVEY 8e asks for tile rows per GPU; the rows are cut further into tiles and dealt
-	   out column-wise because 135 tile rows of uneven cost do not balance over 8 GPUs: every GPU gets the same number of tiles
-	   from all over the screen, and a GPU's part of a G-buffer plane is ONE strided 2D copy); stripe_count = 0 or 1 means
-	   the whole frame */
+	/* multi-GPU split: this pass instance shades the 16x8 screen tiles (tx, ty) with (tx + ty / VKR_TILE_BAND_ROWS) % stripe_count ==
+	   stripe_index (SURVEY 8e asks for tile rows per GPU; the rows are cut further into tiles and dealt out column-wise because
+	   135 tile rows of uneven cost do not balance over 8 GPUs; the columns of a share move on by one every 8 tile rows so that no
+	   share sits on one set of screen columns -- at 1920x1080 every GPU of 8 visits each column phase twice. Every GPU gets the
+	   same number of tiles from all over the screen, and its part of a G-buffer plane is one strided 2D copy per band);
+	   stripe_count = 0 or 1 means the whole frame */
 	uint32_t stripe_index, stripe_count;
 	/* resources */
 	const vkr_scene_t* scene;
@@ -396,7 +398,7 @@ void* vkr_frame_exchange_frame(const vkr_frame_exchange_t* exchange);
 /* Shades this GPU's tiles of one frame into every GPU's frame, signals, waits for the peers: asynchronous on device->stream; once the
    stream has passed this call vkr_frame_exchange_frame() holds the whole frame. All GPUs must call it once per frame. */
 int vkr_shading_pass_run_exchange(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const void* d_gbuffer, vkr_frame_exchange_t* exchange);
-/* Host-buffer variant: uploads this GPU's tile columns of the G-buffer (one strided copy per plane), shades and exchanges as above, and
+/* Host-buffer variant: uploads this GPU's tile columns of the G-buffer (one strided copy per plane and band of tile rows), shades and exchanges as above, and
    if out_rgba32f is not NULL downloads the WHOLE frame; waits. Returns non-zero if a peer failed to arrive. */
 int vkr_shading_pass_run_host_exchange(vkr_shading_pass_t* pass, const vkr_device_t* device, const void* constants, size_t constants_size, const float* gbuffer,
 	vkr_frame_exchange_t* exchange, float* out_rgba32f);

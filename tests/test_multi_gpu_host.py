@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from vulkan_renderer_b200.stripes import ShareGather, share_columns, share_tiles
+from vulkan_renderer_b200.stripes import ShareGather, share_pixels, share_tiles
 
 
 def _pattern(height, width):
@@ -23,8 +23,8 @@ def _worker(rank, world, port, height, width, result_path):
 	try:
 		sg = ShareGather(height, width, rank, world, torch.device("cpu"))
 		frame = torch.full((height, width, 4), -1.0)
-		cols = share_columns(width, rank, world)
-		frame[:, cols] = _pattern(height, width)[:, cols]      # "shade" this rank's tile columns
+		mine = torch.tensor(share_pixels(width, height, rank, world), dtype=torch.long)
+		frame.view(-1, 4)[mine] = _pattern(height, width).view(-1, 4)[mine]      # "shade" this rank's tiles
 		sg.gather_frame(frame)
 		ok = torch.equal(frame, _pattern(height, width))
 		flags = [torch.zeros(1) for _ in range(world)]
@@ -40,16 +40,19 @@ def _free_port():
 	s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close(); return port
 
 
-def test_share_partition_covers_every_column_and_tile_once():
-	for width in (1920, 3840, 100, 16, 7):
+def test_share_partition_covers_every_tile_and_pixel_once():
+	for width, height in ((1920, 1080), (3840, 2160), (100, 75), (16, 8), (7, 200)):
 		for world in (1, 2, 3, 4, 8):
-			cols = sorted(x for r in range(world) for x in share_columns(width, r, world))
-			assert cols == list(range(width))
-			counts = [len(share_columns(width, r, world)) for r in range(world)]
-			assert max(counts) - min(counts) <= 16     # interleaving balances the ranks to one tile column
-			height = 40
-			tiles = sorted(t for r in range(world) for t in share_tiles(width, height, r, world))
-			assert tiles == list(range(((width + 15) // 16) * 5))
+			tiles_x = (width + 15) // 16; tiles_y = (height + 7) // 8
+			shares = [share_tiles(width, height, r, world) for r in range(world)]
+			assert sorted(t for s in shares for t in s) == list(range(tiles_x * tiles_y))
+			if width * height <= 20000:
+				assert sorted(p for r in range(world) for p in share_pixels(width, height, r, world)) == list(range(width * height))
+			# the deal moves on by one column from band to band (8 tile rows): in band b the first column of rank r is (r - b) % world
+			for r in range(world):
+				for band in range((tiles_y + 7) // 8):
+					first = [t % tiles_x for t in shares[r] if t // tiles_x == 8 * band]
+					assert first == list(range((r - band) % world, tiles_x, world))
 	# the shapes of the benchmark configurations divide evenly: every GPU gets the same number of tiles
 	for width, height in ((1920, 1080), (3840, 2160)):
 		for world in (2, 4, 8):
@@ -57,7 +60,7 @@ def test_share_partition_covers_every_column_and_tile_once():
 
 
 def test_gather_reassembles_the_frame_world_size_2(tmp_path):
-	for height, width in ((24, 100), (16, 1080 // 8), (8, 16)):   # ragged last tile; odd tile count; one tile for two ranks (a rank without a column)
+	for height, width in ((24, 100), (136, 1080 // 8), (8, 16)):   # ragged last tile; more than two bands of tile rows; one tile for two ranks (a rank without a tile)
 		result = tmp_path / ("result_%d_%d.txt" % (height, width))
 		mp.spawn(_worker, args=(2, _free_port(), height, width, str(result)), nprocs=2, join=True)
 		assert result.read_text() == "ok"

@@ -16,6 +16,8 @@
 
 using namespace vkr;
 
+uint32_t vkr_share_first_column(const vkr_shading_pass_desc_t& d, uint32_t band);
+
 #define VKR_CUDA_OK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { printf("%s: %s\n", what, cudaGetErrorString(e_)); return 1; } } while (0)
 
 extern "C" size_t vkr_gbuffer_size(uint32_t width, uint32_t height) { return (size_t) width * height * 4 * sizeof(float) * 4; }
@@ -148,7 +150,8 @@ extern "C" int vkr_create_shading_pass(vkr_shading_pass_t* pass, const vkr_devic
 	// The tiles of this instance (column tx of every tile row with tx % stripe_count == stripe_index), row-major: the launch order of the first frame
 	const uint32_t tiles_x = (d.width + VKR_TILE_WIDTH - 1) / VKR_TILE_WIDTH, tiles_y = (d.height + VKR_TILE_ROW_HEIGHT - 1) / VKR_TILE_ROW_HEIGHT;
 	std::vector<uint32_t> tiles;
-	for (uint32_t ty = 0; ty != tiles_y; ++ty) for (uint32_t tx = d.stripe_index; tx < tiles_x; tx += d.stripe_count) tiles.push_back(ty * tiles_x + tx);
+	for (uint32_t ty = 0; ty != tiles_y; ++ty) // the columns of a share move on by one every VKR_TILE_BAND_ROWS tile rows (see vkr_share_first_column)
+		for (uint32_t tx = vkr_share_first_column(d, ty / VKR_TILE_BAND_ROWS); tx < tiles_x; tx += d.stripe_count) tiles.push_back(ty * tiles_x + tx);
 	pass->tile_count = (uint32_t) tiles.size();
 	const size_t list_bytes = sizeof(uint32_t) * (tiles.empty() ? 1 : tiles.size()), cost_bytes = sizeof(uint32_t) * (size_t) tiles_x * tiles_y;
 	if (cudaMalloc(&pass->d_constants, pass->constants_size) != cudaSuccess || cudaMallocHost(&pass->h_constants_pinned, pass->constants_size) != cudaSuccess
@@ -337,20 +340,32 @@ static int launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, 
 	return vkr_launch_shading(pass, device, constants, constants_size, d_gbuffer, d_out, d_stats, 0, nullptr);
 }
 
+// First tile column of this instance in band `band` (VKR_TILE_BAND_ROWS tile rows): column tx of the band belongs to instance (tx + band) % stripe_count.
+uint32_t vkr_share_first_column(const vkr_shading_pass_desc_t& d, uint32_t band) {
+	return (d.stripe_index + d.stripe_count - band % d.stripe_count) % d.stripe_count;
+}
+
 // This instance's part of one plane (or of the frame), host <-> device. A plane is rows of `texel` bytes per pixel; the instance owns tile column tx of
 // every row if tx % stripe_count == stripe_index, which makes its part a 2D array of 16-pixel segments with a pitch of stripe_count segments: one strided copy.
 int vkr_copy_tile_columns(const vkr_shading_pass_desc_t& d, void* dst, const void* src, size_t texel, cudaMemcpyKind kind, cudaStream_t stream) {
 	const size_t row_bytes = (size_t) d.width * texel, seg = (size_t) VKR_TILE_WIDTH * texel;
 	if (d.stripe_count == 1) return cudaMemcpyAsync(dst, src, row_bytes * d.height, kind, stream) != cudaSuccess;
-	const size_t pitch = seg * d.stripe_count, first = seg * d.stripe_index;
-	if (row_bytes % pitch == 0) // every row holds the same number of whole segments of this instance: the rows chain into one 2D array
-		return cudaMemcpy2DAsync((char*) dst + first, pitch, (const char*) src + first, pitch, seg, (row_bytes / pitch) * d.height, kind, stream) != cudaSuccess;
-	for (uint32_t y = 0; y != d.height; ++y) { // ragged rows: whole segments as a 2D copy per row, then the narrow last segment if it is ours
-		const size_t base = row_bytes * y;
-		size_t whole = 0, tail_at = 0, tail = 0;
-		for (size_t at = first; at < row_bytes; at += pitch) { if (at + seg <= row_bytes) ++whole; else { tail_at = at; tail = row_bytes - at; } }
-		if (whole && cudaMemcpy2DAsync((char*) dst + base + first, pitch, (const char*) src + base + first, pitch, seg, whole, kind, stream) != cudaSuccess) return 1;
-		if (tail && cudaMemcpyAsync((char*) dst + base + tail_at, (const char*) src + base + tail_at, tail, kind, stream) != cudaSuccess) return 1;
+	const size_t pitch = seg * d.stripe_count;
+	const uint32_t band_rows = VKR_TILE_BAND_ROWS * VKR_TILE_ROW_HEIGHT;
+	for (uint32_t y0 = 0, band = 0; y0 < d.height; y0 += band_rows, ++band) { // one band of tile rows: the instance owns the same columns in all of its rows
+		const uint32_t rows = (y0 + band_rows <= d.height) ? band_rows : d.height - y0;
+		const size_t first = seg * vkr_share_first_column(d, band), base = row_bytes * y0;
+		if (row_bytes % pitch == 0) { // every row holds the same number of whole segments of this instance: the rows of the band chain into one 2D array
+			if (cudaMemcpy2DAsync((char*) dst + base + first, pitch, (const char*) src + base + first, pitch, seg, (row_bytes / pitch) * rows, kind, stream) != cudaSuccess) return 1;
+			continue;
+		}
+		for (uint32_t y = 0; y != rows; ++y) { // ragged rows: whole segments as a 2D copy per row, then the narrow last segment if it is ours
+			const size_t row = base + row_bytes * y;
+			size_t whole = 0, tail_at = 0, tail = 0;
+			for (size_t at = first; at < row_bytes; at += pitch) { if (at + seg <= row_bytes) ++whole; else { tail_at = at; tail = row_bytes - at; } }
+			if (whole && cudaMemcpy2DAsync((char*) dst + row + first, pitch, (const char*) src + row + first, pitch, seg, whole, kind, stream) != cudaSuccess) return 1;
+			if (tail && cudaMemcpyAsync((char*) dst + row + tail_at, (const char*) src + row + tail_at, tail, kind, stream) != cudaSuccess) return 1;
+		}
 	}
 	return 0;
 }
