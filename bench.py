@@ -11,7 +11,7 @@ clamped optimal heuristic, shadow rays on. C2 (1 light, 4 spp, diffuse only) and
   value  whole-job Msamples/s (pixels*spp / time), inputs resident in HBM, CUDA events on the launching stream, L2 flushed between
          steps, max over ranks
   e2e    same metric through the C-ABI call with HOST buffers (H2D of the G-buffer and D2H of the frame inside the timed region)
-  N > 1  every GPU shades the tile columns tx % N == rank of the frame (strong scaling); the shading kernel stores finished pixels into
+  N > 1  every GPU shades the screen tiles (tx + ty / 8) % N == rank of the frame (strong scaling); the shading kernel stores finished pixels into
          the frames of all GPUs over NVLink (vkr_frame_exchange_t), two one-block kernels form the barrier: all of it inside the timed
          region. After the timed loop every rank's frame is hashed and compared with a single-GPU render of the same frame.
 
@@ -197,9 +197,9 @@ def run_b200(args):
 		if flags.item() < 0.5:
 			if ok: lib.vkr_destroy_frame_exchange(C.byref(exchange), C.byref(frame.device))
 			exchange = None; gather = ShareGather(height, width, rank, world, dev)
-			exchange_kind = "tile columns tx %% %d == rank, one NCCL all_gather of the HDR tile columns (no peer access between the GPUs)" % world
+			exchange_kind = "screen tiles (tx + ty / 8) %% %d == rank, one NCCL all_gather of the HDR tiles (no peer access between the GPUs)" % world
 		else:
-			exchange_kind = "tile columns tx %% %d == rank, pixels stored into every GPU's frame from the kernel epilogue over NVLink peer memory, two one-block barrier kernels" % world
+			exchange_kind = "screen tiles (tx + ty / 8) %% %d == rank, pixels stored into every GPU's frame from the kernel epilogue over NVLink peer memory, two one-block barrier kernels" % world
 
 	def step_device():
 		if exchange is not None:
