@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit of round 2 (under gpurun): bash tools/gpu_round2.sh <tag> [stage ...]
-#   stages: variants tests bench ref c2 c4 matrix builder launches full   (default: all but c4)
+#   stages: variants tests bench ref c2 c4 matrix builder launches fullc2 full   (default: all but c4 and fullc2)
 tag=${1:-r02}; shift
 stages=${@:-variants tests bench ref c2 matrix builder launches full}
 mkdir -p gpurun_out
@@ -16,5 +16,6 @@ if has builder; then
 	for builder in sah lbvh_gpu; do echo "== VKR_BVH_BUILDER=$builder"; VKR_COUNTERS=1 VKR_BVH_BUILDER=$builder timeout 600 python tools/quick_time.py 64 8 1 3 2>&1 | tail -7 | tee gpurun_out/${tag}_builder_$builder.log; done
 fi
 if has launches; then timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-counters > gpurun_out/${tag}_launches_bench.log 2>&1; tail -2 gpurun_out/${tag}_launches_bench.log | cut -c1-200; fi
+if has fullc2; then timeout 600 ncu --set full --clock-control none --import-source on -k regex:shading_kernel -c 1 -o gpurun_out/${tag}_c2_full -f python tools/quick_time.py 4 1 1 0 > gpurun_out/${tag}_c2_full.log 2>&1; ls -la gpurun_out/${tag}_c2_full.ncu-rep; fi
 if has full; then timeout 900 ncu --set full --clock-control none --import-source on -k regex:shading_kernel -c 1 -o gpurun_out/${tag}_full -f python tools/quick_time.py 64 8 1 3 > gpurun_out/${tag}_full.log 2>&1; ls -la gpurun_out/${tag}_full.ncu-rep; fi
 ls gpurun_out | wc -l
