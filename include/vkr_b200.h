@@ -113,6 +113,8 @@ typedef struct vkr_scene_s {
 	   warps of the shading kernels fetch; the float pairs serve the probes and the tests). shadow_grid = minimum xyz, cells per world unit xyz */
 	void* d_shadow_nodes_quantised;
 	float shadow_grid[6];
+	/* and once more as interleaved pairs (64 bytes, the two children's numbers side by side: the packed-FMA edition of the trace warps, vkr_trace.cuh) */
+	void* d_shadow_nodes_interleaved;
 } vkr_scene_t;
 
 /* device may be NULL for vkr_load_scene / vkr_load_ltc_table / vkr_load_noise_table: the files are parsed and the host

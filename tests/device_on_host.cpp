@@ -208,6 +208,23 @@ extern "C" void vkr_device_on_host_trace_quantised(const float* nodes, uint64_t 
 	}
 }
 
+// Interleaved node pairs (vkr_trace.cuh): the float pairs of a tree re-arranged with interleave_node_pair(), then the same rays through occluded() on the float
+// pairs and occluded_interleaved() (the packed-FMA form of the slab test, plain fmaf on the host) on the interleaved ones. visits[2]: pairs fetched by each
+extern "C" void vkr_device_on_host_trace_interleaved(const float* nodes, uint64_t pair_count, const float* tris, uint32_t ray_count, const float* rays, uint8_t* out_float, uint8_t* out_interleaved, float* out_pairs16, uint64_t* visits) {
+	bvh_view bvh; bvh.nodes = reinterpret_cast<const float4*>(nodes); bvh.tris = reinterpret_cast<const float4*>(tris); bvh.tri_ids = nullptr; bvh.tri_count = 0;
+	for (uint64_t i = 0; i != pair_count; ++i) interleave_node_pair(bvh.nodes + 4 * i, out_pairs16 + 16 * i);
+	int stack[kMaxStackDepth + 2];
+	visits[0] = visits[1] = 0;
+	for (uint32_t i = 0; i != ray_count; ++i) {
+		const float* r = rays + 8 * (size_t) i;
+		const f3 o = make3(r[0], r[1], r[2]), d = make3(r[3], r[4], r[5]);
+		int v0 = 0, v1 = 0;
+		out_float[i] = occluded_anchored(bvh, o, d, r[6], r[7], nullptr, 0, 0, 0u, stack, 1, &v0) ? 1 : 0;   // no origin path: the plain traversal, counting its visits
+		out_interleaved[i] = occluded_interleaved(out_pairs16, bvh.tris, o, d, r[6], r[7], stack, 1, &v1) ? 1 : 0;
+		visits[0] += (uint64_t) v0; visits[1] += (uint64_t) v1;
+	}
+}
+
 // Anchored shadow rays (vkr_anchor.cuh): rays from `origins` towards points of a polygonal light through (a) the plain traversal, (b) the anchored one with
 // all siblings of the origin path, (c) with the siblings the light's cone touches; rays = {origin index, dx, dy, dz, tmax}. out[3 * i + {0, 1, 2}] = answers,
 // visits[3]: node pairs fetched in total, info = {rays outside their cone, siblings kept, siblings along the paths}

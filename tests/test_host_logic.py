@@ -281,6 +281,35 @@ def test_quantised_node_pairs_answer_like_the_float_pairs(name):
 	assert np.array_equal(pairs8[:, 6:8], n2[:, 12:14].copy().view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["cornell", "mini_city", "mini_room"])
+def test_interleaved_node_pairs_visit_and_answer_like_the_float_pairs(name):
+	"""The packed-FMA edition of the trace warps walks node pairs whose two children are stored side by side (vkr_trace.cuh): the same numbers in another order and
+	the same IEEE fma per slab plane, so a ray visits exactly the pairs it visits in the float layout and gets the same answer."""
+	from tests.test_device_on_host import _lib
+	dev = _lib(); lib = api.load_library()
+	info = H.dataset(name); vks = H.read_vks(info["vks"])
+	tris = H.oracle.dequantize_for_bvh(vks["positions"], vks["factor"], vks["summand"])
+	nodes, slots, ids, depth = _probe_bvh(lib, tris, BUILDERS["sah"])
+	n2 = np.ascontiguousarray(nodes, dtype=np.float32); sl = np.ascontiguousarray(slots, dtype=np.float32)
+	rng = np.random.default_rng(23)
+	T = tris.reshape(-1, 3, 3); blo = T.reshape(-1, 3).min(0); bhi = T.reshape(-1, 3).max(0)
+	n_rays = 6000
+	origins = rng.uniform(blo, bhi, (n_rays, 3)); targets = T[rng.integers(0, len(T), n_rays)].mean(1) + rng.normal(scale=0.02, size=(n_rays, 3))
+	origins[:2000] = T[rng.integers(0, len(T), 2000)].mean(1)
+	d = targets - origins; length = np.linalg.norm(d, axis=1, keepdims=True); length[length == 0] = 1.0; d /= length
+	rays = np.concatenate([origins, d, np.full((n_rays, 1), 1e-3), length * rng.uniform(0.3, 1.5, (n_rays, 1))], axis=1).astype(np.float32)
+	rays[:60, 3:6] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 60)] * rng.choice([-1.0, 1.0], (60, 1)).astype(np.float32)   # axis-parallel: infinite slab distances, NaN planes
+	out_f = np.zeros(n_rays, dtype=np.uint8); out_i = np.zeros(n_rays, dtype=np.uint8); pairs16 = np.zeros((len(n2), 16), dtype=np.float32); visits = (C.c_uint64 * 2)()
+	dev.vkr_device_on_host_trace_interleaved(n2.ctypes.data_as(C.c_void_p), C.c_uint64(len(n2)), sl.ctypes.data_as(C.c_void_p), C.c_uint32(n_rays), rays.ctypes.data_as(C.c_void_p),
+		out_f.ctypes.data_as(C.c_void_p), out_i.ctypes.data_as(C.c_void_p), pairs16.ctypes.data_as(C.c_void_p), visits)
+	assert np.array_equal(out_f, out_i) and 0.01 < out_f.mean() < 0.995
+	assert visits[0] == visits[1] and visits[0] > n_rays
+	# the layout: centres, then half extents, children side by side; references untouched
+	assert np.array_equal(pairs16[:, 0:6:2], n2[:, 0:3]) and np.array_equal(pairs16[:, 1:6:2], n2[:, 6:9])
+	assert np.array_equal(pairs16[:, 6:12:2], n2[:, 3:6]) and np.array_equal(pairs16[:, 7:12:2], n2[:, 9:12])
+	assert np.array_equal(pairs16[:, 12:14].copy().view(np.uint32), n2[:, 12:14].copy().view(np.uint32))
+
+
 @pytest.mark.parametrize("name,light", [("mini_city", 0), ("mini_city", 2), ("mini_room", 5), ("cornell", 0)])
 def test_anchored_shadow_rays_answer_like_the_plain_traversal(name, light):
 	"""vkr_anchor.cuh (compiled for the CPU): shadow rays that start at the siblings of their pixel's origin path -- all of them, or those the light's cone

@@ -57,7 +57,7 @@ class Scene(C.Structure):
 		("shadow_node_count", C.c_uint64), ("primary_node_count", C.c_uint64),
 		("shadow_max_depth", C.c_uint32), ("primary_max_depth", C.c_uint32), ("build_seconds", C.c_double),
 		("textured", C.c_int), ("d_texture_data", C.c_void_p), ("d_texture_dims", C.c_void_p), ("d_texture_offsets", C.c_void_p), ("texture_texel_count", C.c_uint64), ("shadow_bvh_width", C.c_uint32),
-		("d_shadow_nodes_quantised", C.c_void_p), ("shadow_grid", C.c_float * 6)]
+		("d_shadow_nodes_quantised", C.c_void_p), ("shadow_grid", C.c_float * 6), ("d_shadow_nodes_interleaved", C.c_void_p)]
 
 
 class LtcConstants(C.Structure):

@@ -310,6 +310,8 @@ int vkr_launch_shading(vkr_shading_pass_t* pass, const vkr_device_t* device, con
 		p.stack_depth = (int) d.scene->shadow_max_depth + 2;
 		p.bvh_width = d.scene->shadow_bvh_width ? (int) d.scene->shadow_bvh_width : 2;
 		p.bvh_nodes_q = (const uint4*) d.scene->d_shadow_nodes_quantised;
+		p.bvh_nodes_i = (const float4*) d.scene->d_shadow_nodes_interleaved;
+		if (p.bvh_width == 2 && !p.bvh_nodes_i) { printf("The scene holds no interleaved node pairs for the shadow rays (a scene object that was not made by this library?).\n"); return 1; }
 		for (int k = 0; k != 6; ++k) p.bvh_grid[k] = d.scene->shadow_grid[k];
 	}
 	if (any_textured_light) {

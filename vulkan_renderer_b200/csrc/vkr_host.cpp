@@ -87,7 +87,7 @@ extern "C" void vkr_destroy_scene(vkr_scene_t* scene, const vkr_device_t* device
 	free(scene->material_params);
 	void* dev_ptrs[] = { scene->d_quantized_positions, scene->d_normals_and_tex_coords, scene->d_material_indices, scene->d_material_params,
 		scene->d_shadow_nodes, scene->d_shadow_tris, scene->d_primary_nodes, scene->d_primary_tris, scene->d_primary_tri_ids,
-		scene->d_texture_data, scene->d_texture_dims, scene->d_texture_offsets, scene->d_shadow_nodes_quantised };
+		scene->d_texture_data, scene->d_texture_dims, scene->d_texture_offsets, scene->d_shadow_nodes_quantised, scene->d_shadow_nodes_interleaved };
 	for (void* p : dev_ptrs) if (p) cudaFree(p);
 	memset(scene, 0, sizeof(*scene));
 }
@@ -162,6 +162,10 @@ static int scene_from_arrays(vkr_scene_t* scene, const vkr_device_t* device, con
 			shadow_grid_from_root(root, scene->shadow_grid);
 			if (quantise_node_pairs_device(scene->d_shadow_nodes, scene->shadow_node_count, scene->shadow_grid, &scene->d_shadow_nodes_quantised, device->stream)) {
 				printf("Failed to quantise the acceleration structure for the scene file at path %s.\n", file_path);
+				vkr_destroy_scene(scene, device); return 1;
+			}
+			if (interleave_node_pairs_device(scene->d_shadow_nodes, scene->shadow_node_count, &scene->d_shadow_nodes_interleaved, device->stream)) {
+				printf("Failed to interleave the acceleration structure for the scene file at path %s.\n", file_path);
 				vkr_destroy_scene(scene, device); return 1;
 			}
 		}

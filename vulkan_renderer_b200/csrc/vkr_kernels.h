@@ -39,6 +39,7 @@ struct shading_kernel_params {
 	const float4* bvh_nodes; const float4* bvh_tris; uint32_t tri_count;
 	const uint4* bvh_nodes_q;        // the same node pairs quantised to 32 bytes (vkr_trace.cuh): what the trace warps walk
 	float bvh_grid[6];               // the grid of the quantised boxes: minimum xyz, cells per world unit xyz
+	const float4* bvh_nodes_i;       // the same node pairs with the two children interleaved (vkr_trace.cuh): what the trace warps of the VKR_INTERLEAVED_NODES edition walk
 	int stack_depth;                 // traversal stack entries per lane (BVH depth + 2)
 	int polygon_sampling_technique;  // sample_polygon_technique_t (src/polygonal_light.h:30-66); 0..10 run vkr_related_work_kernel.cu
 	int bvh_width;                   // children per node of bvh_nodes: 2 (node pairs, default) or 4 (experimental, must equal the kernels' VKR_BVH_WIDTH)
@@ -88,5 +89,7 @@ cudaError_t vkr_launch_related_work_kernel_maxv6(const vkr::shading_kernel_param
 cudaError_t vkr_launch_related_work_kernel_maxv7(const vkr::shading_kernel_params& p, cudaStream_t stream);
 // float node pairs -> quantised node pairs (vkr_lbvh_gpu.cu); d_nodes_q: 32 bytes per pair
 cudaError_t vkr_quantise_node_pairs(const float4* d_nodes, uint64_t pair_count, const float grid[6], uint4* d_nodes_q, cudaStream_t stream);
+// float node pairs -> interleaved node pairs (vkr_lbvh_gpu.cu); d_nodes_i: 64 bytes per pair
+cudaError_t vkr_interleave_node_pairs(const float4* d_nodes, uint64_t pair_count, float4* d_nodes_i, cudaStream_t stream);
 cudaError_t vkr_launch_visibility_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);
 cudaError_t vkr_launch_gbuffer_kernel(const vkr::gbuffer_kernel_params& p, cudaStream_t stream);

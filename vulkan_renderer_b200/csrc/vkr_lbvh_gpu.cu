@@ -233,3 +233,33 @@ int quantise_node_pairs_device(const void* d_nodes, uint64_t pair_count, const f
 	return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Interleaved node pairs for the trace warps (vkr_trace.cuh): one thread per pair
+namespace vkr {
+__global__ void interleave_pairs_kernel(const float4* __restrict__ nodes, unsigned long long count, float4* __restrict__ out) {
+	const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	float w[16];
+	interleave_node_pair(nodes + 4 * i, w);
+	for (int k = 0; k != 4; ++k) out[4 * i + k] = make_float4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+} // namespace vkr
+
+cudaError_t vkr_interleave_node_pairs(const float4* d_nodes, uint64_t pair_count, float4* d_nodes_i, cudaStream_t stream) {
+	if (!pair_count) return cudaSuccess;
+	vkr::interleave_pairs_kernel<<<(unsigned) ((pair_count + 255) / 256), 256, 0, stream>>>(d_nodes, (unsigned long long) pair_count, d_nodes_i);
+	return cudaGetLastError();
+}
+
+namespace vkr {
+// For the host code (vkr_host.cpp): allocates the interleaved pairs and fills them from the float pairs on the device
+int interleave_node_pairs_device(const void* d_nodes, uint64_t pair_count, void** d_nodes_i, void* stream) {
+	*d_nodes_i = nullptr;
+	if (cudaMalloc(d_nodes_i, 64 * (size_t) (pair_count ? pair_count : 1)) != cudaSuccess) { *d_nodes_i = nullptr; return 1; }
+	if (vkr_interleave_node_pairs((const float4*) d_nodes, pair_count, (float4*) *d_nodes_i, (cudaStream_t) stream) != cudaSuccess || cudaStreamSynchronize((cudaStream_t) stream) != cudaSuccess) {
+		cudaFree(*d_nodes_i); *d_nodes_i = nullptr; return 1;
+	}
+	return 0;
+}
+}

@@ -51,8 +51,18 @@ constexpr int kNodeLoopMinLanes = VKR_NODE_LOOP_MIN_LANES;
 #ifndef VKR_REFILL_MIN_LANES
 #define VKR_REFILL_MIN_LANES 1
 #endif
+// 1 (default since the last GPU visit of round 2: -4.3 % frame time): the decisions at the end of a node visit -- which child is entered, what is pushed, when the
+// stack is popped, the leaf that is put aside -- are written as predicated instructions (inline PTX) instead of an if / else chain: no divergent branch with
+// its BSSY / BRA / BSYNC inside the visit, 54 instead of 59 instructions. 0 keeps the C++ form (the anchored and 4-wide editions need it).
+#ifndef VKR_LEAN_NODE_STEP
+#define VKR_LEAN_NODE_STEP (!VKR_ANCHORED && VKR_BVH_WIDTH == 2)
+#endif
 #ifndef VKR_LEAF_ONCE
 #define VKR_LEAF_ONCE 0
+#endif
+// 0: a lane leaves the node loop with the first leaf it meets (one leaf reference is picked up after the loop) instead of putting one leaf aside and descending on
+#ifndef VKR_LEAF_POSTPONE
+#define VKR_LEAF_POSTPONE 1
 #endif
 #ifndef VKR_STACK_TOP_IN_REGISTER
 #define VKR_STACK_TOP_IN_REGISTER 0
@@ -80,8 +90,20 @@ VKR_DEV void shading_lockstep_barrier() {
 #ifndef VKR_QUANTISED_NODES
 #define VKR_QUANTISED_NODES 0
 #endif
+// 1 (default: another -1.4 %): the trace warps walk the interleaved node pairs (vkr_trace.cuh: the two children's numbers side by side, so that the slab
+// arithmetic of both children is 9 packed FMAs instead of 18 scalar ones) instead of the plain float pairs. Measured on the B200 (profiles/r02_variants.md):
+// 371.6 ms (C++ step, float pairs) -> 355.7 (predicated step) -> 350.6 (+ packed FMAs); FFMA2 evidently costs more than one issue slot, hence the small second step.
+#ifndef VKR_INTERLEAVED_NODES
+#define VKR_INTERLEAVED_NODES (!VKR_ANCHORED && !VKR_QUANTISED_NODES && VKR_BVH_WIDTH == 2)
+#endif
 #if VKR_ANCHORED && VKR_BVH_WIDTH != 2
 #error "anchored rays walk node pairs"
+#endif
+#if VKR_LEAN_NODE_STEP && (VKR_ANCHORED || VKR_BVH_WIDTH != 2 || VKR_STACK_TOP_IN_REGISTER)
+#error "the predicated node step: not with anchored rays, 4-wide nodes or the stack top in a register (-DVKR_LEAN_NODE_STEP=0)"
+#endif
+#if VKR_INTERLEAVED_NODES && (VKR_ANCHORED || VKR_QUANTISED_NODES || VKR_BVH_WIDTH != 2)
+#error "interleaved node pairs: not with anchored rays, quantised pairs or 4-wide nodes"
 #endif
 #ifndef VKR_RESOLVE_SLEEP_NS
 #define VKR_RESOLVE_SLEEP_NS 512
@@ -292,7 +314,7 @@ VKR_DEV void close_stream(ray_producer& q, int lane, pixel_sum& acc, unsigned lo
 // lane's column of the warp's traversal stack (128 B between levels = one slot per lane).
 template <bool OPTIMAL>
 VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes, const float4* __restrict__ tris, const uint32_t stack_bottom, int lane, unsigned long long* stats = nullptr,
-	const uint4* __restrict__ nodes_q = nullptr, f3 grid_min = f3(), f3 grid_scale = f3())
+	const uint4* __restrict__ nodes_q = nullptr, f3 grid_min = f3(), f3 grid_scale = f3(), const float4* __restrict__ nodes_i = nullptr)
 {
 #ifdef VKR_TRACE_STATS
 	unsigned st_rays = 0, st_hits = 0, st_cache_hits = 0, st_visits = 0, st_leaves = 0, st_tris = 0, st_iters = 0, st_node_iters = 0, st_known = 0, st_polls = 0, st_siblings = 0;
@@ -472,14 +494,52 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			const int ref0 = __float_as_int(q1.z), ref1 = __float_as_int(q1.w);
 			const bool h0 = ray_box_grid(__float_as_uint(q0.x), __float_as_uint(q0.y), __float_as_uint(q0.z), r, tmin, tmax, &tn0);
 			const bool h1 = ray_box_grid(__float_as_uint(q0.w), __float_as_uint(q1.x), __float_as_uint(q1.y), r, tmin, tmax, &tn1);
+#elif VKR_INTERLEAVED_NODES
+			// one interleaved pair (vkr_trace.cuh): the slab arithmetic of both children in packed FMAs
+			const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes_i) + (size_t) ((uint32_t) node << 6));
+			float4 q0, q1, q2, q3;
+			ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3);
+			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
+			bool h0, h1;
+			{
+				const float a[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w }, b[4] = { q2.x, q2.y, q2.z, q2.w };
+				ray_box_pair(a, b, r, tmin, tmax, &h0, &h1, &tn0, &tn1);
+			}
+#else
+#if VKR_LEAN_NODE_STEP
+			// the node's address as base + 32-bit byte offset (a tree has fewer than 2^26 pairs: vkr_host.cpp), so that the step needs no 64-bit multiply
+			const float4* nd = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (size_t) ((uint32_t) node << 6));
 #else
 			const float4* nd = nodes + 4 * (size_t) node;
+#endif
 			float4 q0, q1, q2, q3;
 			ldg_256(nd, q0, q1); ldg_256(nd + 2, q2, q3);
 			const int ref0 = __float_as_int(q3.x), ref1 = __float_as_int(q3.y);
 			const bool h0 = ray_box(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, tmin, tmax, &tn0) && skip != 0;
 			const bool h1 = ray_box(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, tmin, tmax, &tn1) && skip != 1;
 #endif
+#if VKR_LEAN_NODE_STEP
+			{ // The same decisions as below, written out as predicates: no divergent branch (BSSY / BRA / BSYNC) in the step, the far child is stored and the
+			  // stack is popped under predicates. (h0, h1 and the distances come from ray_box(); tn <= tf is false for NaN like there.)
+				const int h0i = h0, h1i = h1;
+				asm volatile("{\n\t.reg .pred h0, h1, both, none, second, take;\n\t.reg .b32 far;\n\t"
+					"setp.ne.b32 h0, %3, 0;\n\tsetp.ne.b32 h1, %4, 0;\n\t"
+					"setp.lt.f32 second, %6, %5;\n\t"                 // child 1 is nearer ...
+					"and.pred both, h0, h1;\n\t"
+					"or.pred none, h0, h1;\n\tnot.pred none, none;\n\t"
+					"not.pred take, h0;\n\tor.pred second, second, take;\n\tand.pred second, second, h1;\n\t"   // ... or the only one hit: it is entered
+					"selp.b32 %1, %8, %7, second;\n\tselp.b32 far, %7, %8, second;\n\t"
+					"@both st.shared.b32 [%0], far;\n\t@both add.u32 %0, %0, 128;\n\t"
+					"@none sub.u32 %0, %0, 128;\n\t@none ld.shared.b32 %1, [%0];\n\t"
+#if VKR_LEAF_POSTPONE
+					// postpone the first leaf, keep descending
+					"setp.lt.s32 take, %1, 0;\n\tsetp.eq.and.s32 take, %2, 0, take;\n\t"
+					"@take mov.b32 %2, %1;\n\t@take sub.u32 %0, %0, 128;\n\t@take ld.shared.b32 %1, [%0];\n\t"
+#endif
+					"}"
+					: "+r"(top), "=&r"(node), "+r"(leaf) : "r"(h0i), "r"(h1i), "f"(tn0), "f"(tn1), "r"(ref0), "r"(ref1) : "memory");
+			}
+#else
 			if (h0 && h1) {
 				const bool swap = tn1 < tn0;   // nearer child first: occluders close to the surface end the query early
 				node = swap ? ref1 : ref0;
@@ -488,10 +548,13 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 			else if (h0) node = ref0;
 			else if (h1) node = ref1;
 			else node = pop();
+#endif
+#if !VKR_LEAN_NODE_STEP && VKR_LEAF_POSTPONE
 			if (node < 0 && leaf == 0) { // postpone the first leaf, keep descending
 				leaf = node;
 				node = pop();
 			}
+#endif
 			// lanes that are done or hold two leaves wait at the loop exit: once too few are left descending, let
 			// everybody test triangles and fetch new rays (affects lane utilisation only, not results)
 #if VKR_NODE_LOOP_CHECK_EVERY > 1
@@ -501,6 +564,9 @@ VKR_DEV void trace_stream(const uint32_t base, const float4* __restrict__ nodes,
 		}
 #endif
 		__syncwarp(kFullMask);
+#if !VKR_LEAF_POSTPONE
+		if (active && node < 0 && leaf == 0) { leaf = node; node = pop(); }
+#endif
 		// --- leaves: `leaf` and possibly `node` (a second leaf)
 #if VKR_LEAF_ONCE
 		if (leaf != 0) {

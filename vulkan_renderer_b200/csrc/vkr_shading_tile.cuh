@@ -53,7 +53,7 @@ VKR_DEV void shade_tile(const shading_kernel_params& p, const LightShader& shade
 			const int t = warp - kShadeWarps;
 			trace_stream<OPTIMAL>(smem_addr(stream_base + stream_floats_per_warp(OPTIMAL) * (t & (kShadeWarps - 1))), p.bvh_nodes, p.bvh_tris,
 				smem_addr(stack_base + p.stack_depth * 32 * t + lane), lane, p.stats, p.bvh_nodes_q,
-				make3(p.bvh_grid[0], p.bvh_grid[1], p.bvh_grid[2]), make3(p.bvh_grid[3], p.bvh_grid[4], p.bvh_grid[5]));
+				make3(p.bvh_grid[0], p.bvh_grid[1], p.bvh_grid[2]), make3(p.bvh_grid[3], p.bvh_grid[4], p.bvh_grid[5]), p.bvh_nodes_i);
 			return;
 		}
 		asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(VKR_SHADE_REGS));

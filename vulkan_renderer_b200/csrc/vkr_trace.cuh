@@ -98,6 +98,68 @@ VKR_DEV bool ray_box(float cx, float cy, float cz, float hx, float hy, float hz,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------------
+// Interleaved node pairs: the same 64 bytes per pair with the two children's numbers next to each other,
+//   float 0..7   c0.x c1.x  c0.y c1.y  c0.z c1.z  h0.x h1.x        float 8..15   h0.y h1.y  h0.z h1.z  ref0 ref1  -  -
+// so that the two 256-bit loads of a visit leave (child 0, child 1) in aligned register pairs and the slab arithmetic of BOTH children is done by
+// the packed FMA of sm_100 (fma.rn.f32x2 -> FFMA2: pair * scalar + pair, the scalar broadcast with its sign / absolute value as operand modifiers):
+// 9 FFMA2 instead of 18 FFMA per visit, each half an IEEE fma with the operands of ray_box(), so a visit decides exactly as before. The trace warps are
+// bound by instruction issue: a visit is ~50 instructions, every one taken out of it is worth 0.8 % of the frame.
+VKR_DEV void interleave_node_pair(const float4* __restrict__ pair, float* out16) {
+	const float4 q0 = pair[0], q1 = pair[1], q2 = pair[2], q3 = pair[3];
+	out16[0] = q0.x; out16[1] = q1.z; out16[2] = q0.y; out16[3] = q1.w; out16[4] = q0.z; out16[5] = q2.x;   // centres
+	out16[6] = q0.w; out16[7] = q2.y; out16[8] = q1.x; out16[9] = q2.z; out16[10] = q1.y; out16[11] = q2.w; // half extents
+	out16[12] = q3.x; out16[13] = q3.y; out16[14] = 0.0f; out16[15] = 0.0f;
+}
+// (d0, d1) = (a0, a1) * s + (c0, c1), one instruction on the device
+VKR_DEV void fma_pair(float& d0, float& d1, float a0, float a1, float s, float c0, float c1) {
+#if defined(__CUDA_ARCH__)
+	asm("{ .reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\tmov.b64 c, {%5, %6};\n\tfma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d; }"
+		: "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(s), "f"(c0), "f"(c1));
+#else
+	d0 = fmaf(a0, s, c0); d1 = fmaf(a1, s, c1);
+#endif
+}
+// ray_box() for the two children of an interleaved pair (a = floats 0..7, b = floats 8..11)
+VKR_DEV void ray_box_pair(const float (&a)[8], const float (&b)[4], const ray_slabs& r, float tmin, float tmax, bool* h0, bool* h1, float* tn0, float* tn1) {
+	float mx0, mx1, my0, my1, mz0, mz1, nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;
+	const float nox = -r.oid.x, noy = -r.oid.y, noz = -r.oid.z;
+	fma_pair(mx0, mx1, a[0], a[1], r.id.x, nox, nox); fma_pair(my0, my1, a[2], a[3], r.id.y, noy, noy); fma_pair(mz0, mz1, a[4], a[5], r.id.z, noz, noz);
+	const float ax = fabsf(r.id.x), ay = fabsf(r.id.y), az = fabsf(r.id.z);
+	fma_pair(nx0, nx1, a[6], a[7], -ax, mx0, mx1); fma_pair(ny0, ny1, b[0], b[1], -ay, my0, my1); fma_pair(nz0, nz1, b[2], b[3], -az, mz0, mz1);
+	fma_pair(fx0, fx1, a[6], a[7], ax, mx0, mx1); fma_pair(fy0, fy1, b[0], b[1], ay, my0, my1); fma_pair(fz0, fz1, b[2], b[3], az, mz0, mz1);
+	*tn0 = fmaxf(fmaxf(nx0, ny0), fmaxf(nz0, tmin)); *tn1 = fmaxf(fmaxf(nx1, ny1), fmaxf(nz1, tmin));
+	const float tf0 = fminf(fminf(fx0, fy0), fminf(fz0, tmax)), tf1 = fminf(fminf(fx1, fy1), fminf(fz1, tmax));
+	*h0 = *tn0 <= tf0; *h1 = *tn1 <= tf1;
+}
+// Per-thread any-hit query over interleaved pairs (16 floats each): the reference form of the trace warps' loop, run on the CPU against occluded().
+VKR_DEV bool occluded_interleaved(const float* __restrict__ pairs16, const float4* __restrict__ tris, f3 o, f3 d, float tmin, float tmax, int* stack, int stride, int* visits) {
+	if (!(tmax > tmin)) return false;
+	const ray_slabs r = make_slabs(o, d);
+	int sp = 0, node = 0;
+	float t, tn0, tn1;
+	while (true) {
+		if (node < 0) {
+			const int first = (node & 0x7fffffff) >> 4, count = node & 15;
+			for (int i = 0; i != count; ++i)
+				if (ray_triangle(tris + 3 * (size_t) (first + i), o, d, tmin, tmax, &t)) return true;
+			if (sp == 0) return false;
+			--sp; node = stack[sp * stride];
+			continue;
+		}
+		if (visits) ++*visits;
+		const float* w = pairs16 + 16 * (size_t) node;
+		const float a[8] = { w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7] }, b[4] = { w[8], w[9], w[10], w[11] };
+		bool h0, h1;
+		ray_box_pair(a, b, r, tmin, tmax, &h0, &h1, &tn0, &tn1);
+		const int ref0 = __float_as_int(w[12]), ref1 = __float_as_int(w[13]);
+		if (h0 && h1) { const bool swap = tn1 < tn0; stack[sp * stride] = swap ? ref0 : ref1; ++sp; node = swap ? ref1 : ref0; }
+		else if (h0) node = ref0;
+		else if (h1) node = ref1;
+		else { if (sp == 0) return false; --sp; node = stack[sp * stride]; }
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------------
 // Quantised node pairs: the form the trace warps of the shading kernels walk. ncu puts those warps at the limit of the L1 data pipe (74 % of its
 // wavefronts, 87 % of them node fetches of lanes that diverge): the lever is bytes per visit, not instructions. A pair shrinks from 64 to 32 bytes
 // -- one 256-bit load, one sector per lane -- by storing the two child boxes as 16-bit coordinates on a grid over the scene's bounding box:
