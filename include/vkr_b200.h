@@ -456,6 +456,10 @@ int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, 
 int vkr_sample_polygon_batch(const vkr_device_t* device, uint32_t vertex_count, const float* vertices_xyz, int biased,
 	uint32_t n, const float* random_numbers, float* out_dirs, float* out_info);
 
+/* ---- arithmetic probe: the kernels' reciprocal square root (one range check in front of the square root's and the reciprocal's fast paths, csrc/vkr_device_math.cuh)
+        against its definition 1.0f / sqrtf(x) for all 2^32 floats on the device; mismatches must come back 0 */
+int vkr_probe_rsqrt_exhaustive(const vkr_device_t* device, uint64_t* out_mismatches, uint32_t* out_first_mismatch_bits);
+
 /* ---- BVH builder probe (structural tests on the host; arrays are malloc'ed, release with vkr_bvh_free_probe).
         nodes: 16 floats per node pair, tris: 12 floats per slot, tri_ids: original index per slot (layout: csrc/vkr_trace.cuh) */
 /* builder: 0 = binned SAH (the default of vkr_load_scene), 1 = linear BVH (the host reference of the GPU builder; VKR_BVH_BUILDER=lbvh) */

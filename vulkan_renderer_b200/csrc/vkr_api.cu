@@ -454,7 +454,38 @@ __global__ void sample_probe_kernel(int vertex_count, const float* vertices, uin
 	out_dirs[3 * i] = d.x; out_dirs[3 * i + 1] = d.y; out_dirs[3 * i + 2] = d.z;
 }
 
+// every float through rsqrt_ieee() and through its definition (vkr_device_math.cuh); a NaN answers a NaN, everything else has to agree bit for bit
+__global__ void rsqrt_probe_kernel(unsigned long long* mismatches, unsigned int* first_bad) {
+	const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+	unsigned local = 0;
+	for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32); i += stride) {
+		const float x = __uint_as_float((unsigned) i);
+		const float a = rsqrt_ieee(x), b = rsqrt_ieee_reference(x);
+		if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) { ++local; atomicMin(first_bad, (unsigned) i); }
+	}
+	if (local) atomicAdd(mismatches, (unsigned long long) local);
+}
+
 } // namespace vkr
+
+extern "C" int vkr_probe_rsqrt_exhaustive(const vkr_device_t* device, uint64_t* out_mismatches, uint32_t* out_first_mismatch_bits) {
+	VKR_CUDA_OK(cudaSetDevice(device->cuda_device), "Failed to select the CUDA device");
+	cudaStream_t stream = (cudaStream_t) device->stream;
+	unsigned long long* d_count = nullptr; unsigned int* d_first = nullptr;
+	VKR_CUDA_OK(cudaMalloc(&d_count, sizeof(unsigned long long)), "Failed to allocate the probe's counter");
+	if (cudaMalloc(&d_first, sizeof(unsigned int)) != cudaSuccess) { cudaFree(d_count); printf("Failed to allocate the probe's result.\n"); return 1; }
+	cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream); cudaMemsetAsync(d_first, 0xff, sizeof(unsigned int), stream);
+	vkr::rsqrt_probe_kernel<<<148 * 8, 256, 0, stream>>>(d_count, d_first);
+	cudaError_t err = cudaGetLastError();
+	unsigned long long count = 0; unsigned int first = 0;
+	cudaMemcpyAsync(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost, stream); cudaMemcpyAsync(&first, d_first, sizeof(first), cudaMemcpyDeviceToHost, stream);
+	cudaError_t err2 = cudaStreamSynchronize(stream);
+	cudaFree(d_count); cudaFree(d_first);
+	VKR_CUDA_OK(err, "Failed to launch the reciprocal square root probe");
+	VKR_CUDA_OK(err2, "The reciprocal square root probe failed");
+	*out_mismatches = (uint64_t) count; *out_first_mismatch_bits = (uint32_t) first;
+	return 0;
+}
 
 extern "C" int vkr_trace_shadow_rays(const vkr_device_t* device, const vkr_scene_t* scene, uint32_t ray_count, const float* rays, uint8_t* out_occluded) {
 	if (!scene->d_shadow_nodes) { printf("Cannot trace shadow rays: the scene was loaded without acceleration structure.\n"); return 1; }
